@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (read-only /root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py [mdct] [nets] [train]
+
+The reference is imported unmodified with the three stubs SURVEY.md section 8c lists
+(torch_scatter, matplotlib -> dummies; bottleneck_transformer_pytorch -> our
+restatement oracle/bottlestack_ref.py, which is therefore "parity unpinned").
+Nothing from the reference is copied into the repo: only its numeric outputs.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MDCTGAN_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    sys.path.insert(0, ROOT)
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter = None
+    sys.modules["torch_scatter"] = ts
+    mp = types.ModuleType("matplotlib")
+    pp = types.ModuleType("matplotlib.pyplot")
+    pp.switch_backend = lambda *a, **k: None
+    mp.pyplot = pp
+    sys.modules["matplotlib"] = mp
+    sys.modules["matplotlib.pyplot"] = pp
+    import oracle.bottlestack_ref as bs
+
+    sys.modules["bottleneck_transformer_pytorch"] = bs
+    sys.path.insert(0, REF)
+
+
+def ref_opt(extra=()):
+    """TrainOptions().parse() with the hot-path flags."""
+    import tempfile
+
+    from options.train_options import TrainOptions
+
+    tmp = tempfile.mkdtemp()
+    argv = ["x", "--name", "g", "--checkpoints_dir", tmp, "--gpu_ids", "-1",
+            "--lr_sampling_rate", "12000", "--sr_sampling_rate", "48000",
+            "--arcsinh_transform", "--abs_spectro", "--arcsinh_gain", "1000", "--center",
+            "--norm_range", "-1", "1", "--abs_norm", "--src_range", "-5", "5"] + list(extra)
+    old = sys.argv
+    sys.argv = argv
+    try:
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt = TrainOptions().parse()
+    finally:
+        sys.argv = old
+    return opt
+
+
+def gen_mdct():
+    from models.mdct import IMDCT4, MDCT4
+    from models.pix2pixHD_model import Audio2MDCT
+    from util.util import kbdwin
+
+    out = {}
+    w = kbdwin(512)
+    out["kbdwin512"] = w.numpy()
+    out["kbdwin1024"] = kbdwin(1024).numpy()
+    out["kbdwin64"] = kbdwin(64).numpy()
+    fwd = MDCT4(n_fft=512, hop_length=256, win_length=512, window=w, device="cpu")
+    inv = IMDCT4(n_fft=512, hop_length=256, win_length=512, window=w, device="cpu")
+
+    # cfg1: one 8192-sample clip, 1-D input (BASELINE.json configs[0])
+    torch.manual_seed(0)
+    x = 0.1 * torch.randn(8192)
+    spec, frames = fwd(x, True)
+    audio, _ = inv(spec.unsqueeze(0).clone())
+    out["c1_x"] = x.numpy()
+    out["c1_spec"] = spec.numpy()
+    out["c1_frames"] = frames.numpy()
+    out["c1_audio"] = audio.numpy()
+
+    # batched 2-D input, 32 frames (network segment length 7936)
+    torch.manual_seed(1)
+    xb = 0.1 * torch.randn(4, 7936)
+    specb, _ = fwd(xb)
+    audiob, _ = inv(specb.clone())
+    out["b4_x"] = xb.numpy()
+    out["b4_spec"] = specb.numpy()
+    out["b4_audio"] = audiob.numpy()
+
+    # ragged lengths: the len(signal)==batch quirk (mdct.py:394-402)
+    torch.manual_seed(2)
+    xr = 0.1 * torch.randn(3, 1000)
+    specr, _ = fwd(xr)
+    out["r3_x"] = xr.numpy()
+    out["r3_spec"] = specr.numpy()
+    spec1, _ = fwd(xr[0])
+    out["r1_spec"] = spec1.numpy()
+    xq = 0.1 * torch.randn(4, 8193)
+    out["q4_x"] = xq.numpy()
+    out["q4_spec"] = fwd(xq)[0].numpy()
+    out["q1_spec"] = fwd(xq[0])[0].numpy()
+    # IMDCT with out_length crop
+    inv_c = IMDCT4(n_fft=512, hop_length=256, win_length=512, window=w, out_length=1000, device="cpu")
+    out["r3_audio_crop"] = inv_c(specr.clone())[0].numpy()
+
+    # a second transform size (n_fft 1024 / hop 512) to pin the generic formulas
+    w2 = kbdwin(1024)
+    f2 = MDCT4(n_fft=1024, hop_length=512, win_length=1024, window=w2, device="cpu")
+    i2 = IMDCT4(n_fft=1024, hop_length=512, win_length=1024, window=w2, device="cpu")
+    torch.manual_seed(3)
+    x2 = 0.1 * torch.randn(2, 4096)
+    s2 = f2(x2)[0]
+    out["n1024_x"] = x2.numpy()
+    out["n1024_spec"] = s2.numpy()
+    out["n1024_audio"] = i2(s2.clone())[0].numpy()
+
+    # Audio2MDCT: arcsinh + abs_norm (the configs' branch), gain 1000, range (-1,1)
+    opt = ref_opt(["--segment_length", "7936", "--bins", "32"])
+    pre = Audio2MDCT(opt)
+    torch.manual_seed(4)
+    ls, pha, prm = pre.to_spectro(xb)
+    out["a2m_log_spectro"] = ls.numpy()
+    out["a2m_max"] = prm["max"].numpy()
+    out["a2m_min"] = prm["min"].numpy()
+    out["a2m_mean"] = prm["mean"].numpy()
+    out["a2m_std"] = prm["std"].numpy()
+    out["a2m_audio"] = pre.to_audio(ls, prm, pha).numpy()
+    # per-sample min/max branch (no --abs_norm) and raw_mdct branch
+    opt2 = ref_opt(["--segment_length", "7936", "--bins", "32"])
+    opt2.abs_norm = False
+    pre2 = Audio2MDCT(opt2)
+    ls2, pha2, prm2 = pre2.to_spectro(xb)
+    out["mm_log_spectro"] = ls2.numpy()
+    out["mm_max"] = prm2["max"].numpy()
+    out["mm_min"] = prm2["min"].numpy()
+    out["mm_audio"] = pre2.to_audio(ls2, prm2, pha2).numpy()
+    opt3 = ref_opt(["--segment_length", "7936", "--bins", "32"])
+    opt3.arcsinh_transform = False
+    opt3.raw_mdct = True
+    pre3 = Audio2MDCT(opt3)
+    ls3, pha3, prm3 = pre3.to_spectro(xb)
+    out["raw_log_spectro"] = ls3.numpy()
+    out["raw_audio"] = pre3.to_audio(ls3, prm3, pha3).numpy()
+
+    np.savez_compressed(os.path.join(HERE, "mdct_golden.npz"), **out)
+    print("wrote mdct_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    import_reference()
+    what = sys.argv[1:] or ["mdct"]
+    if "mdct" in what:
+        gen_mdct()
+    if "nets" in what or "train" in what:
+        from make_golden_nets import gen_nets, gen_train  # noqa: E402
+
+        if "nets" in what:
+            gen_nets()
+        if "train" in what:
+            gen_train()
