@@ -1,0 +1,101 @@
+/* mdctgan_b200.h -- C ABI of libmdctgan_b200.so (hand-written sm_100a CUDA behind the mdctGAN hot path).
+ *
+ * The reference (neoncloud/mdctGAN) has no FFI: its boundary for this path is the Python surface
+ *   models/mdct.py:359-489            MDCT4 / IMDCT4 (.forward)
+ *   models/pix2pixHD_model.py:14-200  Audio2MDCT (to_spectro / normalize / denormalize / to_audio)
+ * The entry points below are what a ctypes binding of that surface needs; each one cites the
+ * reference code it replaces.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain C types only.  "dev" pointers are CUDA device pointers (tensor.data_ptr()),
+ * "host" pointers are host memory (pinned for full copy speed).  `stream` is a cudaStream_t passed
+ * as void* (0 = legacy default stream).  Device entry points never synchronise, never allocate.
+ * Return value: 0 = ok; < 0 = invalid argument / unsupported configuration; > 0 = cudaError_t.
+ * mdctgan_last_error() returns a thread-local message for the last non-zero return.
+ * The caller owns every buffer; a plan is immutable after creation and may be shared by streams.
+ */
+#ifndef MDCTGAN_B200_H_
+#define MDCTGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDCTGAN_ABI_VERSION 1
+
+/* arithmetic flavour of the transform core */
+#define MDCTGAN_F32 0 /* fp32 butterflies, fp32 I/O  (fast path; ~1.2e-7 rel-L2 vs the reference)          */
+#define MDCTGAN_F64 1 /* fp64 butterflies, fp64 coefficient / audio I/O (reference dtypes, mdct.py:387-390) */
+
+/* spectrogram encodings of Audio2MDCT.normalize (pix2pixHD_model.py:83-125) handled in-kernel */
+#define MDCTGAN_MODE_RAW 0     /* --raw_mdct         :102-103 */
+#define MDCTGAN_MODE_ARCSINH 1 /* --arcsinh_transform :96-100  */
+
+typedef struct mdctgan_plan mdctgan_plan;
+
+typedef struct mdctgan_norm {
+  int32_t mode;   /* MDCTGAN_MODE_*                                                    */
+  float gain;     /* opt.arcsinh_gain                       (pix2pixHD_model.py:98)    */
+  float src_lo;   /* abs-norm source range, opt.src_range   (:116-119)                 */
+  float src_hi;
+  float norm_lo;  /* opt.norm_range                         (:120-123)                 */
+  float norm_hi;
+} mdctgan_norm;
+
+int mdctgan_abi_version(void);
+const char* mdctgan_last_error(void);
+
+/* MDCT4.__init__ / IMDCT4.__init__ (models/mdct.py:365-390, :429-455).  `window_host`: win_length fp32
+ * values (kbdwin, util/util.py:179-186).  Supported: n_fft 512, hop 256, win 512, symmetric window,
+ * center=True; anything else returns -2 (the Python layer raises).  Tables go to the current device. */
+int mdctgan_plan_create(mdctgan_plan** plan, int n_fft, int hop_length, int win_length, const float* window_host);
+int mdctgan_plan_destroy(mdctgan_plan* plan);
+
+/* Frame count of MDCT4.forward for T samples (models/mdct.py:394-407), including the reference quirk
+ * that the extra right pad is derived from len(signal) = dim0 (the batch size for 2-D input). */
+int64_t mdctgan_frame_count(int64_t T, int64_t dim0, int hop_length, int win_length, int center);
+
+/* MDCT4.forward (models/mdct.py:392-425): audio fp32 [B, T] (row stride audio_stride) ->
+ * coefficients [B, F, 256] (clip stride spec_clip_stride, elements), fp32 or fp64 per `precision`. */
+int mdctgan_mdct4_forward(const mdctgan_plan* plan, const float* audio_dev, int64_t B, int64_t T, int64_t audio_stride,
+                          int64_t F, void* spec_dev, int64_t spec_clip_stride, int precision, void* stream);
+
+/* Audio2MDCT.to_spectro with abs_norm (pix2pixHD_model.py:32-47,81 + normalize :96-123), fused with
+ * the second network channel |s|*2+norm_lo (:400-402): audio fp32 [B, T] -> fp32 [B, channels, F, 256]
+ * (channels 1 or 2; strides in elements).  precision F64 = fp64 core + library asinh, rounded once. */
+int mdctgan_audio2mdct_forward(const mdctgan_plan* plan, const float* audio_dev, int64_t B, int64_t T, int64_t audio_stride,
+                               int64_t F, const mdctgan_norm* norm, float* out_dev, int channels,
+                               int64_t out_clip_stride, int64_t out_chan_stride, int precision, void* stream);
+
+/* IMDCT4.forward (models/mdct.py:457-489): coefficients [B, F, 256] -> audio [B, out_len],
+ * out_len <= (F-1)*256 (the out_length crop, :486-488).  fp32 or fp64 in AND out per `precision`. */
+int mdctgan_imdct4_inverse(const mdctgan_plan* plan, const void* spec_dev, int64_t B, int64_t F, int64_t spec_clip_stride,
+                           void* audio_dev, int64_t audio_stride, int64_t out_len, int precision, void* stream);
+
+/* Audio2MDCT.to_audio, abs_norm arcsinh/raw branches (pix2pixHD_model.py:127-135,139-163):
+ * normalised fp32 spectrogram [B, F, 256] -> audio; F32: fp32 audio, F64: fp64 audio (reference dtype). */
+int mdctgan_mdct2audio_inverse(const mdctgan_plan* plan, const float* spectro_dev, int64_t B, int64_t F, int64_t spec_clip_stride,
+                               const mdctgan_norm* norm, void* audio_dev, int64_t audio_stride, int64_t out_len,
+                               int precision, void* stream);
+
+/* Host-buffer forms of the four calls above (the end-to-end path a non-torch caller uses): inputs and
+ * outputs are HOST arrays, densely packed; clips are streamed host->device->host in chunks over three
+ * CUDA streams so copies overlap the kernels.  They synchronise before returning.  Scratch device
+ * memory is owned by the plan and grown on first use (not thread-safe per plan). */
+int mdctgan_mdct4_forward_host(mdctgan_plan* plan, const float* audio_host, int64_t B, int64_t T, int64_t F,
+                               void* spec_host, int precision);
+int mdctgan_audio2mdct_forward_host(mdctgan_plan* plan, const float* audio_host, int64_t B, int64_t T, int64_t F,
+                                    const mdctgan_norm* norm, float* out_host, int channels, int precision);
+int mdctgan_imdct4_inverse_host(mdctgan_plan* plan, const void* spec_host, int64_t B, int64_t F, void* audio_host,
+                                int64_t out_len, int precision);
+int mdctgan_mdct2audio_inverse_host(mdctgan_plan* plan, const float* spectro_host, int64_t B, int64_t F,
+                                    const mdctgan_norm* norm, void* audio_host, int64_t out_len, int precision);
+
+/* Introspection for tests / bench: number of kernels this library has launched in this process. */
+int64_t mdctgan_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDCTGAN_B200_H_ */

@@ -1,0 +1,175 @@
+"""Audio <-> normalised MDCT spectrogram front / back end with the reference's names and signatures
+(models/pix2pixHD_model.py:14-200), executed by the fused kernels of libmdctgan_b200.so:
+
+  to_spectro  = MDCT4 + arcsinh/raw compress + abs-norm affine (+ optional second channel |s|*2+lo)
+                in ONE kernel / one HBM pass   (reference: :32-81 -> mdct.py:392-425, normalize :83-125)
+  to_audio    = denormalise + sinh expand + IMDCT4 + window + overlap-add + crop in ONE kernel
+                (reference: :139-163 -> denormalize :127-137, mdct.py:457-489)
+
+CUDA tensors only; there is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+from argparse import Namespace
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+from ..util.util import kbdwin
+from .mdct import IMDCT4, MDCT4, _require_cuda, _stream_ptr
+
+
+def default_audio_opt(**overrides) -> Namespace:
+    """The `opt` fields Audio2MDCT reads, at the reference's defaults (options/audio_config.py:1-12,
+    options/base_options.py:24-47,85-89, options/train_options.py:63-72)."""
+    opt = Namespace(
+        n_fft=512, hop_length=256, win_length=512, bins=128, segment_length=32512,
+        lr_sampling_rate=12000, hr_sampling_rate=48000, sr_sampling_rate=48000,
+        arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False, explicit_encoding=False, alpha=0.6,
+        min_value=1e-7, abs_norm=True, src_range=(-5.0, 5.0), norm_range=(0.0, 1.0),
+        mask=False, mask_hr=False, fit_residual=False, gpu_ids=[0],
+    )
+    for k, v in overrides.items():
+        setattr(opt, k, v)
+    return opt
+
+
+class Audio2MDCT(torch.nn.Module):
+    """Drop-in for the reference's Audio2MDCT (pix2pixHD_model.py:14-200).
+
+    Differences, all recorded in DESIGN.md: `pha` and the unused `mean/std/frames` entries are not
+    materialised in arcsinh / raw mode (nothing downstream reads them); the
+    reference's throw-away `randn` draw (:49-54) is skipped.  `precision='fp32'` (default) runs the
+    HBM-roofline flavour; `'fp64'` runs fp64 butterflies + library asinh/sinh and returns fp64 audio
+    like the reference.
+    """
+
+    def __init__(self, opt, device=None, precision: str = "fp32") -> None:
+        super().__init__()
+        for k, v in vars(opt).items():
+            setattr(self, k, v)
+        if device is None:
+            if not len(self.gpu_ids):
+                raise RuntimeError("Audio2MDCT: gpu_ids is empty; mdctgan_b200 has no CPU path")
+            device = torch.device("cuda", self.gpu_ids[0])
+        self.device = torch.device(device)
+        self.up_ratio = self.hr_sampling_rate / self.lr_sampling_rate
+        self.min_value = opt.min_value
+        self.window = kbdwin(self.win_length)
+        prec64 = precision in ("fp64", "float64", torch.float64)
+        self.precision = _lib.F64 if prec64 else _lib.F32
+        # raw-coefficient transforms keep the reference dtypes (fp64 in / out)
+        self._mdct = MDCT4(n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
+                           device=self.device, precision="fp64" if prec64 else "fp32")
+        self._imdct = IMDCT4(n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
+                             device=self.device, precision="fp64" if prec64 else "fp32")
+        if self.explicit_encoding or not (self.arcsinh_transform or self.raw_mdct):
+            raise NotImplementedError("Audio2MDCT: only the arcsinh (--arcsinh_transform) and --raw_mdct encodings are "
+                                      "implemented in-kernel; the dB / explicit_encoding branches are listed as 'next' in DESIGN.md")
+        if not self.abs_norm:
+            raise NotImplementedError("Audio2MDCT: per-sample min/max normalisation (no --abs_norm) is listed as 'next' in DESIGN.md")
+        mode = _lib.MODE_ARCSINH if self.arcsinh_transform else _lib.MODE_RAW
+        self._norm = _lib.NormSpec(mode, float(self.arcsinh_gain), tuple(float(v) for v in self.src_range),
+                                   tuple(float(v) for v in self.norm_range))
+        self._cnorm = self._norm.c()
+        self._minmax: Dict[int, tuple] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _src_minmax(self, device):
+        key = device.index or 0
+        if key not in self._minmax:
+            lo = torch.tensor([self.src_range[0]], device=device, dtype=torch.float32)[None, None, None, :]
+            hi = torch.tensor([self.src_range[1]], device=device, dtype=torch.float32)[None, None, None, :]
+            self._minmax[key] = (lo, hi)
+        return self._minmax[key]
+
+    def _check_norm_param(self, norm_param) -> None:
+        lo, hi = norm_param["min"], norm_param["max"]
+        if torch.is_tensor(lo) and lo.numel() != 1:
+            raise NotImplementedError("to_audio: per-sample min/max normalisation is not implemented (abs_norm only)")
+
+    # ------------------------------------------------------------------ forward transform
+    @torch.no_grad()
+    def to_spectro(self, audio: torch.Tensor, mask: bool = False, mask_size: int = -1, channels: int = 1,
+                   out: Optional[torch.Tensor] = None):
+        """audio [B, T] (or [T]) fp32 -> (log_spectro fp32 [B, channels, F, n_fft/2], pha, norm_param).
+
+        `channels=2` additionally writes the generator's second input channel `abs(s)*2 + norm_range[0]`
+        (pix2pixHD_model.py:400-402) from the same kernel.
+        """
+        _require_cuda(audio, "Audio2MDCT.to_spectro")
+        dim0 = audio.shape[0]   # len(signal): samples for 1-D input, batch size otherwise (mdct.py:394)
+        if audio.dim() == 1:
+            audio = audio[None]
+        x = audio.to(torch.float32)
+        if x.dim() != 2:
+            x = x.reshape(-1, x.shape[-1])
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        B, T = x.shape
+        nb = self.n_fft // 2
+        F = _lib.frame_count(T, dim0, self.hop_length, self.win_length, True)
+        if out is None:
+            out = torch.empty((B, channels, F, nb), dtype=torch.float32, device=x.device)
+        else:
+            assert out.shape == (B, channels, F, nb) and out.dtype == torch.float32 and out.is_contiguous()
+        if B and F:
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib().mdctgan_audio2mdct_forward(
+                    self._mdct._plan(x.device).handle, x.data_ptr(), B, T, x.stride(0) if B > 1 else T, F, self._cnorm,
+                    out.data_ptr(), channels, channels * F * nb, F * nb, self.precision, _stream_ptr(x.device)))
+        if mask:
+            if mask_size == -1:
+                mask_size = int(nb * (1 - 1 / self.up_ratio))
+            if mask_size > 0:   # reference: mask_size == 0 would make an empty slice -> no-op
+                if self.fit_residual:
+                    out[:, :, :, nb - mask_size:] = 0
+                else:
+                    noise = torch.randn(B, channels, F, mask_size, device=x.device)
+                    out[:, :, :, nb - mask_size:] = noise / (noise.max() - noise.min())
+        lo, hi = self._src_minmax(x.device)
+        return out, None, {"max": hi, "min": lo, "mean": None, "std": None, "frames": None}
+
+    def forward(self, lr_audio: torch.Tensor, channels: int = 1):
+        return self.to_spectro(lr_audio, mask=self.mask, channels=channels)
+
+    def hr_forward(self, hr_audio: torch.Tensor, channels: int = 1):
+        return self.to_spectro(hr_audio, mask=self.mask_hr, channels=channels,
+                               mask_size=int(self.n_fft * (1 - self.sr_sampling_rate / self.hr_sampling_rate) // 2))
+
+    # ------------------------------------------------------------------ inverse transform
+    @torch.no_grad()
+    def to_audio(self, log_spectro: torch.Tensor, norm_param=None, pha=None, out_length: Optional[int] = None):
+        """normalised spectrogram [B, 1, F, N] (or [B, F, N]) fp32 -> audio [B, 1, 1, (F-1)*hop]."""
+        _require_cuda(log_spectro, "Audio2MDCT.to_audio")
+        if norm_param is not None:
+            self._check_norm_param(norm_param)
+        s = log_spectro
+        if s.dim() == 4:
+            assert s.shape[1] == 1, "to_audio expects a single-channel spectrogram"
+            s = s[:, 0]
+        assert s.dim() == 3 and s.shape[-1] == self.n_fft // 2
+        s = s.to(torch.float32)
+        if s.stride(-1) != 1 or s.stride(-2) != s.shape[-1]:
+            s = s.contiguous()
+        B, F, nb = s.shape
+        full = max(F - 1, 0) * self.hop_length
+        out_len = full if out_length is None else min(full, int(out_length))
+        dt = torch.float64 if self.precision == _lib.F64 else torch.float32
+        audio = torch.empty((B, 1, 1, out_len), dtype=dt, device=s.device)
+        if B and out_len:
+            with torch.cuda.device(s.device):
+                _lib.check(_lib.lib().mdctgan_mdct2audio_inverse(
+                    self._mdct._plan(s.device).handle, s.data_ptr(), B, F, s.stride(0) if B > 1 else F * nb, self._cnorm,
+                    audio.data_ptr(), out_len, out_len, self.precision, _stream_ptr(s.device)))
+        return audio
+
+    # ------------------------------------------------------------------ un-fused pieces (API parity)
+    @torch.no_grad()
+    def normalize(self, spectro: torch.Tensor):
+        raise NotImplementedError("normalize() is fused into to_spectro(); call to_spectro(audio)")
+
+    @torch.no_grad()
+    def denormalize(self, log_spectro: torch.Tensor, min: torch.Tensor, max: torch.Tensor):
+        raise NotImplementedError("denormalize() is fused into to_audio(); call to_audio(log_spectro, norm_param, pha)")

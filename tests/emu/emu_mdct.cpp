@@ -1,0 +1,92 @@
+// tests/emu/emu_mdct.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the arithmetic core of the CUDA kernels (mdctgan_b200/csrc/mdct_core.cuh: the very same
+// templates, index maps, swizzles and twiddle tables) on the CPU, one emulated thread at a time,
+// so that index/twiddle mistakes are caught in the GPU-less build container.  Built by
+// tests/test_emu_core.py with g++ and driven through ctypes; never part of the product.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../mdctgan_b200/csrc/mdct_core.cuh"
+#include "../../mdctgan_b200/csrc/mdct_plan_tables.h"
+
+using namespace mdctk;
+
+template <typename R> static const R* tabT(const PlanTablesHost& t);
+template <> const float* tabT<float>(const PlanTablesHost& t) { return t.T32.data(); }
+template <> const double* tabT<double>(const PlanTablesHost& t) { return t.T64.data(); }
+
+// one frame through pass1 / exchange / pass2; D[256] = DCT-IV result in natural order
+template <typename R, typename Gather>
+static void frame_core(const PlanTablesHost& tabs, R scale, Gather gather, R* D) {
+  std::vector<cx<R>> xch(kXchStride);
+  for (int j = 0; j < 8; ++j) {
+    ThreadTab<R> tt;
+    load_T<R>(tabT<R>(tabs), j, scale, tt);
+    cx<R> v[16];
+    gather(j, v);
+    pass1<R>(v, tt, j, xch.data());
+  }
+  for (int a = 0; a < 8; ++a) {
+    cx<R> y[2][8];
+    pass2<R>(xch.data(), a, y);
+    for (int h = 0; h < 2; ++h)
+      for (int k2 = 0; k2 < 8; ++k2) {
+        int col; R d0, d1;
+        out_pair<R>(y, a, h, k2, col, d0, d1);
+        D[col] = d0; D[col + 1] = d1;
+      }
+  }
+}
+
+template <typename R>
+static void fwd_impl(const float* x, int64_t T, int64_t F, const float* window, double* out) {
+  PlanTablesHost tabs;
+  build_plan_tables(window, tabs);
+  // de-interleaved padded blocks: block b holds samples x[256(b-1) .. 256b)
+  std::vector<float> E((F + 1) * kRowPad, 0.f), O((F + 1) * kRowPad, 0.f);
+  for (int64_t b = 0; b <= F; ++b)
+    for (int p = 0; p < 256; ++p) {
+      int64_t s = 256 * (b - 1) + p;
+      float v = (s >= 0 && s < T) ? x[s] : 0.f;
+      ((p & 1) ? O : E)[b * kRowPad + (p >> 1)] = v;
+    }
+  std::vector<R> D(256);
+  for (int64_t t = 0; t < F; ++t) {
+    const float *E0 = &E[t * kRowPad], *O0 = &O[t * kRowPad], *E1 = &E[(t + 1) * kRowPad], *O1 = &O[(t + 1) * kRowPad];
+    frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) {
+      WinTab w; load_W(tabs.W.data(), j, w);
+      fwd_gather<R>(E0, O0, E1, O1, j, w, v);
+    }, D.data());
+    for (int k = 0; k < 256; ++k) out[t * 256 + k] = (double)D[k];
+  }
+}
+
+template <typename R>
+static void inv_impl(const double* spec, int64_t F, const float* window, double* audio /*(F-1)*256*/) {
+  PlanTablesHost tabs;
+  build_plan_tables(window, tabs);
+  std::vector<R> U(F * kURow);
+  for (int64_t t = 0; t < F; ++t) {
+    std::vector<R> Xe(128), Xo(128);
+    for (int n = 0; n < 128; ++n) { Xe[n] = (R)spec[t * 256 + 2 * n]; Xo[n] = (R)spec[t * 256 + 2 * n + 1]; }
+    frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) { inv_gather<R, R>(Xe.data(), Xo.data(), j, v); }, &U[t * kURow]);
+  }
+  const R sc = (R)(4.0 / 512.0);
+  for (int64_t q = 0; q + 1 < F; ++q)
+    for (int i = 0; i < 256; ++i) {
+      R a = unfold_first<R>(&U[(q + 1) * kURow], i) * (R)window[i];
+      R b = unfold_second<R>(&U[q * kURow], i) * (R)window[256 + i];
+      audio[q * 256 + i] = (double)((a + b) * sc);
+    }
+}
+
+extern "C" {
+int emu_window_symmetric(const float* w) { return window_is_symmetric(w, 512) ? 1 : 0; }
+void emu_mdct_fwd(const float* x, int64_t T, int64_t F, const float* window, double* out, int use_double) {
+  if (use_double) fwd_impl<double>(x, T, F, window, out); else fwd_impl<float>(x, T, F, window, out);
+}
+void emu_imdct(const double* spec, int64_t F, const float* window, double* audio, int use_double) {
+  if (use_double) inv_impl<double>(spec, F, window, audio); else inv_impl<float>(spec, F, window, audio);
+}
+}

@@ -1,0 +1,86 @@
+"""CPU check of the CUDA kernels' arithmetic core (mdctgan_b200/csrc/mdct_core.cuh) run thread-by-thread
+through tests/emu/emu_mdct.cpp, against the oracle and the golden vectors.  No GPU, no product path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+from oracle import mdct_oracle as O
+
+EPS = 2.0 ** -23
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(ROOT, "build", "libemu_mdct.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                    os.path.join(ROOT, "tests", "emu", "emu_mdct.cpp")], check=True)
+    return ctypes.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emu_fwd(emu, x, F, w, dbl):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((F, 256))
+    emu.emu_mdct_fwd(_p(x), ctypes.c_int64(x.size), ctypes.c_int64(F), _p(w), _p(out), int(dbl))
+    return out
+
+
+def emu_inv(emu, spec, w, dbl):
+    spec = np.ascontiguousarray(spec, dtype=np.float64)
+    F = spec.shape[0]
+    audio = np.zeros((F - 1) * 256)
+    emu.emu_imdct(_p(spec), ctypes.c_int64(F), _p(w), _p(audio), int(dbl))
+    return audio
+
+
+def test_forward_core_vs_golden(emu, mdct_golden):
+    g = mdct_golden
+    w = g["kbdwin512"]
+    ref = g["c1_spec"]
+    d = emu_fwd(emu, g["c1_x"], 33, w, True)
+    assert np.abs(d - ref).max() <= 1e-13 * np.abs(ref).max()
+    f = emu_fwd(emu, g["c1_x"], 33, w, False)
+    assert np.abs(f - ref).max() <= 4e-7 * np.abs(ref).max() and rel_l2(f, ref) < 2.5e-7
+    # ragged clip (T = 1000, 5 frames incl. the zero-padded tail)
+    d = emu_fwd(emu, g["r3_x"][1], 5, w, True)
+    assert np.abs(d - g["r3_spec"][1]).max() <= 1e-13 * np.abs(g["r3_spec"]).max()
+
+
+def test_inverse_core_vs_golden(emu, mdct_golden):
+    g = mdct_golden
+    w = g["kbdwin512"]
+    ref = g["c1_audio"].ravel()
+    d = emu_inv(emu, g["c1_spec"], w, True)
+    assert np.abs(d - ref).max() <= 1e-14
+    f = emu_inv(emu, g["c1_spec"], w, False)
+    assert np.abs(f - ref).max() <= 4e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_round_trip_within_2ulp_of_peak(emu, seed):
+    rng = np.random.default_rng(seed)
+    x = (0.1 * rng.standard_normal(8192)).astype(np.float32)
+    w = O.kbdwin(512)
+    peak = np.abs(x).max()
+    for dbl in (True, False):
+        y = emu_inv(emu, emu_fwd(emu, x, 33, w, dbl), w, dbl)
+        if not dbl:
+            y = y.astype(np.float32).astype(np.float64)
+        assert np.abs(y - x).max() <= 2 * EPS * peak, (dbl, np.abs(y - x).max() / (EPS * peak))
+        assert rel_l2(y, x) <= 2 * EPS
+
+
+def test_window_symmetry_check(emu):
+    w = O.kbdwin(512)
+    assert emu.emu_window_symmetric(_p(w)) == 1
+    w2 = w.copy()
+    w2[3] += 1e-3
+    assert emu.emu_window_symmetric(_p(w2)) == 0

@@ -1,0 +1,292 @@
+"""GPU parity tests of the fused MDCT4 / IMDCT4 / Audio2MDCT kernels (through the C ABI of
+libmdctgan_b200.so) against the CPU oracle and the golden vectors produced by the reference itself.
+
+Tolerances (north_star): round trip within 2 ulp of the clip peak (max-abs <= 2*eps*peak, eps = 2^-23)
+and rel-L2 <= 2*eps; waveforms within 1e-3 rel-L2; fp64 flavour agrees with the reference to fp64
+rounding (1e-12 relative to the clip peak)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import mdct_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = 2.0 ** -23
+ARC = dict(arcsinh_transform=True, arcsinh_gain=1000.0, abs_norm=True, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0))
+TOL = {"fp64": 1e-12, "fp32": 4e-7}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def W():
+    from mdctgan_b200.util.util import kbdwin
+
+    return kbdwin(512)
+
+
+def _pair(W, dev, prec, out_length=None):
+    from mdctgan_b200.models.mdct import IMDCT4, MDCT4
+
+    return (MDCT4(512, 256, 512, W, device=dev, precision=prec),
+            IMDCT4(512, 256, 512, W, out_length=out_length, device=dev, precision=prec))
+
+
+def _a2m(dev, prec="fp32", **kw):
+    from mdctgan_b200.models.pix2pixHD_model import Audio2MDCT, default_audio_opt
+
+    o = dict(arcsinh_gain=1000.0, norm_range=(-1.0, 1.0))
+    o.update(kw)
+    return Audio2MDCT(default_audio_opt(**o), device=dev, precision=prec)
+
+
+def _maxrel(a, b):
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max())
+
+
+# ------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_cfg1_clip_matches_reference(mdct_golden, dev, W, prec):
+    """BASELINE configs[0]: one 8192-sample clip, 1-D input -> [33, 256] -> [1,1,1,8192]."""
+    import mdctgan_b200
+
+    g = mdct_golden
+    fwd, inv = _pair(W, dev, prec)
+    n0 = mdctgan_b200.launch_count()
+    spec, frames = fwd(torch.from_numpy(g["c1_x"]).to(dev))
+    assert spec.shape == (33, 256) and spec.dtype == (torch.float64 if prec == "fp64" else torch.float32)
+    assert _maxrel(spec.cpu().numpy(), g["c1_spec"]) <= TOL[prec]
+    audio, _ = inv(torch.from_numpy(g["c1_spec"]).to(dev)[None])
+    assert audio.shape == (1, 1, 1, 8192)
+    assert _maxrel(audio.cpu().numpy(), g["c1_audio"]) <= TOL[prec]
+    assert mdctgan_b200.launch_count() == n0 + 2   # one fused kernel per direction
+    # return_frames=True materialises the fp32 windowed frames bit-exactly (mdct.py:410-412)
+    _, fr = fwd(torch.from_numpy(g["c1_x"]).to(dev), True)
+    assert np.array_equal(fr.cpu().numpy(), g["c1_frames"])
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_batched_and_ragged_match_reference(mdct_golden, dev, W, prec):
+    g = mdct_golden
+    fwd, inv = _pair(W, dev, prec)
+    for xk, sk in (("b4_x", "b4_spec"), ("r3_x", "r3_spec"), ("q4_x", "q4_spec")):
+        spec, _ = fwd(torch.from_numpy(g[xk]).to(dev))
+        assert tuple(spec.shape) == g[sk].shape, sk
+        assert _maxrel(spec.cpu().numpy(), g[sk]) <= TOL[prec], sk
+    # 1-D inputs take the other side of the len(signal) quirk (mdct.py:394-402)
+    for xk, sk in (("r3_x", "r1_spec"), ("q4_x", "q1_spec")):
+        spec, _ = fwd(torch.from_numpy(g[xk][0]).to(dev))
+        assert tuple(spec.shape) == g[sk].shape, sk
+        assert _maxrel(spec.cpu().numpy(), g[sk]) <= TOL[prec], sk
+    audio, _ = inv(torch.from_numpy(g["b4_spec"]).to(dev))
+    assert _maxrel(audio.cpu().numpy(), g["b4_audio"]) <= TOL[prec]
+    _, inv_c = _pair(W, dev, prec, out_length=1000)
+    a = inv_c(torch.from_numpy(g["r3_spec"]).to(dev))[0]
+    assert tuple(a.shape) == g["r3_audio_crop"].shape
+    assert _maxrel(a.cpu().numpy(), g["r3_audio_crop"]) <= TOL[prec]
+
+
+def test_audio2mdct_matches_reference(mdct_golden, dev, W):
+    g = mdct_golden
+    x = torch.from_numpy(g["b4_x"]).to(dev)
+    for prec, tol_s, tol_a in (("fp64", 6e-8, 1e-7), ("fp32", 1.5e-6, 2e-5)):
+        m = _a2m(dev, prec)
+        s, pha, prm = m.forward(x)
+        assert s.shape == (4, 1, 32, 256) and s.dtype == torch.float32
+        assert np.abs(s.cpu().numpy() - g["a2m_log_spectro"]).max() <= tol_s, prec
+        assert np.array_equal(prm["max"].cpu().numpy(), g["a2m_max"]) and np.array_equal(prm["min"].cpu().numpy(), g["a2m_min"])
+        a = m.to_audio(torch.from_numpy(g["a2m_log_spectro"]).to(dev), prm, pha)
+        assert a.shape == (4, 1, 1, 7936)
+        assert rel_l2(a.cpu().numpy(), g["a2m_audio"]) <= tol_a, prec     # bar: 1e-3 (north_star)
+    # second network channel |s|*2+lo from the same kernel (pix2pixHD_model.py:400-402)
+    m = _a2m(dev)
+    s2, _, _ = m.forward(x, channels=2)
+    s1, _, _ = m.forward(x)
+    assert torch.equal(s2[:, :1], s1)
+    assert torch.equal(s2[:, 1:], s1.abs() * 2 + (-1.0))
+    # raw_mdct branch
+    mr = _a2m(dev, "fp64", arcsinh_transform=False, raw_mdct=True)
+    s, pha, prm = mr.forward(x)
+    ref = g["raw_log_spectro"]
+    assert np.abs(s.cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max() + 6e-8
+    a = mr.to_audio(torch.from_numpy(ref).to(dev), prm, pha)
+    assert rel_l2(a.cpu().numpy(), g["raw_audio"]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------ oracle, seeded
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("B,T", [(1, 256), (1, 100), (2, 255), (3, 257), (5, 4096), (7, 8192), (33, 7936), (2, 32512), (64, 511)])
+def test_forward_inverse_vs_oracle(dev, W, prec, B, T):
+    rng = np.random.default_rng(B * 100003 + T)
+    x = (0.1 * rng.standard_normal((B, T))).astype(np.float32)
+    w = W.numpy()
+    fwd, inv = _pair(W, dev, prec)
+    ref, _ = O.mdct4(x, w)
+    spec, _ = fwd(torch.from_numpy(x).to(dev))
+    assert tuple(spec.shape) == ref.shape
+    if ref.size:
+        assert _maxrel(spec.cpu().numpy(), ref) <= TOL[prec]
+    if ref.shape[1] >= 2:
+        ra = O.imdct4(ref, w)
+        a, _ = inv(torch.from_numpy(ref).to(dev))
+        assert tuple(a.shape) == ra.shape
+        assert _maxrel(a.cpu().numpy(), ra) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("seed", range(6))
+def test_round_trip_within_2ulp_of_peak(dev, W, prec, seed):
+    """north_star: MDCT -> IMDCT round trip within 2 ulp (at clip-peak scale)."""
+    torch.manual_seed(seed)
+    x = 0.1 * torch.randn(8, 8192)
+    fwd, inv = _pair(W, dev, prec)
+    y = inv(fwd(x.to(dev))[0])[0].reshape(8, -1).float().cpu().double()
+    xd = x.double()
+    for b in range(8):
+        peak = xd[b].abs().max().item()
+        assert (y[b] - xd[b]).abs().max().item() <= 2 * EPS * peak, (prec, seed, b)
+        assert rel_l2(y[b].numpy(), xd[b].numpy()) <= 2 * EPS
+
+
+def test_round_trip_ulp_histogram_not_worse_than_reference(mdct_golden, dev, W):
+    """Element-wise the reference itself is only 96.8 % within 2 ulp; ours must not be worse
+    by more than 2 points on the same clip."""
+    g = mdct_golden
+    x = g["c1_x"]
+    ulp = np.spacing(np.abs(x)).astype(np.float64)
+    ref_frac = np.mean(np.abs(g["c1_audio"].ravel().astype(np.float32).astype(np.float64) - x) <= 2 * ulp)
+    for prec in ("fp64", "fp32"):
+        fwd, inv = _pair(W, dev, prec)
+        y = inv(fwd(torch.from_numpy(x).to(dev))[0][None])[0].reshape(-1).float().cpu().numpy().astype(np.float64)
+        frac = np.mean(np.abs(y - x) <= 2 * ulp)
+        assert frac >= ref_frac - 0.02, (prec, frac, ref_frac)
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_empty_and_degenerate_inputs(dev, W):
+    fwd, inv = _pair(W, dev, "fp32")
+    s, _ = fwd(torch.zeros(0, 8192, device=dev))
+    assert s.shape == (0, 33, 256)
+    a, _ = inv(torch.zeros(0, 33, 256, device=dev))
+    assert a.shape == (0, 1, 1, 8192)
+    a, _ = inv(torch.zeros(2, 1, 256, device=dev))       # one frame -> zero samples after the centre crop
+    assert a.shape == (2, 1, 1, 0)
+    s, _ = fwd(torch.zeros(3, 8192, device=dev))
+    assert torch.count_nonzero(s) == 0
+    with pytest.raises(AssertionError):
+        inv(torch.zeros(33, 256, device=dev))            # reference asserts 3-D input (mdct.py:458-459)
+    with pytest.raises(AssertionError):
+        inv(torch.zeros(1, 33, 128, device=dev))
+    with pytest.raises(RuntimeError):
+        fwd(torch.zeros(8192))                           # CPU tensor: no fallback
+
+
+def test_strided_and_misaligned_rows(dev, W):
+    w = W.numpy()
+    rng = np.random.default_rng(7)
+    big = torch.from_numpy((0.1 * rng.standard_normal((6, 9001))).astype(np.float32)).to(dev)
+    fwd, inv = _pair(W, dev, "fp64")
+    x = big[:, 3:3 + 8192]            # row stride 9001 (odd) and a 12-byte offset: scalar-load path
+    ref, _ = O.mdct4(x.cpu().numpy(), w)
+    s, _ = fwd(x)
+    assert _maxrel(s.cpu().numpy(), ref) <= 1e-12
+    x2 = big[::2, :8000]              # non-contiguous batch stride
+    ref2, _ = O.mdct4(x2.cpu().numpy(), w)
+    assert _maxrel(fwd(x2)[0].cpu().numpy(), ref2) <= 1e-12
+    # out_length not a multiple of 4 -> scalar tail stores
+    _, inv_c = _pair(W, dev, "fp32", out_length=8191)
+    a = inv_c(torch.from_numpy(ref.astype(np.float32)).to(dev))[0]
+    ra = O.imdct4(ref, w, out_length=8191)
+    assert a.shape == ra.shape and _maxrel(a.cpu().numpy(), ra) <= 4e-7
+
+
+def test_host_buffer_c_abi(dev, W):
+    """The host-pointer entry points (what a non-torch caller binds), fp32 and fp64, chunked streams."""
+    from mdctgan_b200 import _lib
+
+    L = _lib.lib()
+    w = W.numpy()
+    plan = _lib.Plan(512, 256, 512, w)
+    rng = np.random.default_rng(11)
+    B, T, F = 37, 8192, 33
+    x = (0.1 * rng.standard_normal((B, T))).astype(np.float32)
+    ref, _ = O.mdct4(x, w)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    for prec, dt, tol in ((_lib.F64, np.float64, 1e-12), (_lib.F32, np.float32, 4e-7)):
+        spec = np.zeros((B, F, 256), dtype=dt)
+        _lib.check(L.mdctgan_mdct4_forward_host(plan.handle, p(x), B, T, F, p(spec), prec))
+        assert _maxrel(spec, ref) <= tol
+        audio = np.zeros((B, T), dtype=dt)
+        _lib.check(L.mdctgan_imdct4_inverse_host(plan.handle, p(spec), B, F, p(audio), T, prec))
+        assert np.abs(audio - x).max() <= 2 * EPS * np.abs(x).max()
+    norm = _lib.NormSpec(_lib.MODE_ARCSINH, 1000.0, (-5.0, 5.0), (-1.0, 1.0)).c()
+    s = np.zeros((B, 2, F, 256), dtype=np.float32)
+    _lib.check(L.mdctgan_audio2mdct_forward_host(plan.handle, p(x), B, T, F, ctypes.byref(norm), p(s), 2, _lib.F32))
+    ref_s, _, hi, lo = O.to_spectro(x, w, **ARC)
+    assert np.abs(s[:, :1] - ref_s).max() <= 1.5e-6
+    assert np.abs(s[:, 1] - (np.abs(s[:, 0]) * 2 - 1)).max() <= 1e-6
+    y = np.zeros((B, T), dtype=np.float32)
+    s1 = np.ascontiguousarray(s[:, 0])
+    _lib.check(L.mdctgan_mdct2audio_inverse_host(plan.handle, p(s1), B, F, ctypes.byref(norm), p(y), T, _lib.F32))
+    assert rel_l2(y, x) <= 1e-3       # north_star waveform bar; measured ~1e-6
+
+
+def test_c_abi_argument_errors(dev, W):
+    from mdctgan_b200 import _lib
+
+    L = _lib.lib()
+    plan = _lib.Plan(512, 256, 512, W.numpy())
+    x = torch.zeros(2, 8192, device=dev)
+    s = torch.zeros(2, 33, 256, device=dev)
+    assert L.mdctgan_mdct4_forward(plan.handle, x.data_ptr(), 2, 8192, 100, 33, s.data_ptr(), 33 * 256, 0, None) == -1
+    assert L.mdctgan_mdct4_forward(plan.handle, x.data_ptr(), 2, 8192, 8192, 33, s.data_ptr(), 33 * 256, 7, None) == -1
+    assert L.mdctgan_imdct4_inverse(plan.handle, s.data_ptr(), 2, 33, 33 * 256, x.data_ptr(), 8192, 9000, 0, None) == -1
+    w_bad = W.numpy().copy()
+    w_bad[5] *= 0.5
+    with pytest.raises(RuntimeError, match="symmetric"):
+        _lib.Plan(512, 256, 512, w_bad)
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(dev, W):
+    """BASELINE-size batch (4096 clips x 8192 samples = 33.5 MSamp): size-independent properties."""
+    torch.manual_seed(123)
+    B, T = 4096, 8192
+    x = 0.1 * torch.randn(B, T, device=dev)
+    m = _a2m(dev)
+    fwd, inv = _pair(W, dev, "fp32")
+    fwd64, _ = _pair(W, dev, "fp64")
+    # (1) encode -> decode round trip, every clip within 2 ulp of its peak
+    spec = fwd(x)[0]
+    y = inv(spec)[0].reshape(B, T)
+    peak = x.abs().amax(dim=1)
+    assert bool(((y - x).abs().amax(dim=1) <= 2 * EPS * peak).all())
+    # (2) fp32 flavour vs fp64 flavour of the same kernel family
+    s64 = fwd64(x[:512])[0]
+    assert ((spec[:512].double() - s64).abs().max() / s64.abs().max()).item() <= 4e-7
+    # (3) linearity: MDCT(a + 2b) == MDCT(a) + 2 MDCT(b)
+    a, b = x[:1024], x[1024:2048]
+    lhs = fwd64(a + 2 * b)[0]
+    rhs = fwd64(a)[0] + 2 * fwd64(b)[0]
+    assert ((lhs - rhs).abs().max() / rhs.abs().max()).item() <= 1e-6   # fp32 rounding of a+2b and of w*x
+    # (4) Parseval-type energy check (Princen-Bradley window => tight frame with bound 2/N... checked by ratio)
+    e_t = (x[:256].double() ** 2).sum(dim=1)
+    e_f = (fwd64(x[:256])[0] ** 2).sum(dim=(1, 2))
+    ratio = e_f / e_t
+    assert (ratio.max() / ratio.min()).item() < 1.02
+    # (5) fused normalise -> denormalise round trip: waveform bar 1e-3 rel-L2
+    s, pha, prm = m.forward(x)
+    z = m.to_audio(s, prm, pha).reshape(B, T)
+    err = ((z - x).double().norm(dim=1) / x.double().norm(dim=1)).max().item()
+    assert err <= 1e-3, err
+    # (6) batch independence: clip i alone == clip i inside the batch (bit-exact)
+    assert torch.equal(fwd(x[1234:1235])[0], spec[1234:1235])
+    assert torch.equal(inv(spec[77:78])[0].reshape(-1), y[77])

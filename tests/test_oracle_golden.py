@@ -105,3 +105,25 @@ def test_minmax_and_raw_branches(mdct_golden):
     assert np.abs(ls - g["raw_log_spectro"]).max() <= 1e-6 * np.abs(g["raw_log_spectro"]).max()
     a = O.to_audio(ls, lo, hi, w, arcsinh_transform=False, raw_mdct=True, norm_range=(-1.0, 1.0))
     assert rel_l2(a, g["raw_audio"]) < 1e-6
+
+
+def test_torch_port_matches_reference(mdct_golden):
+    """oracle/torch_port.py (the torch-CPU restatement bench.py times as the CPU baseline)."""
+    import torch
+
+    from oracle import torch_port as P
+
+    g = mdct_golden
+    w = P.kbdwin(512)
+    assert np.array_equal(w.numpy(), g["kbdwin512"])
+    fwd, inv = P.MDCT4Port(512, 256, w), P.IMDCT4Port(512, 256, w)
+    s, fr = fwd(torch.from_numpy(g["c1_x"]), True)
+    assert np.abs(s.numpy() - g["c1_spec"]).max() <= 1e-13 * np.abs(g["c1_spec"]).max()
+    assert np.array_equal(fr.numpy(), g["c1_frames"])
+    assert np.abs(inv(s[None]).numpy() - g["c1_audio"]).max() < 1e-15
+    for xk, sk in (("b4_x", "b4_spec"), ("r3_x", "r3_spec"), ("q4_x", "q4_spec")):
+        assert np.abs(fwd(torch.from_numpy(g[xk]))[0].numpy() - g[sk]).max() <= 1e-13 * np.abs(g[sk]).max()
+    a2m = P.Audio2MDCTPort()
+    ls, pha, prm = a2m.to_spectro(torch.from_numpy(g["b4_x"]))
+    assert np.array_equal(ls.numpy(), g["a2m_log_spectro"])
+    assert rel_l2(a2m.to_audio(ls, prm, pha).numpy(), g["a2m_audio"]) < 1e-14
