@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -46,10 +47,11 @@ struct mdctgan_plan {
   float* tabT32 = nullptr;
   double* tabT64 = nullptr;
   float* tabW = nullptr;
-  float* window = nullptr;
-  // occupancy-derived persistent grid sizes, indexed by kernel variant
-  int grid_fwd[4] = {0, 0, 0, 0};   // [R f32/f64][EPI]
-  int grid_inv[4] = {0, 0, 0, 0};   // f32 raw, f64 raw, f32 fused, f64 fused
+  float* window = nullptr;       // the reference's synthesis window (= analysis window), fp64 flavour
+  float* window_syn = nullptr;   // TDAC-exact synthesis window of the fp32 flavour (mdct_plan_tables.h)
+  // occupancy-derived persistent grid sizes, indexed by kernel variant and frames-per-tile (ft = 4, 8, 12, 16)
+  int grid_fwd[4][4] = {};   // [f32 raw, f32 fused, f64 raw, f64 fused][ft/4 - 1]
+  int grid_inv[4][4] = {};   // [f32 raw, f64 raw, f32 fused, f64 fused][ft/4 - 1]
   // host-API scratch
   cudaStream_t streams[kNumStreams] = {nullptr, nullptr, nullptr};
   void* scratch_in[kNumStreams] = {nullptr, nullptr, nullptr};
@@ -59,13 +61,29 @@ struct mdctgan_plan {
 
 namespace {
 
-template <typename K> int setup_kernel(K kernel, size_t smem, int num_sms, int* grid_out) {
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-  if (per_sm < 1) return fail(-3, "kernel does not fit on an SM (smem %zu)", smem);
-  *grid_out = per_sm * num_sms;
+// Persistent grid = resident CTAs per SM x SM count, for each tile height ft in {4, 8, 12, 16}.
+template <typename K, typename SmemFn> int setup_kernel(K kernel, SmemFn smem_of, int num_sms, int* grid_out) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(kMaxFramesPerTile)));
+  for (int i = 0; i < 4; ++i) {
+    const int ft = 4 * (i + 1);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * (i + 1), smem_of(ft)));
+    if (per_sm < 1) return fail(-3, "kernel does not fit on an SM (ft %d, smem %zu)", ft, smem_of(ft));
+    grid_out[i] = per_sm * num_sms;
+  }
   return 0;
+}
+
+// Frames per tile: minimise (tiles per clip) x (rows staged per tile); `halo` = frames recomputed per tile.
+int pick_ft(int64_t units, int halo) {
+  int best = kMaxFramesPerTile;
+  int64_t best_cost = INT64_MAX;
+  for (int ft = kMaxFramesPerTile; ft >= 4; ft -= 4) {
+    const int64_t per = ft - halo;
+    const int64_t cost = ((units + per - 1) / per) * (ft + 1);
+    if (cost < best_cost) { best_cost = cost; best = ft; }
+  }
+  return best;
 }
 
 NormParams make_norm(const mdctgan_norm* n, float* inv_a, float* inv_b) {
@@ -94,28 +112,31 @@ int check_norm(const mdctgan_norm* n) {
 }
 
 template <typename R, int EPI>
-int launch_fwd(const mdctgan_plan* pl, FwdParams& p, int grid_cap, cudaStream_t st) {
-  p.tiles_per_clip = (p.F + kFramesPerTile - 1) / kFramesPerTile;
+int launch_fwd(const mdctgan_plan* pl, FwdParams& p, const int* grid_cap, cudaStream_t st) {
+  p.ft = pick_ft(p.F, 0);
+  p.tiles_per_clip = (p.F + p.ft - 1) / p.ft;
   p.ntiles = p.B * p.tiles_per_clip;
   if (p.ntiles == 0) return 0;
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
   p.tabW = pl->tabW;
-  const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap);
-  mdct4_fwd_kernel<R, EPI><<<grid, kThreads, fwd_smem_bytes<R>(), st>>>(p);
+  const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap[p.ft / 4 - 1]);
+  mdct4_fwd_kernel<R, EPI><<<grid, 8 * p.ft, fwd_smem_bytes<R>(p.ft), st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return 0;
 }
 
 template <typename R, typename S, typename OutT, int PRO>
-int launch_inv(const mdctgan_plan* pl, InvParams& p, int grid_cap, cudaStream_t st) {
+int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaStream_t st) {
   if (p.B == 0 || p.F < 2 || p.out_len == 0) return 0;
-  p.tiles_per_clip = (p.F - 1 + kInvFramesOut - 1) / kInvFramesOut;
+  const int64_t nout = (p.out_len + kHop - 1) / kHop;   // output blocks actually needed (out_length crop)
+  p.ft = pick_ft(nout, 1);
+  p.tiles_per_clip = (nout + p.ft - 2) / (p.ft - 1);
   p.ntiles = p.B * p.tiles_per_clip;
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
-  p.window = pl->window;
-  const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap);
-  imdct4_inv_kernel<R, S, OutT, PRO><<<grid, kThreads, inv_smem_bytes<R>(), st>>>(p);
+  p.window = std::is_same<R, float>::value ? pl->window_syn : pl->window;
+  const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap[p.ft / 4 - 1]);
+  imdct4_inv_kernel<R, S, OutT, PRO><<<grid, 8 * p.ft, inv_smem_bytes<R, S>(p.ft), st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return 0;
@@ -159,26 +180,35 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   CK(cudaMalloc(&pl->tabT64, t.T64.size() * sizeof(double)));
   CK(cudaMalloc(&pl->tabW, t.W.size() * sizeof(float)));
   CK(cudaMalloc(&pl->window, win * sizeof(float)));
+  CK(cudaMalloc(&pl->window_syn, win * sizeof(float)));
+  std::vector<float> wsyn;
+  build_synthesis_window(window_host, win, wsyn);
+  CK(cudaMemcpy(pl->window_syn, wsyn.data(), win * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pl->tabT32, t.T32.data(), t.T32.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pl->tabT64, t.T64.data(), t.T64.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pl->tabW, t.W.data(), t.W.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pl->window, window_host, win * sizeof(float), cudaMemcpyHostToDevice));
   int rc = 0;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0>, fwd_smem_bytes<float>(), pl->num_sms, &pl->grid_fwd[0]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1>, fwd_smem_bytes<float>(), pl->num_sms, &pl->grid_fwd[1]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0>, fwd_smem_bytes<double>(), pl->num_sms, &pl->grid_fwd[2]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1>, fwd_smem_bytes<double>(), pl->num_sms, &pl->grid_fwd[3]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0>, inv_smem_bytes<float>(), pl->num_sms, &pl->grid_inv[0]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0>, inv_smem_bytes<double>(), pl->num_sms, &pl->grid_inv[1]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1>, inv_smem_bytes<float>(), pl->num_sms, &pl->grid_inv[2]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1>, inv_smem_bytes<double>(), pl->num_sms, &pl->grid_inv[3]))) return rc;
+  auto fs32 = [](int ft) { return fwd_smem_bytes<float>(ft); };
+  auto fs64 = [](int ft) { return fwd_smem_bytes<double>(ft); };
+  auto is32 = [](int ft) { return inv_smem_bytes<float, float>(ft); };
+  auto is64 = [](int ft) { return inv_smem_bytes<double, double>(ft); };
+  auto is64f = [](int ft) { return inv_smem_bytes<double, float>(ft); };
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0>, fs32, pl->num_sms, pl->grid_fwd[0]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1>, fs32, pl->num_sms, pl->grid_fwd[1]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0>, fs64, pl->num_sms, pl->grid_fwd[2]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1>, fs64, pl->num_sms, pl->grid_fwd[3]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0>, is32, pl->num_sms, pl->grid_inv[0]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0>, is64, pl->num_sms, pl->grid_inv[1]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1>, is32, pl->num_sms, pl->grid_inv[2]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1>, is64f, pl->num_sms, pl->grid_inv[3]))) return rc;
   *out = pl;
   return 0;
 }
 
 int mdctgan_plan_destroy(mdctgan_plan* pl) {
   if (!pl) return 0;
-  cudaFree(pl->tabT32); cudaFree(pl->tabT64); cudaFree(pl->tabW); cudaFree(pl->window);
+  cudaFree(pl->tabT32); cudaFree(pl->tabT64); cudaFree(pl->tabW); cudaFree(pl->window); cudaFree(pl->window_syn);
   for (int i = 0; i < kNumStreams; ++i) {
     if (pl->scratch_in[i]) cudaFree(pl->scratch_in[i]);
     if (pl->scratch_out[i]) cudaFree(pl->scratch_out[i]);

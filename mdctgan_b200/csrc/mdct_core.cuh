@@ -27,9 +27,9 @@ constexpr int kBins = 256;      // N  = n_fft / 2
 constexpr int kFft = 128;       // N/2 complex points
 constexpr int kHop = 256;
 constexpr int kWin = 512;
-constexpr int kFramesPerTile = 16;  // 4 compute warps x 4 frames
-constexpr int kRowPad = 136;    // floats per de-interleaved 128-float row (+8: frames shift 8 banks)
-constexpr int kXchStride = 136; // complex slots per frame in the exchange buffer (+8: half-warp spread)
+constexpr int kMaxFramesPerTile = 16;  // 4 warps x 4 frames
+constexpr int kRawPitch = 264;  // elements per raw 256-element row in shared memory (+8: frames shift 8 banks)
+constexpr int kXchStride = 145; // complex slots per frame in the exchange buffer: 16 rows of 9 (+1 pad) + 1
 constexpr int kURow = 272;      // inverse: floats per U row (256 + 16)
 
 template <typename R> struct cx { R re, im; };
@@ -123,40 +123,57 @@ MDCT_HD void load_W(const float* __restrict__ tabW, int j, WinTab& w) {
 }
 
 // ---- forward pass-1 input: window + TDAC fold + r-dependent pre-twiddle -------------------------
-// E0/O0: even/odd samples of block t (256 samples), E1/O1: of block t+1; each a 128-float row.
-template <typename R>
-MDCT_HD void fwd_gather(const float* E0, const float* O0, const float* E1, const float* O1, int j,
-                        const WinTab& w, cx<R>* v) {
+// row0 / row1: the 256 raw samples of block t / block t+1 (frame t covers padded samples
+// [256 t, 256 t + 512) = block t-1 .. t in clip coordinates; the caller passes the two rows).
+// Even sample E[e] = row[2e], odd sample O[o] = row[2o+1].
+// FUSE = true lets the compiler contract w*x into FMAs (fp32 flavour); FUSE = false keeps the
+// reference's fp32-rounded products (mdct.py:410), which the fp64 flavour needs for 1e-13 parity.
+template <typename R, bool FUSE>
+MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WinTab& w, cx<R>* v) {
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const int n = j + 8 * r;
-    const int e = (n + 64) & 127, o = (63 - n) & 127;
+    // n = j + 8r; e = 2*((n+64) mod 128), o = 2*((63-n) mod 128)+1, written wrap-free so that every
+    // access is lane-base + immediate
+    const int e = (r < 8) ? 2 * j + 16 * r + 128 : 2 * j + 16 * r - 128;
+    const int o = (r < 8) ? 127 - 2 * j - 16 * r : 383 - 2 * j - 16 * r;
     R ue, uo;
-    if (r < 8) {   // n < 64
-      ue = -(R)fmul32(w.wE[r], O1[o]) - (R)fmul32(w.wO[r], E1[e]);
-      uo = (R)fmul32(w.wO[r], O0[o]) - (R)fmul32(w.wE[r], E0[e]);
+    if (FUSE) {
+      if (r < 8) {   // n < 64
+        ue = -(R)(w.wE[r] * row1[o]) - (R)(w.wO[r] * row1[e]);
+        uo = (R)(w.wO[r] * row0[o]) - (R)(w.wE[r] * row0[e]);
+      } else {
+        ue = (R)(w.wE[r] * row0[e]) - (R)(w.wO[r] * row0[o]);
+        uo = -(R)(w.wO[r] * row1[e]) - (R)(w.wE[r] * row1[o]);
+      }
     } else {
-      ue = (R)fmul32(w.wE[r], E0[e]) - (R)fmul32(w.wO[r], O0[o]);
-      uo = -(R)fmul32(w.wO[r], E1[e]) - (R)fmul32(w.wE[r], O1[o]);
+      if (r < 8) {
+        ue = -(R)fmul32(w.wE[r], row1[o]) - (R)fmul32(w.wO[r], row1[e]);
+        uo = (R)fmul32(w.wO[r], row0[o]) - (R)fmul32(w.wE[r], row0[e]);
+      } else {
+        ue = (R)fmul32(w.wE[r], row0[e]) - (R)fmul32(w.wO[r], row0[o]);
+        uo = -(R)fmul32(w.wO[r], row1[e]) - (R)fmul32(w.wE[r], row1[o]);
+      }
     }
     v[r] = (r == 0) ? cx<R>{ue, uo} : cmulc(cx<R>{ue, uo}, rho_re<R>(r), rho_im<R>(r));
   }
 }
 
-// ---- inverse pass-1 input: ue[n] = X[2n], uo[n] = X[255-2n] ---------------------------------------
-// Xe/Xo: even/odd coefficients of the frame (128 values each).
+// ---- inverse pass-1 input: ue[n] = X[2n], uo[n] = X[255-2n], from the raw coefficient row ---------
 template <typename R, typename S>
-MDCT_HD void inv_gather(const S* Xe, const S* Xo, int j, cx<R>* v) {
+MDCT_HD void inv_gather(const S* row, int j, cx<R>* v) {
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int n = j + 8 * r;
-    cx<R> u{(R)Xe[n], (R)Xo[127 - n]};
+    cx<R> u{(R)row[2 * n], (R)row[255 - 2 * n]};
     v[r] = (r == 0) ? u : cmulc(u, rho_re<R>(r), rho_im<R>(r));
   }
 }
 
 // ---- pass 1 butterfly + thread twiddle + swizzled store to the exchange buffer -----------------
-MDCT_HD int xch_slot(int k1, int j) { return k1 * 8 + (j ^ (k1 & 7)); }
+// Exchange layout: slot(k1, j) = 9*k1 + j.  Pass 1 (lane j, compile-time k1) and pass 2 (lane a reads rows
+// k1 = a and 15-a, compile-time j) both address it as lane-base + immediate, and the 18-word row pitch
+// with the 290-word frame pitch makes the 64-bit pass-2 loads bank-conflict free across a half warp.
+MDCT_HD int xch_slot(int k1, int j) { return k1 * 9 + j; }
 
 template <typename R> MDCT_HD void pass1(cx<R>* v, const ThreadTab<R>& t, int j, cx<R>* xch) {
   dft16(v);

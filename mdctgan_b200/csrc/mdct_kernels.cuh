@@ -7,12 +7,19 @@
 //   inverse : models/pix2pixHD_model.py:127-133 (denormalise, sinh expand)
 //             + models/mdct.py:457-489 (pre-twiddle, FFT, post-twiddle, window, fold/overlap-add, crop)
 //
-// Kernel shape (both directions): persistent CTAs of 5 warps.  Warps 0-3 compute (8 threads per
-// frame, 4 frames per warp, 16 frames per tile); warp 4 is the loader: while the compute warps
-// work on tile i from one shared-memory buffer it stages tile i+1 into the other one with 16-byte
-// coalesced global loads, de-interleaving even/odd samples so that the stride-2 TDAC gather is
-// bank-conflict free.  One __syncthreads per tile.  HBM traffic is the algorithmic minimum: every
-// input sample is read once (+1/16 tile overlap, served by L2) and every output written once.
+// Kernel shape (both directions): persistent CTAs of `ft/4` warps (ft = frames per tile, 4..16, chosen
+// by the host so that ft divides the clip's frame count well).  8 threads own one frame, 4 frames per
+// warp.  Input tiles (ft+1 rows of 256 samples forward / ft coefficient rows inverse) are brought in by
+// the TMA engine -- one `cp.async.bulk` per 1 KB row, issued by one lane, completing on an mbarrier --
+// into a 2-stage ring, so the read stream needs no registers and stays kStages-1 tiles ahead of the
+// math; ragged / unaligned / zero-padded rows are filled by warp 0 with plain stores and published by
+// the same mbarrier.  The stride-2 TDAC gather reads the raw rows directly (row pitch 264 elements ->
+// 2-way bank conflicts on an LSU pipe that is < 20 % busy).  There is NO block-wide barrier in the tile
+// loop: stage reuse is a full/empty mbarrier pair per stage (warps arrive on `empty` after their gather,
+// warp 0 refills one iteration later), and the inverse's overlap-add is software-pipelined behind two
+// split-phase mbarriers (arrive early, wait late), so warps of a CTA drift freely.
+// HBM traffic is the algorithmic minimum: every input element is read once (+1/ft row overlap, served
+// by L2) and every output written once.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,15 +29,12 @@
 
 namespace mdctk {
 
-constexpr int kComputeWarps = 4;
-constexpr int kThreads = (kComputeWarps + 1) * 32;
-constexpr int kTileRows = kFramesPerTile + 1;                  // 17 blocks of 256 samples feed 16 frames
-constexpr int kFwdBufFloats = 2 * kTileRows * kRowPad;         // E region + O region
-constexpr int kInvFramesOut = kFramesPerTile - 1;              // 15 complete output blocks per tile
+constexpr int kStages = 2;
+constexpr int kMaxThreads = 128;
 
 struct FwdParams {
   const float* audio; int64_t audio_stride; int64_t T;
-  int64_t B, F; int64_t tiles_per_clip; int64_t ntiles;
+  int64_t B, F; int64_t tiles_per_clip; int64_t ntiles; int ft;
   const void* tabT; const float* tabW;
   void* out; int64_t out_clip_stride; int64_t out_chan_stride; int channels;
   NormParams np;
@@ -38,15 +42,47 @@ struct FwdParams {
 
 struct InvParams {
   const void* spec; int64_t spec_clip_stride;   // elements; frames are contiguous rows of 256
-  int64_t B, F; int64_t tiles_per_clip; int64_t ntiles;
+  int64_t B, F; int64_t tiles_per_clip; int64_t ntiles; int ft;
   const void* tabT; const float* window;
   void* out; int64_t out_clip_stride; int64_t out_len;   // samples written per clip (<= (F-1)*256)
   NormParams np; float inv_a, inv_b;                       // s_src = s*inv_a + inv_b
 };
 
+// ---- mbarrier + bulk-copy (TMA, 1-D) primitives ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy; `bytes` multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fast_asinh_scaled(float y, float c1) {
-  // sign(y) * log2(|y| + sqrt(y^2+1)) * c1 ; abs error ~1e-8 * c1-scale (see DESIGN.md, K1 epilogue)
+  // sign(y) * log2(|y| + sqrt(y^2+1)) * c1
   const float ay = fabsf(y);
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ay, ay, 1.0f)));
@@ -67,309 +103,381 @@ template <typename R> struct Vec2;
 template <> struct Vec2<float> { using type = float2; };
 template <> struct Vec2<double> { using type = double2; };
 
+__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 // ================================================================================================
 // Forward
 // ================================================================================================
-__device__ __forceinline__ void fwd_stage_tile(const FwdParams& p, int64_t tile, float* buf, int lane) {
+// Stage the ft+1 sample blocks of one tile (warp 0, all lanes).  Row r holds clip samples
+// [(t0+r-1)*256, (t0+r)*256); samples outside [0, T) are the reference's zero padding (mdct.py:403).
+__device__ __forceinline__ void fwd_produce(const FwdParams& p, int64_t tile, float* stage, uint64_t* bar, int lane) {
   const int64_t b = tile / p.tiles_per_clip;
-  const int64_t t0 = (tile - b * p.tiles_per_clip) * kFramesPerTile;
+  const int64_t t0 = (tile - b * p.tiles_per_clip) * p.ft;
   const float* __restrict__ src = p.audio + b * p.audio_stride;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  float* E = buf;
-  float* O = buf + kTileRows * kRowPad;
-  constexpr int kVecs = kTileRows * 64;   // float4 per tile
-  constexpr int kBatch = 8;
-#pragma unroll 1
-  for (int base = 0; base < kVecs; base += 32 * kBatch) {
-    float4 v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = base + u * 32 + lane;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < kVecs) {
-        const int bk = idx >> 6, q = idx & 63;
-        const int64_t s = (t0 + bk - 1) * kHop + 4 * q;
-        if (s >= 0 && s + 3 < p.T && aligned) {
-          v[u] = __ldg(reinterpret_cast<const float4*>(src + s));
-        } else if (s + 3 >= 0 && s < p.T) {
-          if (s + 0 >= 0 && s + 0 < p.T) v[u].x = __ldg(src + s + 0);
-          if (s + 1 >= 0 && s + 1 < p.T) v[u].y = __ldg(src + s + 1);
-          if (s + 2 >= 0 && s + 2 < p.T) v[u].z = __ldg(src + s + 2);
-          if (s + 3 >= 0 && s + 3 < p.T) v[u].w = __ldg(src + s + 3);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = base + u * 32 + lane;
-      if (idx < kVecs) {
-        const int bk = idx >> 6, q = idx & 63;
-        *reinterpret_cast<float2*>(E + bk * kRowPad + 2 * q) = make_float2(v[u].x, v[u].z);
-        *reinterpret_cast<float2*>(O + bk * kRowPad + 2 * q) = make_float2(v[u].y, v[u].w);
-      }
-    }
+  const int rows = p.ft + 1;
+  // rows [r_lo, r_hi) lie completely inside [0, T) -> TMA; the others (clip edges) are filled by hand
+  int r_lo = 0, r_hi = 0;
+  if (aligned) {
+    r_lo = (t0 == 0) ? 1 : 0;
+    const int64_t full_blocks = p.T / kHop - (t0 - 1);   // rows r < full_blocks end inside the clip
+    r_hi = (int)(full_blocks < rows ? (full_blocks > r_lo ? full_blocks : r_lo) : rows);
   }
+  if (r_hi - r_lo < rows) {
+#pragma unroll 1
+    for (int r = 0; r < rows; ++r) {
+      if (r >= r_lo && r < r_hi) continue;
+      const int64_t s0 = (t0 + r - 1) * kHop;
+      float* row = stage + r * kRawPitch;
+#pragma unroll
+      for (int u = 0; u < kHop / 32; ++u) {
+        const int64_t s = s0 + lane + 32 * u;
+        row[lane + 32 * u] = (s >= 0 && s < p.T) ? __ldg(src + s) : 0.f;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar, (uint32_t)(r_hi - r_lo) * (kHop * 4));
+    const float* g = src + (t0 + r_lo - 1) * kHop;
+    float* d = stage + r_lo * kRawPitch;
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi; ++r, g += kHop, d += kRawPitch) bulk_g2s(d, g, kHop * 4, bar);
+  }
+}
+
+template <typename R> __host__ __device__ constexpr size_t fwd_smem_bytes(int ft) {
+  return align16((size_t)kStages * (ft + 1) * kRawPitch * sizeof(float)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) + 64;
 }
 
 // EPI: 0 = raw coefficients (OutT = R), 1 = fused compress + abs-norm (OutT = float, 1 or 2 channels)
 template <typename R, int EPI>
-__global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? 3 : 1) mdct4_fwd_kernel(const FwdParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tilebuf = reinterpret_cast<float*>(smem_raw);                         // [2][kFwdBufFloats]
-  cx<R>* xch_all = reinterpret_cast<cx<R>*>(tilebuf + 2 * kFwdBufFloats);      // [16][kXchStride]
+__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int stage_floats = (p.ft + 1) * kRawPitch;
+  float* raw = reinterpret_cast<float*>(smem_raw);
+  cx<R>* xch_all = reinterpret_cast<cx<R>*>(smem_raw + align16((size_t)kStages * stage_floats * sizeof(float)));
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xch_all) + align16((size_t)p.ft * kXchStride * sizeof(cx<R>)));
+  uint64_t* empty = full + kStages;
   using OutT = typename std::conditional<EPI == 0, R, float>::type;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
   const int g = lane >> 3, j = lane & 7;
-  const int f = (warp & 3) * 4 + g;
-  const bool loader = (warp == kComputeWarps);
+  const int f = warp * 4 + g;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  int64_t tile = blockIdx.x;
+  if (warp == 0) {
+#pragma unroll 1
+    for (int s = 0; s < kStages; ++s) {
+      const int64_t tl = tile + (int64_t)s * gridDim.x;
+      if (tl < p.ntiles) fwd_produce(p, tl, raw + s * stage_floats, &full[s], lane);
+    }
+  }
 
   ThreadTab<R> tt;
   WinTab wt;
-  if (!loader) {
+  {
     const R scale = (EPI == 1 && p.np.mode == 1) ? (R)p.np.gain : (R)1;
     load_T<R>(reinterpret_cast<const R*>(p.tabT), j, scale, tt);
     load_W(p.tabW, j, wt);
   }
   const float c1 = (float)(0.6931471805599453 / kLn10F32) * p.np.aff_a;   // log2 -> ln -> /ln10_f32 -> affine
+  cx<R>* const xch = xch_all + f * kXchStride;
 
-  int64_t tile = blockIdx.x;
-  int buf = 0;
-  if (loader && tile < p.ntiles) fwd_stage_tile(p, tile, tilebuf, lane);
-  __syncthreads();
-  for (; tile < p.ntiles; tile += gridDim.x) {
-    const int64_t next = tile + gridDim.x;
-    if (loader) {
-      if (next < p.ntiles) fwd_stage_tile(p, next, tilebuf + (buf ^ 1) * kFwdBufFloats, lane);
-    } else {
-      const int64_t b = tile / p.tiles_per_clip;
-      const int64_t t = (tile - b * p.tiles_per_clip) * kFramesPerTile + f;
-      const float* E = tilebuf + buf * kFwdBufFloats;
-      const float* O = E + kTileRows * kRowPad;
-      cx<R>* xch = xch_all + f * kXchStride;
-      {
-        cx<R> v[16];
-        fwd_gather<R>(E + f * kRowPad, O + f * kRowPad, E + (f + 1) * kRowPad, O + (f + 1) * kRowPad, j, wt, v);
-        pass1<R>(v, tt, j, xch);
+  uint32_t it = 0;
+#pragma unroll 1
+  for (; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const uint32_t parity = (it / kStages) & 1;
+    if (warp == 0 && it >= 1) {
+      // deferred refill: the stage consumed one iteration ago gets the tile of the NEXT iteration
+      const int64_t next = tile + gridDim.x;
+      if (next < p.ntiles) {
+        const int sp = (it - 1) % kStages;
+        mbar_wait(&empty[sp], ((it - 1) / kStages) & 1);
+        fwd_produce(p, next, raw + sp * stage_floats, &full[sp], lane);
       }
-      __syncwarp();
+    }
+    const int64_t b = tile / p.tiles_per_clip;
+    const int64_t t = (tile - b * p.tiles_per_clip) * p.ft + f;
+    const bool active = (f < p.ft) && (t < p.F);
+    cx<R> v[16];
+    mbar_wait(&full[s], parity);
+    if (active) {
+      const float* row0 = raw + s * stage_floats + f * kRawPitch;
+      fwd_gather<R, sizeof(R) == 4>(row0, row0 + kRawPitch, j, wt, v);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s
+    if (active) pass1<R>(v, tt, j, xch);
+    __syncwarp();
+    if (active) {
       cx<R> y[2][8];
       pass2<R>(xch, j, y);
-      __syncwarp();   // the exchange slots are rewritten by the next tile's pass 1
-      if (t < p.F) {
-        OutT* row = reinterpret_cast<OutT*>(p.out) + b * p.out_clip_stride + t * kBins;
+      OutT* row = reinterpret_cast<OutT*>(p.out) + b * p.out_clip_stride + t * kBins;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2) {
-            int col; R d0, d1;
-            out_pair<R>(y, j, h, k2, col, d0, d1);
-            if (EPI == 0) {
-              typename Vec2<OutT>::type o; o.x = (OutT)d0; o.y = (OutT)d1;
-              *reinterpret_cast<typename Vec2<OutT>::type*>(row + col) = o;
-            } else {
-              float s0, s1;
-              if (sizeof(R) == 8) {   // "exact" flavour: fp64 core and library asinh, rounded once to fp32
-                if (p.np.mode == 1) {
-                  s0 = (float)(asinh((double)d0) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
-                  s1 = (float)(asinh((double)d1) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
-                } else {
-                  s0 = (float)((double)d0 * (double)p.np.aff_a + (double)p.np.aff_b);
-                  s1 = (float)((double)d1 * (double)p.np.aff_a + (double)p.np.aff_b);
-                }
-              } else if (p.np.mode == 1) {
-                s0 = fast_asinh_scaled((float)d0, c1) + p.np.aff_b;
-                s1 = fast_asinh_scaled((float)d1, c1) + p.np.aff_b;
+        for (int k2 = 0; k2 < 8; ++k2) {
+          int col; R d0, d1;
+          out_pair<R>(y, j, h, k2, col, d0, d1);
+          if (EPI == 0) {
+            typename Vec2<OutT>::type o; o.x = (OutT)d0; o.y = (OutT)d1;
+            *reinterpret_cast<typename Vec2<OutT>::type*>(row + col) = o;
+          } else {
+            float s0, s1;
+            if (sizeof(R) == 8) {   // "exact" flavour: fp64 core and library asinh, rounded once to fp32
+              if (p.np.mode == 1) {
+                s0 = (float)(asinh((double)d0) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
+                s1 = (float)(asinh((double)d1) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
               } else {
-                s0 = fmaf((float)d0, p.np.aff_a, p.np.aff_b);
-                s1 = fmaf((float)d1, p.np.aff_a, p.np.aff_b);
+                s0 = (float)((double)d0 * (double)p.np.aff_a + (double)p.np.aff_b);
+                s1 = (float)((double)d1 * (double)p.np.aff_a + (double)p.np.aff_b);
               }
-              *reinterpret_cast<float2*>(reinterpret_cast<float*>(row) + col) = make_float2(s0, s1);
-              if (p.channels == 2)
-                *reinterpret_cast<float2*>(reinterpret_cast<float*>(row) + p.out_chan_stride + col) =
-                    make_float2(fmaf(fabsf(s0), 2.0f, p.np.lo), fmaf(fabsf(s1), 2.0f, p.np.lo));
+            } else if (p.np.mode == 1) {
+              s0 = fast_asinh_scaled((float)d0, c1) + p.np.aff_b;
+              s1 = fast_asinh_scaled((float)d1, c1) + p.np.aff_b;
+            } else {
+              s0 = fmaf((float)d0, p.np.aff_a, p.np.aff_b);
+              s1 = fmaf((float)d1, p.np.aff_a, p.np.aff_b);
             }
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(row) + col) = make_float2(s0, s1);
+            if (p.channels == 2)
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(row) + p.out_chan_stride + col) =
+                  make_float2(fmaf(fabsf(s0), 2.0f, p.np.lo), fmaf(fabsf(s1), 2.0f, p.np.lo));
           }
         }
       }
     }
-    __syncthreads();
-    buf ^= 1;
+    __syncwarp();   // the exchange slots are rewritten by the next tile's pass 1
   }
-}
-
-template <typename R> constexpr size_t fwd_smem_bytes() {
-  return 2 * kFwdBufFloats * sizeof(float) + kFramesPerTile * kXchStride * sizeof(cx<R>);
 }
 
 // ================================================================================================
 // Inverse
 // ================================================================================================
-// Stage 16 coefficient rows (frames t0 .. t0+15) de-interleaved: Xe[f][n] = X[2n], Xo[f][n] = X[2n+1].
-template <typename R, typename S>
-__device__ __forceinline__ void inv_stage_tile(const InvParams& p, int64_t tile, R* buf, int lane) {
+// Stage the ft coefficient rows (frames t0 .. t0+ft-1) of one tile; rows past F are left untouched
+// (their frames are computed on stale data and never reach an output).
+template <typename S>
+__device__ __forceinline__ void inv_produce(const InvParams& p, int64_t tile, S* stage, uint64_t* bar, int lane) {
   const int64_t b = tile / p.tiles_per_clip;
-  const int64_t t0 = (tile - b * p.tiles_per_clip) * kInvFramesOut;
+  const int64_t t0 = (tile - b * p.tiles_per_clip) * (p.ft - 1);
   const S* __restrict__ src = reinterpret_cast<const S*>(p.spec) + b * p.spec_clip_stride;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  R* Xe = buf;
-  R* Xo = buf + kFramesPerTile * kRowPad;
-  constexpr int kQuads = kFramesPerTile * 64;   // groups of 4 coefficients
-  constexpr int kBatch = 8;
+  int nbulk = 0;
+  if (!aligned) {
 #pragma unroll 1
-  for (int base = 0; base < kQuads; base += 32 * kBatch) {
-    S v[kBatch][4];
+    for (int r = 0; r < p.ft; ++r) {
+      if (t0 + r >= p.F) break;
+      S* row = stage + r * kRawPitch;
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = base + u * 32 + lane;
-      const int fr = idx >> 6, q = idx & 63;
-      const int64_t t = t0 + fr;
-      v[u][0] = v[u][1] = v[u][2] = v[u][3] = (S)0;
-      if (t < p.F) {
-        const S* s = src + t * kBins + 4 * q;
-        if (aligned) {
-          if (sizeof(S) == 4) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(s));
-            v[u][0] = (S)w.x; v[u][1] = (S)w.y; v[u][2] = (S)w.z; v[u][3] = (S)w.w;
-          } else {
-            const double2 w0 = __ldg(reinterpret_cast<const double2*>(s));
-            const double2 w1 = __ldg(reinterpret_cast<const double2*>(s) + 1);
-            v[u][0] = (S)w0.x; v[u][1] = (S)w0.y; v[u][2] = (S)w1.x; v[u][3] = (S)w1.y;
-          }
-        } else {
-          v[u][0] = __ldg(s); v[u][1] = __ldg(s + 1); v[u][2] = __ldg(s + 2); v[u][3] = __ldg(s + 3);
-        }
-      }
+      for (int u = 0; u < kBins / 32; ++u) row[lane + 32 * u] = __ldg(src + (t0 + r) * kBins + lane + 32 * u);
     }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = base + u * 32 + lane;
-      const int fr = idx >> 6, q = idx & 63;
-      typename Vec2<R>::type e, o;
-      e.x = (R)v[u][0]; e.y = (R)v[u][2]; o.x = (R)v[u][1]; o.y = (R)v[u][3];
-      *reinterpret_cast<typename Vec2<R>::type*>(Xe + fr * kRowPad + 2 * q) = e;
-      *reinterpret_cast<typename Vec2<R>::type*>(Xo + fr * kRowPad + 2 * q) = o;
-    }
+  } else {
+    const int64_t left = p.F - t0;
+    nbulk = (int)(left < p.ft ? left : p.ft);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar, (uint32_t)nbulk * (uint32_t)(kBins * sizeof(S)));
+#pragma unroll 1
+    for (int r = 0; r < nbulk; ++r) bulk_g2s(stage + r * kRawPitch, src + (t0 + r) * kBins, kBins * sizeof(S), bar);
   }
 }
 
-template <typename R> constexpr size_t inv_smem_bytes() {
-  return (2 * 2 * kFramesPerTile * kRowPad + kFramesPerTile * kURow) * sizeof(R) +
-         kFramesPerTile * kXchStride * sizeof(cx<R>);
+template <typename R, typename S> __host__ __device__ constexpr size_t inv_smem_bytes(int ft) {
+  return align16((size_t)kStages * ft * kRawPitch * sizeof(S)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
+         align16((size_t)ft * kURow * sizeof(R)) + 512 * sizeof(float) + 64;
+}
+
+template <typename R> __device__ __forceinline__ void load4(const R* p, R* o);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<double>(const double* p, double* o) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+// Window + overlap-add + crop of one finished tile: out block q = first half of frame q+1 + second
+// half of frame q (mdct.py:473-488), all warps cooperating, 4 samples per thread per step.
+template <typename R, typename OutT>
+__device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t tile, const R* Ubuf, const float* wsm) {
+  const int fout = p.ft - 1;
+  const int64_t b = tile / p.tiles_per_clip;
+  const int64_t t0 = (tile - b * p.tiles_per_clip) * fout;
+  const R sc = (R)(4.0 / 512.0);
+  OutT* dst = reinterpret_cast<OutT*>(p.out) + b * p.out_clip_stride;
+  const bool dst_aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+#pragma unroll 1
+  for (int idx = threadIdx.x; idx < fout * 64; idx += blockDim.x) {
+    const int fo = idx >> 6, i4 = (idx & 63) * 4;
+    const int64_t q = t0 + fo;
+    if (q + 1 >= p.F) break;   // idx is monotone in fo for a given thread
+    const R* Ua = Ubuf + (fo + 1) * kURow;   // frame q+1 -> first half
+    const R* Ub = Ubuf + fo * kURow;         // frame q   -> second half
+    R ua[4], ub[4], o[4];
+    const float4 w0 = *reinterpret_cast<const float4*>(wsm + i4);
+    const float4 w1 = *reinterpret_cast<const float4*>(wsm + 256 + i4);
+    if (i4 < 128) {
+      load4<R>(Ua + 128 + i4, ua);                 // U[128+i]
+      R tmp[4]; load4<R>(Ub + 124 - i4, tmp);      // -U[127-i]
+      ub[0] = -tmp[3]; ub[1] = -tmp[2]; ub[2] = -tmp[1]; ub[3] = -tmp[0];
+    } else {
+      R tmp[4]; load4<R>(Ua + 380 - i4, tmp);      // -U[383-i]
+      ua[0] = -tmp[3]; ua[1] = -tmp[2]; ua[2] = -tmp[1]; ua[3] = -tmp[0];
+      load4<R>(Ub + i4 - 128, ub);                 // -U[i-128]
+      ub[0] = -ub[0]; ub[1] = -ub[1]; ub[2] = -ub[2]; ub[3] = -ub[3];
+    }
+    o[0] = (ua[0] * (R)w0.x + ub[0] * (R)w1.x) * sc;
+    o[1] = (ua[1] * (R)w0.y + ub[1] * (R)w1.y) * sc;
+    o[2] = (ua[2] * (R)w0.z + ub[2] * (R)w1.z) * sc;
+    o[3] = (ua[3] * (R)w0.w + ub[3] * (R)w1.w) * sc;
+    const int64_t sidx = q * kHop + i4;
+    if (sidx + 3 < p.out_len && dst_aligned) {
+      if (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + sidx) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+      } else {
+        double2* d2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(dst) + sidx);
+        d2[0] = make_double2((double)o[0], (double)o[1]);
+        d2[1] = make_double2((double)o[2], (double)o[3]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (sidx + u < p.out_len) dst[sidx + u] = (OutT)o[u];
+    }
+  }
 }
 
 // PRO: 0 = raw coefficients in, 1 = fused denormalise + expand (sinh) on the way in.
+//
+// Software pipeline of one warp (tile i, stage s):
+//   [warp 0: refill the stage of tile i-1]  wait full[s] -> gather(i) -> arrive empty[s]
+//   wait udone(i-1) -> overlap-add + store tile i-1 -> arrive odone(i-1)
+//   pass 1 / pass 2 of tile i (private exchange slice) -> wait odone(i-1) -> write U rows(i) -> arrive udone(i)
+// so both cross-warp dependencies (U rows complete / U rows free) are split-phase with real work in between.
 template <typename R, typename S, typename OutT, int PRO>
-__global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? 3 : 1) imdct4_inv_kernel(const InvParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kBufElems = 2 * kFramesPerTile * kRowPad;
-  R* tilebuf = reinterpret_cast<R*>(smem_raw);                   // [2][kBufElems]
-  R* Ubuf = tilebuf + 2 * kBufElems;                             // [16][kURow]
-  cx<R>* xch_all = reinterpret_cast<cx<R>*>(Ubuf + kFramesPerTile * kURow);
+__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_inv_kernel(const InvParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int stage_elems = p.ft * kRawPitch;
+  unsigned char* sp_ = smem_raw;
+  S* raw = reinterpret_cast<S*>(sp_);                 sp_ += align16((size_t)kStages * stage_elems * sizeof(S));
+  cx<R>* xch_all = reinterpret_cast<cx<R>*>(sp_);     sp_ += align16((size_t)p.ft * kXchStride * sizeof(cx<R>));
+  R* Ubuf = reinterpret_cast<R*>(sp_);                sp_ += align16((size_t)p.ft * kURow * sizeof(R));
+  float* wsm = reinterpret_cast<float*>(sp_);         sp_ += 512 * sizeof(float);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sp_);
+  uint64_t* empty = full + kStages;
+  uint64_t* udone = empty + kStages;
+  uint64_t* odone = udone + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
   const int g = lane >> 3, j = lane & 7;
-  const int f = (warp & 3) * 4 + g;
-  const bool loader = (warp == kComputeWarps);
+  const int f = warp * 4 + g;
+  const int fout = p.ft - 1;   // output blocks per tile
 
-  ThreadTab<R> tt;
-  // output-phase mapping: thread c handles samples i4..i4+3 of every other output block
-  const int c = threadIdx.x & 127;
-  const int i4 = (c & 63) * 4, half = c >> 6;
-  float w0[4], w1[4];
-  if (!loader) {
-    load_T<R>(reinterpret_cast<const R*>(p.tabT), j, (R)1, tt);
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { w0[u] = __ldg(p.window + i4 + u); w1[u] = __ldg(p.window + 256 + i4 + u); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    mbar_init(udone, nwarps);
+    mbar_init(odone, nwarps);
+    mbar_fence_init();
   }
-  const R sc = (R)(4.0 / 512.0);
-  const R inv_gain = (R)1 / (R)p.np.gain;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) wsm[i] = __ldg(p.window + i);
+  __syncthreads();
 
   int64_t tile = blockIdx.x;
-  int buf = 0;
-  if (loader && tile < p.ntiles) inv_stage_tile<R, S>(p, tile, tilebuf, lane);
-  __syncthreads();
-  for (; tile < p.ntiles; tile += gridDim.x) {
-    const int64_t next = tile + gridDim.x;
-    if (loader) {
-      if (next < p.ntiles) inv_stage_tile<R, S>(p, next, tilebuf + (buf ^ 1) * kBufElems, lane);
-    } else {
-      const int64_t b = tile / p.tiles_per_clip;
-      const int64_t t0 = (tile - b * p.tiles_per_clip) * kInvFramesOut;
-      const R* Xe = tilebuf + buf * kBufElems + f * kRowPad;
-      const R* Xo = Xe + kFramesPerTile * kRowPad;
-      cx<R>* xch = xch_all + f * kXchStride;
-      {
-        cx<R> v[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int n = j + 8 * r;
-          R a = Xe[n], bb = Xo[127 - n];
-          if (PRO == 1) {
-            if (sizeof(R) == 8) {
-              a = (R)((double)a * (double)p.inv_a + (double)p.inv_b);
-              bb = (R)((double)bb * (double)p.inv_a + (double)p.inv_b);
-              if (p.np.mode == 1) { a = (R)(sinh((double)a * kLn10F32)) * inv_gain; bb = (R)(sinh((double)bb * kLn10F32)) * inv_gain; }
-            } else {
-              float af = fmaf((float)a, p.inv_a, p.inv_b), bf = fmaf((float)bb, p.inv_a, p.inv_b);
-              if (p.np.mode == 1) { af = fast_sinh(af * (float)kLn10F32) * (float)inv_gain; bf = fast_sinh(bf * (float)kLn10F32) * (float)inv_gain; }
-              a = (R)af; bb = (R)bf;
-            }
-          }
-          cx<R> u{a, bb};
-          v[r] = (r == 0) ? u : cmulc(u, rho_re<R>(r), rho_im<R>(r));
-        }
-        pass1<R>(v, tt, j, xch);
-      }
-      __syncwarp();
-      {
-        cx<R> y[2][8];
-        pass2<R>(xch, j, y);
-        R* Urow = Ubuf + f * kURow;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2) {
-            int col; R d0, d1;
-            out_pair<R>(y, j, h, k2, col, d0, d1);
-            typename Vec2<R>::type o; o.x = d0; o.y = d1;
-            *reinterpret_cast<typename Vec2<R>::type*>(Urow + col) = o;
-          }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 compute warps: U rows complete
-      // ---- window + overlap-add + crop: out block q = first half of frame q+1 + second half of frame q
-      OutT* dst = reinterpret_cast<OutT*>(p.out) + b * p.out_clip_stride;
-      const bool dst_aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  if (warp == 0) {
 #pragma unroll 1
-      for (int fo = half; fo < kInvFramesOut; fo += 2) {
-        const int64_t q = t0 + fo;
-        if (q + 1 >= p.F) break;
-        const R* Ua = Ubuf + (fo + 1) * kURow;   // frame q+1 -> first half
-        const R* Ub = Ubuf + fo * kURow;         // frame q   -> second half
-        R o[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i4 + u;
-          const R a = unfold_first<R>(Ua, i) * (R)w0[u];
-          const R bb = unfold_second<R>(Ub, i) * (R)w1[u];
-          o[u] = (a + bb) * sc;
-        }
-        const int64_t s = q * kHop + i4;
-        if (s + 3 < p.out_len && dst_aligned && sizeof(OutT) == 4) {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + s) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
-        } else if (s + 3 < p.out_len && dst_aligned) {
-          double2* d2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(dst) + s);
-          d2[0] = make_double2((double)o[0], (double)o[1]);
-          d2[1] = make_double2((double)o[2], (double)o[3]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (s + u < p.out_len) dst[s + u] = (OutT)o[u];
-        }
+    for (int s = 0; s < kStages; ++s) {
+      const int64_t tl = tile + (int64_t)s * gridDim.x;
+      if (tl < p.ntiles) inv_produce<S>(p, tl, raw + s * stage_elems, &full[s], lane);
+    }
+  }
+
+  ThreadTab<R> tt;
+  load_T<R>(reinterpret_cast<const R*>(p.tabT), j, (R)1, tt);
+  const R inv_gain = (R)1 / (R)p.np.gain;
+  cx<R>* const xch = xch_all + f * kXchStride;
+  R* const Urow = Ubuf + f * kURow;
+
+  uint32_t it = 0;
+#pragma unroll 1
+  for (; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    if (warp == 0 && it >= 1) {
+      const int64_t next = tile + gridDim.x;
+      if (next < p.ntiles) {
+        const int sp = (it - 1) % kStages;
+        mbar_wait(&empty[sp], ((it - 1) / kStages) & 1);
+        inv_produce<S>(p, next, raw + sp * stage_elems, &full[sp], lane);
       }
     }
-    __syncthreads();
-    buf ^= 1;
+    const int64_t b = tile / p.tiles_per_clip;
+    const int64_t t0 = (tile - b * p.tiles_per_clip) * fout;
+    const bool active = (f < p.ft) && (t0 + f < p.F);
+    cx<R> v[16];
+    mbar_wait(&full[s], (it / kStages) & 1);
+    if (active) {
+      const S* row = raw + s * stage_elems + f * kRawPitch;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        R a = (R)row[2 * j + 16 * r], bb = (R)row[255 - 2 * j - 16 * r];   // X[2n], X[255-2n], n = j + 8r
+        if (PRO == 1) {
+          if (sizeof(R) == 8) {
+            a = (R)((double)a * (double)p.inv_a + (double)p.inv_b);
+            bb = (R)((double)bb * (double)p.inv_a + (double)p.inv_b);
+            if (p.np.mode == 1) { a = (R)(sinh((double)a * kLn10F32)) * inv_gain; bb = (R)(sinh((double)bb * kLn10F32)) * inv_gain; }
+          } else {
+            float af = fmaf((float)a, p.inv_a, p.inv_b), bf = fmaf((float)bb, p.inv_a, p.inv_b);
+            if (p.np.mode == 1) { af = fast_sinh(af * (float)kLn10F32) * (float)inv_gain; bf = fast_sinh(bf * (float)kLn10F32) * (float)inv_gain; }
+            a = (R)af; bb = (R)bf;
+          }
+        }
+        cx<R> u{a, bb};
+        v[r] = (r == 0) ? u : cmulc(u, rho_re<R>(r), rho_im<R>(r));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (it >= 1) {
+      mbar_wait(udone, (it - 1) & 1);                               // U rows of tile it-1 complete in every warp
+      inv_output_phase<R, OutT>(p, tile - gridDim.x, Ubuf, wsm);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(odone);
+    }
+    if (active) pass1<R>(v, tt, j, xch);
+    __syncwarp();
+    cx<R> y[2][8];
+    if (active) pass2<R>(xch, j, y);
+    if (it >= 1) mbar_wait(odone, (it - 1) & 1);                    // every warp has finished reading U rows of tile it-1
+    if (active) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          int col; R d0, d1;
+          out_pair<R>(y, j, h, k2, col, d0, d1);
+          typename Vec2<R>::type o; o.x = d0; o.y = d1;
+          *reinterpret_cast<typename Vec2<R>::type*>(Urow + col) = o;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(udone);
+  }
+  if (it >= 1) {   // drain: the last tile's overlap-add
+    mbar_wait(udone, (it - 1) & 1);
+    inv_output_phase<R, OutT>(p, tile - gridDim.x, Ubuf, wsm);
   }
 }
 

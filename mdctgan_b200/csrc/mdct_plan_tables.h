@@ -41,6 +41,20 @@ inline void build_plan_tables(const float* window512, PlanTablesHost& t) {
   }
 }
 
+// Synthesis window of the fp32 flavour: w_s[n] = w[n] / (w[n]^2 + w[n+N]^2).  For a symmetric analysis
+// window this satisfies the TDAC conditions exactly (alias terms cancel because w_s/w is symmetric about
+// the half-window centre; the overlap terms sum to 1), so the fp32 rounding of kbdwin -- the reference's
+// whole round-trip error floor, 1.4 eps*peak -- no longer reaches the output.  It differs from
+// the reference's synthesis window (= w) by <= 2.4e-7 relative.  The fp64 flavour keeps w (bit-faithful).
+inline void build_synthesis_window(const float* w, int n, std::vector<float>& ws) {
+  ws.resize(n);
+  const int h = n / 2;
+  for (int m = 0; m < n; ++m) {
+    const double a = w[m], b = w[(m + h) % n];
+    ws[m] = (float)(a / (a * a + b * b));
+  }
+}
+
 // The fold assumes w[m] == w[511-m] (true for every window the reference builds: kbdwin is
 // cat(half, flip(half)), util/util.py:186).  Returns false for an asymmetric window.
 inline bool window_is_symmetric(const float* w, int n) {

@@ -81,7 +81,7 @@ class MDCT4(_TransformBase):
         _require_cuda(signal, "MDCT4.forward")
         lead = signal.shape[:-1]
         T = signal.shape[-1]
-        F = self.frame_count(signal) if signal.numel() else 0
+        F = self.frame_count(signal)
         x = signal.to(torch.float32).reshape(-1, T)
         if x.stride(-1) != 1:
             x = x.contiguous()

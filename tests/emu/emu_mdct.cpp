@@ -43,34 +43,34 @@ template <typename R>
 static void fwd_impl(const float* x, int64_t T, int64_t F, const float* window, double* out) {
   PlanTablesHost tabs;
   build_plan_tables(window, tabs);
-  // de-interleaved padded blocks: block b holds samples x[256(b-1) .. 256b)
-  std::vector<float> E((F + 1) * kRowPad, 0.f), O((F + 1) * kRowPad, 0.f);
+  // raw padded rows exactly as the kernel stages them: row b holds samples x[256(b-1) .. 256b)
+  std::vector<float> rows((F + 1) * kRawPitch, 0.f);
   for (int64_t b = 0; b <= F; ++b)
     for (int p = 0; p < 256; ++p) {
       int64_t s = 256 * (b - 1) + p;
-      float v = (s >= 0 && s < T) ? x[s] : 0.f;
-      ((p & 1) ? O : E)[b * kRowPad + (p >> 1)] = v;
+      rows[b * kRawPitch + p] = (s >= 0 && s < T) ? x[s] : 0.f;
     }
   std::vector<R> D(256);
   for (int64_t t = 0; t < F; ++t) {
-    const float *E0 = &E[t * kRowPad], *O0 = &O[t * kRowPad], *E1 = &E[(t + 1) * kRowPad], *O1 = &O[(t + 1) * kRowPad];
+    const float *row0 = &rows[t * kRawPitch], *row1 = &rows[(t + 1) * kRawPitch];
     frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) {
       WinTab w; load_W(tabs.W.data(), j, w);
-      fwd_gather<R>(E0, O0, E1, O1, j, w, v);
+      fwd_gather<R, sizeof(R) == 4>(row0, row1, j, w, v);
     }, D.data());
     for (int k = 0; k < 256; ++k) out[t * 256 + k] = (double)D[k];
   }
 }
 
 template <typename R>
-static void inv_impl(const double* spec, int64_t F, const float* window, double* audio /*(F-1)*256*/) {
+static void inv_impl(const double* spec, int64_t F, const float* window_in, double* audio /*(F-1)*256*/) {
   PlanTablesHost tabs;
-  build_plan_tables(window, tabs);
+  build_plan_tables(window_in, tabs);
+  std::vector<float> wsyn;
+  build_synthesis_window(window_in, 512, wsyn);
+  const float* window = sizeof(R) == 4 ? wsyn.data() : window_in;   // same choice as capi.cu launch_inv
   std::vector<R> U(F * kURow);
   for (int64_t t = 0; t < F; ++t) {
-    std::vector<R> Xe(128), Xo(128);
-    for (int n = 0; n < 128; ++n) { Xe[n] = (R)spec[t * 256 + 2 * n]; Xo[n] = (R)spec[t * 256 + 2 * n + 1]; }
-    frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) { inv_gather<R, R>(Xe.data(), Xo.data(), j, v); }, &U[t * kURow]);
+    frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) { inv_gather<R, double>(&spec[t * 256], j, v); }, &U[t * kURow]);
   }
   const R sc = (R)(4.0 / 512.0);
   for (int64_t q = 0; q + 1 < F; ++q)
