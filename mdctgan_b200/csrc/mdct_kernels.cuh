@@ -73,6 +73,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// Returns true in exactly one warp per use of `cnt`: the one whose lane 0 incremented it last.
+__device__ __forceinline__ bool warp_is_last(uint32_t* cnt, int nwarps, int lane) {
+  uint32_t old = 0;
+  if (lane == 0) old = atomicAdd(cnt, 1u);
+  old = __shfl_sync(0xffffffffu, old, 0);
+  return old == (uint32_t)(nwarps - 1);
+}
 // global -> shared bulk copy; `bytes` multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -89,6 +96,15 @@ __device__ __forceinline__ float fast_asinh_scaled(float y, float c1) {
   float l;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(ay + r));
   return copysignf(l * c1, y);
+}
+__device__ __forceinline__ float fast_asinh_affine(float y, float c1, float b) {
+  // sign(y) * log2(|y| + sqrt(y^2+1)) * c1 + b, the sign carried by the scale so that one FFMA finishes it
+  const float ay = fabsf(y);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(ay, ay, 1.0f)));
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(ay + r));
+  return fmaf(l, copysignf(c1, y), b);
 }
 __device__ __forceinline__ float fast_sinh(float t) {
   // (2^(t*log2e) - 2^(-t*log2e)) / 2
@@ -159,6 +175,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
   cx<R>* xch_all = reinterpret_cast<cx<R>*>(smem_raw + align16((size_t)kStages * stage_floats * sizeof(float)));
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xch_all) + align16((size_t)p.ft * kXchStride * sizeof(cx<R>)));
   uint64_t* empty = full + kStages;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(empty + kStages);
   using OutT = typename std::conditional<EPI == 0, R, float>::type;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); cnt[s] = 0; }
     mbar_fence_init();
   }
   __syncthreads();
@@ -197,15 +214,6 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
   for (; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int s = it % kStages;
     const uint32_t parity = (it / kStages) & 1;
-    if (warp == 0 && it >= 1) {
-      // deferred refill: the stage consumed one iteration ago gets the tile of the NEXT iteration
-      const int64_t next = tile + gridDim.x;
-      if (next < p.ntiles) {
-        const int sp = (it - 1) % kStages;
-        mbar_wait(&empty[sp], ((it - 1) / kStages) & 1);
-        fwd_produce(p, next, raw + sp * stage_floats, &full[sp], lane);
-      }
-    }
     const int64_t b = tile / p.tiles_per_clip;
     const int64_t t = (tile - b * p.tiles_per_clip) * p.ft + f;
     const bool active = (f < p.ft) && (t < p.F);
@@ -216,7 +224,18 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
       fwd_gather<R, sizeof(R) == 4>(row0, row0 + kRawPitch, j, wt, v);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s
+    {   // this warp is done with stage s; the LAST warp to get here refills it with the tile kStages ahead
+      const bool last = warp_is_last(&cnt[s], nwarps, lane);
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (last) {
+        const int64_t next = tile + (int64_t)kStages * gridDim.x;
+        if (lane == 0) cnt[s] = 0;
+        if (next < p.ntiles) {
+          mbar_wait(&empty[s], parity);   // acquire: every warp's reads of the stage are complete
+          fwd_produce(p, next, raw + s * stage_floats, &full[s], lane);
+        }
+      }
+    }
     if (active) pass1<R>(v, tt, j, xch);
     __syncwarp();
     if (active) {
@@ -243,8 +262,8 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
                 s1 = (float)((double)d1 * (double)p.np.aff_a + (double)p.np.aff_b);
               }
             } else if (p.np.mode == 1) {
-              s0 = fast_asinh_scaled((float)d0, c1) + p.np.aff_b;
-              s1 = fast_asinh_scaled((float)d1, c1) + p.np.aff_b;
+              s0 = fast_asinh_affine((float)d0, c1, p.np.aff_b);
+              s1 = fast_asinh_affine((float)d1, c1, p.np.aff_b);
             } else {
               s0 = fmaf((float)d0, p.np.aff_a, p.np.aff_b);
               s1 = fmaf((float)d1, p.np.aff_a, p.np.aff_b);
@@ -315,7 +334,6 @@ __device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t til
   const int fout = p.ft - 1;
   const int64_t b = tile / p.tiles_per_clip;
   const int64_t t0 = (tile - b * p.tiles_per_clip) * fout;
-  const R sc = (R)(4.0 / 512.0);
   OutT* dst = reinterpret_cast<OutT*>(p.out) + b * p.out_clip_stride;
   const bool dst_aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll 1
@@ -326,22 +344,23 @@ __device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t til
     const R* Ua = Ubuf + (fo + 1) * kURow;   // frame q+1 -> first half
     const R* Ub = Ubuf + fo * kURow;         // frame q   -> second half
     R ua[4], ub[4], o[4];
-    const float4 w0 = *reinterpret_cast<const float4*>(wsm + i4);
+    const float4 w0 = *reinterpret_cast<const float4*>(wsm + i4);         // window pre-scaled by 4/n_fft
     const float4 w1 = *reinterpret_cast<const float4*>(wsm + 256 + i4);
-    if (i4 < 128) {
-      load4<R>(Ua + 128 + i4, ua);                 // U[128+i]
-      R tmp[4]; load4<R>(Ub + 124 - i4, tmp);      // -U[127-i]
-      ub[0] = -tmp[3]; ub[1] = -tmp[2]; ub[2] = -tmp[1]; ub[3] = -tmp[0];
-    } else {
-      R tmp[4]; load4<R>(Ua + 380 - i4, tmp);      // -U[383-i]
-      ua[0] = -tmp[3]; ua[1] = -tmp[2]; ua[2] = -tmp[1]; ua[3] = -tmp[0];
-      load4<R>(Ub + i4 - 128, ub);                 // -U[i-128]
-      ub[0] = -ub[0]; ub[1] = -ub[1]; ub[2] = -ub[2]; ub[3] = -ub[3];
+    if (i4 < 128) {   // first half: U[128+i], second half: -U[127-i]
+      load4<R>(Ua + 128 + i4, ua);
+      load4<R>(Ub + 124 - i4, ub);
+      o[0] = ua[0] * (R)w0.x - ub[3] * (R)w1.x;
+      o[1] = ua[1] * (R)w0.y - ub[2] * (R)w1.y;
+      o[2] = ua[2] * (R)w0.z - ub[1] * (R)w1.z;
+      o[3] = ua[3] * (R)w0.w - ub[0] * (R)w1.w;
+    } else {          // first half: -U[383-i], second half: -U[i-128]
+      load4<R>(Ua + 380 - i4, ua);
+      load4<R>(Ub + i4 - 128, ub);
+      o[0] = -(ua[3] * (R)w0.x + ub[0] * (R)w1.x);
+      o[1] = -(ua[2] * (R)w0.y + ub[1] * (R)w1.y);
+      o[2] = -(ua[1] * (R)w0.z + ub[2] * (R)w1.z);
+      o[3] = -(ua[0] * (R)w0.w + ub[3] * (R)w1.w);
     }
-    o[0] = (ua[0] * (R)w0.x + ub[0] * (R)w1.x) * sc;
-    o[1] = (ua[1] * (R)w0.y + ub[1] * (R)w1.y) * sc;
-    o[2] = (ua[2] * (R)w0.z + ub[2] * (R)w1.z) * sc;
-    o[3] = (ua[3] * (R)w0.w + ub[3] * (R)w1.w) * sc;
     const int64_t sidx = q * kHop + i4;
     if (sidx + 3 < p.out_len && dst_aligned) {
       if (sizeof(OutT) == 4) {
@@ -379,6 +398,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
   uint64_t* empty = full + kStages;
   uint64_t* udone = empty + kStages;
   uint64_t* odone = udone + 1;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(odone + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -388,12 +408,12 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); cnt[s] = 0; }
     mbar_init(udone, nwarps);
     mbar_init(odone, nwarps);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) wsm[i] = __ldg(p.window + i);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) wsm[i] = __ldg(p.window + i) * (float)(4.0 / 512.0);   // exact (power of 2)
   __syncthreads();
 
   int64_t tile = blockIdx.x;
@@ -405,8 +425,13 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
     }
   }
 
+  // fp32 fused prologue: sinh(x ln10)/gain = (2^u - 2^-u) * (0.5/gain), u = (s*inv_a + inv_b) * ln10_f32 * log2(e);
+  // the constant factor rides on the thread twiddles
+  const bool fast_sinh_path = (PRO == 1 && sizeof(R) == 4 && p.np.mode == 1);
+  const float kexp = (float)(kLn10F32 * 1.4426950408889634);
+  const float ka = fast_sinh_path ? p.inv_a * kexp : p.inv_a, kb = fast_sinh_path ? p.inv_b * kexp : p.inv_b;
   ThreadTab<R> tt;
-  load_T<R>(reinterpret_cast<const R*>(p.tabT), j, (R)1, tt);
+  load_T<R>(reinterpret_cast<const R*>(p.tabT), j, fast_sinh_path ? (R)(0.5f / p.np.gain) : (R)1, tt);
   const R inv_gain = (R)1 / (R)p.np.gain;
   cx<R>* const xch = xch_all + f * kXchStride;
   R* const Urow = Ubuf + f * kURow;
@@ -415,19 +440,12 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
 #pragma unroll 1
   for (; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int s = it % kStages;
-    if (warp == 0 && it >= 1) {
-      const int64_t next = tile + gridDim.x;
-      if (next < p.ntiles) {
-        const int sp = (it - 1) % kStages;
-        mbar_wait(&empty[sp], ((it - 1) / kStages) & 1);
-        inv_produce<S>(p, next, raw + sp * stage_elems, &full[sp], lane);
-      }
-    }
+    const uint32_t parity = (it / kStages) & 1;
     const int64_t b = tile / p.tiles_per_clip;
     const int64_t t0 = (tile - b * p.tiles_per_clip) * fout;
     const bool active = (f < p.ft) && (t0 + f < p.F);
     cx<R> v[16];
-    mbar_wait(&full[s], (it / kStages) & 1);
+    mbar_wait(&full[s], parity);
     if (active) {
       const S* row = raw + s * stage_elems + f * kRawPitch;
 #pragma unroll
@@ -439,8 +457,15 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
             bb = (R)((double)bb * (double)p.inv_a + (double)p.inv_b);
             if (p.np.mode == 1) { a = (R)(sinh((double)a * kLn10F32)) * inv_gain; bb = (R)(sinh((double)bb * kLn10F32)) * inv_gain; }
           } else {
-            float af = fmaf((float)a, p.inv_a, p.inv_b), bf = fmaf((float)bb, p.inv_a, p.inv_b);
-            if (p.np.mode == 1) { af = fast_sinh(af * (float)kLn10F32) * (float)inv_gain; bf = fast_sinh(bf * (float)kLn10F32) * (float)inv_gain; }
+            float af = fmaf((float)a, ka, kb), bf = fmaf((float)bb, ka, kb);
+            if (p.np.mode == 1) {
+              float pa, qa, pb, qb;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(af));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(qa) : "f"(-af));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pb) : "f"(bf));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(qb) : "f"(-bf));
+              af = pa - qa; bf = pb - qb;
+            }
             a = (R)af; bb = (R)bf;
           }
         }
@@ -449,15 +474,26 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    {   // this warp is done with stage s; the LAST warp to get here refills it with the tile kStages ahead
+      const bool last = warp_is_last(&cnt[s], nwarps, lane);
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (last) {
+        const int64_t next = tile + (int64_t)kStages * gridDim.x;
+        if (lane == 0) cnt[s] = 0;
+        if (next < p.ntiles) {
+          mbar_wait(&empty[s], parity);
+          inv_produce<S>(p, next, raw + s * stage_elems, &full[s], lane);
+        }
+      }
+    }
+    if (active) pass1<R>(v, tt, j, xch);
+    __syncwarp();
     if (it >= 1) {
       mbar_wait(udone, (it - 1) & 1);                               // U rows of tile it-1 complete in every warp
       inv_output_phase<R, OutT>(p, tile - gridDim.x, Ubuf, wsm);
       __syncwarp();
       if (lane == 0) mbar_arrive(odone);
     }
-    if (active) pass1<R>(v, tt, j, xch);
-    __syncwarp();
     cx<R> y[2][8];
     if (active) pass2<R>(xch, j, y);
     if (it >= 1) mbar_wait(odone, (it - 1) & 1);                    // every warp has finished reading U rows of tile it-1
