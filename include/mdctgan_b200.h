@@ -92,6 +92,39 @@ int mdctgan_imdct4_inverse_host(mdctgan_plan* plan, const void* spec_host, int64
 int mdctgan_mdct2audio_inverse_host(mdctgan_plan* plan, const float* spectro_host, int64_t B, int64_t F,
                                     const mdctgan_norm* norm, void* audio_host, int64_t out_len, int precision);
 
+/* ------------------------------------------------------------------------------------------------
+ * Network layers (reference: models/networks.py).  Activations are NHWC fp32 device buffers; weights are
+ * packed [kh*kw*Cin][Cout] (Conv2d weight [Cout,Cin,kh,kw] permuted (2,3,1,0); ConvTranspose2d weight
+ * [Cin,Cout,kh,kw] permuted (2,3,0,1)).  Normalisation layers are split between the producing
+ * convolution (statistics, `stats` = [B][Cout][2] doubles (sum, sumsq), accumulated atomically: zero it
+ * first) and the consumer (v = act(x*scale + shift), `in_scale/in_shift` = [B][Cin] when
+ * in_per_sample, else [Cin]).  act codes: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 tanh.
+ * pad_mode: 0 zeros, 1 reflection (nn.ReflectionPad2d in front of an unpadded conv, networks.py:308,430).
+ */
+/* nn.Conv2d / nn.ConvTranspose2d forward (networks.py:308-352, :387-417, :649-670). */
+int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* w, const float* bias, float* y, int Ho, int Wo,
+                        int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
+                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, void* stream);
+/* InstanceNorm2d(affine=False) (mode 0, networks.py:26) / BatchNorm2d train (1) / eval (2) statistics ->
+ * per-(sample,)channel scale & shift; BatchNorm also updates its running buffers in train mode. */
+int mdctgan_norm_finalize(const double* stats, int B, int C, double count, float eps, int mode, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float* scale, float* shift, void* stream);
+/* y = act_out( act_a(a*sa+ta) [+ act_b(b*sb+tb)] ): ResnetBlock `x + conv_block(x)` (networks.py:461-463),
+ * LocalEnhancer branch sum (:266-267), BottleStack shortcut. */
+int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const float* b,
+                       const float* b_scale, const float* b_shift, int b_per_sample, int b_act, float* y, int B, int HW, int C,
+                       int act_out, void* stream);
+/* nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (networks.py:249-250, :525-526). */
+int mdctgan_avgpool3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* BoTNet attention with absolute position embedding (bottleneck_transformer_pytorch==0.1.4 `Attention`,
+ * called from networks.py:342-344): qkv NHWC [B, Hh*Ww, 3*heads*d] -> out [B, Hh*Ww, heads*d];
+ * `stats` (nullable) receives the per-channel (sum, sumsq) for the BatchNorm2d that follows. */
+int mdctgan_attention_abs_pos(const float* qkv, const float* emb_h, const float* emb_w, float* out, int B, int Hh, int Ww, int heads,
+                               int d, float scale, double* stats, void* stream);
+/* layout changes at the network boundary (the reference's modules take and return NCHW) */
+int mdctgan_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream);
+int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* stream);
+
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);
 

@@ -28,6 +28,21 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+}  // namespace
+
+// shared with the other translation units of the library (nn_capi.cu)
+int mdctgan_set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+void mdctgan_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
 int cuda_fail(cudaError_t e, const char* what) {
   return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
 }

@@ -1,0 +1,158 @@
+// nn_capi.cu -- C ABI of the network kernels (see include/mdctgan_b200.h, "network layers").
+#include <cstdio>
+#include <string>
+
+#include "../../include/mdctgan_b200.h"
+#include "nn_kernels.cuh"
+
+using namespace nnk;
+
+int mdctgan_set_error(int code, const char* fmt, ...);   // capi.cu
+void mdctgan_count_launch();                              // capi.cu
+
+#define CKN(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) return mdctgan_set_error((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* w, const float* bias, float* y, int Ho, int Wo,
+                        int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
+                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, void* stream) {
+  if (!x || !w || !y) return mdctgan_set_error(-1, "conv2d: NULL buffer");
+  if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+    return mdctgan_set_error(-1, "conv2d: bad shape");
+  if (Cin > 1024) return mdctgan_set_error(-2, "conv2d: Cin %d > 1024 unsupported", Cin);
+  if (pad_mode == kPadReflect && (pad >= H || pad >= W)) return mdctgan_set_error(-1, "conv2d: reflection pad %d >= input size %dx%d", pad, H, W);
+  if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d: in_scale / in_shift must come together");
+  if (B == 0) return 0;
+  ConvParams p{};
+  p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w = w; p.bias = bias; p.y = y; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
+  p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_scale ? in_act : in_act;
+  p.act = act; p.stats = stats;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HWo = Ho * Wo;
+  if (Cout == 1) {
+    if (stats) return mdctgan_set_error(-2, "conv2d: statistics of a 1-channel output are not supported");
+    const int bps = (HWo + 31) / 32;
+    const size_t smem = ((size_t)kh * kw * Cin + 2 * (size_t)Cin) * sizeof(float);
+    if (smem > 48 * 1024) CKN(cudaFuncSetAttribute(conv2d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv2d_cout1_kernel<<<B * bps, 256, smem, st>>>(p);
+  } else {
+    const int bn = Cout >= 64 ? 64 : 32;
+    int bm = 64;
+    if ((long long)B * ((HWo + 63) / 64) * ((Cout + bn - 1) / bn) < 148) bm = 32;
+    p.tiles_per_sample = (HWo + bm - 1) / bm;
+    dim3 grid(B * p.tiles_per_sample, (Cout + bn - 1) / bn);
+    if (bm == 64 && bn == 64) conv2d_nhwc_kernel<64, 64><<<grid, 256, 0, st>>>(p);
+    else if (bm == 64) conv2d_nhwc_kernel<64, 32><<<grid, 256, 0, st>>>(p);
+    else if (bn == 64) conv2d_nhwc_kernel<32, 64><<<grid, 256, 0, st>>>(p);
+    else conv2d_nhwc_kernel<32, 32><<<grid, 256, 0, st>>>(p);
+  }
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_norm_finalize(const double* stats, int B, int C, double count, float eps, int mode, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float* scale, float* shift, void* stream) {
+  if (!scale || !shift) return mdctgan_set_error(-1, "norm_finalize: NULL output");
+  if (mode != 2 && !stats) return mdctgan_set_error(-1, "norm_finalize: NULL statistics");
+  if (mode == 2 && (!running_mean || !running_var)) return mdctgan_set_error(-1, "norm_finalize: eval mode needs running statistics");
+  if (mode < 0 || mode > 2) return mdctgan_set_error(-1, "norm_finalize: bad mode %d", mode);
+  NormFinalizeParams p{stats, B, C, count, eps, mode, gamma, beta, running_mean, running_var, momentum, scale, shift};
+  const int n = mode == 0 ? B * C : C;
+  if (n == 0) return 0;
+  norm_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const float* b,
+                       const float* b_scale, const float* b_shift, int b_per_sample, int b_act, float* y, int B, int HW, int C,
+                       int act_out, void* stream) {
+  if (!a || !y) return mdctgan_set_error(-1, "norm_apply: NULL buffer");
+  if (C % 4) return mdctgan_set_error(-2, "norm_apply: C %d must be a multiple of 4", C);
+  ApplyParams p{};
+  p.a = a; p.na = InputNorm{a_scale, a_shift, a_per_sample, a_act};
+  p.b = b; p.nb = InputNorm{b_scale, b_shift, b_per_sample, b_act};
+  p.y = y; p.B = B; p.HW = HW; p.C = C; p.act_out = act_out;
+  const size_t total4 = (size_t)B * HW * C / 4;
+  if (total4 == 0) return 0;
+  norm_apply_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_avgpool3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y) return mdctgan_set_error(-1, "avgpool: NULL buffer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * Ho * Wo * C;
+  if (total == 0) return 0;
+  avgpool3s2_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, Ho, Wo);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_attention_abs_pos(const float* qkv, const float* emb_h, const float* emb_w, float* out, int B, int Hh, int Ww, int heads,
+                               int d, float scale, double* stats, void* stream) {
+  if (!qkv || !emb_h || !emb_w || !out) return mdctgan_set_error(-1, "attention: NULL buffer");
+  const int L = Hh * Ww;
+  if (d % 32 || d > 128) return mdctgan_set_error(-2, "attention: dim_head %d must be a multiple of 32, <= 128", d);
+  if (L > 256) return mdctgan_set_error(-2, "attention: %d tokens > 256 unsupported (feature map %dx%d)", L, Hh, Ww);
+  const size_t smem = ((size_t)L * (d + 1) + (size_t)L * d + 8 * (size_t)d) * sizeof(float);
+  if (smem > 227 * 1024) return mdctgan_set_error(-2, "attention: %zu bytes of shared memory needed (L=%d, d=%d)", smem, L, d);
+  if (B == 0) return 0;
+  AttnParams p{qkv, emb_h, emb_w, out, B, Hh, Ww, heads, d, scale, stats};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kpl = (L + 31) / 32;
+#define LAUNCH_ATTN(K)                                                                                                     \
+  do {                                                                                                                     \
+    CKN(cudaFuncSetAttribute(attention_abs_pos_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    attention_abs_pos_kernel<K><<<B * heads, 256, smem, st>>>(p);                                                          \
+  } while (0)
+  if (kpl <= 1) LAUNCH_ATTN(1);
+  else if (kpl <= 2) LAUNCH_ATTN(2);
+  else if (kpl <= 4) LAUNCH_ATTN(4);
+  else LAUNCH_ATTN(8);
+#undef LAUNCH_ATTN
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream) {
+  if (!x || !y) return mdctgan_set_error(-1, "layout: NULL buffer");
+  const size_t total = (size_t)B * C * HW;
+  if (total == 0) return 0;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, C, HW);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* stream) {
+  if (!x || !y) return mdctgan_set_error(-1, "layout: NULL buffer");
+  const size_t total = (size_t)B * C * HW;
+  if (total == 0) return 0;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, C, HW);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

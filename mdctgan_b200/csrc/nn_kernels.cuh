@@ -1,0 +1,530 @@
+// nn_kernels.cuh -- fp32 CUDA-core kernels for the generator / discriminator stacks (sm_100a).
+//
+// These are the shape-generic kernels of the network half of the hot path (reference: models/networks.py
+// GlobalGenerator :301-372, LocalEnhancer :173-298, ResnetBlock :421-463, NLayerDiscriminator :641-692):
+// every convolution flavour the reference builds (k 7/5/4/3/1, stride 1/2, zero / reflection padding,
+// ConvTranspose2d k3 s2 p1 op1), InstanceNorm2d(affine=False) / BatchNorm2d folded into the producer's
+// epilogue (statistics) and the consumer's prologue (normalise + activation), the residual / branch adds,
+// AvgPool2d(3, 2, 1, count_include_pad=False) and the Cout = 1 heads with tanh.
+// Activations are NHWC fp32 ([B, H, W, C], channels contiguous); weights are packed [kh*kw*Cin][Cout].
+//
+// The tcgen05 implicit-GEMM kernel (conv_umma.cuh) takes over the 3x3 stride-1 residual-block convolutions,
+// which are > 80 % of the generator's FLOPs; the kernels here remain the reference
+// implementation on the device for those and the production path for the degenerate shapes
+// (Cin = 2 stem, Cout = 1 head, strided / transposed layers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nnk {
+
+enum Act : int { kActNone = 0, kActRelu = 1, kActLeaky = 2, kActTanh = 3 };
+enum PadMode : int { kPadZero = 0, kPadReflect = 1 };
+
+// How a consumer sees a producer's raw output: v = act(x * scale[b][c] + shift[b][c]).
+// Built by norm_finalize_kernel from the producer's (sum, sumsq) statistics (InstanceNorm: per sample and
+// channel; BatchNorm: per channel) -- or absent (identity) when `scale` is null.
+struct InputNorm {
+  const float* scale;   // [B][C] or [C] (per_sample = 0), null = identity
+  const float* shift;
+  int per_sample;
+  int act;              // activation applied after the affine (kActNone / kActRelu / kActLeaky)
+};
+
+struct ConvParams {
+  const float* x; int B, H, W, Cin;
+  const float* w;       // [kh*kw*Cin][Cout]
+  const float* bias;    // [Cout] or null
+  float* y; int Ho, Wo, Cout;
+  int kh, kw, stride, pad, pad_mode, transposed;
+  InputNorm in;
+  int act;              // epilogue activation
+  double* stats;        // [B][Cout][2] (sum, sumsq) accumulated with atomics, or null
+  int tiles_per_sample;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == kActRelu) return fmaxf(v, 0.f);
+  if (act == kActLeaky) return v > 0.f ? v : 0.2f * v;
+  if (act == kActTanh) return tanhf(v);
+  return v;
+}
+
+// input coordinate of output pixel `o` for tap `k` along one axis; returns -1 when the tap reads padding
+__device__ __forceinline__ int in_coord(int o, int k, int n_in, int stride, int pad, int pad_mode, int transposed) {
+  if (!transposed) {
+    int i = o * stride - pad + k;
+    if (pad_mode == kPadReflect) {
+      if (i < 0) i = -i;
+      if (i >= n_in) i = 2 * n_in - 2 - i;
+      return i;
+    }
+    return (i >= 0 && i < n_in) ? i : -1;
+  }
+  const int t = o + pad - k;   // ConvTranspose2d: o = i*stride - pad + k
+  if (t < 0 || (t % stride) != 0) return -1;
+  const int i = t / stride;
+  return i < n_in ? i : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution, fp32 FFMA.  CTA tile: BM output pixels (of ONE sample) x BN output channels,
+// K = kh*kw*Cin walked in chunks of 16; 256 threads, (BM/16) x (BN/16) outputs per thread.
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
+  constexpr int BK = 16;
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  __shared__ float s_scale[1024], s_shift[1024];   // Cin <= 1024 (train.sh config: 896)
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / p.tiles_per_sample;
+  const int m0 = (blockIdx.x - b * p.tiles_per_sample) * BM;   // first output pixel of the tile within the sample
+  const int n0 = blockIdx.y * BN;
+  const int HWo = p.Ho * p.Wo;
+  const int K = p.kh * p.kw * p.Cin;
+  const bool has_norm = p.in.scale != nullptr;
+  if (has_norm) {
+    const float* sc = p.in.scale + (p.in.per_sample ? (size_t)b * p.Cin : 0);
+    const float* sh = p.in.shift + (p.in.per_sample ? (size_t)b * p.Cin : 0);
+    for (int c = tid; c < p.Cin; c += 256) { s_scale[c] = sc[c]; s_shift[c] = sh[c]; }
+  }
+  __syncthreads();
+
+  // A-load assignment: thread loads 4 consecutive k for pixel (tid % BM) in rounds; with 256 threads and
+  // BM x 16 elements per chunk = BM*4 float4 -> BM*4/256 rounds
+  constexpr int A_ROUNDS = (BM * 4 + 255) / 256;
+  constexpr int B_ROUNDS = (BN * 4 + 255) / 256;
+  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+  const bool vec_ok = (p.Cin % 4) == 0;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jn = 0; jn < TN; ++jn) acc[i][jn] = 0.f;
+
+  const int ty = tid / 16, tx = tid % 16;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // ---- stage A (im2col gather with the producer's normalisation + activation applied on the fly)
+#pragma unroll
+    for (int rd = 0; rd < A_ROUNDS; ++rd) {
+      const int idx = tid + rd * 256;
+      if (idx < BM * 4) {
+        const int pm = idx / 4, kq = (idx % 4) * 4;
+        const int m = m0 + pm;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < HWo) {
+          const int oy = m / p.Wo, ox = m - oy * p.Wo;
+          if (vec_ok) {
+            const int k = k0 + kq;
+            if (k < K) {
+              const int tap = k / p.Cin, c = k - tap * p.Cin;
+              const int ky = tap / p.kw, kx = tap - ky * p.kw;
+              const int iy = in_coord(oy, ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+              const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+              if (iy >= 0 && ix >= 0) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix) * p.Cin + c));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                if (has_norm) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) v[u] = apply_act(fmaf(v[u], s_scale[c + u], s_shift[c + u]), p.in.act);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = k0 + kq + u;
+              if (k < K) {
+                const int tap = k / p.Cin, c = k - tap * p.Cin;
+                const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                const int iy = in_coord(oy, ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+                const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+                if (iy >= 0 && ix >= 0) {
+                  float t = __ldg(xb + ((size_t)iy * p.W + ix) * p.Cin + c);
+                  if (has_norm) t = apply_act(fmaf(t, s_scale[c], s_shift[c]), p.in.act);
+                  v[u] = t;
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) As[kq + u][pm] = v[u];
+      }
+    }
+    // ---- stage B (weights, [K][Cout])
+#pragma unroll
+    for (int rd = 0; rd < B_ROUNDS; ++rd) {
+      const int idx = tid + rd * 256;
+      if (idx < BN * 4) {
+        const int kk = idx / (BN / 4), nq = (idx % (BN / 4)) * 4;
+        const int k = k0 + kk, n = n0 + nq;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          if (n + 3 < p.Cout && (p.Cout % 4) == 0) {
+            q = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.Cout + n));
+          } else {
+            if (n + 0 < p.Cout) q.x = __ldg(p.w + (size_t)k * p.Cout + n + 0);
+            if (n + 1 < p.Cout) q.y = __ldg(p.w + (size_t)k * p.Cout + n + 1);
+            if (n + 2 < p.Cout) q.z = __ldg(p.w + (size_t)k * p.Cout + n + 2);
+            if (n + 3 < p.Cout) q.w = __ldg(p.w + (size_t)k * p.Cout + n + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[kk][nq]) = q;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int jn = 0; jn < TN; ++jn) bv[jn] = Bs[kk][tx * TN + jn];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int jn = 0; jn < TN; ++jn) acc[i][jn] = fmaf(a[i], bv[jn], acc[i][jn]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, activation, store, InstanceNorm / BatchNorm statistics
+  float csum[TN], csq[TN];
+#pragma unroll
+  for (int jn = 0; jn < TN; ++jn) { csum[jn] = 0.f; csq[jn] = 0.f; }
+  float* yb = p.y + (size_t)b * HWo * p.Cout;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+#pragma unroll
+    for (int jn = 0; jn < TN; ++jn) {
+      const int n = n0 + tx * TN + jn;
+      if (m < HWo && n < p.Cout) {
+        float v = acc[i][jn] + (p.bias ? __ldg(p.bias + n) : 0.f);
+        csum[jn] += v; csq[jn] += v * v;     // statistics are taken BEFORE the epilogue activation (norm follows conv)
+        yb[(size_t)m * p.Cout + n] = apply_act(v, p.act);
+      }
+    }
+  }
+  if (p.stats) {
+    // reduce over the 16 ty-rows of the CTA through shared memory, then one atomic per channel per CTA
+    __shared__ float red[2][16][BN];
+#pragma unroll
+    for (int jn = 0; jn < TN; ++jn) { red[0][ty][tx * TN + jn] = csum[jn]; red[1][ty][tx * TN + jn] = csq[jn]; }
+    __syncthreads();
+    if (tid < BN) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { s += red[0][r][tid]; q += red[1][r][tid]; }
+      const int n = n0 + tid;
+      if (n < p.Cout) {
+        double* st = p.stats + ((size_t)b * p.Cout + n) * 2;
+        atomicAdd(st, (double)s);
+        atomicAdd(st + 1, (double)q);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cout = 1 convolution (generator head 7x7 -> tanh, discriminator head 4x4): 8 lanes per output pixel,
+// lanes split the channels in float4, shuffle-reduce.  Optional residual add after the activation
+// (fit_residual: sr = tanh(conv) ... + lr handled by the caller) is not fused here.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
+  extern __shared__ float s_w[];   // [kh*kw*Cin] weights, then scale/shift [Cin] x2 when normalising
+  const int K = p.kh * p.kw * p.Cin;
+  float* s_scale = s_w + K;
+  float* s_shift = s_scale + p.Cin;
+  const int HWo = p.Ho * p.Wo;
+  const int groups_per_block = 256 / 8;
+  const int blocks_per_sample = (HWo + groups_per_block - 1) / groups_per_block;
+  const int b = blockIdx.x / blocks_per_sample;
+  const int m = (blockIdx.x - b * blocks_per_sample) * groups_per_block + threadIdx.x / 8;
+  const int l8 = threadIdx.x % 8;
+  for (int i = threadIdx.x; i < K; i += 256) s_w[i] = __ldg(p.w + i);
+  const bool has_norm = p.in.scale != nullptr;
+  if (has_norm) {
+    const float* sc = p.in.scale + (p.in.per_sample ? (size_t)b * p.Cin : 0);
+    const float* sh = p.in.shift + (p.in.per_sample ? (size_t)b * p.Cin : 0);
+    for (int c = threadIdx.x; c < p.Cin; c += 256) { s_scale[c] = sc[c]; s_shift[c] = sh[c]; }
+  }
+  __syncthreads();
+  float acc = 0.f;
+  if (m < HWo) {
+    const int oy = m / p.Wo, ox = m - oy * p.Wo;
+    const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = in_coord(oy, ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+      if (iy < 0) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+        if (ix < 0) continue;
+        const float* px = xb + ((size_t)iy * p.W + ix) * p.Cin;
+        const float* wt = s_w + (ky * p.kw + kx) * p.Cin;
+        for (int c = l8 * 4; c < p.Cin; c += 32) {
+          if (c + 3 < p.Cin && (p.Cin % 4) == 0) {
+            float4 q = __ldg(reinterpret_cast<const float4*>(px + c));
+            float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (has_norm) v[u] = apply_act(fmaf(v[u], s_scale[c + u], s_shift[c + u]), p.in.act);
+              acc = fmaf(v[u], wt[c + u], acc);
+            }
+          } else {
+            for (int u = 0; u < 4 && c + u < p.Cin; ++u) {
+              float v = __ldg(px + c + u);
+              if (has_norm) v = apply_act(fmaf(v, s_scale[c + u], s_shift[c + u]), p.in.act);
+              acc = fmaf(v, wt[c + u], acc);
+            }
+          }
+        }
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (m < HWo && l8 == 0) {
+    const float v = acc + (p.bias ? __ldg(p.bias) : 0.f);
+    p.y[(size_t)b * HWo + m] = apply_act(v, p.act);
+    // (no statistics: the reference never normalises a 1-channel map)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (sum, sumsq) -> (scale, shift).  InstanceNorm2d(affine=False, eps): per (b, c); BatchNorm2d: per c, with
+// optional affine and running-statistics update (momentum) in training mode, or running statistics in eval.
+// ------------------------------------------------------------------------------------------------
+struct NormFinalizeParams {
+  const double* stats;   // [B][C][2]
+  int B, C; double count;   // elements per (b, c) plane
+  float eps;
+  int batch_norm;        // 0: instance (per b, c)   1: batch statistics over b   2: eval (running statistics)
+  const float* gamma; const float* beta;        // BatchNorm affine (nullable)
+  float* running_mean; float* running_var; float momentum;   // BatchNorm buffers (nullable)
+  float* scale; float* shift;                    // out: [B][C] (instance) or [C] (batch)
+};
+
+__global__ void norm_finalize_kernel(const NormFinalizeParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.batch_norm == 0) {
+    if (i >= p.B * p.C) return;
+    const double mean = p.stats[2 * (size_t)i] / p.count;
+    double var = p.stats[2 * (size_t)i + 1] / p.count - mean * mean;
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + (double)p.eps);
+    p.scale[i] = (float)rstd;
+    p.shift[i] = (float)(-mean * rstd);
+    return;
+  }
+  if (i >= p.C) return;
+  double mean, var;
+  if (p.batch_norm == 1) {
+    double s = 0, q = 0;
+    for (int b = 0; b < p.B; ++b) { s += p.stats[2 * ((size_t)b * p.C + i)]; q += p.stats[2 * ((size_t)b * p.C + i) + 1]; }
+    const double n = p.count * p.B;
+    mean = s / n;
+    var = q / n - mean * mean;
+    if (var < 0) var = 0;
+    if (p.running_mean) {   // torch: running_var uses the unbiased estimate
+      p.running_mean[i] = (1.f - p.momentum) * p.running_mean[i] + p.momentum * (float)mean;
+      p.running_var[i] = (1.f - p.momentum) * p.running_var[i] + p.momentum * (float)(var * n / (n - 1.0));
+    }
+  } else {
+    mean = p.running_mean[i];
+    var = p.running_var[i];
+  }
+  const double rstd = 1.0 / sqrt(var + (double)p.eps);
+  const double g = p.gamma ? (double)p.gamma[i] : 1.0, be = p.beta ? (double)p.beta[i] : 0.0;
+  p.scale[i] = (float)(rstd * g);
+  p.shift[i] = (float)(be - mean * rstd * g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = act_a(a * sa + ta) [+ act_b(b * sb + tb)]   (materialises a normalised tensor: residual-block
+// output x + IN(conv), LocalEnhancer branch sum, BottleStack shortcut).  float4 over channels.
+// ------------------------------------------------------------------------------------------------
+struct ApplyParams {
+  const float* a; InputNorm na;
+  const float* b; InputNorm nb;   // b nullable
+  float* y; int B, HW, C; int act_out;
+};
+
+__global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
+  const size_t total4 = (size_t)p.B * p.HW * p.C / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int c = (int)(e % p.C);
+    const int bi = (int)(e / ((size_t)p.HW * p.C));
+    float4 va = __ldg(reinterpret_cast<const float4*>(p.a + e));
+    float v[4] = {va.x, va.y, va.z, va.w};
+    if (p.na.scale) {
+      const float* sc = p.na.scale + (p.na.per_sample ? (size_t)bi * p.C : 0) + c;
+      const float* sh = p.na.shift + (p.na.per_sample ? (size_t)bi * p.C : 0) + c;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = fmaf(v[u], __ldg(sc + u), __ldg(sh + u));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = apply_act(v[u], p.na.act);
+    if (p.b) {
+      float4 vb = __ldg(reinterpret_cast<const float4*>(p.b + e));
+      float w[4] = {vb.x, vb.y, vb.z, vb.w};
+      if (p.nb.scale) {
+        const float* sc = p.nb.scale + (p.nb.per_sample ? (size_t)bi * p.C : 0) + c;
+        const float* sh = p.nb.shift + (p.nb.per_sample ? (size_t)bi * p.C : 0) + c;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = fmaf(w[u], __ldg(sc + u), __ldg(sh + u));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] += apply_act(w[u], p.nb.act);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = apply_act(v[u], p.act_out);
+    *reinterpret_cast<float4*>(p.y + e) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AvgPool2d(3, stride 2, padding 1, count_include_pad=False) on NHWC (networks.py:249-250, :525-526)
+// ------------------------------------------------------------------------------------------------
+__global__ void avgpool3s2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+  const size_t total = (size_t)B * Ho * Wo * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float s = 0.f; int n = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = oy * 2 + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = ox * 2 + dx;
+        if (ix < 0 || ix >= W) continue;
+        s += __ldg(x + (((size_t)b * H + iy) * W + ix) * C + c);
+        ++n;
+      }
+    }
+    y[i] = s / (float)n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BoTNet multi-head self-attention with absolute position embedding (bottleneck_transformer_pytorch 0.1.4
+// `Attention`, called from networks.py:342-344):  out = softmax(scale*q.(k + emb)^T) v,
+// emb[(y,x)] = height[y] + width[x].  One CTA per (sample, head); K+emb and V live in shared memory, one
+// warp per query row: lanes own keys for the scores (shuffle max / sum softmax) and channels for P.V.
+// qkv: NHWC [B, L, 3*heads*d] (q | k | v, channel = head*d + i); out: [B, L, heads*d].
+// Optionally accumulates per-channel (sum, sumsq) of the output for the BatchNorm2d that follows.
+// ------------------------------------------------------------------------------------------------
+struct AttnParams {
+  const float* qkv; const float* emb_h; const float* emb_w; float* out;
+  int B, Hh, Ww, heads, d; float scale; double* stats;
+};
+
+template <int KPL>   // keys per lane = ceil(L / 32)
+__global__ void __launch_bounds__(256) attention_abs_pos_kernel(const AttnParams p) {
+  extern __shared__ float sm[];
+  const int L = p.Hh * p.Ww, d = p.d, C = p.heads * d;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  float* Kp = sm;                       // [L][d+1]
+  float* V = Kp + (size_t)L * (d + 1);  // [L][d]
+  float* qrow = V + (size_t)L * d;      // [8 warps][d]
+  const float* base = p.qkv + (size_t)b * L * 3 * C;
+  for (int i = threadIdx.x; i < L * d; i += 256) {
+    const int j = i / d, dd = i - j * d;
+    const int y = j / p.Ww, x = j - y * p.Ww;
+    const float* tok = base + (size_t)j * 3 * C + h * d + dd;
+    Kp[j * (d + 1) + dd] = __ldg(tok + C) + __ldg(p.emb_h + y * d + dd) + __ldg(p.emb_w + x * d + dd);
+    V[j * d + dd] = __ldg(tok + 2 * C);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = qrow + warp * d;
+  const int dpl = d / 32;               // channels per lane (d % 32 == 0)
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = warp; i < L; i += 8) {
+    for (int dd = lane; dd < d; dd += 32) q[dd] = __ldg(base + (size_t)i * 3 * C + h * d + dd) * p.scale;
+    __syncwarp();
+    float sc[KPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+      const int j = lane + 32 * u;
+      float a = -INFINITY;
+      if (j < L) {
+        a = 0.f;
+        const float* kr = Kp + j * (d + 1);
+        for (int dd = 0; dd < d; ++dd) a = fmaf(q[dd], kr[dd], a);
+      }
+      sc[u] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+      sc[u] = (lane + 32 * u < L) ? __expf(sc[u] - mx) : 0.f;
+      sum += sc[u];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+      for (int l = 0; l < 32; ++l) {
+        const int j = l + 32 * u;
+        if (j >= L) break;
+        const float pj = __shfl_sync(0xffffffffu, sc[u], l);
+        for (int t = 0; t < dpl; ++t) acc[t] = fmaf(pj, V[j * d + lane + 32 * t], acc[t]);
+      }
+    }
+    for (int t = 0; t < dpl; ++t) {
+      const float o = acc[t] * inv;
+      p.out[((size_t)b * L + i) * C + h * d + lane + 32 * t] = o;
+      ssum[t] += o; ssq[t] += o * o;
+    }
+    __syncwarp();
+  }
+  if (p.stats) {
+    for (int t = 0; t < dpl; ++t) {
+      double* st = p.stats + ((size_t)b * C + h * d + lane + 32 * t) * 2;
+      atomicAdd(st, (double)ssum[t]);
+      atomicAdd(st + 1, (double)ssq[t]);
+    }
+  }
+}
+
+// NCHW <-> NHWC (network boundary: the reference's modules take / return NCHW tensors)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
+  const size_t total = (size_t)B * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t r = i / C;
+    const int pix = (int)(r % HW);
+    const int b = (int)(r / HW);
+    y[i] = __ldg(x + ((size_t)b * C + c) * HW + pix);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
+  const size_t total = (size_t)B * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const size_t r = i / HW;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    y[i] = __ldg(x + ((size_t)b * HW + pix) * C + c);
+  }
+}
+
+}  // namespace nnk

@@ -1,0 +1,470 @@
+"""Generator / discriminator stacks with the reference's constructors, module tree and state_dict keys
+(models/networks.py), executed by the hand-written CUDA kernels of libmdctgan_b200.so.
+
+The module tree exists to own parameters under the reference's names (`model.1.weight`,
+`model.13.conv_block.1.bias`, `scale0_layer2.0.weight`, ...) so that the published `*_net_G.pth` files load
+unchanged (models/base_model.py:43-111).  Leaf layers never compute: `forward` of a container walks its
+children with `run_layers`, which fuses
+
+    ReflectionPad2d -> Conv2d -> InstanceNorm2d -> ReLU
+
+into: one convolution launch (reflection handled by its gather, (sum, sumsq) taken in its epilogue), one
+tiny statistics->scale/shift launch, and nothing else -- the normalisation and the activation are applied
+by whichever kernel reads the tensor next (nn_ops.Feat).
+
+Forward only in this round: the layers run under no_grad (the reference's `inference()` path,
+pix2pixHD_model.py:618-638); the training kernels (dgrad / wgrad / norm backward / Adam) are listed as next
+in DESIGN.md.
+"""
+from __future__ import annotations
+
+import functools
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import nn_ops as ops
+from ..nn_ops import Feat
+
+_NO_DIRECT = "mdctgan_b200 leaf layers hold parameters only; call the enclosing network (no cuDNN / eager fallback)"
+
+
+# ------------------------------------------------------------------------------------------- leaf layers
+class _PackedWeight:
+    """Caches the kernel-side layout of a parameter until the parameter changes."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, p: torch.Tensor, fn):
+        key = (p.data_ptr(), p._version, p.device)
+        if key != self._key:
+            self._val = fn(p)
+            self._key = key
+        return self._val
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d as a parameter holder (same init, same names); executed by run_layers."""
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError(_NO_DIRECT)
+
+    def packed(self):
+        if not hasattr(self, "_pk"):
+            self._pk = _PackedWeight()
+        return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, False))
+
+    def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
+        kh, kw = self.kernel_size
+        assert self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1] and self.dilation == (1, 1) and self.groups == 1
+        pad, mode = (pad_reflect, ops.PAD_REFLECT) if pad_reflect else (self.padding[0], ops.PAD_ZERO)
+        if pad_reflect and self.padding[0]:
+            raise RuntimeError("ReflectionPad2d in front of a zero-padded convolution is not a reference configuration")
+        return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=pad, pad_mode=mode, act=act,
+                          want_stats=want_stats)
+
+
+class ConvTranspose2d(nn.ConvTranspose2d):
+    def forward(self, x, output_size=None):  # pragma: no cover
+        raise RuntimeError(_NO_DIRECT)
+
+    def packed(self):
+        if not hasattr(self, "_pk"):
+            self._pk = _PackedWeight()
+        return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, True))
+
+    def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
+        assert not pad_reflect
+        kh, kw = self.kernel_size
+        return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=self.padding[0], transposed=True,
+                          output_padding=self.output_padding[0], act=act, want_stats=want_stats)
+
+
+class InstanceNorm2d(nn.InstanceNorm2d):
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError(_NO_DIRECT)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError(_NO_DIRECT)
+
+
+class ReflectionPad2d(nn.Module):
+    def __init__(self, padding: int):
+        super().__init__()
+        self.padding = int(padding)
+
+    def extra_repr(self):
+        return str((self.padding,) * 4)
+
+
+class ReLU(nn.Module):
+    def __init__(self, inplace: bool = False):
+        super().__init__()
+        self.inplace = inplace
+
+
+class LeakyReLU(nn.Module):
+    def __init__(self, negative_slope: float = 0.2, inplace: bool = False):
+        super().__init__()
+        if abs(negative_slope - 0.2) > 1e-12:
+            raise NotImplementedError("LeakyReLU slope is 0.2 everywhere in the reference (networks.py:650)")
+        self.negative_slope, self.inplace = negative_slope, inplace
+
+
+class Tanh(nn.Module):
+    pass
+
+
+class AvgPool3s2(nn.Module):
+    """nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False) (networks.py:249-250, :525-526)."""
+
+
+_ACT_CODE = {ReLU: ops.ACT_RELU, LeakyReLU: ops.ACT_LEAKY, Tanh: ops.ACT_TANH}
+
+
+def _act_of(layer) -> Optional[int]:
+    return _ACT_CODE.get(type(layer))
+
+
+# ------------------------------------------------------------------------------------------- executor
+def run_layers(layers: Sequence[nn.Module], f: Feat) -> Feat:
+    """Execute a reference-ordered layer list on a Feat, fusing pad / norm / activation into the convolutions."""
+    i, n = 0, len(layers)
+    pad_reflect = 0
+    while i < n:
+        L = layers[i]
+        nxt = layers[i + 1] if i + 1 < n else None
+        if isinstance(L, ReflectionPad2d):
+            pad_reflect = L.padding
+            i += 1
+        elif isinstance(L, (Conv2d, ConvTranspose2d)):
+            want_stats = isinstance(nxt, (InstanceNorm2d, BatchNorm2d))
+            act, skip = ops.ACT_NONE, 0
+            if not want_stats and nxt is not None and _act_of(nxt) is not None:
+                act, skip = _act_of(nxt), 1          # conv -> activation with no norm in between: epilogue
+            f = L.run(f, pad_reflect=pad_reflect, act=act, want_stats=want_stats)
+            pad_reflect = 0
+            i += 1 + skip
+        elif isinstance(L, InstanceNorm2d):
+            if L.affine or L.track_running_stats:
+                raise NotImplementedError("InstanceNorm2d(affine=False, track_running_stats=False) only (networks.py:26)")
+            f = ops.finalize_norm(f, eps=L.eps, mode=0)
+            i += 1
+        elif isinstance(L, BatchNorm2d):
+            mode = 1 if (L.training or not L.track_running_stats) else 2
+            f = ops.finalize_norm(f, eps=L.eps, mode=mode, gamma=L.weight, beta=L.bias, running_mean=L.running_mean,
+                                  running_var=L.running_var, momentum=L.momentum if L.momentum is not None else 0.1)
+            if mode == 1 and L.track_running_stats and L.num_batches_tracked is not None:
+                L.num_batches_tracked += 1
+            i += 1
+        elif _act_of(L) is not None:
+            f = ops.with_act(f, _act_of(L))
+            i += 1
+        elif isinstance(L, AvgPool3s2):
+            f = ops.avgpool3s2(f)
+            i += 1
+        elif hasattr(L, "run"):
+            if pad_reflect:
+                raise RuntimeError("ReflectionPad2d must be followed by a convolution")
+            f = L.run(f)
+            i += 1
+        elif isinstance(L, nn.Sequential):
+            f = run_layers(list(L), f)
+            i += 1
+        else:
+            raise NotImplementedError(f"run_layers: no kernel mapping for {type(L).__name__}")
+    return f
+
+
+def _forward_nchw(layers, x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError(f"expected a CUDA tensor, got device={x.device}; mdctgan_b200 has no CPU path")
+    with torch.no_grad():
+        return ops.to_nchw(run_layers(layers, ops.to_nhwc(x.to(torch.float32).contiguous())))
+
+
+# ------------------------------------------------------------------------------------------- init helpers
+def weights_init(m):
+    """Same rule as the reference (networks.py:13-19): N(0, 0.02) on every class whose name contains
+    'Conv2d' (so NOT ConvTranspose2d), N(1, 0.02) / 0 on BatchNorm2d."""
+    classname = m.__class__.__name__
+    if classname.find("Conv2d") != -1:
+        m.weight.data.normal_(0.0, 0.02)
+    elif classname.find("BatchNorm2d") != -1:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0)
+
+
+def get_norm_layer(norm_type="instance"):
+    if norm_type == "batch":
+        return functools.partial(BatchNorm2d, affine=True)
+    if norm_type == "instance":
+        return functools.partial(InstanceNorm2d, affine=False)
+    raise NotImplementedError("normalization layer [%s] is not found" % norm_type)
+
+
+# ------------------------------------------------------------------------------------------- blocks
+class ResnetBlock(nn.Module):
+    """x + [ReflPad1, Conv3x3, IN, ReLU, ReflPad1, Conv3x3, IN](x)   (networks.py:421-463)."""
+
+    def __init__(self, dim, padding_type, norm_layer, activation=None, use_dropout=False):
+        super().__init__()
+        if padding_type != "reflect":
+            raise NotImplementedError("ResnetBlock: padding_type 'reflect' is the only one the reference constructs (networks.py:174,302)")
+        if use_dropout:
+            raise NotImplementedError("ResnetBlock: use_dropout is never enabled by the reference")
+        activation = activation if activation is not None else ReLU(True)
+        self.conv_block = nn.Sequential(ReflectionPad2d(1), Conv2d(dim, dim, kernel_size=3, padding=0), norm_layer(dim), activation,
+                                        ReflectionPad2d(1), Conv2d(dim, dim, kernel_size=3, padding=0), norm_layer(dim))
+
+    def run(self, f: Feat) -> Feat:
+        return ops.combine(f, run_layers(list(self.conv_block), f))
+
+    def forward(self, x):
+        return _forward_nchw([self], x)
+
+
+class ConvResBlock(nn.Module):
+    """downsample_type='resconv' (networks.py:403-417): conv1 (k, s, p; C->C) then conv2 5x5 p2 + conv_res 3x3 p1."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding):
+        super().__init__()
+        self.conv1 = Conv2d(in_channels, in_channels, kernel_size, stride, padding)
+        self.conv2 = Conv2d(in_channels, out_channels, 5, padding=2)
+        self.conv_res = Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+
+    def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
+        x = self.conv1.run(f)
+        y = ops.combine(self.conv2.run(x), self.conv_res.run(x))
+        if act != ops.ACT_NONE:
+            y = ops.with_act(y, act)
+        if want_stats:
+            raise NotImplementedError("ConvResBlock followed by a norm layer needs a statistics pass (DESIGN.md: next)")
+        return y
+
+
+# ------------------------------------------------------------------------------------------- generators
+class GlobalGenerator(nn.Module):
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=3, n_blocks=9, norm_layer=None, padding_type="reflect",
+                 upsample_type="transconv", downsample_type="conv", n_attn_g=0, input_size=(128, 256), proj_factor_g=4, heads_g=4,
+                 dim_head_g=128):
+        assert n_blocks >= 0
+        super().__init__()
+        norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
+        activation = ReLU(True)   # ONE shared instance, as in the reference (keeps the positional state_dict keys)
+        if downsample_type != "conv" or upsample_type != "transconv":
+            raise NotImplementedError("downsample_type='resconv' / upsample_type='interpolate' are listed as next in DESIGN.md")
+        model: List[nn.Module] = [ReflectionPad2d(3), Conv2d(input_nc, ngf, kernel_size=7, padding=0), norm_layer(ngf), activation]
+        for i in range(n_downsampling):
+            mult = 2 ** i
+            model += [Conv2d(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf * mult * 2), activation]
+        mult = 2 ** n_downsampling
+        bottle_neck: List[nn.Module] = [ResnetBlock(ngf * mult, padding_type=padding_type, activation=activation, norm_layer=norm_layer)
+                                        for _ in range(n_blocks)]
+        if n_attn_g > 0:
+            from .bottleneck import BottleStack
+
+            fmap = tuple(s // mult for s in input_size)
+            bottle_neck.insert(n_blocks // 2, BottleStack(dim=ngf * mult, fmap_size=fmap, dim_out=ngf * mult, num_layers=n_attn_g,
+                                                          proj_factor=proj_factor_g, downsample=False, heads=heads_g,
+                                                          dim_head=dim_head_g, activation=activation, rel_pos_emb=False))
+        model += bottle_neck
+        for i in range(n_downsampling):
+            mult = 2 ** (n_downsampling - i)
+            model += [ConvTranspose2d(in_channels=ngf * mult, out_channels=int(ngf * mult / 2), kernel_size=3, stride=2, padding=1,
+                                      output_padding=1), norm_layer(int(ngf * mult / 2)), activation]
+        model += [ReflectionPad2d(3), Conv2d(ngf, output_nc, kernel_size=7, padding=0), Tanh()]
+        self.model = nn.Sequential(*model)
+        self.freeze = False
+
+    def run(self, f: Feat) -> Feat:
+        return run_layers(list(self.model), f)
+
+    def forward(self, input):
+        return _forward_nchw(list(self.model), input)
+
+    def set_freeze(self, freeze=True, *unused):
+        """Reference: networks.py:359-372.  Accepts (and ignores) the extra positional arguments that
+        Pix2PixHDModel.initialize passes (pix2pixHD_model.py:241-242) -- the reference itself raises there."""
+        if self.freeze == freeze:
+            return
+        self.freeze = freeze
+        for name, layer in self.model.named_children():
+            module_name = layer.__class__.__name__
+            if "ResnetBlock" in module_name or "BottleStack" in module_name:
+                break
+            for param in layer.parameters():
+                param.requires_grad = not freeze
+
+
+class LocalEnhancer(nn.Module):
+    def __init__(self, input_nc, output_nc, ngf=32, n_downsample_global=3, n_blocks_global=9, n_local_enhancers=1, n_blocks_local=3,
+                 norm_layer=None, padding_type="reflect", downsample_type="conv", upsample_type="transconv", n_attn_g=0, n_attn_l=0,
+                 input_size=(128, 256), proj_factor_g=4, heads_g=4, dim_head_g=128, proj_factor_l=4, heads_l=4, dim_head_l=128):
+        super().__init__()
+        norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
+        self.n_local_enhancers = n_local_enhancers
+        if n_attn_l > 0:
+            raise NotImplementedError("n_attn_l > 0 (local attention sandwich, networks.py:218-237) is listed as next in DESIGN.md")
+        if downsample_type != "conv" or upsample_type != "transconv":
+            raise NotImplementedError("downsample_type='resconv' / upsample_type='interpolate' are listed as next in DESIGN.md")
+        ngf_global = ngf * (2 ** n_local_enhancers)
+        g = GlobalGenerator(input_nc, output_nc, ngf_global, n_downsample_global, n_blocks_global, norm_layer,
+                            downsample_type=downsample_type, upsample_type=upsample_type, input_size=tuple(s // 2 for s in input_size),
+                            n_attn_g=n_attn_g, proj_factor_g=proj_factor_g, heads_g=heads_g, dim_head_g=dim_head_g).model
+        self.model = nn.Sequential(*[g[i] for i in range(len(g) - 3)])       # drop ReflPad, Conv7x7, Tanh
+        ngf_global = ngf * (2 ** (n_local_enhancers - 1))
+        model_downsample = [ReflectionPad2d(3), Conv2d(input_nc, ngf_global, kernel_size=7, padding=0), norm_layer(ngf_global), ReLU(True),
+                            Conv2d(ngf_global, ngf_global * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global * 2), ReLU(True)]
+        model_upsample: List[nn.Module] = [ResnetBlock(ngf_global * 2, padding_type=padding_type, norm_layer=norm_layer)
+                                           for _ in range(n_blocks_local)]
+        model_upsample += [ConvTranspose2d(in_channels=ngf_global * 2, out_channels=ngf_global, kernel_size=3, stride=2, padding=1,
+                                           output_padding=1), norm_layer(ngf_global), ReLU(True)]
+        model_upsample += [ReflectionPad2d(3), Conv2d(ngf, output_nc, kernel_size=7, padding=0), Tanh()]
+        self.model1_1 = nn.Sequential(*model_downsample)
+        self.model1_2 = nn.Sequential(*model_upsample)
+        self.downsample = AvgPool3s2()
+        self.freeze = False
+
+    def run(self, f: Feat) -> Feat:
+        pyramid = [f]
+        for _ in range(self.n_local_enhancers):
+            pyramid.append(ops.avgpool3s2(pyramid[-1]))
+        coarse = run_layers(list(self.model), pyramid[-1])
+        fine = run_layers(list(self.model1_1), pyramid[0])
+        return run_layers(list(self.model1_2), ops.combine(fine, coarse))   # only one enhancer level runs (networks.py:260-267)
+
+    def forward(self, input):
+        return _forward_nchw([self], input)
+
+    def set_freeze(self, freeze_global_d=True, freeze_global_u=False, freeze_local_d=True, freeze_local_u=False):
+        for name, layer in self.model.named_children():
+            module_name = layer.__class__.__name__
+            if "Conv2d" in module_name or "ConvResBlock" in module_name:
+                for param in layer.parameters():
+                    param.requires_grad = not freeze_global_d
+            elif any(k in module_name for k in ("InterpolateUpsample", "ConvTranspose2d", "ResnetBlock", "BottleStack")):
+                for param in layer.parameters():
+                    param.requires_grad = not freeze_global_u
+        for param in self.model1_1.parameters():
+            param.requires_grad = not freeze_local_d
+        for param in self.model1_2.parameters():
+            param.requires_grad = not freeze_local_u
+
+
+def define_G(input_nc, output_nc, ngf, netG, n_downsample_global=3, n_blocks_global=9, n_local_enhancers=1, n_blocks_local=3,
+             norm="instance", gpu_ids=[], upsample_type="transconv", downsample_type="conv", input_size=(128, 256), n_attn_g=0,
+             n_attn_l=0, proj_factor_g=4, heads_g=4, dim_head_g=128, proj_factor_l=4, heads_l=4, dim_head_l=128):
+    """Reference: networks.py:33-56 (same signature; the module is not printed)."""
+    norm_layer = get_norm_layer(norm_type=norm)
+    if netG == "global":
+        net = GlobalGenerator(input_nc, output_nc, ngf, n_downsample_global, n_blocks_global, norm_layer, downsample_type=downsample_type,
+                              upsample_type=upsample_type, input_size=input_size, n_attn_g=n_attn_g, proj_factor_g=proj_factor_g,
+                              heads_g=heads_g, dim_head_g=dim_head_g)
+    elif netG == "local":
+        net = LocalEnhancer(input_nc, output_nc, ngf, n_downsample_global, n_blocks_global, n_local_enhancers, n_blocks_local, norm_layer,
+                            downsample_type=downsample_type, upsample_type=upsample_type, input_size=input_size, n_attn_g=n_attn_g,
+                            proj_factor_g=proj_factor_g, heads_g=heads_g, dim_head_g=dim_head_g, n_attn_l=n_attn_l,
+                            proj_factor_l=proj_factor_l, heads_l=heads_l, dim_head_l=dim_head_l)
+    else:
+        raise NotImplementedError("generator [%s] is not implemented (reference: 'global' | 'local'; 'encoder' is dead code)" % netG)
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.cuda(gpu_ids[0])
+    net.apply(weights_init)
+    return net
+
+
+# ------------------------------------------------------------------------------------------- discriminator
+class NLayerDiscriminator(nn.Module):
+    """PatchGAN (networks.py:641-692): Conv4x4 s2 p2 + LReLU; (n_layers-1) x [Conv4x4 s2 p2, IN, LReLU];
+    Conv4x4 s1 p2, IN, LReLU; Conv4x4 s1 p2 -> 1."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, getIntermFeat=False):
+        super().__init__()
+        norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
+        if use_sigmoid:
+            raise NotImplementedError("use_sigmoid (--no_lsgan) is listed as next in DESIGN.md")
+        self.getIntermFeat, self.n_layers = getIntermFeat, n_layers
+        kw, padw = 4, 2
+        sequence = [[Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), LeakyReLU(0.2, True)]]
+        nf = ndf
+        for n in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            sequence += [[Conv2d(nf_prev, nf, kernel_size=kw, stride=2, padding=padw), norm_layer(nf), LeakyReLU(0.2, True)]]
+        nf_prev, nf = nf, min(nf * 2, 512)
+        sequence += [[Conv2d(nf_prev, nf, kernel_size=kw, stride=1, padding=padw), norm_layer(nf), LeakyReLU(0.2, True)]]
+        sequence += [[Conv2d(nf, 1, kernel_size=kw, stride=1, padding=padw)]]
+        if getIntermFeat:
+            for n in range(len(sequence)):
+                setattr(self, "model" + str(n), nn.Sequential(*sequence[n]))
+        else:
+            self.model = nn.Sequential(*[m for s in sequence for m in s])
+
+    def stages(self):
+        if self.getIntermFeat:
+            return [getattr(self, "model" + str(n)) for n in range(self.n_layers + 2)]
+        return [self.model]
+
+    def run(self, f: Feat) -> List[Feat]:
+        outs = []
+        for st in self.stages():
+            f = run_layers(list(st), f)
+            outs.append(f)
+        return outs if self.getIntermFeat else outs[-1:]
+
+    def forward(self, input):
+        with torch.no_grad():
+            outs = self.run(ops.to_nhwc(input.to(torch.float32).contiguous()))
+            res = [ops.to_nchw(o) for o in outs]
+        return res if self.getIntermFeat else res[0]
+
+
+class MultiscaleDiscriminator(nn.Module):
+    """num_D PatchGANs on an AvgPool pyramid (networks.py:507-550); returns list[num_D] of list[n_layers+2]."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, num_D=3, getIntermFeat=False):
+        super().__init__()
+        self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        for i in range(num_D):
+            netD = NLayerDiscriminator(input_nc, ndf, n_layers, norm_layer, use_sigmoid, getIntermFeat)
+            if getIntermFeat:
+                for j in range(n_layers + 2):
+                    setattr(self, "scale" + str(i) + "_layer" + str(j), getattr(netD, "model" + str(j)))
+            else:
+                setattr(self, "layer" + str(i), netD.model)
+        self.downsample = AvgPool3s2()
+
+    def _stages(self, i):
+        if self.getIntermFeat:
+            return [getattr(self, "scale" + str(i) + "_layer" + str(j)) for j in range(self.n_layers + 2)]
+        return [getattr(self, "layer" + str(i))]
+
+    def forward(self, input):
+        with torch.no_grad():
+            f = ops.to_nhwc(input.to(torch.float32).contiguous())
+            result = []
+            for i in range(self.num_D):
+                outs, g = [], f
+                for st in self._stages(self.num_D - 1 - i):
+                    g = run_layers(list(st), g)
+                    outs.append(ops.to_nchw(g))
+                result.append(outs if self.getIntermFeat else [outs[-1]])
+                if i != self.num_D - 1:
+                    f = ops.avgpool3s2(f)
+        return result
+
+
+def define_D(input_nc, ndf, n_layers_D, norm="instance", use_sigmoid=False, num_D=1, getIntermFeat=False, gpu_ids=[]):
+    """Reference: networks.py:59-68."""
+    netD = MultiscaleDiscriminator(input_nc, ndf, n_layers_D, get_norm_layer(norm_type=norm), use_sigmoid, num_D, getIntermFeat)
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        netD.cuda(gpu_ids[0])
+    netD.apply(weights_init)
+    return netD
