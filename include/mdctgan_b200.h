@@ -121,6 +121,10 @@ int mdctgan_avgpool3s2_nhwc(const float* x, float* y, int B, int H, int W, int C
  * `stats` (nullable) receives the per-channel (sum, sumsq) for the BatchNorm2d that follows. */
 int mdctgan_attention_abs_pos(const float* qkv, const float* emb_h, const float* emb_w, float* out, int B, int Hh, int Ww, int heads,
                                int d, float scale, double* stats, void* stream);
+/* --fit_residual at inference (pix2pixHD_model.py:631-635): y = sr with the first lr_bins columns scaled by
+ * low_scale, plus lr; sr, y: [rows, nbins] dense, lr: rows of nbins with row stride lr_row_stride. */
+int mdctgan_residual_scale_add(const float* sr, const float* lr, int64_t lr_row_stride, float* y, int64_t rows, int nbins, int lr_bins,
+                                float low_scale, void* stream);
 /* layout changes at the network boundary (the reference's modules take and return NCHW) */
 int mdctgan_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream);
 int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* stream);

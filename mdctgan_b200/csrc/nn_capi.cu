@@ -135,6 +135,18 @@ int mdctgan_attention_abs_pos(const float* qkv, const float* emb_h, const float*
   return 0;
 }
 
+int mdctgan_residual_scale_add(const float* sr, const float* lr, int64_t lr_row_stride, float* y, int64_t rows, int nbins, int lr_bins,
+                                float low_scale, void* stream) {
+  if (!sr || !lr || !y) return mdctgan_set_error(-1, "residual: NULL buffer");
+  if (rows < 0 || nbins <= 0 || lr_bins < 0 || lr_bins > nbins || lr_row_stride < nbins) return mdctgan_set_error(-1, "residual: bad shape");
+  const size_t total = (size_t)rows * nbins;
+  if (total == 0) return 0;
+  residual_scale_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(sr, lr, lr_row_stride, y, rows, nbins, lr_bins, low_scale);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream) {
   if (!x || !y) return mdctgan_set_error(-1, "layout: NULL buffer");
   const size_t total = (size_t)B * C * HW;

@@ -505,6 +505,21 @@ __global__ void __launch_bounds__(256) attention_abs_pos_kernel(const AttnParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Inference residual of --fit_residual (pix2pixHD_model.py:631-635):
+//   sr[..., :lr_bins] *= low_scale (1e-3);  sr += lr          on [rows, nbins] fp32 (rows = B*F)
+// ------------------------------------------------------------------------------------------------
+__global__ void residual_scale_add_kernel(const float* __restrict__ sr, const float* __restrict__ lr, int64_t lr_row_stride,
+                                          float* __restrict__ y, int64_t rows, int nbins, int lr_bins, float low_scale) {
+  const size_t total = (size_t)rows * nbins;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % nbins);
+    const size_t r = i / nbins;
+    const float v = sr[i];
+    y[i] = (k < lr_bins ? v * low_scale : v) + lr[r * lr_row_stride + k];
+  }
+}
+
 // NCHW <-> NHWC (network boundary: the reference's modules take / return NCHW tensors)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
   const size_t total = (size_t)B * C * HW;

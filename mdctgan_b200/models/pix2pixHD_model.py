@@ -173,3 +173,139 @@ class Audio2MDCT(torch.nn.Module):
     @torch.no_grad()
     def denormalize(self, log_spectro: torch.Tensor, min: torch.Tensor, max: torch.Tensor):
         raise NotImplementedError("denormalize() is fused into to_audio(); call to_audio(log_spectro, norm_param, pha)")
+
+
+# =====================================================================================================
+# Model facade (reference: models/pix2pixHD_model.py:203-714, models/base_model.py)
+# =====================================================================================================
+import os  # noqa: E402
+
+from . import networks  # noqa: E402
+from .. import nn_ops as _ops  # noqa: E402
+
+
+class BaseModel(torch.nn.Module):
+    def name(self):
+        return "BaseModel"
+
+    def initialize(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        if not len(self.gpu_ids):
+            raise RuntimeError("mdctgan_b200 needs --gpu_ids >= 0: there is no CPU path")
+        self.device = torch.device("cuda", self.gpu_ids[0])
+
+    def save_network(self, network, network_label, epoch_label, gpu_ids=None):
+        """`<checkpoints_dir>/<name>/<epoch>_net_<label>.pth` = plain state_dict (base_model.py:43-46)."""
+        os.makedirs(self.save_dir, exist_ok=True)
+        torch.save(network.state_dict(), os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label)))
+
+    def load_network(self, network, network_label, epoch_label, save_dir=""):
+        """Three-level fallback of the reference (base_model.py:49-111): strict load -> keys present in the
+        model -> `--param_key_map` remap of the second key component."""
+        save_path = os.path.join(save_dir or self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label))
+        if not os.path.isfile(save_path):
+            if network_label == "G":
+                raise FileNotFoundError("Generator must exist! (%s)" % save_path)
+            print("%s not exists yet!" % save_path)
+            return
+        pretrained = torch.load(save_path, map_location="cpu")
+        try:
+            network.load_state_dict(pretrained)
+        except RuntimeError:
+            model_dict = network.state_dict()
+            try:
+                network.load_state_dict({k: v for k, v in pretrained.items() if k in model_dict})
+            except RuntimeError:
+                module_map = getattr(self.opt, "param_key_map", None) or {}
+                for name, param in pretrained.items():
+                    if name not in model_dict or param.size() != model_dict[name].size():
+                        parts = name.split(".")
+                        key = parts[0] + "." + parts[1] if len(parts) > 1 else name
+                        if key not in module_map:
+                            continue
+                        parts[1] = module_map[key]
+                        name = ".".join(parts)
+                    model_dict[name] = param
+                network.load_state_dict(model_dict)
+        network.to(self.device)
+
+
+class Pix2PixHDModel(BaseModel):
+    """Drop-in for the reference facade.  This round implements the inference graph (`inference`, and the
+    generator half of `forward`); the loss / optimiser half of `_forward` raises NotImplementedError
+    (DESIGN.md: next)."""
+
+    loss_names = ["G_GAN", "G_GAN_Feat", "D_real", "D_fake"]
+
+    def name(self):
+        return "Pix2PixHDModel"
+
+    def initialize(self, opt):
+        BaseModel.initialize(self, opt)
+        for k, v in vars(opt).items():
+            setattr(self, k, v)
+        self.isTrain = opt.isTrain
+        input_nc = opt.label_nc if getattr(opt, "label_nc", 0) != 0 else opt.input_nc
+        self.preprocess = Audio2MDCT(opt, device=self.device, precision=getattr(opt, "mdct_precision", "fp32"))
+        self.freeze = opt.freeze_g_d or opt.freeze_g_u or opt.freeze_l_d or opt.freeze_l_u
+        self.netG = networks.define_G(input_nc, opt.output_nc, opt.ngf, opt.netG, opt.n_downsample_global, opt.n_blocks_global,
+                                      opt.n_local_enhancers, opt.n_blocks_local, opt.norm, gpu_ids=self.gpu_ids,
+                                      upsample_type=opt.upsample_type, downsample_type=opt.downsample_type,
+                                      input_size=(opt.bins, opt.n_fft // 2), n_attn_g=opt.n_blocks_attn_g, n_attn_l=opt.n_blocks_attn_l,
+                                      proj_factor_g=opt.proj_factor_g, heads_g=opt.heads_g, dim_head_g=opt.dim_head_g,
+                                      proj_factor_l=opt.proj_factor_l, heads_l=opt.heads_l, dim_head_l=opt.dim_head_l)
+        self.netG.set_freeze(opt.freeze_g_d, opt.freeze_g_u, opt.freeze_l_d, opt.freeze_l_u)
+        if self.isTrain:
+            self.netD = networks.define_D(input_nc + opt.output_nc, opt.ndf, opt.n_layers_D, opt.norm, opt.no_lsgan, opt.num_D,
+                                          not opt.no_ganFeat_loss, gpu_ids=self.gpu_ids)
+        if not self.isTrain or opt.continue_train or opt.load_pretrain:
+            pretrained_path = "" if not self.isTrain else opt.load_pretrain
+            self.load_network(self.netG, "G", opt.which_epoch, pretrained_path)
+            if self.isTrain:
+                self.load_network(self.netD, "D", opt.which_epoch, pretrained_path)
+        self._two_channel = bool(self.abs_spectro and self.arcsinh_transform)
+
+    # ---- generator graph ---------------------------------------------------------------------------------
+    def _lr_input(self, lr_audio):
+        """(lr_spectro [B,1,F,N], generator input [B,1|2,F,N]) from ONE fused MDCT launch (second channel
+        |s|*2+lo written by the same kernel, pix2pixHD_model.py:400-402,624-628)."""
+        ch = 2 if self._two_channel else 1
+        lr_input, lr_pha, lr_norm_param = self.preprocess.forward(lr_audio, channels=ch)
+        return lr_input[:, :1], lr_input, lr_pha, lr_norm_param
+
+    def forward(self, lr_audio, hr_audio):
+        """Generator half of the training graph (pix2pixHD_model.py:394-414), no autograd in this round."""
+        lr_spectro, lr_input, lr_pha, lr_norm_param = self._lr_input(lr_audio)
+        hr_spectro, hr_pha, hr_norm_param = self.preprocess.hr_forward(hr_audio)
+        sr_spectro = self.netG.forward(lr_input)
+        if self.fit_residual:
+            sr_spectro = _ops.residual_scale_add(sr_spectro, lr_spectro, 0, 1.0)
+        return sr_spectro, None, hr_spectro, hr_pha, hr_norm_param, lr_spectro, lr_pha, lr_norm_param
+
+    def _forward(self, lr_audio, hr_audio, infer=False):
+        raise NotImplementedError("Pix2PixHDModel._forward (discriminator losses + backward) is not built in this round: "
+                                  "the sm_100a training kernels (dgrad / wgrad / norm backward / fused Adam) are next (DESIGN.md)")
+
+    @torch.no_grad()
+    def inference(self, lr_audio):
+        """pix2pixHD_model.py:618-638 -> (sr_spectro, sr_audio, lr_pha, lr_norm_param, lr_spectro)."""
+        lr_spectro, lr_input, lr_pha, lr_norm_param = self._lr_input(lr_audio)
+        sr_spectro = self.netG.forward(lr_input)
+        if self.fit_residual:
+            lr_part = int(sr_spectro.size(-1) / self.preprocess.up_ratio)
+            sr_spectro = _ops.residual_scale_add(sr_spectro, lr_spectro, lr_part, 1e-3)
+        sr_audio = self.preprocess.to_audio(sr_spectro, lr_norm_param, lr_pha)
+        return sr_spectro, sr_audio, lr_pha, lr_norm_param, lr_spectro
+
+    def save(self, which_epoch):
+        self.save_network(self.netG, "G", which_epoch, self.gpu_ids)
+        if hasattr(self, "netD"):
+            self.save_network(self.netD, "D", which_epoch, self.gpu_ids)
+
+
+class InferenceModel(Pix2PixHDModel):
+    def forward(self, lr_audio):
+        return self.inference(lr_audio)

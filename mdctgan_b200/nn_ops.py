@@ -11,7 +11,7 @@ them (and the ReLU / LeakyReLU) while it gathers its input.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_double, c_float, c_int, c_void_p
+from ctypes import c_double, c_float, c_int, c_int64, c_void_p
 from dataclasses import dataclass
 from typing import Optional
 
@@ -38,6 +38,7 @@ def _L():
                                          c_int, c_int, c_int, c_int, c_void_p]
         L.mdctgan_attention_abs_pos.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                                 c_void_p]
+        L.mdctgan_residual_scale_add.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]
         L.mdctgan_avgpool3s2_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
         L.mdctgan_nchw_to_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
         L.mdctgan_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
@@ -214,3 +215,18 @@ def attention(qkv: Feat, emb_h: torch.Tensor, emb_w: torch.Tensor, heads: int, d
             _lib.check(_L().mdctgan_attention_abs_pos(qkv.x.data_ptr(), emb_h.data_ptr(), emb_w.data_ptr(), out.data_ptr(), B, H, W, heads,
                                                       dim_head, scale, _ptr(stats), _stream(out)))
     return Feat(out, stats=stats)
+
+
+def residual_scale_add(sr: torch.Tensor, lr: torch.Tensor, lr_bins: int, low_scale: float = 1e-3) -> torch.Tensor:
+    """sr[..., :lr_bins] *= low_scale; sr + lr   (pix2pixHD_model.py:631-635).  sr: [B,1,F,N] contiguous;
+    lr: [B,1,F,N] or the first channel of a [B,2,F,N] tensor (rows of N with a uniform row stride)."""
+    _req(sr, "residual sr")
+    B, C, Fr, N = sr.shape
+    assert C == 1 and lr.shape[0] == B and lr.shape[-2:] == (Fr, N) and lr.stride(-1) == 1 and lr.stride(-2) == N
+    if B > 1 and lr.stride(0) != Fr * N:
+        lr = lr[:, :1].contiguous()
+    y = torch.empty_like(sr)
+    if y.numel():
+        with torch.cuda.device(sr.device):
+            _lib.check(_L().mdctgan_residual_scale_add(sr.data_ptr(), lr.data_ptr(), N, y.data_ptr(), B * Fr, N, lr_bins, low_scale, _stream(sr)))
+    return y

@@ -159,10 +159,14 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["mdct"]
     if "mdct" in what:
         gen_mdct()
-    if "nets" in what or "train" in what:
+    if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 
         if "nets" in what:
             gen_nets()
+        if "infer" in what:
+            from make_golden_nets import gen_infer
+
+            gen_infer()
         if "train" in what:
             gen_train()

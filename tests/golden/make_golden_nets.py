@@ -84,5 +84,48 @@ def gen_nets():
     print("wrote nets_golden.npz")
 
 
+INFER_FLAGS = {
+    # BASELINE configs[2]: LocalEnhancer + 2 BottleStack attention layers, 12 -> 48 kHz, 32-frame segments, --fit_residual
+    "inf_cfg3": (["--netG", "local", "--ngf", "32", "--n_downsample_global", "3", "--n_blocks_global", "9", "--n_blocks_attn_g", "2",
+                  "--heads_g", "4", "--dim_head_g", "64", "--n_blocks_local", "3", "--num_D", "3", "--segment_length", "7936",
+                  "--bins", "32", "--fit_residual"], 2, 7936, 4242),
+    "inf_small": (["--netG", "local", "--ngf", "8", "--n_downsample_global", "2", "--n_blocks_global", "2", "--n_blocks_attn_g", "0",
+                   "--n_blocks_local", "1", "--num_D", "2", "--segment_length", "3840", "--bins", "16"], 3, 3840, 4243),
+}
+
+
+def make_lr_audio(batch, T, seed, cutoff_hz=6000.0, sr=48000.0):
+    """Seeded band-limited 'LR' audio at the HR rate: 0.1*randn low-passed by an FFT brick wall at 6 kHz."""
+    rng = np.random.default_rng(seed)
+    x = 0.1 * rng.standard_normal((batch, T))
+    X = np.fft.rfft(x, axis=-1)
+    X[:, np.fft.rfftfreq(T, 1.0 / sr) > cutoff_hz] = 0
+    return torch.from_numpy(np.fft.irfft(X, n=T, axis=-1).astype(np.float32))
+
+
+def gen_infer():
+    """Pix2PixHDModel.inference of the reference (create_model(opt)) on seeded weights / audio."""
+    from make_golden import ref_opt
+    from models.models import create_model
+
+    path = os.path.join(HERE, "nets_golden.npz")
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    for name, (flags, batch, T, seed) in INFER_FLAGS.items():
+        opt = ref_opt(flags)
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = create_model(opt)
+        model.eval()
+        lr = make_lr_audio(batch, T, seed)
+        sr_spectro, sr_audio, lr_pha, prm, lr_spectro = model.inference(lr)
+        out[f"{name}_lr_audio"] = lr.numpy()
+        out[f"{name}_sr_spectro"] = sr_spectro.numpy()
+        out[f"{name}_sr_audio"] = sr_audio.numpy()
+        out[f"{name}_lr_spectro"] = lr_spectro.numpy()
+        out[f"{name}_G_cksum"] = state_checksum(model.netG.state_dict())
+        print(name, "done", sr_audio.shape, sr_audio.dtype)
+    np.savez_compressed(path, **out)
+
+
 def gen_train():
     raise SystemExit("train-step goldens: not generated in this round")

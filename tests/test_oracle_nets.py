@@ -68,3 +68,38 @@ def test_discriminator_oracle_matches_reference(nets_golden, name):
             st = nets_golden[f"{name}_f{i}{j}_stats"]
             assert tuple(f.shape) == tuple(int(v) for v in st[2:])
             assert abs(float((f.double() ** 2).sum()) - st[1]) <= 1e-5 * st[1]
+
+
+INFER_CFG = {
+    "inf_cfg3": dict(n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=2, heads=4, dim_head=64, fit_residual=True),
+    "inf_small": dict(n_down=2, n_blocks_global=2, n_blocks_local=1, n_attn=0, fit_residual=False),
+}
+
+
+def our_opt(name, gpu="-1"):
+    from make_golden_nets import INFER_FLAGS
+    from mdctgan_b200.options.train_options import TrainOptions
+
+    flags = INFER_FLAGS[name][0]
+    base = ["--name", "g", "--gpu_ids", gpu, "--lr_sampling_rate", "12000", "--sr_sampling_rate", "48000", "--arcsinh_transform",
+            "--abs_spectro", "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1", "--abs_norm", "--src_range", "-5", "5"]
+    return TrainOptions().parse(save=False, args=base + flags)
+
+
+@pytest.mark.parametrize("name", ["inf_small", "inf_cfg3"])
+def test_inference_oracle_matches_reference(nets_golden, name):
+    from make_golden_nets import INFER_FLAGS
+    from mdctgan_b200.models import networks
+    from oracle import model_oracle as MOD
+
+    g = nets_golden
+    opt = our_opt(name)
+    torch.manual_seed(INFER_FLAGS[name][3])
+    netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.n_downsample_global, opt.n_blocks_global,
+                             opt.n_local_enhancers, opt.n_blocks_local, opt.norm, input_size=(opt.bins, opt.n_fft // 2),
+                             n_attn_g=opt.n_blocks_attn_g, heads_g=opt.heads_g, dim_head_g=opt.dim_head_g)
+    np.testing.assert_allclose(state_checksum(netG.state_dict()), g[f"{name}_G_cksum"], rtol=1e-12, atol=1e-12)
+    sr, audio, lr = MOD.inference(netG.state_dict(), g[f"{name}_lr_audio"], **INFER_CFG[name])
+    assert np.abs(lr - g[f"{name}_lr_spectro"]).max() <= 6e-8     # 1 ulp flips where the fp64 FFT orders differ
+    assert rel_l2(sr, g[f"{name}_sr_spectro"]) < 2e-6
+    assert rel_l2(audio, g[f"{name}_sr_audio"]) < 2e-5    # sinh(ln10*5*s) amplifies the 1e-6 spectrogram difference ~10x
