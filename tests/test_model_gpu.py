@@ -31,14 +31,19 @@ def test_inference_matches_reference(nets_golden, name, prec):
     g = nets_golden
     opt = our_opt(name, gpu="0")
     opt.mdct_precision = prec
-    opt.isTrain = False              # InferenceModel: no discriminator, no checkpoint on disk -> build the seeded G by hand
-    torch.manual_seed(INFER_FLAGS[name][3])
+    opt.num_D = 1
+    from mdctgan_b200.models import networks
     from mdctgan_b200.models.pix2pixHD_model import InferenceModel
 
     model = InferenceModel()
-    opt.isTrain = True               # seeded fresh weights instead of loading a checkpoint (same construction order as the reference)
-    opt.num_D = 1
-    model.initialize(opt)
+    model.initialize(opt)            # isTrain=True: fresh weights instead of a checkpoint on disk
+    # the golden weights were drawn from the CPU generator (the reference ran with --gpu_ids -1); with gpu_ids=[0]
+    # define_G moves the net to the GPU before weights_init, i.e. draws from the CUDA generator -> load the CPU-seeded ones
+    torch.manual_seed(INFER_FLAGS[name][3])
+    cpu_G = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.n_downsample_global, opt.n_blocks_global,
+                              opt.n_local_enhancers, opt.n_blocks_local, opt.norm, input_size=(opt.bins, opt.n_fft // 2),
+                              n_attn_g=opt.n_blocks_attn_g, heads_g=opt.heads_g, dim_head_g=opt.dim_head_g)
+    model.netG.load_state_dict(cpu_G.state_dict())
     model.eval()
     n0 = mdctgan_b200.launch_count()
     sr_spectro, sr_audio, lr_pha, prm, lr_spectro = model.inference(torch.from_numpy(g[f"{name}_lr_audio"]).cuda())
