@@ -47,7 +47,9 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
     if (stats) return mdctgan_set_error(-2, "conv2d: statistics of a 1-channel output are not supported");
     const int bps = (HWo + 31) / 32;
     const size_t smem = ((size_t)kh * kw * Cin + 2 * (size_t)Cin) * sizeof(float);
-    if (smem > 48 * 1024) CKN(cudaFuncSetAttribute(conv2d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 200 * 1024) return mdctgan_set_error(-2, "conv2d: Cout=1 kernel needs %zu bytes of shared memory", smem);
+    static bool attr_set = false;   // once, outside any stream capture in practice (first eager call)
+    if (!attr_set) { CKN(cudaFuncSetAttribute(conv2d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     conv2d_cout1_kernel<<<B * bps, 256, smem, st>>>(p);
   } else {
     const int bn = Cout >= 64 ? 64 : 32;
@@ -122,7 +124,11 @@ int mdctgan_attention_abs_pos(const float* qkv, const float* emb_h, const float*
   const int kpl = (L + 31) / 32;
 #define LAUNCH_ATTN(K)                                                                                                     \
   do {                                                                                                                     \
-    CKN(cudaFuncSetAttribute(attention_abs_pos_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    static bool attr_set = false;                                                                                          \
+    if (!attr_set) {                                                                                                       \
+      CKN(cudaFuncSetAttribute(attention_abs_pos_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
+      attr_set = true;                                                                                                     \
+    }                                                                                                                      \
     attention_abs_pos_kernel<K><<<B * heads, 256, smem, st>>>(p);                                                          \
   } while (0)
   if (kpl <= 1) LAUNCH_ATTN(1);
