@@ -241,9 +241,9 @@ class LaunchProfiler:
         self.torch, self.dev = torch, dev
         self.L = nn_ops._L()
         self.names = [n for n in dir(self.L) if n.startswith("mdctgan_")] or []
-        self.names = ["mdctgan_conv2d_nhwc", "mdctgan_norm_finalize", "mdctgan_norm_apply", "mdctgan_attention_abs_pos",
+        self.names = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_norm_finalize", "mdctgan_norm_apply", "mdctgan_attention_abs_pos",
                       "mdctgan_avgpool3s2_nhwc", "mdctgan_nchw_to_nhwc", "mdctgan_nhwc_to_nchw", "mdctgan_residual_scale_add",
-                      "mdctgan_audio2mdct_forward", "mdctgan_mdct2audio_inverse", "mdctgan_conv3x3_umma"]
+                      "mdctgan_audio2mdct_forward", "mdctgan_mdct2audio_inverse"]
         self.orig, self.records = {}, []
 
     def __enter__(self):
@@ -261,10 +261,11 @@ class LaunchProfiler:
                 rc = _f(*a)
                 e1.record(st)
                 tag = _n
-                if _n == "mdctgan_conv2d_nhwc":
+                if _n in ("mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma"):
                     B, H, W, Cin, Cout, kh, stride, transposed = a[1], a[2], a[3], a[4], a[10], a[11], a[13], a[16]
                     Ho, Wo = a[8], a[9]
-                    tag = f"conv k{kh} s{stride}{' T' if transposed else ''} {Cin}->{Cout} @{Ho}x{Wo}"
+                    eng = "umma" if _n.endswith("umma") else "direct"
+                    tag = f"conv[{eng}] k{kh} s{stride}{' T' if transposed else ''} {Cin}->{Cout} @{Ho}x{Wo}"
                     self.records.append((tag, e0, e1, 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)))
                 else:
                     self.records.append((tag, e0, e1, 0.0))
@@ -393,11 +394,13 @@ def run_ours(args):
             "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(),
-            "roofline": {"bound": "tensor", "kernel": f"conv2d_nhwc_kernel ({dom_tag}; fp32 CUDA-core implicit GEMM -- the tcgen05 kernel "
-                         f"replaces it next)", "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": f"{'conv2d_umma_kernel<64,true> (tcgen05 kind::tf32, 3xTF32 split, cluster split-K)' if 'umma' in dom_tag else 'conv2d_nhwc_kernel (fp32 FFMA)'}: {dom_tag}",
+                         "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
                          "frac": flops / (dom_ms * 1e-3) / 1e12 / bf16_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_flops_per_launch": flops, "avg_launch_ms": dom_ms, "share_of_step": dom[1] / tot_ms,
-                         "note": "peak = measured dense bf16 cuBLAS burst; this kernel computes in fp32 on CUDA cores"},
+                         "note": "algorithmic flops = 2*M*N*K of the convolution (the 3xTF32 split issues 3x that on the tensor pipe); "
+                                 "peak = measured dense bf16 cuBLAS burst; at batch 4 x 4x32 pixels the layer is 0.6 GFLOP over 2.4 MB of "
+                                 "weights: latency / weight-bandwidth bound, not tensor bound (DESIGN.md)"},
             "kernel_table": kernel_table,
             "mdct": mdct,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},

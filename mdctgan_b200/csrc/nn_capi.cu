@@ -4,6 +4,7 @@
 
 #include "../../include/mdctgan_b200.h"
 #include "nn_kernels.cuh"
+#include "conv_umma.cuh"
 
 using namespace nnk;
 
@@ -168,6 +169,108 @@ int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* s
   const size_t total = (size_t)B * C * HW;
   if (total == 0) return 0;
   nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, C, HW);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- tcgen05 implicit-GEMM convolution (conv_umma.cuh) --------------------------------------------------
+namespace {
+template <int BN, bool SPLIT3>
+int umma_max_clusters(int splits) {   // how many clusters of `splits` CTAs fit on the device at once (cached)
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cache[splits]) return cache[splits];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, splits, 1);
+  cfg.blockDim = dim3(umma::kThreads);
+  cfg.dynamicSmemBytes = umma::Cfg<BN, SPLIT3>::kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = splits; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, umma::conv2d_umma_kernel<BN, SPLIT3>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 148 / splits;   // conservative guess
+  }
+  cache[splits] = n;
+  return n;
+}
+
+template <int BN, bool SPLIT3>
+int launch_umma(umma::ConvUmmaParams& p, int n_tiles, cudaStream_t st) {
+  using C = umma::Cfg<BN, SPLIT3>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CKN(cudaFuncSetAttribute(umma::conv2d_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * n_tiles;
+  // split K over a cluster while the whole grid still fits the device in one wave
+  int splits = 1;
+  for (int s = 8; s >= 2; --s) {
+    if (s > p.kchunks) continue;
+    if (tiles <= umma_max_clusters<BN, SPLIT3>(s)) { splits = s; break; }
+  }
+  p.splits = splits;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles, splits, 1);
+  cfg.blockDim = dim3(umma::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = splits; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CKN(cudaLaunchKernelEx(&cfg, umma::conv2d_umma_kernel<BN, SPLIT3>, p));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mdctgan_conv2d_umma_supported(int Cin, int Cout) { return (Cin % 4 == 0 && Cin <= umma::kMaxCin && Cout % 32 == 0) ? 1 : 0; }
+
+int64_t mdctgan_conv2d_umma_packed_floats(int K, int Cout) { return (int64_t)((K + umma::kKC - 1) / umma::kKC) * 2 * Cout * umma::kKC; }
+
+int mdctgan_conv2d_umma_pack_weight(const float* w_kn, int K, int Cout, float* out, void* stream) {
+  if (!w_kn || !out) return mdctgan_set_error(-1, "umma pack: NULL buffer");
+  if (K <= 0 || Cout <= 0 || Cout % 8) return mdctgan_set_error(-1, "umma pack: bad shape K=%d Cout=%d", K, Cout);
+  const int kchunks = (K + umma::kKC - 1) / umma::kKC;
+  const size_t total = (size_t)kchunks * umma::kKC * Cout;
+  umma::pack_weight_umma_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_kn, out, K, Cout, kchunks);
+  mdctgan_count_launch();
+  CKN(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const float* w_packed, const float* bias, float* y, int Ho, int Wo,
+                        int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
+                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, int precision, void* stream) {
+  if (!x || !w_packed || !y) return mdctgan_set_error(-1, "conv2d_umma: NULL buffer");
+  if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+    return mdctgan_set_error(-1, "conv2d_umma: bad shape");
+  if (!mdctgan_conv2d_umma_supported(Cin, Cout))
+    return mdctgan_set_error(-2, "conv2d_umma: Cin %d (need %%4, <= %d) / Cout %d (need %%32) unsupported", Cin, umma::kMaxCin, Cout);
+  if (pad_mode == kPadReflect && (pad >= H || pad >= W)) return mdctgan_set_error(-1, "conv2d_umma: reflection pad %d >= input size %dx%d", pad, H, W);
+  if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_umma: in_scale / in_shift must come together");
+  if (precision != 0 && precision != 1) return mdctgan_set_error(-1, "conv2d_umma: precision %d (0 = 3xTF32 fp32-class, 1 = TF32)", precision);
+  if ((long long)B * Ho * Wo > 0x7fffffffLL - 128) return mdctgan_set_error(-2, "conv2d_umma: too many output pixels");
+  if (B == 0) return 0;
+  umma::ConvUmmaParams p{};
+  p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.wp = w_packed; p.bias = bias; p.y = y; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
+  p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
+  p.act = act; p.stats = stats;
+  p.K = kh * kw * Cin; p.kchunks = (p.K + umma::kKC - 1) / umma::kKC;
+  p.m_total = B * Ho * Wo; p.m_tiles = (p.m_total + umma::kBM - 1) / umma::kBM;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, st) : launch_umma<64, false>(p, Cout / 64, st);
+  else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, st) : launch_umma<32, false>(p, Cout / 32, st);
+  if (rc) return rc;
   mdctgan_count_launch();
   CKN(cudaGetLastError());
   return 0;

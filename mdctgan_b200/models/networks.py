@@ -57,6 +57,14 @@ class Conv2d(nn.Conv2d):
             self._pk = _PackedWeight()
         return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, False))
 
+    def packed_umma(self):
+        """tcgen05 kernel's weight image, or None for the shapes that stay on the direct kernels."""
+        if not ops.umma_supported(self.in_channels, self.out_channels):
+            return None
+        if not hasattr(self, "_pku"):
+            self._pku = _PackedWeight()
+        return self._pku.get(self.weight, lambda w: ops.pack_conv_weight_umma(self.packed()))
+
     def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
         kh, kw = self.kernel_size
         assert self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1] and self.dilation == (1, 1) and self.groups == 1
@@ -64,7 +72,7 @@ class Conv2d(nn.Conv2d):
         if pad_reflect and self.padding[0]:
             raise RuntimeError("ReflectionPad2d in front of a zero-padded convolution is not a reference configuration")
         return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=pad, pad_mode=mode, act=act,
-                          want_stats=want_stats)
+                          want_stats=want_stats, w_umma=self.packed_umma())
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):
@@ -76,11 +84,18 @@ class ConvTranspose2d(nn.ConvTranspose2d):
             self._pk = _PackedWeight()
         return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, True))
 
+    def packed_umma(self):
+        if not ops.umma_supported(self.in_channels, self.out_channels):
+            return None
+        if not hasattr(self, "_pku"):
+            self._pku = _PackedWeight()
+        return self._pku.get(self.weight, lambda w: ops.pack_conv_weight_umma(self.packed()))
+
     def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
         assert not pad_reflect
         kh, kw = self.kernel_size
         return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=self.padding[0], transposed=True,
-                          output_padding=self.output_padding[0], act=act, want_stats=want_stats)
+                          output_padding=self.output_padding[0], act=act, want_stats=want_stats, w_umma=self.packed_umma())
 
 
 class InstanceNorm2d(nn.InstanceNorm2d):

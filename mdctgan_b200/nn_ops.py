@@ -19,8 +19,16 @@ import torch
 
 from . import _lib
 
+import os
+
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
+
+# Which convolution kernel runs the tensor-core-shaped layers (Cin % 4 == 0, Cout % 32 == 0):
+#   "umma"   tcgen05 implicit GEMM, 3xTF32 split (fp32-class results)            [default]
+#   "tf32"   tcgen05 implicit GEMM, single TF32 pass (what cuDNN does under torch's default allow_tf32)
+#   "direct" fp32 FFMA kernel of nn_kernels.cuh (the on-device cross-check of the two above)
+CONV_ENGINE = os.environ.get("MDCTGAN_CONV_ENGINE", "umma")
 
 _bound = False
 
@@ -32,6 +40,13 @@ def _L():
         L.mdctgan_conv2d_nhwc.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                           c_void_p]
+        L.mdctgan_conv2d_umma.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                          c_int, c_void_p]
+        L.mdctgan_conv2d_umma_pack_weight.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+        L.mdctgan_conv2d_umma_packed_floats.argtypes = [c_int, c_int]
+        L.mdctgan_conv2d_umma_packed_floats.restype = c_int64
+        L.mdctgan_conv2d_umma_supported.argtypes = [c_int, c_int]
         L.mdctgan_norm_finalize.argtypes = [c_void_p, c_int, c_int, c_double, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_float, c_void_p, c_void_p, c_void_p]
         L.mdctgan_norm_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
@@ -111,9 +126,24 @@ def pack_conv_weight(w: torch.Tensor, transposed: bool = False) -> torch.Tensor:
     return w.reshape(kh * kw * cin, cout).contiguous()
 
 
+def umma_supported(cin: int, cout: int) -> bool:
+    return CONV_ENGINE != "direct" and bool(_L().mdctgan_conv2d_umma_supported(int(cin), int(cout)))
+
+
+def pack_conv_weight_umma(w_kn: torch.Tensor) -> torch.Tensor:
+    """[K, Cout] fp32 (pack_conv_weight) -> the tcgen05 kernel's shared-memory image
+    [ceil(K/32)][hi|lo][Cout][32] with TF32 hi / lo parts (conv_umma.cuh).  One small launch per weight version."""
+    _req(w_kn, "pack_conv_weight_umma")
+    K, cout = w_kn.shape
+    out = torch.empty(int(_L().mdctgan_conv2d_umma_packed_floats(K, cout)), dtype=torch.float32, device=w_kn.device)
+    with torch.cuda.device(w_kn.device):
+        _lib.check(_L().mdctgan_conv2d_umma_pack_weight(w_kn.data_ptr(), K, cout, out.data_ptr(), _stream(w_kn)))
+    return out
+
+
 def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1, pad: int = 0,
            pad_mode: int = PAD_ZERO, transposed: bool = False, output_padding: int = 0, act: int = ACT_NONE,
-           want_stats: bool = False) -> Feat:
+           want_stats: bool = False, w_umma: Optional[torch.Tensor] = None) -> Feat:
     x = f.x
     _req(x, "conv2d input")
     B, H, W, Cin = x.shape
@@ -136,9 +166,15 @@ def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh:
         x, in_act = f.x, ACT_NONE
     if B:
         with torch.cuda.device(x.device):
-            _lib.check(_L().mdctgan_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w_packed.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
-                                                kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
-                                                1 if f.per_sample else 0, in_act, act, _ptr(stats), _stream(x)))
+            if w_umma is not None and CONV_ENGINE != "direct":
+                _lib.check(_L().mdctgan_conv2d_umma(x.data_ptr(), B, H, W, Cin, w_umma.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
+                                                    kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
+                                                    1 if f.per_sample else 0, in_act, act, _ptr(stats),
+                                                    1 if CONV_ENGINE == "tf32" else 0, _stream(x)))
+            else:
+                _lib.check(_L().mdctgan_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w_packed.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
+                                                    kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
+                                                    1 if f.per_sample else 0, in_act, act, _ptr(stats), _stream(x)))
     return Feat(y, stats=stats)
 
 
