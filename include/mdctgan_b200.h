@@ -101,19 +101,37 @@ int mdctgan_mdct2audio_inverse_host(mdctgan_plan* plan, const float* spectro_hos
  * in_per_sample, else [Cin]).  act codes: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 tanh.
  * pad_mode: 0 zeros, 1 reflection (nn.ReflectionPad2d in front of an unpadded conv, networks.py:308,430).
  */
-/* nn.Conv2d / nn.ConvTranspose2d forward (networks.py:308-352, :387-417, :649-670). */
+/* A consumer may also take the producer's InstanceNorm2d(affine=False) statistics raw: `in_stats` = the producer's
+ * [B][Cin][2] (sum, sumsq), `in_count` = elements per plane, `in_eps`; it then derives scale = rstd and
+ * shift = -mean*rstd itself and no norm_finalize launch is needed (in_scale / in_shift must be NULL). */
+/* nn.Conv2d / nn.ConvTranspose2d forward (networks.py:308-352, :387-417, :649-670): direct fp32 FFMA kernels --
+ * every shape, incl. the Cin = 2 stem and the Cout = 1 heads. */
 int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* w, const float* bias, float* y, int Ho, int Wo,
                         int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
-                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, void* stream);
+                        const float* in_shift, int in_per_sample, int in_act, const double* in_stats, double in_count, float in_eps,
+                        int act, double* stats, void* stream);
+/* The same layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulator, TMA bulk-copied
+ * weights, cluster split-K; csrc/conv_umma.cuh) for Cin % 4 == 0, Cin <= 1024, Cout % 32 == 0
+ * (mdctgan_conv2d_umma_supported).  `w_packed` is the image written by mdctgan_conv2d_umma_pack_weight from the
+ * [kh*kw*Cin][Cout] weights (mdctgan_conv2d_umma_packed_floats floats).  precision 0: 3xTF32 split, fp32-class
+ * results; 1: single TF32 pass.  With in_stats and B > 1 the (per parity class) plane must be a multiple of 128
+ * pixels. */
+int mdctgan_conv2d_umma_supported(int Cin, int Cout);
+int64_t mdctgan_conv2d_umma_packed_floats(int K, int Cout);
+int mdctgan_conv2d_umma_pack_weight(const float* w_kn, int K, int Cout, float* out, void* stream);
+int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const float* w_packed, const float* bias, float* y, int Ho, int Wo,
+                        int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
+                        const float* in_shift, int in_per_sample, int in_act, const double* in_stats, double in_count, float in_eps,
+                        int act, double* stats, int precision, void* stream);
 /* InstanceNorm2d(affine=False) (mode 0, networks.py:26) / BatchNorm2d train (1) / eval (2) statistics ->
  * per-(sample,)channel scale & shift; BatchNorm also updates its running buffers in train mode. */
 int mdctgan_norm_finalize(const double* stats, int B, int C, double count, float eps, int mode, const float* gamma, const float* beta,
                           float* running_mean, float* running_var, float momentum, float* scale, float* shift, void* stream);
 /* y = act_out( act_a(a*sa+ta) [+ act_b(b*sb+tb)] ): ResnetBlock `x + conv_block(x)` (networks.py:461-463),
  * LocalEnhancer branch sum (:266-267), BottleStack shortcut. */
-int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const float* b,
-                       const float* b_scale, const float* b_shift, int b_per_sample, int b_act, float* y, int B, int HW, int C,
-                       int act_out, void* stream);
+int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const double* a_stats,
+                       const float* b, const float* b_scale, const float* b_shift, int b_per_sample, int b_act, const double* b_stats,
+                       double count, float eps, float* y, int B, int HW, int C, int act_out, void* stream);
 /* nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (networks.py:249-250, :525-526). */
 int mdctgan_avgpool3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);
 /* BoTNet attention with absolute position embedding (bottleneck_transformer_pytorch==0.1.4 `Attention`,

@@ -49,7 +49,9 @@ struct ConvUmmaParams {
   nnk::InputNorm in;
   int act;
   double* stats;        // [B][Cout][2] or null
-  int K, kchunks, splits, m_total, m_tiles;
+  int K, kchunks, splits;
+  int classes;          // 1, or stride^2 output parity classes of a ConvTranspose2d (see TileGeom)
+  int m_total, m_tiles; // output pixels / 128-row tiles PER CLASS
 };
 
 // ---- PTX primitives ------------------------------------------------------------------------------
@@ -171,6 +173,35 @@ struct Cfg {
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
 };
 
+// Which output pixels a CTA tile covers.  Ordinary convolutions: rows are the flattened (b, oy, ox) pixels.
+// ConvTranspose2d with stride s: the s*s output parity classes ((oy + pad) % s, (ox + pad) % s) each see only the
+// taps ky = py + s*i, kx = px + s*j (for k3 s2 p1: 1, 2, 2 or 4 of the 9 taps), so tiles are formed per class and
+// the K loop walks the live taps only -- 4x fewer chunks than zero-filling the dead ones.
+struct TileGeom {
+  int cs, py, px, offy, offx;   // class stride (1 = no classes), class parities, first oy / ox of the class
+  int nkx, cpt;                 // live taps along x; K chunks per tap (Cin / 32)
+  int hw, woc;                  // pixels per sample in this class; class-local row width
+  int kchunks;                  // K chunks this tile walks
+};
+
+__device__ __forceinline__ TileGeom make_geom(const ConvUmmaParams& p, int cls) {
+  TileGeom g;
+  if (p.classes > 1) {
+    g.cs = p.stride; g.py = cls / g.cs; g.px = cls - g.py * g.cs;
+    g.offy = ((g.py - p.pad) % g.cs + g.cs) % g.cs;
+    g.offx = ((g.px - p.pad) % g.cs + g.cs) % g.cs;
+    const int nky = (p.kh - g.py + g.cs - 1) / g.cs;
+    g.nkx = (p.kw - g.px + g.cs - 1) / g.cs;
+    g.cpt = p.Cin / kKC;
+    g.woc = p.Wo / g.cs; g.hw = (p.Ho / g.cs) * g.woc;
+    g.kchunks = nky * g.nkx * g.cpt;
+  } else {
+    g.cs = 1; g.py = g.px = g.offy = g.offx = 0; g.nkx = p.kw; g.cpt = 0;
+    g.woc = p.Wo; g.hw = p.Ho * p.Wo; g.kchunks = p.kchunks;
+  }
+  return g;
+}
+
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmmaParams p) {
   using C = Cfg<BN, SPLIT3>;
@@ -184,13 +215,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = blockIdx.x % p.m_tiles, nt = blockIdx.x / p.m_tiles;
+  int bx = blockIdx.x;
+  const int mt = bx % p.m_tiles; bx /= p.m_tiles;
+  const int cls = bx % p.classes, nt = bx / p.classes;
+  const TileGeom tg = make_geom(p, cls);
   const int split = blockIdx.y;                       // == rank of this CTA in its cluster (cluster = (1, splits, 1))
   const int m0 = mt * kBM, n0 = nt * BN;
-  const int kc_begin = (int)((long long)p.kchunks * split / p.splits);
-  const int kc_end = (int)((long long)p.kchunks * (split + 1) / p.splits);
+  const int kc_begin = (int)((long long)tg.kchunks * split / p.splits);
+  const int kc_end = (int)((long long)tg.kchunks * (split + 1) / p.splits);
   const int nk = kc_end - kc_begin;
-  const int HWo = p.Ho * p.Wo;
 
   if (warp == kProducerWarps) {
     if (lane == 0) {
@@ -201,16 +234,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     __syncwarp();
     tmem_alloc(tmem_slot, C::kTmemCols);
   }
-  // the deferred normalisation of the producing layer: when the whole tile belongs to one sample (or the
-  // affine is per channel only) its scale / shift live in shared memory, else they are fetched per row
-  const bool has_norm = p.in.scale != nullptr;
-  const int b_first = m0 / HWo;
+  // The deferred normalisation of the producing layer.  When the whole tile belongs to one sample (or the affine is
+  // per channel only) its scale / shift live in shared memory -- taken ready-made, or computed here from the
+  // producer's raw (sum, sumsq) statistics (InstanceNorm2d: no separate finalize launch) -- else fetched per row.
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  const int b_first = m0 / tg.hw;
   const int m_last = (m0 + kBM < p.m_total ? m0 + kBM : p.m_total) - 1;
-  const bool one_sample = (m_last / HWo) == b_first;
+  const bool one_sample = (m_last / tg.hw) == b_first;
   const bool norm_in_smem = has_norm && (one_sample || !p.in.per_sample);
   if (norm_in_smem) {
     const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
-    for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
+    if (p.in.stats) {
+      const double inv_n = 1.0 / (double)p.in.count;
+      for (int c = tid; c < p.Cin; c += kThreads) {
+        const double mean = p.in.stats[2 * (off + c)] * inv_n;
+        double var = p.in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
+        s_scale[c] = (float)rstd;
+        s_shift[c] = (float)(-mean * rstd);
+      }
+    } else {
+      for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -226,70 +272,105 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     for (int i = 0; i < 4; ++i) {
       const int g = m0 + rb + 32 * i;
       if (g < p.m_total) {
-        bb[i] = g / HWo;
-        const int pix = g - bb[i] * HWo;
-        oy[i] = pix / p.Wo;
-        ox[i] = pix - oy[i] * p.Wo;
+        bb[i] = g / tg.hw;
+        const int pix = g - bb[i] * tg.hw;
+        const int oyc = pix / tg.woc;
+        oy[i] = oyc * tg.cs + tg.offy;
+        ox[i] = (pix - oyc * tg.woc) * tg.cs + tg.offx;
       } else {
         bb[i] = -1; oy[i] = 0; ox[i] = 0;
       }
     }
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % C::kStages;
-      const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(&empty[s], ph ^ 1u);
-      const int k = (kc_begin + it) * kKC + j * 4;
-      const bool kvalid = k < p.K;
-      const int tap = k / p.Cin, c = k - tap * p.Cin;
-      const int ky = tap / p.kw, kx = tap - ky * p.kw;
-      float4 v[4];
-      bool ok[4];
+    // The gather is latency bound (one L2 round trip per chunk), so the loads of kGroup chunks are issued before
+    // the first of them is consumed; the stage's `empty` barrier is only needed before the shared-memory stores.
+    constexpr int kGroup = C::kStages < 4 ? C::kStages : 4;
+    for (int it0 = 0; it0 < nk; it0 += kGroup) {
+      float4 v[kGroup][4];
+      int cc[kGroup];
+      uint32_t okmask = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ok[i] = false;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kvalid && bb[i] >= 0) {
-          const int iy = nnk::in_coord(oy[i], ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
-          const int ix = nnk::in_coord(ox[i], kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
-          if (iy >= 0 && ix >= 0) {
-            ok[i] = true;
-            v[i] = __ldg(reinterpret_cast<const float4*>(p.x + (((size_t)bb[i] * p.H + iy) * p.W + ix) * p.Cin + c));
+      for (int gi = 0; gi < kGroup; ++gi) {
+        const int it = it0 + gi;
+        cc[gi] = -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[gi][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < nk) {
+          const int kc = kc_begin + it;
+          int ky, kx, c;
+          bool kvalid = true;
+          if (p.classes > 1) {
+            const int t = kc / tg.cpt;
+            c = (kc - t * tg.cpt) * kKC + j * 4;
+            const int ty = t / tg.nkx;
+            ky = tg.py + tg.cs * ty;
+            kx = tg.px + tg.cs * (t - ty * tg.nkx);
+          } else {
+            const int k = kc * kKC + j * 4;
+            kvalid = k < p.K;
+            const int tap = k / p.Cin;
+            c = k - tap * p.Cin;
+            ky = tap / p.kw;
+            kx = tap - ky * p.kw;
           }
-        }
-      }
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (norm_in_smem && kvalid) {
-        sc = *reinterpret_cast<const float4*>(s_scale + c);
-        sh = *reinterpret_cast<const float4*>(s_shift + c);
-      }
-      uint8_t* a_hi = smem + s * C::kStageBytes;
-      uint8_t* a_lo = a_hi + C::kABytes;
+          if (kvalid) {
+            cc[gi] = c;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-        if (ok[i]) {
-          if (has_norm) {
-            if (!norm_in_smem) {
-              sc = __ldg(reinterpret_cast<const float4*>(p.in.scale + (size_t)bb[i] * p.Cin + c));
-              sh = __ldg(reinterpret_cast<const float4*>(p.in.shift + (size_t)bb[i] * p.Cin + c));
+            for (int i = 0; i < 4; ++i) {
+              if (bb[i] >= 0) {
+                const int iy = nnk::in_coord(oy[i], ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+                const int ix = nnk::in_coord(ox[i], kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+                if (iy >= 0 && ix >= 0) {
+                  okmask |= 1u << (gi * 4 + i);
+                  v[gi][i] = __ldg(reinterpret_cast<const float4*>(p.x + (((size_t)bb[i] * p.H + iy) * p.W + ix) * p.Cin + c));
+                }
+              }
             }
-            e[0] = fmaf(e[0], sc.x, sh.x); e[1] = fmaf(e[1], sc.y, sh.y); e[2] = fmaf(e[2], sc.z, sh.z); e[3] = fmaf(e[3], sc.w, sh.w);
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) e[u] = nnk::apply_act(e[u], p.in.act);
-        }
-        const int r = rb + 32 * i;
-        const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-        float4 hi = make_float4(tf32_part(e[0]), tf32_part(e[1]), tf32_part(e[2]), tf32_part(e[3]));
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        if (SPLIT3) {
-          *reinterpret_cast<float4*>(a_lo + off) =
-              make_float4(tf32_part(e[0] - hi.x), tf32_part(e[1] - hi.y), tf32_part(e[2] - hi.z), tf32_part(e[3] - hi.w));
         }
       }
-      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+      for (int gi = 0; gi < kGroup; ++gi) {
+        const int it = it0 + gi;
+        if (it < nk) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const int c = cc[gi];
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (norm_in_smem && c >= 0) {
+            sc = *reinterpret_cast<const float4*>(s_scale + c);
+            sh = *reinterpret_cast<const float4*>(s_shift + c);
+          }
+          uint8_t* a_hi = smem + s * C::kStageBytes;
+          uint8_t* a_lo = a_hi + C::kABytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float e[4] = {v[gi][i].x, v[gi][i].y, v[gi][i].z, v[gi][i].w};
+            if (okmask & (1u << (gi * 4 + i))) {
+              if (has_norm) {
+                if (!norm_in_smem) {
+                  sc = __ldg(reinterpret_cast<const float4*>(p.in.scale + (size_t)bb[i] * p.Cin + c));
+                  sh = __ldg(reinterpret_cast<const float4*>(p.in.shift + (size_t)bb[i] * p.Cin + c));
+                }
+                e[0] = fmaf(e[0], sc.x, sh.x); e[1] = fmaf(e[1], sc.y, sh.y); e[2] = fmaf(e[2], sc.z, sh.z); e[3] = fmaf(e[3], sc.w, sh.w);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) e[u] = nnk::apply_act(e[u], p.in.act);
+            }
+            const int r = rb + 32 * i;
+            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            const float4 hi = make_float4(tf32_part(e[0]), tf32_part(e[1]), tf32_part(e[2]), tf32_part(e[3]));
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            if (SPLIT3) {
+              *reinterpret_cast<float4*>(a_lo + off) =
+                  make_float4(tf32_part(e[0] - hi.x), tf32_part(e[1] - hi.y), tf32_part(e[2] - hi.z), tf32_part(e[3] - hi.w));
+            }
+          }
+          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+        }
+      }
     }
     // ================= epilogue part 1: accumulator TMEM -> registers -> staging tile in shared memory =========
     mbar_wait(tmem_full, 0);
@@ -343,7 +424,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::kParts * C::kBBytes));
         uint8_t* b_hi = smem + s * C::kStageBytes + C::kParts * C::kABytes;
-        const float* src = p.wp + (((size_t)(kc_begin + it) * 2) * p.Cout + n0) * kKC;
+        int wkc = kc_begin + it;    // chunk index in the packed weights: (ky*kw + kx) * Cin/32 + channel chunk
+        if (p.classes > 1) {
+          const int t = wkc / tg.cpt, ty = t / tg.nkx;
+          wkc = ((tg.py + tg.cs * ty) * p.kw + tg.px + tg.cs * (t - ty * tg.nkx)) * tg.cpt + (wkc - t * tg.cpt);
+        }
+        const float* src = p.wp + (((size_t)wkc * 2) * p.Cout + n0) * kKC;
         bulk_g2s(b_hi, src, C::kBBytes, &full[s]);
         if (SPLIT3) bulk_g2s(b_hi + C::kBBytes, src + (size_t)p.Cout * kKC, C::kBBytes, &full[s]);
       }
@@ -371,37 +457,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     const int n = n0 + cq * 4;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const float* peer[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) peer[s] = (p.splits > 1 && s < p.splits) ? cluster.map_shared_rank(stage_out, s) : stage_out;
     int cur_b = -1;
     for (int r = r_begin + rg; r < r_end; r += RP) {
       const int g = m0 + r;
       if (g >= p.m_total) break;
-      float4 acc = bias;
-      for (int s = 0; s < p.splits; ++s) {
-        const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
-        const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-      }
-      if (p.stats) {
-        if (!one_sample) {            // tile spans samples (planes smaller than 128 pixels): flush per sample
-          const int b = g / HWo;
-          if (b != cur_b) {
-            if (cur_b >= 0) {
+      float4 t[8];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                double* st = p.stats + ((size_t)cur_b * p.Cout + n + u) * 2;
-                atomicAdd(st, (double)ssum[u]); atomicAdd(st + 1, (double)ssq[u]);
-                ssum[u] = 0.f; ssq[u] = 0.f;
-              }
+      for (int s = 0; s < 8; ++s)
+        t[s] = s < p.splits ? *reinterpret_cast<const float4*>(peer[s] + r * C::kPitch + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = bias;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }   // rank order: deterministic
+      const int b = g / tg.hw;
+      if (p.stats) {
+        if (!one_sample && b != cur_b) {   // tile spans samples (planes smaller than 128 pixels): flush per sample
+          if (cur_b >= 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              double* st = p.stats + ((size_t)cur_b * p.Cout + n + u) * 2;
+              atomicAdd(st, (double)ssum[u]); atomicAdd(st + 1, (double)ssq[u]);
+              ssum[u] = 0.f; ssq[u] = 0.f;
             }
-            cur_b = b;
           }
+          cur_b = b;
         }
         ssum[0] += acc.x; ssq[0] += acc.x * acc.x; ssum[1] += acc.y; ssq[1] += acc.y * acc.y;
         ssum[2] += acc.z; ssq[2] += acc.z * acc.z; ssum[3] += acc.w; ssq[3] += acc.w * acc.w;
       }
       acc.x = nnk::apply_act(acc.x, p.act); acc.y = nnk::apply_act(acc.y, p.act);
       acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
-      *reinterpret_cast<float4*>(p.y + (size_t)g * p.Cout + n) = acc;
+      const int pix = g - b * tg.hw;
+      const int oyc = pix / tg.woc;
+      const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
+      *reinterpret_cast<float4*>(p.y + (((size_t)b * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
     }
     if (p.stats && !one_sample && cur_b >= 0) {
 #pragma unroll

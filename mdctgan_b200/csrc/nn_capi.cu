@@ -29,8 +29,11 @@ extern "C" {
 
 int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* w, const float* bias, float* y, int Ho, int Wo,
                         int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
-                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, void* stream) {
+                        const float* in_shift, int in_per_sample, int in_act, const double* in_stats, double in_count, float in_eps,
+                        int act, double* stats, void* stream) {
   if (!x || !w || !y) return mdctgan_set_error(-1, "conv2d: NULL buffer");
+  if (in_stats && (in_scale || !in_per_sample || in_count <= 0))
+    return mdctgan_set_error(-1, "conv2d: in_stats is the InstanceNorm2d form (per sample, count > 0, no in_scale)");
   if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
     return mdctgan_set_error(-1, "conv2d: bad shape");
   if (Cin > 1024) return mdctgan_set_error(-2, "conv2d: Cin %d > 1024 unsupported", Cin);
@@ -40,7 +43,8 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
   ConvParams p{};
   p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w = w; p.bias = bias; p.y = y; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
-  p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_scale ? in_act : in_act;
+  p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
+  p.in.stats = in_stats; p.in.count = (float)in_count; p.in.eps = in_eps;
   p.act = act; p.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   const int HWo = Ho * Wo;
@@ -83,18 +87,24 @@ int mdctgan_norm_finalize(const double* stats, int B, int C, double count, float
   return 0;
 }
 
-int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const float* b,
-                       const float* b_scale, const float* b_shift, int b_per_sample, int b_act, float* y, int B, int HW, int C,
-                       int act_out, void* stream) {
+int mdctgan_norm_apply(const float* a, const float* a_scale, const float* a_shift, int a_per_sample, int a_act, const double* a_stats,
+                       const float* b, const float* b_scale, const float* b_shift, int b_per_sample, int b_act, const double* b_stats,
+                       double count, float eps, float* y, int B, int HW, int C, int act_out, void* stream) {
   if (!a || !y) return mdctgan_set_error(-1, "norm_apply: NULL buffer");
-  if (C % 4) return mdctgan_set_error(-2, "norm_apply: C %d must be a multiple of 4", C);
+  if (C % 4 || C > 1024) return mdctgan_set_error(-2, "norm_apply: C %d must be a multiple of 4, <= 1024", C);
+  if ((a_stats && (a_scale || !a_per_sample)) || (b_stats && (b_scale || !b_per_sample)) || ((a_stats || b_stats) && count <= 0))
+    return mdctgan_set_error(-1, "norm_apply: *_stats is the InstanceNorm2d form (per sample, count > 0, no scale)");
   ApplyParams p{};
-  p.a = a; p.na = InputNorm{a_scale, a_shift, a_per_sample, a_act};
-  p.b = b; p.nb = InputNorm{b_scale, b_shift, b_per_sample, b_act};
+  p.a = a; p.na = InputNorm{a_scale, a_shift, a_per_sample, a_act, a_stats, (float)count, eps};
+  p.b = b; p.nb = InputNorm{b_scale, b_shift, b_per_sample, b_act, b_stats, (float)count, eps};
   p.y = y; p.B = B; p.HW = HW; p.C = C; p.act_out = act_out;
-  const size_t total4 = (size_t)B * HW * C / 4;
-  if (total4 == 0) return 0;
-  norm_apply_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  const size_t per_sample4 = (size_t)HW * C / 4;
+  if (per_sample4 == 0 || B == 0) return 0;
+  if (B > 65535) return mdctgan_set_error(-2, "norm_apply: batch %d > 65535", B);
+  int chunks = (int)((per_sample4 + 255) / 256);
+  const int cap = (148 * 8 + B - 1) / B;
+  if (chunks > cap) chunks = cap;
+  norm_apply_kernel<<<dim3(chunks, B), 256, 0, (cudaStream_t)stream>>>(p);
   mdctgan_count_launch();
   CKN(cudaGetLastError());
   return 0;
@@ -200,18 +210,18 @@ int umma_max_clusters(int splits) {   // how many clusters of `splits` CTAs fit 
 }
 
 template <int BN, bool SPLIT3>
-int launch_umma(umma::ConvUmmaParams& p, int n_tiles, cudaStream_t st) {
+int launch_umma(umma::ConvUmmaParams& p, int n_tiles, int min_kchunks, cudaStream_t st) {
   using C = umma::Cfg<BN, SPLIT3>;
   static bool attr_set = false;
   if (!attr_set) {
     CKN(cudaFuncSetAttribute(umma::conv2d_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * n_tiles;
+  const int tiles = p.m_tiles * p.classes * n_tiles;
   // split K over a cluster while the whole grid still fits the device in one wave
   int splits = 1;
   for (int s = 8; s >= 2; --s) {
-    if (s > p.kchunks) continue;
+    if (s > min_kchunks) continue;
     if (tiles <= umma_max_clusters<BN, SPLIT3>(s)) { splits = s; break; }
   }
   p.splits = splits;
@@ -248,7 +258,8 @@ int mdctgan_conv2d_umma_pack_weight(const float* w_kn, int K, int Cout, float* o
 
 int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const float* w_packed, const float* bias, float* y, int Ho, int Wo,
                         int Cout, int kh, int kw, int stride, int pad, int pad_mode, int transposed, const float* in_scale,
-                        const float* in_shift, int in_per_sample, int in_act, int act, double* stats, int precision, void* stream) {
+                        const float* in_shift, int in_per_sample, int in_act, const double* in_stats, double in_count, float in_eps,
+                        int act, double* stats, int precision, void* stream) {
   if (!x || !w_packed || !y) return mdctgan_set_error(-1, "conv2d_umma: NULL buffer");
   if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
     return mdctgan_set_error(-1, "conv2d_umma: bad shape");
@@ -265,11 +276,25 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
   p.act = act; p.stats = stats;
   p.K = kh * kw * Cin; p.kchunks = (p.K + umma::kKC - 1) / umma::kKC;
-  p.m_total = B * Ho * Wo; p.m_tiles = (p.m_total + umma::kBM - 1) / umma::kBM;
+  int min_kchunks = p.kchunks;
+  // ConvTranspose2d: tiles per output parity class, K loop over the live taps only (conv_umma.cuh TileGeom)
+  p.classes = 1;
+  if (transposed && stride > 1 && Ho % stride == 0 && Wo % stride == 0 && Cin % umma::kKC == 0 && kh >= stride && kw >= stride) {
+    p.classes = stride * stride;
+    min_kchunks = (kh / stride) * (kw / stride) * (Cin / umma::kKC);
+  }
+  const int hw_class = (Ho * Wo) / p.classes;
+  p.m_total = B * hw_class; p.m_tiles = (p.m_total + umma::kBM - 1) / umma::kBM;
+  if (in_stats) {
+    if (in_scale) return mdctgan_set_error(-1, "conv2d_umma: pass either in_scale/in_shift or in_stats");
+    if (!in_per_sample || in_count <= 0) return mdctgan_set_error(-1, "conv2d_umma: in_stats is the InstanceNorm2d form (per sample, count > 0)");
+    if (B > 1 && hw_class % umma::kBM) return mdctgan_set_error(-2, "conv2d_umma: in_stats needs tiles within one sample (%d pixels per sample)", hw_class);
+    p.in.stats = in_stats; p.in.count = (float)in_count; p.in.eps = in_eps;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, st) : launch_umma<64, false>(p, Cout / 64, st);
-  else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, st) : launch_umma<32, false>(p, Cout / 32, st);
+  if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
+  else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, min_kchunks, st) : launch_umma<32, false>(p, Cout / 32, min_kchunks, st);
   if (rc) return rc;
   mdctgan_count_launch();
   CKN(cudaGetLastError());

@@ -29,6 +29,9 @@ struct InputNorm {
   const float* shift;
   int per_sample;
   int act;              // activation applied after the affine (kActNone / kActRelu / kActLeaky)
+  // alternative to scale / shift for InstanceNorm2d(affine=False): the producer's raw [B][C][2] (sum, sumsq); the
+  // consumer derives scale = rstd, shift = -mean*rstd itself (no finalize launch).  tcgen05 convolution only.
+  const double* stats; float count; float eps;
 };
 
 struct ConvParams {
@@ -42,6 +45,24 @@ struct ConvParams {
   double* stats;        // [B][Cout][2] (sum, sumsq) accumulated with atomics, or null
   int tiles_per_sample;
 };
+
+// scale / shift of sample `b` into shared memory: ready-made, or derived from the raw InstanceNorm statistics
+__device__ __forceinline__ void norm_to_smem(const InputNorm& in, int b, int C, float* s_scale, float* s_shift, int tid, int nthreads) {
+  const size_t off = in.per_sample ? (size_t)b * C : 0;
+  if (in.stats) {
+    const double inv_n = 1.0 / (double)in.count;
+    for (int c = tid; c < C; c += nthreads) {
+      const double mean = in.stats[2 * (off + c)] * inv_n;
+      double var = in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      const double rstd = 1.0 / sqrt(var + (double)in.eps);
+      s_scale[c] = (float)rstd;
+      s_shift[c] = (float)(-mean * rstd);
+    }
+  } else if (in.scale) {
+    for (int c = tid; c < C; c += nthreads) { s_scale[c] = __ldg(in.scale + off + c); s_shift[c] = __ldg(in.shift + off + c); }
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == kActRelu) return fmaxf(v, 0.f);
@@ -85,12 +106,8 @@ __global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
   const int n0 = blockIdx.y * BN;
   const int HWo = p.Ho * p.Wo;
   const int K = p.kh * p.kw * p.Cin;
-  const bool has_norm = p.in.scale != nullptr;
-  if (has_norm) {
-    const float* sc = p.in.scale + (p.in.per_sample ? (size_t)b * p.Cin : 0);
-    const float* sh = p.in.shift + (p.in.per_sample ? (size_t)b * p.Cin : 0);
-    for (int c = tid; c < p.Cin; c += 256) { s_scale[c] = sc[c]; s_shift[c] = sh[c]; }
-  }
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  if (has_norm) norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
   __syncthreads();
 
   // A-load assignment: thread loads 4 consecutive k for pixel (tid % BM) in rounds; with 256 threads and
@@ -249,12 +266,8 @@ __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
   const int m = (blockIdx.x - b * blocks_per_sample) * groups_per_block + threadIdx.x / 8;
   const int l8 = threadIdx.x % 8;
   for (int i = threadIdx.x; i < K; i += 256) s_w[i] = __ldg(p.w + i);
-  const bool has_norm = p.in.scale != nullptr;
-  if (has_norm) {
-    const float* sc = p.in.scale + (p.in.per_sample ? (size_t)b * p.Cin : 0);
-    const float* sh = p.in.shift + (p.in.per_sample ? (size_t)b * p.Cin : 0);
-    for (int c = threadIdx.x; c < p.Cin; c += 256) { s_scale[c] = sc[c]; s_shift[c] = sh[c]; }
-  }
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  if (has_norm) norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, threadIdx.x, 256);
   __syncthreads();
   float acc = 0.f;
   if (m < HWo) {
@@ -357,37 +370,42 @@ struct ApplyParams {
   float* y; int B, HW, C; int act_out;
 };
 
+// grid = (chunks per sample, B): a block stays inside one sample so the (possibly statistics-derived) scale / shift
+// of that sample sit in shared memory
 __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
-  const size_t total4 = (size_t)p.B * p.HW * p.C / 4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+  __shared__ float sa[2][1024], sb[2][1024];
+  const int bi = blockIdx.y;
+  const bool na = p.na.scale != nullptr || p.na.stats != nullptr;
+  const bool nb = p.b != nullptr && (p.nb.scale != nullptr || p.nb.stats != nullptr);
+  if (na) norm_to_smem(p.na, bi, p.C, sa[0], sa[1], threadIdx.x, 256);
+  if (nb) norm_to_smem(p.nb, bi, p.C, sb[0], sb[1], threadIdx.x, 256);
+  __syncthreads();
+  const size_t per_sample4 = (size_t)p.HW * p.C / 4;
+  const size_t base = (size_t)bi * p.HW * p.C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t e = i * 4;
     const int c = (int)(e % p.C);
-    const int bi = (int)(e / ((size_t)p.HW * p.C));
-    float4 va = __ldg(reinterpret_cast<const float4*>(p.a + e));
+    float4 va = __ldg(reinterpret_cast<const float4*>(p.a + base + e));
     float v[4] = {va.x, va.y, va.z, va.w};
-    if (p.na.scale) {
-      const float* sc = p.na.scale + (p.na.per_sample ? (size_t)bi * p.C : 0) + c;
-      const float* sh = p.na.shift + (p.na.per_sample ? (size_t)bi * p.C : 0) + c;
+    if (na) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = fmaf(v[u], __ldg(sc + u), __ldg(sh + u));
+      for (int u = 0; u < 4; ++u) v[u] = fmaf(v[u], sa[0][c + u], sa[1][c + u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = apply_act(v[u], p.na.act);
     if (p.b) {
-      float4 vb = __ldg(reinterpret_cast<const float4*>(p.b + e));
+      float4 vb = __ldg(reinterpret_cast<const float4*>(p.b + base + e));
       float w[4] = {vb.x, vb.y, vb.z, vb.w};
-      if (p.nb.scale) {
-        const float* sc = p.nb.scale + (p.nb.per_sample ? (size_t)bi * p.C : 0) + c;
-        const float* sh = p.nb.shift + (p.nb.per_sample ? (size_t)bi * p.C : 0) + c;
+      if (nb) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = fmaf(w[u], __ldg(sc + u), __ldg(sh + u));
+        for (int u = 0; u < 4; ++u) w[u] = fmaf(w[u], sb[0][c + u], sb[1][c + u]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] += apply_act(w[u], p.nb.act);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = apply_act(v[u], p.act_out);
-    *reinterpret_cast<float4*>(p.y + e) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p.y + base + e) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 

@@ -199,7 +199,7 @@ def run_layers(layers: Sequence[nn.Module], f: Feat) -> Feat:
 def _forward_nchw(layers, x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError(f"expected a CUDA tensor, got device={x.device}; mdctgan_b200 has no CPU path")
-    with torch.no_grad():
+    with torch.no_grad(), ops.stats_pass(x.device):
         return ops.to_nchw(run_layers(layers, ops.to_nhwc(x.to(torch.float32).contiguous())))
 
 
@@ -434,7 +434,7 @@ class NLayerDiscriminator(nn.Module):
         return outs if self.getIntermFeat else outs[-1:]
 
     def forward(self, input):
-        with torch.no_grad():
+        with torch.no_grad(), ops.stats_pass(input.device):
             outs = self.run(ops.to_nhwc(input.to(torch.float32).contiguous()))
             res = [ops.to_nchw(o) for o in outs]
         return res if self.getIntermFeat else res[0]
@@ -461,7 +461,7 @@ class MultiscaleDiscriminator(nn.Module):
         return [getattr(self, "layer" + str(i))]
 
     def forward(self, input):
-        with torch.no_grad():
+        with torch.no_grad(), ops.stats_pass(input.device):
             f = ops.to_nhwc(input.to(torch.float32).contiguous())
             result = []
             for i in range(self.num_D):

@@ -38,19 +38,19 @@ def _L():
     L = _lib.lib()
     if not _bound:
         L.mdctgan_conv2d_nhwc.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                          c_void_p]
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_double,
+                                          c_float, c_int, c_void_p, c_void_p]
         L.mdctgan_conv2d_umma.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                          c_int, c_void_p]
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_double,
+                                          c_float, c_int, c_void_p, c_int, c_void_p]
         L.mdctgan_conv2d_umma_pack_weight.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
         L.mdctgan_conv2d_umma_packed_floats.argtypes = [c_int, c_int]
         L.mdctgan_conv2d_umma_packed_floats.restype = c_int64
         L.mdctgan_conv2d_umma_supported.argtypes = [c_int, c_int]
         L.mdctgan_norm_finalize.argtypes = [c_void_p, c_int, c_int, c_double, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_float, c_void_p, c_void_p, c_void_p]
-        L.mdctgan_norm_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                                         c_int, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_norm_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                         c_void_p, c_double, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
         L.mdctgan_attention_abs_pos.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                                 c_void_p]
         L.mdctgan_residual_scale_add.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]
@@ -85,14 +85,80 @@ class Feat:
     per_sample: bool = True
     act: int = ACT_NONE
     stats: Optional[torch.Tensor] = None     # [B, C, 2] float64 (sum, sumsq) left by the producer, not yet finalised
+    # InstanceNorm2d(affine=False) still in raw form: the consumer derives scale = rstd, shift = -mean*rstd from the
+    # producer's statistics itself (no finalize launch); mutually exclusive with scale / shift
+    norm_stats: Optional[torch.Tensor] = None
+    norm_count: float = 0.0
+    norm_eps: float = 1e-5
 
     @property
     def shape(self):
         return self.x.shape
 
     @property
+    def has_norm(self) -> bool:
+        return self.scale is not None or self.norm_stats is not None
+
+    @property
     def is_plain(self) -> bool:
-        return self.scale is None and self.act == ACT_NONE
+        return not self.has_norm and self.act == ACT_NONE
+
+
+class _StatsArena:
+    """Zeroed float64 scratch for the (sum, sumsq) statistics of one pass.  Inside `stats_pass(device)` every
+    statistics buffer is a slice of one arena that is cleared with a single memset at the start of the pass
+    (instead of one torch.zeros launch per normalised layer)."""
+
+    def __init__(self, device, capacity=1 << 21):
+        self.buf = torch.zeros(capacity, dtype=torch.float64, device=device)
+        self.used = 0
+        self.dirty = 0
+        self.depth = 0
+
+    def take(self, n):
+        n = (n + 15) // 16 * 16
+        if self.depth == 0 or self.used + n > self.buf.numel():
+            return None
+        out = self.buf[self.used:self.used + n]
+        self.used += n
+        self.dirty = max(self.dirty, self.used)
+        return out
+
+
+_arenas = {}
+
+
+class stats_pass:
+    """Context manager around one forward pass (inference, or a whole training step); nests."""
+
+    def __init__(self, device):
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _arenas:
+            _arenas[key] = _StatsArena(device)
+        self.arena = _arenas[key]
+
+    def __enter__(self):
+        a = self.arena
+        if a.depth == 0:
+            if a.dirty:
+                a.buf[:a.dirty].zero_()
+            a.used = 0
+        a.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        self.arena.depth -= 1
+
+
+def _new_stats(B, C, device):
+    device = torch.device(device)
+    a = _arenas.get((device.type, device.index if device.index is not None else torch.cuda.current_device()))
+    if a is not None:
+        t = a.take(B * C * 2)
+        if t is not None:
+            return t[:B * C * 2].view(B, C, 2)
+    return torch.zeros((B, C, 2), dtype=torch.float64, device=device)
 
 
 def to_nhwc(x_nchw: torch.Tensor) -> Feat:
@@ -159,32 +225,44 @@ def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh:
     if f.stats is not None:
         raise RuntimeError("conv2d: input still carries un-finalised statistics (missing norm layer?)")
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
-    stats = torch.zeros((B, Cout, 2), dtype=torch.float64, device=x.device) if want_stats else None
+    stats = _new_stats(B, Cout, x.device) if want_stats else None
     in_act = f.act
-    if f.scale is None and f.act != ACT_NONE:
+    if not f.has_norm and f.act != ACT_NONE:
         f = materialize(f)      # an activation without an affine in front of it: apply it for real
         x, in_act = f.x, ACT_NONE
+    use_umma = w_umma is not None and CONV_ENGINE != "direct"
+    if use_umma and f.norm_stats is not None and B > 1:
+        # the tensor-core kernel derives the normalisation from raw statistics only when every 128-pixel tile lies
+        # within one sample (per output parity class for a strided ConvTranspose2d)
+        s2 = stride * stride if (transposed and stride > 1 and Ho % stride == 0 and Wo % stride == 0 and Cin % 32 == 0) else 1
+        if ((Ho * Wo) // s2) % 128:
+            f = resolve_norm(f)
     if B:
         with torch.cuda.device(x.device):
-            if w_umma is not None and CONV_ENGINE != "direct":
+            if use_umma:
                 _lib.check(_L().mdctgan_conv2d_umma(x.data_ptr(), B, H, W, Cin, w_umma.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
                                                     kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
-                                                    1 if f.per_sample else 0, in_act, act, _ptr(stats),
-                                                    1 if CONV_ENGINE == "tf32" else 0, _stream(x)))
+                                                    1 if f.per_sample else 0, in_act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
+                                                    act, _ptr(stats), 1 if CONV_ENGINE == "tf32" else 0, _stream(x)))
             else:
                 _lib.check(_L().mdctgan_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w_packed.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
                                                     kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
-                                                    1 if f.per_sample else 0, in_act, act, _ptr(stats), _stream(x)))
+                                                    1 if f.per_sample else 0, in_act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
+                                                    act, _ptr(stats), _stream(x)))
     return Feat(y, stats=stats)
 
 
 def finalize_norm(f: Feat, *, eps: float = 1e-5, mode: int = 0, gamma=None, beta=None, running_mean=None, running_var=None,
-                  momentum: float = 0.1) -> Feat:
+                  momentum: float = 0.1, eager: bool = False) -> Feat:
     """mode 0: InstanceNorm2d(affine=False); 1: BatchNorm2d training (batch statistics, updates the running
-    buffers); 2: BatchNorm2d eval (running statistics).  Returns the same raw tensor with scale/shift set."""
+    buffers); 2: BatchNorm2d eval (running statistics).  Returns the same raw tensor with the normalisation
+    attached: BatchNorm as scale / shift (one small launch); InstanceNorm as the raw statistics (no launch -- every
+    consumer kernel derives rstd / mean itself) unless `eager`."""
     B, H, W, C = f.x.shape
     if mode != 2 and f.stats is None:
         raise RuntimeError("finalize_norm: the producer did not record statistics")
+    if mode == 0 and not eager:
+        return Feat(f.x, per_sample=True, act=ACT_NONE, norm_stats=f.stats, norm_count=float(H * W), norm_eps=float(eps))
     n = B * C if mode == 0 else C
     scale = torch.empty(n, dtype=torch.float32, device=f.x.device)
     shift = torch.empty(n, dtype=torch.float32, device=f.x.device)
@@ -196,10 +274,19 @@ def finalize_norm(f: Feat, *, eps: float = 1e-5, mode: int = 0, gamma=None, beta
     return Feat(f.x, scale=scale, shift=shift, per_sample=(mode == 0), act=ACT_NONE)
 
 
+def resolve_norm(f: Feat) -> Feat:
+    """Turn a deferred InstanceNorm (raw statistics) into explicit scale / shift with the finalize kernel."""
+    if f.norm_stats is None:
+        return f
+    B, H, W, C = f.x.shape
+    g = finalize_norm(Feat(f.x, stats=f.norm_stats), eps=f.norm_eps, mode=0, eager=True)
+    return Feat(f.x, g.scale, g.shift, True, f.act)
+
+
 def with_act(f: Feat, act: int) -> Feat:
     if f.act != ACT_NONE:
         f = materialize(f)
-    return Feat(f.x, f.scale, f.shift, f.per_sample, act, f.stats)
+    return Feat(f.x, f.scale, f.shift, f.per_sample, act, f.stats, f.norm_stats, f.norm_count, f.norm_eps)
 
 
 def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
@@ -210,12 +297,17 @@ def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
     if a.stats is not None or (b is not None and b.stats is not None):
         raise RuntimeError("combine: input carries un-finalised statistics")
     y = torch.empty_like(a.x)
+    if b is not None and a.norm_stats is not None and b.norm_stats is not None and (a.norm_count, a.norm_eps) != (b.norm_count, b.norm_eps):
+        b = resolve_norm(b)
+    count, eps = (a.norm_count, a.norm_eps) if a.norm_stats is not None else ((b.norm_count, b.norm_eps) if b is not None else (0.0, 1e-5))
     if y.numel():
         with torch.cuda.device(y.device):
             _lib.check(_L().mdctgan_norm_apply(a.x.data_ptr(), _ptr(a.scale), _ptr(a.shift), 1 if a.per_sample else 0, a.act,
-                                               _ptr(b.x) if b is not None else None, _ptr(b.scale) if b is not None else None,
-                                               _ptr(b.shift) if b is not None else None, 1 if (b is not None and b.per_sample) else 0,
-                                               b.act if b is not None else 0, y.data_ptr(), B, H * W, C, act_out, _stream(y)))
+                                               _ptr(a.norm_stats), _ptr(b.x) if b is not None else None,
+                                               _ptr(b.scale) if b is not None else None, _ptr(b.shift) if b is not None else None,
+                                               1 if (b is not None and b.per_sample) else 0, b.act if b is not None else 0,
+                                               _ptr(b.norm_stats) if b is not None else None, count, eps, y.data_ptr(), B, H * W, C, act_out,
+                                               _stream(y)))
     return Feat(y)
 
 
@@ -245,7 +337,7 @@ def attention(qkv: Feat, emb_h: torch.Tensor, emb_w: torch.Tensor, heads: int, d
     if C3 != 3 * C:
         raise RuntimeError(f"attention: qkv has {C3} channels, expected 3*{heads}*{dim_head}")
     out = torch.empty((B, H, W, C), dtype=torch.float32, device=qkv.x.device)
-    stats = torch.zeros((B, C, 2), dtype=torch.float64, device=out.device) if want_stats else None
+    stats = _new_stats(B, C, out.device) if want_stats else None
     if B:
         with torch.cuda.device(out.device):
             _lib.check(_L().mdctgan_attention_abs_pos(qkv.x.data_ptr(), emb_h.data_ptr(), emb_w.data_ptr(), out.data_ptr(), B, H, W, heads,

@@ -88,7 +88,8 @@ def test_conv2d_umma_matches_torch_and_direct(dev, case, engine, tol, monkeypatc
     np.testing.assert_allclose(st[..., 1].numpy(), (ref.double() ** 2).sum(dim=(2, 3)).numpy(), rtol=rt)
 
 
-def test_conv2d_umma_fused_norm_act_chain_and_determinism(dev, monkeypatch):
+@pytest.mark.parametrize("eager_norm", [False, True])
+def test_conv2d_umma_fused_norm_act_chain_and_determinism(dev, monkeypatch, eager_norm):
     """ResnetBlock through the tensor-core path: x + IN(conv(relu(IN(conv(x))))), deferred norm applied in the gather."""
     from mdctgan_b200 import nn_ops as ops
 
@@ -105,9 +106,9 @@ def test_conv2d_umma_fused_norm_act_chain_and_determinism(dev, monkeypatch):
         f = ops.Feat(_nhwc(x).to(dev))
         k1, k2 = ops.pack_conv_weight(w1.to(dev)), ops.pack_conv_weight(w2.to(dev))
         a = ops.conv2d(f, k1, b1.to(dev), kh=3, kw=3, pad=1, pad_mode=ops.PAD_REFLECT, want_stats=True, w_umma=ops.pack_conv_weight_umma(k1))
-        a = ops.with_act(ops.finalize_norm(a), ops.ACT_RELU)
+        a = ops.with_act(ops.finalize_norm(a, eager=eager_norm), ops.ACT_RELU)   # raw statistics, or explicit scale / shift
         c = ops.conv2d(a, k2, b2.to(dev), kh=3, kw=3, pad=1, pad_mode=ops.PAD_REFLECT, want_stats=True, w_umma=ops.pack_conv_weight_umma(k2))
-        return ops.combine(f, ops.finalize_norm(c)).x.cpu()
+        return ops.combine(f, ops.finalize_norm(c, eager=eager_norm)).x.cpu()
 
     out1, out2 = block(), block()
     assert rel_l2(_nchw(out1).numpy(), ref.numpy()) < 2e-5
@@ -142,3 +143,28 @@ def test_conv2d_umma_rejects_unsupported_shapes(dev):
     x = ops.Feat(torch.zeros(1, 4, 4, 6, device=dev))
     with pytest.raises(RuntimeError, match="conv2d_umma"):
         ops.conv2d(x, torch.zeros(6, 8, device=dev), None, kh=1, kw=1, w_umma=torch.zeros(64, device=dev))
+
+
+def test_stats_arena_and_small_plane_fallback(dev, monkeypatch):
+    """32-pixel planes (cfg3 global bottleneck): a 128-row tile spans 4 samples, so the deferred InstanceNorm is
+    resolved by the finalize kernel; inside a stats_pass the statistics are slices of the zeroed arena."""
+    from mdctgan_b200 import nn_ops as ops
+
+    monkeypatch.setattr(ops, "CONV_ENGINE", "umma")
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 8, 64, 2, 16
+    x = torch.randn(B, C, H, W, generator=g)
+    w1, w2 = torch.randn(C, C, 3, 3, generator=g) * 0.05, torch.randn(C, C, 3, 3, generator=g) * 0.05
+    h = F.relu(F.instance_norm(F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w1)))
+    ref = F.instance_norm(F.conv2d(F.pad(h, (1,) * 4, mode="reflect"), w2))
+    k1, k2 = ops.pack_conv_weight(w1.to(dev)), ops.pack_conv_weight(w2.to(dev))
+    u1, u2 = ops.pack_conv_weight_umma(k1), ops.pack_conv_weight_umma(k2)
+    for _ in range(2):      # second pass re-zeroes the arena
+        with ops.stats_pass(dev):
+            f = ops.Feat(_nhwc(x).to(dev))
+            a = ops.conv2d(f, k1, None, kh=3, kw=3, pad=1, pad_mode=ops.PAD_REFLECT, want_stats=True, w_umma=u1)
+            assert a.stats.data_ptr() != 0 and a.stats._base is not None      # a view of the arena
+            a = ops.with_act(ops.finalize_norm(a), ops.ACT_RELU)
+            c = ops.conv2d(a, k2, None, kh=3, kw=3, pad=1, pad_mode=ops.PAD_REFLECT, want_stats=True, w_umma=u2)
+            out = ops.materialize(ops.finalize_norm(c)).x.cpu()
+        assert rel_l2(_nchw(out).numpy(), ref.numpy()) < 2e-5
