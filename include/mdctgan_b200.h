@@ -117,6 +117,9 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
  * results; 1: single TF32 pass.  With in_stats and B > 1 the (per parity class) plane must be a multiple of 128
  * pixels. */
 int mdctgan_conv2d_umma_supported(int Cin, int Cout);
+/* debug aid: subsequent mdctgan_conv2d_umma launches write per-CTA phase timestamps into dev_buf
+ * ([grid.y * grid.x][16] int64; slot 0 globaltimer ns, slots 1.. clock64 at the phase boundaries); NULL = off */
+int mdctgan_conv2d_umma_set_trace(long long* dev_buf);
 int64_t mdctgan_conv2d_umma_packed_floats(int K, int Cout);
 int mdctgan_conv2d_umma_pack_weight(const float* w_kn, int K, int Cout, float* out, void* stream);
 int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const float* w_packed, const float* bias, float* y, int Ho, int Wo,

@@ -35,7 +35,10 @@ namespace cg = cooperative_groups;
 
 constexpr int kBM = 128;              // UMMA M: output pixels per CTA tile
 constexpr int kKC = 32;               // K elements per chunk = one 128-byte swizzle row of fp32
-constexpr int kProducerWarps = 8;     // gather + epilogue warps
+constexpr int kProducerWarps = 16;    // gather + epilogue warps (the gather is issue bound: 4 warps per scheduler)
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kRows = kBM * 8 / kProducerThreads;   // rows of the A tile per producer thread (8 threads per 128-byte row)
+static_assert(kRows == 2, "validity queue packs 2 bits per chunk");
 constexpr int kThreads = (kProducerWarps + 2) * 32;   // + MMA warp + weight-loader warp
 constexpr int kMaxCin = 1024;
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;           // sign + 8 exponent + 10 mantissa bits
@@ -51,8 +54,18 @@ struct ConvUmmaParams {
   double* stats;        // [B][Cout][2] or null
   int K, kchunks, splits;
   int classes;          // 1, or stride^2 output parity classes of a ConvTranspose2d (see TileGeom)
-  int m_total, m_tiles; // output pixels / 128-row tiles PER CLASS
+  int m_tiles;          // 128-pixel tiles per (sample, class)
+  long long* trace;     // debug: per-CTA phase timestamps [CTA][16] (clock64; slot 0 = globaltimer), or null
 };
+
+__device__ __forceinline__ void trace_mark(const ConvUmmaParams& p, int slot, bool who) {
+  if (p.trace && who) {
+    long long t;
+    if (slot == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = clock64();
+    p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+  }
+}
 
 // ---- PTX primitives ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,7 +81,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C ABI), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
   long long t0 = 0;
@@ -92,6 +105,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// statistics live in global memory: a plain reduction, not the generic-address atomic (which carries a shared-memory CAS path)
+__device__ __forceinline__ void red_add_f64(double* gptr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(gptr)), "d"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -147,15 +164,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
-// nearest TF32 (10-bit mantissa) value, as an fp32 whose low 13 bits are zero: exact in the tensor core whatever
-// rounding the hardware applies to fp32 containers.  x = hi + lo with lo = tf32(x - hi): |x - hi - lo| <= 2^-23 |x|.
-__host__ __device__ __forceinline__ float tf32_part(float v) {
+// 3xTF32 split x = hi + lo.  hi keeps the top 10 mantissa bits (low 13 bits cleared: exact in the tensor core whatever
+// rounding the hardware applies to fp32 containers); lo = x - hi is exact in fp32 (<= 13 significant bits) and is
+// consumed as TF32 by the tensor core (its own truncation / rounding of lo leaves a residual <= 2^-21 |x|).
+__host__ __device__ __forceinline__ float tf32_hi(float v) {
 #ifdef __CUDA_ARCH__
-  return __uint_as_float((__float_as_uint(v) + 0x1000u) & kTf32Mask);
+  return __uint_as_float(__float_as_uint(v) & kTf32Mask);
 #else
-  union { float f; uint32_t u; } c; c.f = v; c.u = (c.u + 0x1000u) & kTf32Mask; return c.f;
+  union { float f; uint32_t u; } c; c.f = v; c.u &= kTf32Mask; return c.f;
 #endif
 }
+
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & kTf32Mask); }
 
 template <int BN, bool SPLIT3>
 struct Cfg {
@@ -163,25 +183,30 @@ struct Cfg {
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  static constexpr int kStages = (192 * 1024 / kStageBytes) > 6 ? 6 : (192 * 1024 / kStageBytes);
+  static constexpr int kStages = (192 * 1024 / kStageBytes) >= 8 ? 8 : ((192 * 1024 / kStageBytes) >= 4 ? 4 : 2);
   static constexpr int kPitch = BN + 4;                                   // staging row pitch (floats)
   static constexpr int kStagingBytes = ((kBM * kPitch * 4 + 1023) / 1024) * 1024;
-  static constexpr int kRedBytes = 2 * 1024 * 4;                          // [2][RP][BN] floats, RP*BN = 1024
+  static constexpr int kRedBytes = 2 * kProducerThreads * 4 * 4;          // [2][RP][BN] floats, RP*BN = 4 * producer threads
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kMaxCin * 4 + 256;
   static_assert(kStagingBytes + kRedBytes <= kStages * kStageBytes, "staging must fit in the pipeline buffers");
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
 };
 
-// Which output pixels a CTA tile covers.  Ordinary convolutions: rows are the flattened (b, oy, ox) pixels.
-// ConvTranspose2d with stride s: the s*s output parity classes ((oy + pad) % s, (ox + pad) % s) each see only the
-// taps ky = py + s*i, kx = px + s*j (for k3 s2 p1: 1, 2, 2 or 4 of the 9 taps), so tiles are formed per class and
-// the K loop walks the live taps only -- 4x fewer chunks than zero-filling the dead ones.
+// Which output pixels a CTA tile covers: up to 128 pixels of ONE sample (so the per-sample InstanceNorm affine of the
+// input and the per-sample statistics of the output are CTA-uniform).  Ordinary convolutions: consecutive pixels of
+// the sample.  ConvTranspose2d with stride s: the s*s output parity classes ((oy + pad) % s, (ox + pad) % s) each
+// see only the taps ky = py + s*i, kx = px + s*j (for k3 s2 p1: 1, 2, 2 or 4 of the 9 taps), so tiles are formed per
+// class and the K loop walks the live taps only -- 4x fewer chunks than zero-filling the dead ones.
+// Input coordinate of class-local output (oyc, oxc) at class-local tap (ky, kx):  iy = oyb + sgn*ky,
+//   convolution:           oyb = oyc*stride - pad,          sgn = +1
+//   transposed, classes:   oyb = oyc + (offy + pad - py)/s, sgn = -1   (oy = oyc*s + offy, real tap = py + s*ky)
 struct TileGeom {
   int cs, py, px, offy, offx;   // class stride (1 = no classes), class parities, first oy / ox of the class
-  int nkx, cpt;                 // live taps along x; K chunks per tap (Cin / 32)
+  int nkx, cpt, ntaps;          // live taps along x; K chunks per tap (Cin / 32, classes only); live taps in total
   int hw, woc;                  // pixels per sample in this class; class-local row width
   int kchunks;                  // K chunks this tile walks
+  int sgn, mul, addy, addx;     // oyb = oyc*mul + addy, oxb = oxc*mul + addx
 };
 
 __device__ __forceinline__ TileGeom make_geom(const ConvUmmaParams& p, int cls) {
@@ -194,19 +219,41 @@ __device__ __forceinline__ TileGeom make_geom(const ConvUmmaParams& p, int cls) 
     g.nkx = (p.kw - g.px + g.cs - 1) / g.cs;
     g.cpt = p.Cin / kKC;
     g.woc = p.Wo / g.cs; g.hw = (p.Ho / g.cs) * g.woc;
-    g.kchunks = nky * g.nkx * g.cpt;
+    g.ntaps = nky * g.nkx;
+    g.kchunks = g.ntaps * g.cpt;
+    g.sgn = -1; g.mul = 1; g.addy = (g.offy + p.pad - g.py) / g.cs; g.addx = (g.offx + p.pad - g.px) / g.cs;
   } else {
-    g.cs = 1; g.py = g.px = g.offy = g.offx = 0; g.nkx = p.kw; g.cpt = 0;
+    g.cs = 1; g.py = g.px = g.offy = g.offx = 0; g.nkx = p.kw; g.cpt = 0; g.ntaps = p.kh * p.kw;
     g.woc = p.Wo; g.hw = p.Ho * p.Wo; g.kchunks = p.kchunks;
+    if (p.transposed) { g.sgn = -1; g.mul = 1; g.addy = g.addx = p.pad; }          // stride 1 only (host-checked)
+    else { g.sgn = 1; g.mul = p.stride; g.addy = g.addx = -p.pad; }
   }
   return g;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmmaParams p) {
   using C = Cfg<BN, SPLIT3>;
+  static_assert((C::kStages & (C::kStages - 1)) == 0, "stage count must be a power of two");
+  constexpr int kStageMask = C::kStages - 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t smem_a = smem_u32(smem);
   float* s_scale = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
   float* s_shift = s_scale + kMaxCin;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_shift + kMaxCin);
@@ -215,18 +262,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  trace_mark(p, 0, tid == 0);
+  trace_mark(p, 1, tid == 0);
   int bx = blockIdx.x;
   const int mt = bx % p.m_tiles; bx /= p.m_tiles;
+  const int b = bx % p.B; bx /= p.B;
   const int cls = bx % p.classes, nt = bx / p.classes;
   const TileGeom tg = make_geom(p, cls);
   const int split = blockIdx.y;                       // == rank of this CTA in its cluster (cluster = (1, splits, 1))
-  const int m0 = mt * kBM, n0 = nt * BN;
+  const int m0 = mt * kBM, n0 = nt * BN;              // first class-local pixel of the tile within sample b
   const int kc_begin = (int)((long long)tg.kchunks * split / p.splits);
   const int kc_end = (int)((long long)tg.kchunks * (split + 1) / p.splits);
   const int nk = kc_end - kc_begin;
 
   if (warp == kProducerWarps) {
     if (lane == 0) {
+#pragma unroll 1
       for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], kProducerWarps + 1); mbar_init(&empty[s], 1); }
       mbar_init(tmem_full, 1);
       fence_barrier_init();
@@ -234,18 +285,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     __syncwarp();
     tmem_alloc(tmem_slot, C::kTmemCols);
   }
-  // The deferred normalisation of the producing layer.  When the whole tile belongs to one sample (or the affine is
-  // per channel only) its scale / shift live in shared memory -- taken ready-made, or computed here from the
-  // producer's raw (sum, sumsq) statistics (InstanceNorm2d: no separate finalize launch) -- else fetched per row.
-  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
-  const int b_first = m0 / tg.hw;
-  const int m_last = (m0 + kBM < p.m_total ? m0 + kBM : p.m_total) - 1;
-  const bool one_sample = (m_last / tg.hw) == b_first;
-  const bool norm_in_smem = has_norm && (one_sample || !p.in.per_sample);
-  if (norm_in_smem) {
-    const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
+  // The deferred normalisation of the producing layer, CTA-uniform: scale / shift of sample b into shared memory --
+  // ready-made, derived here from the producer's raw (sum, sumsq) statistics (InstanceNorm2d: no separate finalize
+  // launch), or the identity.
+  {
+    const size_t off = p.in.per_sample ? (size_t)b * p.Cin : 0;
     if (p.in.stats) {
       const double inv_n = 1.0 / (double)p.in.count;
+#pragma unroll 1
       for (int c = tid; c < p.Cin; c += kThreads) {
         const double mean = p.in.stats[2 * (off + c)] * inv_n;
         double var = p.in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
@@ -254,136 +301,137 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         s_scale[c] = (float)rstd;
         s_shift[c] = (float)(-mean * rstd);
       }
-    } else {
+    } else if (p.in.scale) {
+#pragma unroll 1
       for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
+    } else {
+#pragma unroll 1
+      for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = 1.f; s_shift[c] = 0.f; }
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  trace_mark(p, 2, tid == 0);
 
   if (warp < kProducerWarps) {
     // ================= A producers: implicit im2col gather -> normalise -> TF32 hi/lo -> swizzled smem =========
+    // The gather is instruction-issue and instruction-fetch bound (short kernel, cold I-cache on every SM), so the
+    // loop is rolled and small: cp.async (LDGSTS, zero-fill for padding) drops each thread's 16-byte pieces of chunk
+    // `it` straight into their swizzled slot of the stage, kAhead chunks ahead; the same thread later reads its own
+    // pieces back, applies  v = max(e, slope*e), e = x*scale + shift  (slope 1 / 0 / 0.2 = none / ReLU / LeakyReLU)
+    // and rewrites them in place as TF32 hi (+ lo in the second buffer).  Row offsets are recomputed per tap only.
+    constexpr int kAhead = C::kStages - 1;
+    constexpr int kRowStep = kProducerThreads / 8;
     const int j = tid & 7;        // 16-byte piece (4 channels) of the 128-byte row
-    const int rb = tid >> 3;      // rows rb, rb+32, rb+64, rb+96
-    int oy[4], ox[4], bb[4];
+    const int rb = tid >> 3;      // rows rb, rb + 64
+    const uint32_t row_off = (uint32_t)(rb >> 3) * 1024u + (uint32_t)(rb & 7) * 128u + (uint32_t)((j ^ (rb & 7)) << 4);
+    const float slope = p.in.act == nnk::kActRelu ? 0.f : (p.in.act == nnk::kActLeaky ? 0.2f : 1.f);
+    const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+    int oyb[kRows], oxb[kRows];
+    bool rvalid[kRows];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = m0 + rb + 32 * i;
-      if (g < p.m_total) {
-        bb[i] = g / tg.hw;
-        const int pix = g - bb[i] * tg.hw;
-        const int oyc = pix / tg.woc;
-        oy[i] = oyc * tg.cs + tg.offy;
-        ox[i] = (pix - oyc * tg.woc) * tg.cs + tg.offx;
-      } else {
-        bb[i] = -1; oy[i] = 0; ox[i] = 0;
-      }
+    for (int i = 0; i < kRows; ++i) {
+      const int pix = m0 + rb + kRowStep * i;
+      rvalid[i] = pix < tg.hw;
+      const int oyc = pix / tg.woc;
+      oyb[i] = oyc * tg.mul + tg.addy;
+      oxb[i] = (pix - oyc * tg.woc) * tg.mul + tg.addx;
     }
-    // The gather is latency bound (one L2 round trip per chunk), so the loads of kGroup chunks are issued before
-    // the first of them is consumed; the stage's `empty` barrier is only needed before the shared-memory stores.
-    constexpr int kGroup = C::kStages < 4 ? C::kStages : 4;
-    for (int it0 = 0; it0 < nk; it0 += kGroup) {
-      float4 v[kGroup][4];
-      int cc[kGroup];
-      uint32_t okmask = 0;
+    // issue-side walker over the tile's K space (live taps x Cin), and a second channel walker for the process side
+    int k0 = kc_begin * kKC + j * 4;
+    int tap = k0 / p.Cin;
+    int c = k0 - tap * p.Cin;
+    int ky = tap / tg.nkx, kx = tap - ky * tg.nkx;
+    int c2 = c;
+    bool tap_dirty = true;
+    int rowoff[kRows];
+    uint32_t okq = 0;             // validity bits of the chunks in flight, 2 per chunk, newest in the low bits
+#pragma unroll 1
+    for (int it = 0; it < nk + kAhead; ++it) {
+      if (it >= kAhead) {
+        // ---- process chunk q = it - kAhead
+        const int q = it - kAhead;
+        if (it < nk) cp_async_wait<kAhead - 1>(); else cp_async_wait<0>();
+        const int newer = (it < nk ? it : nk) - 1 - q;          // chunks issued after q
+        const uint32_t ok2 = (okq >> (2 * newer)) & 3u;
+        const int s = q & kStageMask;
+        const uint32_t a_hi = smem_a + s * C::kStageBytes + row_off;
+        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c2);
+        const float4 sh = *reinterpret_cast<const float4*>(s_shift + c2);
 #pragma unroll
-      for (int gi = 0; gi < kGroup; ++gi) {
-        const int it = it0 + gi;
-        cc[gi] = -1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[gi][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it < nk) {
-          const int kc = kc_begin + it;
-          int ky, kx, c;
-          bool kvalid = true;
-          if (p.classes > 1) {
-            const int t = kc / tg.cpt;
-            c = (kc - t * tg.cpt) * kKC + j * 4;
-            const int ty = t / tg.nkx;
-            ky = tg.py + tg.cs * ty;
-            kx = tg.px + tg.cs * (t - ty * tg.nkx);
+        for (int i = 0; i < kRows; ++i) {
+          float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok2 & (1u << i)) {
+            e = lds128(a_hi + i * (kRowStep * 128));
+            e.x = fmaf(e.x, sc.x, sh.x); e.y = fmaf(e.y, sc.y, sh.y); e.z = fmaf(e.z, sc.z, sh.z); e.w = fmaf(e.w, sc.w, sh.w);
+            e.x = fmaxf(e.x, slope * e.x); e.y = fmaxf(e.y, slope * e.y); e.z = fmaxf(e.z, slope * e.z); e.w = fmaxf(e.w, slope * e.w);
+          }
+          if (SPLIT3) {
+            const float4 hi = make_float4(tf32_hi(e.x), tf32_hi(e.y), tf32_hi(e.z), tf32_hi(e.w));
+            sts128(a_hi + i * (kRowStep * 128), hi);
+            sts128(a_hi + C::kABytes + i * (kRowStep * 128), make_float4(e.x - hi.x, e.y - hi.y, e.z - hi.z, e.w - hi.w));
           } else {
-            const int k = kc * kKC + j * 4;
-            kvalid = k < p.K;
-            const int tap = k / p.Cin;
-            c = k - tap * p.Cin;
-            ky = tap / p.kw;
-            kx = tap - ky * p.kw;
-          }
-          if (kvalid) {
-            cc[gi] = c;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (bb[i] >= 0) {
-                const int iy = nnk::in_coord(oy[i], ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
-                const int ix = nnk::in_coord(ox[i], kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
-                if (iy >= 0 && ix >= 0) {
-                  okmask |= 1u << (gi * 4 + i);
-                  v[gi][i] = __ldg(reinterpret_cast<const float4*>(p.x + (((size_t)bb[i] * p.H + iy) * p.W + ix) * p.Cin + c));
-                }
-              }
-            }
+            sts128(a_hi + i * (kRowStep * 128), make_float4(tf32_rn(e.x), tf32_rn(e.y), tf32_rn(e.z), tf32_rn(e.w)));
           }
         }
+        c2 += kKC;
+        while (c2 >= p.Cin) c2 -= p.Cin;
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (q == 0) trace_mark(p, 3, tid == 0);
       }
+      if (it < nk) {
+        // ---- issue chunk it
+        const int s = it & kStageMask;
+        mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
+        if (tap_dirty) {
+          tap_dirty = false;
 #pragma unroll
-      for (int gi = 0; gi < kGroup; ++gi) {
-        const int it = it0 + gi;
-        if (it < nk) {
-          const int s = it % C::kStages;
-          const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          const int c = cc[gi];
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (norm_in_smem && c >= 0) {
-            sc = *reinterpret_cast<const float4*>(s_scale + c);
-            sh = *reinterpret_cast<const float4*>(s_shift + c);
-          }
-          uint8_t* a_hi = smem + s * C::kStageBytes;
-          uint8_t* a_lo = a_hi + C::kABytes;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float e[4] = {v[gi][i].x, v[gi][i].y, v[gi][i].z, v[gi][i].w};
-            if (okmask & (1u << (gi * 4 + i))) {
-              if (has_norm) {
-                if (!norm_in_smem) {
-                  sc = __ldg(reinterpret_cast<const float4*>(p.in.scale + (size_t)bb[i] * p.Cin + c));
-                  sh = __ldg(reinterpret_cast<const float4*>(p.in.shift + (size_t)bb[i] * p.Cin + c));
-                }
-                e[0] = fmaf(e[0], sc.x, sh.x); e[1] = fmaf(e[1], sc.y, sh.y); e[2] = fmaf(e[2], sc.z, sh.z); e[3] = fmaf(e[3], sc.w, sh.w);
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) e[u] = nnk::apply_act(e[u], p.in.act);
+          for (int i = 0; i < kRows; ++i) {
+            int iy = oyb[i] + tg.sgn * ky, ix = oxb[i] + tg.sgn * kx;
+            bool ok = rvalid[i] && tap < tg.ntaps;
+            if (p.pad_mode == nnk::kPadReflect) {
+              iy = iy < 0 ? -iy : iy; iy = iy >= p.H ? 2 * p.H - 2 - iy : iy;
+              ix = ix < 0 ? -ix : ix; ix = ix >= p.W ? 2 * p.W - 2 - ix : ix;
+            } else {
+              ok = ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
             }
-            const int r = rb + 32 * i;
-            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-            const float4 hi = make_float4(tf32_part(e[0]), tf32_part(e[1]), tf32_part(e[2]), tf32_part(e[3]));
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            if (SPLIT3) {
-              *reinterpret_cast<float4*>(a_lo + off) =
-                  make_float4(tf32_part(e[0] - hi.x), tf32_part(e[1] - hi.y), tf32_part(e[2] - hi.z), tf32_part(e[3] - hi.w));
-            }
+            rowoff[i] = ok ? (iy * p.W + ix) * p.Cin : -1;
           }
-          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
+        }
+        const uint32_t dst = smem_a + s * C::kStageBytes + row_off;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          const bool ok = rowoff[i] >= 0;
+          bits |= ok ? (1u << i) : 0u;
+          cp_async16_zfill(dst + i * (kRowStep * 128), ok ? xb + rowoff[i] + c : xb, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        okq = (okq << 2) | bits;
+        c += kKC;
+        while (c >= p.Cin) {
+          c -= p.Cin; ++tap; tap_dirty = true;
+          if (++kx == tg.nkx) { kx = 0; ++ky; }
         }
       }
     }
+    trace_mark(p, 4, tid == 0);
     // ================= epilogue part 1: accumulator TMEM -> registers -> staging tile in shared memory =========
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    trace_mark(p, 5, tid == 0);
     float* stage_out = reinterpret_cast<float*>(smem);
-    const int q = warp & 3, half = warp >> 2;          // warp w may only touch TMEM lanes 32*(w%4) .. +31
-    const int row = q * 32 + lane;
-    constexpr int kColsPerWarp = BN / 2;
-#pragma unroll
-    for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+    const int q4 = warp & 3;                            // warp w may only touch TMEM lanes 32*(w%4) .. +31
+    const int row = q4 * 32 + lane;
+#pragma unroll 1
+    for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += (kProducerWarps / 4) * 16) {   // 16-column slices round-robin over the 4 warps of a lane quarter
       float a[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kColsPerWarp + c0), a);
-      float* dst = stage_out + row * C::kPitch + half * kColsPerWarp + c0;
+      tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, a);
+      float* dst = stage_out + row * C::kPitch + c0;
 #pragma unroll
       for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(a[u], a[u + 1], a[u + 2], a[u + 3]);
     }
@@ -392,12 +440,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(BN);
+#pragma unroll 1
       for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-        mbar_wait(&full[s], ph);
+        const int s = it & kStageMask;
+        mbar_wait(&full[s], (uint32_t)(it / C::kStages) & 1u);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t a_hi = smem_a + s * C::kStageBytes;
         const uint32_t a_lo = a_hi + C::kABytes;
         const uint32_t b_hi = a_hi + C::kParts * C::kABytes;
         const uint32_t b_lo = b_hi + C::kBBytes;
@@ -413,15 +461,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         umma_commit(&empty[s]);     // stage reusable once these MMAs have read it
       }
       umma_commit(tmem_full);       // accumulator complete
+      trace_mark(p, 11, true);
     }
     __syncwarp();
   } else {
     // ================= weight loader: TMA bulk copies of the pre-swizzled tile image =================
     if (lane == 0) {
+#pragma unroll 1
       for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
+        const int s = it & kStageMask;
+        mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::kParts * C::kBBytes));
         uint8_t* b_hi = smem + s * C::kStageBytes + C::kParts * C::kABytes;
         int wkc = kc_begin + it;    // chunk index in the packed weights: (ky*kw + kx) * Cin/32 + channel chunk
@@ -438,86 +487,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   }
 
   __syncthreads();   // staging tile complete; every tcgen05 operation of this CTA has retired
+  trace_mark(p, 6, tid == 0);
   if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
   cg::cluster_group cluster = cg::this_cluster();
   if (p.splits > 1) cluster.sync();   // all partial tiles of the cluster are parked
+  trace_mark(p, 7, tid == 0);
 
   // ================= epilogue part 2: split-K reduction over DSMEM, bias, statistics, activation, store =======
   float* stage_out = reinterpret_cast<float*>(smem);
   float* red = reinterpret_cast<float*>(smem + C::kStagingBytes);
-  constexpr int CQ = BN / 4;          // float4 columns per row
-  constexpr int RP = 256 / CQ;        // rows per pass over 256 threads
+  constexpr int CQ = BN / 4;                  // float4 columns per row
+  constexpr int RP = kProducerThreads / CQ;   // rows per pass over the producer threads
+  constexpr int kRedHalf = kProducerThreads * 4;
   const int r_begin = kBM * split / p.splits, r_end = kBM * (split + 1) / p.splits;
   const int cq = tid % CQ, rg = tid / CQ;
-  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tid < 256) {
+  if (tid < kProducerThreads) {
+    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n = n0 + cq * 4;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    const float* peer[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) peer[s] = (p.splits > 1 && s < p.splits) ? cluster.map_shared_rank(stage_out, s) : stage_out;
-    int cur_b = -1;
+#pragma unroll 1
     for (int r = r_begin + rg; r < r_end; r += RP) {
-      const int g = m0 + r;
-      if (g >= p.m_total) break;
-      float4 t[8];
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        t[s] = s < p.splits ? *reinterpret_cast<const float4*>(peer[s] + r * C::kPitch + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int pix = m0 + r;
+      if (pix >= tg.hw) break;
       float4 acc = bias;
 #pragma unroll
-      for (int s = 0; s < 8; ++s) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }   // rank order: deterministic
-      const int b = g / tg.hw;
-      if (p.stats) {
-        if (!one_sample && b != cur_b) {   // tile spans samples (planes smaller than 128 pixels): flush per sample
-          if (cur_b >= 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              double* st = p.stats + ((size_t)cur_b * p.Cout + n + u) * 2;
-              atomicAdd(st, (double)ssum[u]); atomicAdd(st + 1, (double)ssq[u]);
-              ssum[u] = 0.f; ssq[u] = 0.f;
-            }
-          }
-          cur_b = b;
+      for (int s = 0; s < 8; ++s) {             // rank order: deterministic
+        if (s < p.splits) {
+          const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
+          const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
-        ssum[0] += acc.x; ssq[0] += acc.x * acc.x; ssum[1] += acc.y; ssq[1] += acc.y * acc.y;
-        ssum[2] += acc.z; ssq[2] += acc.z * acc.z; ssum[3] += acc.w; ssq[3] += acc.w * acc.w;
       }
+      ssum.x += acc.x; ssq.x += acc.x * acc.x; ssum.y += acc.y; ssq.y += acc.y * acc.y;
+      ssum.z += acc.z; ssq.z += acc.z * acc.z; ssum.w += acc.w; ssq.w += acc.w * acc.w;
       acc.x = nnk::apply_act(acc.x, p.act); acc.y = nnk::apply_act(acc.y, p.act);
       acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
-      const int pix = g - b * tg.hw;
       const int oyc = pix / tg.woc;
       const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
       *reinterpret_cast<float4*>(p.y + (((size_t)b * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
     }
-    if (p.stats && !one_sample && cur_b >= 0) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        double* st = p.stats + ((size_t)cur_b * p.Cout + n + u) * 2;
-        atomicAdd(st, (double)ssum[u]); atomicAdd(st + 1, (double)ssq[u]);
-      }
+    if (p.stats) {
+      *reinterpret_cast<float4*>(red + rg * BN + cq * 4) = ssum;
+      *reinterpret_cast<float4*>(red + kRedHalf + rg * BN + cq * 4) = ssq;
     }
   }
-  if (p.stats && one_sample) {        // block-uniform branch
-    if (tid < 256) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { red[rg * BN + cq * 4 + u] = ssum[u]; red[1024 + rg * BN + cq * 4 + u] = ssq[u]; }
-    }
+  trace_mark(p, 8, tid == 0);
+  if (p.stats) {        // block-uniform branch
     __syncthreads();
     if (tid < BN) {
       float s = 0.f, q = 0.f;
-#pragma unroll
-      for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[1024 + r * BN + tid]; }
-      double* st = p.stats + ((size_t)b_first * p.Cout + n0 + tid) * 2;
-      atomicAdd(st, (double)s);
-      atomicAdd(st + 1, (double)q);
+#pragma unroll 4
+      for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
+      double* st = p.stats + ((size_t)b * p.Cout + n0 + tid) * 2;
+      red_add_f64(st, (double)s);
+      red_add_f64(st + 1, (double)q);
     }
   }
+  trace_mark(p, 9, tid == 0);
   if (p.splits > 1) cluster.sync();   // no CTA may exit while a peer still reads its shared memory
+  trace_mark(p, 10, tid == 0);
 }
 
 // [K][Cout] fp32 (nn_ops.pack_conv_weight layout) -> the kernel's shared-memory image, TF32 hi / lo parts
@@ -527,8 +559,8 @@ __global__ void pack_weight_umma_kernel(const float* __restrict__ w, float* __re
     const int n = (int)(i % Cout);
     const int k = (int)(i / Cout);
     const float v = k < K ? __ldg(w + (size_t)k * Cout + n) : 0.f;
-    const float hi = tf32_part(v);
-    const float lo = tf32_part(v - hi);
+    const float hi = tf32_hi(v);
+    const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & kTf32Mask);   // nearest TF32 of the remainder
     const int kc = k >> 5, kk = k & 31;
     const int piece = (kk >> 2) ^ (n & 7);
     const size_t dst = (((size_t)kc * 2) * Cout + n) * kKC + piece * 4 + (kk & 3);

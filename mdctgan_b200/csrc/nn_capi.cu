@@ -217,7 +217,7 @@ int launch_umma(umma::ConvUmmaParams& p, int n_tiles, int min_kchunks, cudaStrea
     CKN(cudaFuncSetAttribute(umma::conv2d_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.classes * n_tiles;
+  const int tiles = p.m_tiles * p.B * p.classes * n_tiles;
   // split K over a cluster while the whole grid still fits the device in one wave
   int splits = 1;
   for (int s = 8; s >= 2; --s) {
@@ -239,7 +239,12 @@ int launch_umma(umma::ConvUmmaParams& p, int n_tiles, int min_kchunks, cudaStrea
 }
 }  // namespace
 
+static long long* g_umma_trace = nullptr;
+
 extern "C" {
+
+/* debug: per-CTA phase timestamps of the following mdctgan_conv2d_umma launches ([grid.y][grid.x][16] int64), NULL = off */
+int mdctgan_conv2d_umma_set_trace(long long* dev_buf) { g_umma_trace = dev_buf; return 0; }
 
 int mdctgan_conv2d_umma_supported(int Cin, int Cout) { return (Cin % 4 == 0 && Cin <= umma::kMaxCin && Cout % 32 == 0) ? 1 : 0; }
 
@@ -268,13 +273,14 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   if (pad_mode == kPadReflect && (pad >= H || pad >= W)) return mdctgan_set_error(-1, "conv2d_umma: reflection pad %d >= input size %dx%d", pad, H, W);
   if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_umma: in_scale / in_shift must come together");
   if (precision != 0 && precision != 1) return mdctgan_set_error(-1, "conv2d_umma: precision %d (0 = 3xTF32 fp32-class, 1 = TF32)", precision);
-  if ((long long)B * Ho * Wo > 0x7fffffffLL - 128) return mdctgan_set_error(-2, "conv2d_umma: too many output pixels");
+  if ((long long)B * Ho * Wo > 0x7fffffffLL - 128 || (long long)B * H * W * Cin > 0x7fffffffLL)
+    return mdctgan_set_error(-2, "conv2d_umma: tensor too large for 32-bit offsets");
   if (B == 0) return 0;
   umma::ConvUmmaParams p{};
   p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.wp = w_packed; p.bias = bias; p.y = y; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
   p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
-  p.act = act; p.stats = stats;
+  p.act = act; p.stats = stats; p.trace = g_umma_trace;
   p.K = kh * kw * Cin; p.kchunks = (p.K + umma::kKC - 1) / umma::kKC;
   int min_kchunks = p.kchunks;
   // ConvTranspose2d: tiles per output parity class, K loop over the live taps only (conv_umma.cuh TileGeom)
@@ -283,12 +289,14 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
     p.classes = stride * stride;
     min_kchunks = (kh / stride) * (kw / stride) * (Cin / umma::kKC);
   }
+  else if (transposed && stride > 1)
+    return mdctgan_set_error(-2, "conv2d_umma: ConvTranspose2d stride %d needs Ho, Wo %% stride == 0, Cin %% 32 == 0, k >= stride", stride);
+  if (transposed && pad_mode == kPadReflect) return mdctgan_set_error(-1, "conv2d_umma: reflection padding on a transposed convolution");
   const int hw_class = (Ho * Wo) / p.classes;
-  p.m_total = B * hw_class; p.m_tiles = (p.m_total + umma::kBM - 1) / umma::kBM;
+  p.m_tiles = (hw_class + umma::kBM - 1) / umma::kBM;     // tiles never span samples
   if (in_stats) {
     if (in_scale) return mdctgan_set_error(-1, "conv2d_umma: pass either in_scale/in_shift or in_stats");
     if (!in_per_sample || in_count <= 0) return mdctgan_set_error(-1, "conv2d_umma: in_stats is the InstanceNorm2d form (per sample, count > 0)");
-    if (B > 1 && hw_class % umma::kBM) return mdctgan_set_error(-2, "conv2d_umma: in_stats needs tiles within one sample (%d pixels per sample)", hw_class);
     p.in.stats = in_stats; p.in.count = (float)in_count; p.in.eps = in_eps;
   }
   cudaStream_t st = (cudaStream_t)stream;

@@ -231,12 +231,8 @@ def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh:
         f = materialize(f)      # an activation without an affine in front of it: apply it for real
         x, in_act = f.x, ACT_NONE
     use_umma = w_umma is not None and CONV_ENGINE != "direct"
-    if use_umma and f.norm_stats is not None and B > 1:
-        # the tensor-core kernel derives the normalisation from raw statistics only when every 128-pixel tile lies
-        # within one sample (per output parity class for a strided ConvTranspose2d)
-        s2 = stride * stride if (transposed and stride > 1 and Ho % stride == 0 and Wo % stride == 0 and Cin % 32 == 0) else 1
-        if ((Ho * Wo) // s2) % 128:
-            f = resolve_norm(f)
+    if use_umma and transposed and stride > 1 and (Ho % stride or Wo % stride or Cin % 32 or kh < stride or kw < stride):
+        use_umma = False        # the tensor-core kernel runs strided transposed convolutions per output parity class only
     if B:
         with torch.cuda.device(x.device):
             if use_umma:
