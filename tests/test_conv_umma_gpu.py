@@ -84,7 +84,9 @@ def test_conv2d_umma_matches_torch_and_direct(dev, case, engine, tol, monkeypatc
     assert rel_l2(y.x.cpu().numpy(), y_direct.x.cpu().numpy()) < tol
     st = y.stats.cpu()
     rt = 1e-4 if engine == "umma" else 5e-3
-    np.testing.assert_allclose(st[..., 0].numpy(), ref.double().sum(dim=(2, 3)).numpy(), rtol=rt, atol=1e-3 if engine == "umma" else 0.5)
+    # plane sums cancel (zero-mean data): the absolute bar is the per-element bar (tol x rms) summed over the plane in quadrature, x4
+    atol = 4.0 * tol * float(ref.pow(2).mean().sqrt()) * float(ref.shape[2] * ref.shape[3]) ** 0.5
+    np.testing.assert_allclose(st[..., 0].numpy(), ref.double().sum(dim=(2, 3)).numpy(), rtol=rt, atol=max(atol, 1e-3))
     np.testing.assert_allclose(st[..., 1].numpy(), (ref.double() ** 2).sum(dim=(2, 3)).numpy(), rtol=rt)
 
 
