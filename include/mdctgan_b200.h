@@ -150,6 +150,48 @@ int mdctgan_residual_scale_add(const float* sr, const float* lr, int64_t lr_row_
 int mdctgan_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream);
 int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Train step (reference: what torch autograd derives for models/pix2pixHD_model.py:416-451 + train.py:175-202).
+ * dgrad has no entry of its own: the input gradient of nn.Conv2d is mdctgan_conv2d_nhwc / _umma with transposed = 1
+ * on the output gradient with the weights packed [kh*kw*Cout][Cin]; of nn.ConvTranspose2d the plain convolution.
+ */
+/* dW (+= , float atomics) and dbias (+=) of nn.Conv2d / nn.ConvTranspose2d: x = the layer's raw input with its deferred
+ * normalisation / activation (as in mdctgan_conv2d_nhwc), dy = gradient of the raw convolution output [B,Ho,Wo,Cout];
+ * dW[co][ci][tap] lives at dw[co*s_co + ci*s_ci + tap*s_tap] (the parameter's own layout, e.g. a slice of the flat bucket). */
+int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const float* dy, int Ho, int Wo, int Cout, int kh, int kw, int stride,
+                         int pad, int pad_mode, int transposed, const float* in_scale, const float* in_shift, int in_per_sample, int in_act,
+                         const double* in_stats, double in_count, float in_eps, float* dw, int64_t s_co, int64_t s_ci, int64_t s_tap,
+                         float* dbias, void* stream);
+/* Backward of v = act(norm(x)): mode 0 InstanceNorm2d(affine=False) (networks.py:26), 1 train-mode BatchNorm2d (BottleStack).
+ * stats = the forward (sum, sumsq) [B][C][2]; red = zeroed [B][C][2] scratch; dgamma / dbeta accumulated (mode 1, nullable). */
+int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
+                         const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int HW, int C, void* stream);
+/* g = dy * act'(y) from the activated value y (epilogue LeakyReLU / tanh, plain ReLU views) */
+int mdctgan_act_bwd(const float* dy, const float* y, float* g, int64_t n, int act, void* stream);
+int mdctgan_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+/* nn.ReflectionPad2d backward: dpad [B,H+2p,W+2p,C] -> dx [B,H,W,C] */
+int mdctgan_reflect_pad_bwd(const float* dpad, float* dx, int B, int H, int W, int C, int pad, void* stream);
+int mdctgan_avgpool3s2_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);
+/* backward of mdctgan_attention_abs_pos: dqkv [B,L,3*heads*d] written, demb_h / demb_w accumulated (nullable) */
+int mdctgan_attention_abs_pos_bwd(const float* qkv, const float* emb_h, const float* emb_w, const float* dout, float* dqkv, float* demb_h,
+                                   float* demb_w, int B, int Hh, int Ww, int heads, int d, float scale, void* stream);
+/* GANLoss, LSGAN branch (networks.py:127-137): *slot += coef * sum((x - target)^2); g (+)= 2*coef*(*gscale)*(x - target) */
+int mdctgan_mse_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream);
+int mdctgan_mse_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream);
+/* feature matching (pix2pixHD_model.py:447-451): *slot += coef * sum|a - b|; g (+)= coef*(*gscale)*sign(a - b) */
+int mdctgan_l1_pair_fwd(const float* a, const float* b, int64_t n, double coef, double* slot, void* stream);
+int mdctgan_l1_pair_bwd(const float* a, const float* b, int64_t n, float coef, const float* gscale, float* g, int accumulate, void* stream);
+int mdctgan_f64_to_f32(const double* a, float* y, int n, void* stream);
+/* cat(lr_spectro, s, |s|*2+lo) (pix2pixHD_model.py:369,420-427) as NHWC [clips*per_clip][3]; backward ds = g1 + 2 sign(s) g2 */
+int mdctgan_disc_input_fwd(const float* lr, int64_t lr_clip_stride, const float* s, float* out, int64_t clips, int64_t per_clip, float lo,
+                           void* stream);
+int mdctgan_disc_input_bwd(const float* g, const float* s, float* ds, int64_t n, void* stream);
+/* torch.optim.Adam (pix2pixHD_model.py:350-364; no weight decay) on one flat fp32 buffer; g is multiplied by grad_scale
+ * (1/world after the all-reduce).  step: 1-based, or read from step_dev when non-NULL (CUDA-graph replays). */
+int mdctgan_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
+int mdctgan_counter_inc(int64_t* counter_dev, void* stream);
+
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);
 

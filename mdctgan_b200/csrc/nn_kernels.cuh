@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
 // lanes split the channels in float4, shuffle-reduce.  Optional residual add after the activation
 // (fit_residual: sr = tanh(conv) ... + lr handled by the caller) is not fused here.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
+static __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
   extern __shared__ float s_w[];   // [kh*kw*Cin] weights, then scale/shift [Cin] x2 when normalising
   const int K = p.kh * p.kw * p.Cin;
   float* s_scale = s_w + K;
@@ -325,7 +325,7 @@ struct NormFinalizeParams {
   float* scale; float* shift;                    // out: [B][C] (instance) or [C] (batch)
 };
 
-__global__ void norm_finalize_kernel(const NormFinalizeParams p) {
+static __global__ void norm_finalize_kernel(const NormFinalizeParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (p.batch_norm == 0) {
     if (i >= p.B * p.C) return;
@@ -372,7 +372,7 @@ struct ApplyParams {
 
 // grid = (chunks per sample, B): a block stays inside one sample so the (possibly statistics-derived) scale / shift
 // of that sample sit in shared memory
-__global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
+static __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
   __shared__ float sa[2][1024], sb[2][1024];
   const int bi = blockIdx.y;
   const bool na = p.na.scale != nullptr || p.na.stats != nullptr;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const ApplyParams p) {
 // ------------------------------------------------------------------------------------------------
 // AvgPool2d(3, stride 2, padding 1, count_include_pad=False) on NHWC (networks.py:249-250, :525-526)
 // ------------------------------------------------------------------------------------------------
-__global__ void avgpool3s2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+static __global__ void avgpool3s2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
   const size_t total = (size_t)B * Ho * Wo * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) attention_abs_pos_kernel(const AttnParams
 // Inference residual of --fit_residual (pix2pixHD_model.py:631-635):
 //   sr[..., :lr_bins] *= low_scale (1e-3);  sr += lr          on [rows, nbins] fp32 (rows = B*F)
 // ------------------------------------------------------------------------------------------------
-__global__ void residual_scale_add_kernel(const float* __restrict__ sr, const float* __restrict__ lr, int64_t lr_row_stride,
+static __global__ void residual_scale_add_kernel(const float* __restrict__ sr, const float* __restrict__ lr, int64_t lr_row_stride,
                                           float* __restrict__ y, int64_t rows, int nbins, int lr_bins, float low_scale) {
   const size_t total = (size_t)rows * nbins;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -539,7 +539,7 @@ __global__ void residual_scale_add_kernel(const float* __restrict__ sr, const fl
 }
 
 // NCHW <-> NHWC (network boundary: the reference's modules take / return NCHW tensors)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
+static __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
   const size_t total = (size_t)B * C * HW;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -549,7 +549,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
     y[i] = __ldg(x + ((size_t)b * C + c) * HW + pix);
   }
 }
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
+static __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW) {
   const size_t total = (size_t)B * C * HW;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int pix = (int)(i % HW);

@@ -1,0 +1,265 @@
+// train_capi.cu -- C ABI of the train-step kernels (include/mdctgan_b200.h, "train step").
+#include <cstdio>
+
+#include "../../include/mdctgan_b200.h"
+#include "train_kernels.cuh"
+
+using namespace trk;
+
+int mdctgan_set_error(int code, const char* fmt, ...);   // capi.cu
+void mdctgan_count_launch();                              // capi.cu
+
+#define CKT(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) return mdctgan_set_error((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const float* dy, int Ho, int Wo, int Cout, int kh, int kw, int stride,
+                         int pad, int pad_mode, int transposed, const float* in_scale, const float* in_shift, int in_per_sample, int in_act,
+                         const double* in_stats, double in_count, float in_eps, float* dw, int64_t s_co, int64_t s_ci, int64_t s_tap,
+                         float* dbias, void* stream) {
+  if (!x || !dy || !dw) return mdctgan_set_error(-1, "conv2d_wgrad: NULL buffer");
+  if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+    return mdctgan_set_error(-1, "conv2d_wgrad: bad shape");
+  if (Cin > 1024) return mdctgan_set_error(-2, "conv2d_wgrad: Cin %d > 1024 unsupported", Cin);
+  if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_wgrad: in_scale / in_shift must come together");
+  if (in_stats && (in_scale || !in_per_sample || in_count <= 0))
+    return mdctgan_set_error(-1, "conv2d_wgrad: in_stats is the InstanceNorm2d form (per sample, count > 0, no in_scale)");
+  if (B == 0) return 0;
+  WgradParams p{};
+  p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.dy = dy; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
+  p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
+  p.in.stats = in_stats; p.in.count = (float)in_count; p.in.eps = in_eps;
+  p.dw = dw; p.s_co = s_co; p.s_ci = s_ci; p.s_tap = s_tap; p.dbias = dbias;
+  const int K = kh * kw * Cin, HWo = Ho * Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout <= 4) {
+    const int kblocks = (K + 255) / 256;
+    int chunks = (296 + kblocks * B - 1) / (kblocks * B);
+    const int max_chunks = (HWo + 255) / 256;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    p.pix_per_chunk = ((HWo + chunks - 1) / chunks + 15) / 16 * 16;
+    p.chunks_per_sample = (HWo + p.pix_per_chunk - 1) / p.pix_per_chunk;
+    if ((long long)B * p.chunks_per_sample > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
+    conv_wgrad_small_cout_kernel<<<dim3(kblocks, B * p.chunks_per_sample), 256, 0, st>>>(p);
+  } else {
+    const int k_tiles = (K + 63) / 64;
+    p.n_tiles = (Cout + 63) / 64;
+    const int tiles = k_tiles * p.n_tiles;
+    int chunks = (296 + tiles * B - 1) / (tiles * B);
+    const int max_chunks = (HWo + 63) / 64;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    p.pix_per_chunk = ((HWo + chunks - 1) / chunks + 15) / 16 * 16;
+    p.chunks_per_sample = (HWo + p.pix_per_chunk - 1) / p.pix_per_chunk;
+    if ((long long)B * p.chunks_per_sample > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
+    conv_wgrad_kernel<<<dim3(tiles, B * p.chunks_per_sample), 256, 0, st>>>(p);
+  }
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
+                         const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int HW, int C, void* stream) {
+  if (!x || !dv || !dx || !stats || !red) return mdctgan_set_error(-1, "norm_act_bwd: NULL buffer");
+  if (mode != 0 && mode != 1) return mdctgan_set_error(-1, "norm_act_bwd: mode %d (0 InstanceNorm2d, 1 train-mode BatchNorm2d)", mode);
+  if (C % 4 || C > 1024) return mdctgan_set_error(-2, "norm_act_bwd: C %d must be a multiple of 4, <= 1024", C);
+  if (act == kActTanh) return mdctgan_set_error(-2, "norm_act_bwd: tanh after a normalisation is not a reference configuration");
+  if (B == 0 || HW == 0) return 0;
+  if (B > 65535) return mdctgan_set_error(-2, "norm_act_bwd: batch %d > 65535", B);
+  NormBwdParams p{x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, C, B};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int groups = C / 4, pstep = 256 / groups;
+  int chunks = (HW + pstep - 1) / pstep;
+  const int cap = (148 * 4 + B - 1) / B;
+  if (chunks > cap) chunks = cap;
+  norm_bwd_reduce_kernel<<<dim3(chunks, B), 256, 0, st>>>(p);
+  mdctgan_count_launch();
+  const size_t per_sample4 = (size_t)HW * C / 4;
+  int chunks2 = (int)((per_sample4 + 255) / 256);
+  const int cap2 = (148 * 8 + B - 1) / B;
+  if (chunks2 > cap2) chunks2 = cap2;
+  norm_bwd_apply_kernel<<<dim3(chunks2, B), 256, 0, st>>>(p);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_act_bwd(const float* dy, const float* y, float* g, int64_t n, int act, void* stream) {
+  if (!dy || !y || !g) return mdctgan_set_error(-1, "act_bwd: NULL buffer");
+  if (n <= 0) return 0;
+  act_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, g, (size_t)n, act);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_add(const float* a, const float* b, float* y, int64_t n, void* stream) {
+  if (!a || !b || !y) return mdctgan_set_error(-1, "add: NULL buffer");
+  if (n <= 0) return 0;
+  add_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, (size_t)n);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_reflect_pad_bwd(const float* dpad, float* dx, int B, int H, int W, int C, int pad, void* stream) {
+  if (!dpad || !dx) return mdctgan_set_error(-1, "reflect_pad_bwd: NULL buffer");
+  if (pad < 0 || pad >= H || pad >= W) return mdctgan_set_error(-1, "reflect_pad_bwd: pad %d vs %dx%d", pad, H, W);
+  const size_t total = (size_t)B * H * W * C;
+  if (!total) return 0;
+  reflect_fold_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpad, dx, B, H, W, C, pad);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_avgpool3s2_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  if (!dy || !dx) return mdctgan_set_error(-1, "avgpool_bwd: NULL buffer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * H * W * C;
+  if (!total) return 0;
+  avgpool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, H, W, C, Ho, Wo);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_attention_abs_pos_bwd(const float* qkv, const float* emb_h, const float* emb_w, const float* dout, float* dqkv, float* demb_h,
+                                   float* demb_w, int B, int Hh, int Ww, int heads, int d, float scale, void* stream) {
+  if (!qkv || !emb_h || !emb_w || !dout || !dqkv) return mdctgan_set_error(-1, "attention_bwd: NULL buffer");
+  const int L = Hh * Ww;
+  if (d % 32 || d > 128) return mdctgan_set_error(-2, "attention_bwd: dim_head %d must be a multiple of 32, <= 128", d);
+  if (L > 256) return mdctgan_set_error(-2, "attention_bwd: %d tokens > 256 unsupported", L);
+  const size_t smem = (2 * (size_t)L * (d + 1) + 2 * (size_t)L * d + 16 * (size_t)d) * sizeof(float);
+  if (smem > 227 * 1024) return mdctgan_set_error(-2, "attention_bwd: %zu bytes of shared memory needed (L=%d, d=%d)", smem, L, d);
+  if (B == 0) return 0;
+  AttnBwdParams p{qkv, emb_h, emb_w, dout, dqkv, demb_h, demb_w, B, Hh, Ww, heads, d, scale};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kpl = (L + 31) / 32;
+#define LAUNCH_ATTN_BWD(K)                                                                                             \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      CKT(cudaFuncSetAttribute(attention_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    attention_bwd_kernel<K><<<B * heads, 256, smem, st>>>(p);                                                          \
+  } while (0)
+  if (kpl <= 1) LAUNCH_ATTN_BWD(1);
+  else if (kpl <= 2) LAUNCH_ATTN_BWD(2);
+  else if (kpl <= 4) LAUNCH_ATTN_BWD(4);
+  else LAUNCH_ATTN_BWD(8);
+#undef LAUNCH_ATTN_BWD
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_mse_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream) {
+  if (!x || !slot) return mdctgan_set_error(-1, "mse_const_fwd: NULL buffer");
+  if (n <= 0) return 0;
+  int g = grid_for((size_t)n, 256 * 8);
+  mse_const_fwd_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, target, coef, slot);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_mse_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream) {
+  if (!x || !g) return mdctgan_set_error(-1, "mse_const_bwd: NULL buffer");
+  if (n <= 0) return 0;
+  mse_const_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, target, coef, gscale, g, accumulate);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_l1_pair_fwd(const float* a, const float* b, int64_t n, double coef, double* slot, void* stream) {
+  if (!a || !b || !slot) return mdctgan_set_error(-1, "l1_pair_fwd: NULL buffer");
+  if (n <= 0) return 0;
+  l1_pair_fwd_kernel<<<grid_for((size_t)n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, coef, slot);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_l1_pair_bwd(const float* a, const float* b, int64_t n, float coef, const float* gscale, float* g, int accumulate, void* stream) {
+  if (!a || !b || !g) return mdctgan_set_error(-1, "l1_pair_bwd: NULL buffer");
+  if (n <= 0) return 0;
+  l1_pair_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)n, coef, gscale, g, accumulate);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_f64_to_f32(const double* a, float* y, int n, void* stream) {
+  if (!a || !y) return mdctgan_set_error(-1, "f64_to_f32: NULL buffer");
+  if (n <= 0) return 0;
+  f64_to_f32_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, y, n);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_disc_input_fwd(const float* lr, int64_t lr_clip_stride, const float* s, float* out, int64_t clips, int64_t per_clip, float lo,
+                           void* stream) {
+  if (!lr || !s || !out) return mdctgan_set_error(-1, "disc_input_fwd: NULL buffer");
+  const size_t total = (size_t)clips * per_clip;
+  if (!total) return 0;
+  disc_input_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(lr, lr_clip_stride, s, out, clips, per_clip, lo);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_disc_input_bwd(const float* g, const float* s, float* ds, int64_t n, void* stream) {
+  if (!g || !s || !ds) return mdctgan_set_error(-1, "disc_input_bwd: NULL buffer");
+  if (n <= 0) return 0;
+  disc_input_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(g, s, ds, (size_t)n);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float grad_scale, int64_t step, const int64_t* step_dev, void* stream) {
+  if (!p || !g || !m || !v) return mdctgan_set_error(-1, "adam_flat: NULL buffer");
+  if (!step_dev && step < 1) return mdctgan_set_error(-1, "adam_flat: step %lld (1-based)", (long long)step);
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return mdctgan_set_error(-1, "adam_flat: buffers must be 16-byte aligned");
+  if (n <= 0) return 0;
+  AdamParams a{p, g, m, v, (size_t)n, lr, beta1, beta2, eps, grad_scale, 1.f, 1.f, (const long long*)step_dev};
+  if (!step_dev) {
+    a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  }
+  const int grid = grid_for((size_t)n / 4 + 1, 256);
+  adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
+  if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
+  counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,629 @@
+// train_kernels.cuh -- backward / loss / optimiser kernels of the GAN train step (sm_100a, fp32).
+//
+// Reference graph (all through torch autograd there): models/pix2pixHD_model.py:416-451 (_forward: three
+// discriminator passes, LSGAN + feature-matching losses), train.py:175-202 (loss_G / loss_D backward, two Adam
+// steps), models/networks.py:97-137 (GANLoss).  What autograd derives there is written out here:
+//
+//   conv_wgrad_kernel      dW, dbias of nn.Conv2d / nn.ConvTranspose2d: implicit GEMM  dW[k][co] = sum_m A[m][k]*dY[m][co]
+//                          with A gathered exactly like the forward kernels do (reflection / zero padding, stride,
+//                          transposed taps, the producer's deferred InstanceNorm / BatchNorm + activation), written with
+//                          float atomics straight into the parameter-layout gradient buffer (the flat NCCL bucket).
+//                          (dgrad needs no kernel of its own: it is the forward convolution on the transposed geometry
+//                          with the same weights, nn_kernels.cuh / conv_umma.cuh.)
+//   norm_bwd_*             backward of  v = act(norm(x))  for InstanceNorm2d(affine=False) and train-mode BatchNorm2d
+//   act_bwd_kernel         backward of an epilogue activation (LeakyReLU of the first PatchGAN layer, tanh head)
+//   reflect_fold_kernel    backward of nn.ReflectionPad2d
+//   avgpool3s2_bwd_kernel  backward of AvgPool2d(3, 2, 1, count_include_pad=False)
+//   attention_bwd_kernel   backward of the BoTNet attention (abs. position embedding)
+//   mse_const_* / l1_pair_*   LSGAN (networks.py:127-137) and feature matching (pix2pixHD_model.py:447-451)
+//   disc_input_*           cat(lr, s, |s|*2+lo) (pix2pixHD_model.py:420-427, :369) written directly as NHWC, and its backward
+//   adam_flat_kernel       torch.optim.Adam (pix2pixHD_model.py:350-364) over one flat buffer
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nn_kernels.cuh"
+
+namespace trk {
+using nnk::InputNorm;
+using nnk::apply_act;
+using nnk::in_coord;
+using nnk::kActLeaky;
+using nnk::kActNone;
+using nnk::kActRelu;
+using nnk::kActTanh;
+
+__device__ __forceinline__ float act_grad_from_pre(float pre, int act) {   // d act(pre) / d pre   (ReLU / LeakyReLU / none)
+  if (act == kActRelu) return pre > 0.f ? 1.f : 0.f;
+  if (act == kActLeaky) return pre > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {     // same, from the activated value
+  if (act == kActTanh) return 1.f - y * y;
+  return act_grad_from_pre(y, act);   // ReLU / LeakyReLU keep the sign
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient.  grid = (k_tiles * n_tiles, B * chunks_per_sample); 256 threads; tile 64 (k) x 64 (co),
+// 4x4 per thread; the reduction dimension (pixels of one sample chunk) is walked 16 at a time.
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  const float* x; int B, H, W, Cin;
+  InputNorm in;
+  const float* dy; int Ho, Wo, Cout;
+  int kh, kw, stride, pad, pad_mode, transposed;
+  float* dw; long long s_co, s_ci, s_tap;   // element offset of dW[co][ci][tap] in the parameter's own layout
+  float* dbias;
+  int n_tiles, chunks_per_sample, pix_per_chunk;
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
+  constexpr int TK = 64, TN = 64, MS = 16;
+  __shared__ __align__(16) float As[MS][TK + 4];
+  __shared__ __align__(16) float Bs[MS][TN];
+  __shared__ float s_scale[1024], s_shift[1024];
+  const int tid = threadIdx.x;
+  const int kt = blockIdx.x / p.n_tiles, nt = blockIdx.x - kt * p.n_tiles;
+  const int b = blockIdx.y / p.chunks_per_sample;
+  const int chunk = blockIdx.y - b * p.chunks_per_sample;
+  const int HWo = p.Ho * p.Wo;
+  const int m_begin = chunk * p.pix_per_chunk;
+  const int m_end = min(HWo, m_begin + p.pix_per_chunk);
+  const int K = p.kh * p.kw * p.Cin;
+  const int k0 = kt * TK, n0 = nt * TN;
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  if (has_norm) nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
+  __syncthreads();
+  if (m_begin >= m_end) return;
+
+  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+  const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
+  const bool vec_a = (p.Cin % 4) == 0;
+  const bool vec_b = (p.Cout % 4) == 0;
+  // A-load role: pixel slot pm, 4 consecutive k starting at kq (loop invariant -> tap decode hoisted)
+  const int pm = tid >> 4, kq = (tid & 15) * 4;
+  int a_ky[4], a_kx[4], a_c[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = k0 + kq + u;
+    if (k < K) {
+      const int tap = k / p.Cin;
+      a_c[u] = k - tap * p.Cin;
+      a_ky[u] = tap / p.kw;
+      a_kx[u] = tap - a_ky[u] * p.kw;
+    } else { a_c[u] = -1; a_ky[u] = 0; a_kx[u] = 0; }
+  }
+  const int nq = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int mb = m_begin; mb < m_end; mb += MS) {
+    const int m = mb + pm;
+    float va[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < m_end) {
+      const int oy = m / p.Wo, ox = m - oy * p.Wo;
+      if (vec_a) {
+        if (a_c[0] >= 0) {
+          const int iy = in_coord(oy, a_ky[0], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+          const int ix = in_coord(ox, a_kx[0], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+          if (iy >= 0 && ix >= 0) {
+            const int c = a_c[0];
+            const float4 q = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix) * p.Cin + c));
+            va[0] = q.x; va[1] = q.y; va[2] = q.z; va[3] = q.w;
+            if (has_norm) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) va[u] = apply_act(fmaf(va[u], s_scale[c + u], s_shift[c + u]), p.in.act);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (a_c[u] >= 0) {
+            const int iy = in_coord(oy, a_ky[u], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+            const int ix = in_coord(ox, a_kx[u], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+            if (iy >= 0 && ix >= 0) {
+              float t = __ldg(xb + ((size_t)iy * p.W + ix) * p.Cin + a_c[u]);
+              if (has_norm) t = apply_act(fmaf(t, s_scale[a_c[u]], s_shift[a_c[u]]), p.in.act);
+              va[u] = t;
+            }
+          }
+        }
+      }
+      const int n = n0 + nq;
+      const float* dr = dyb + (size_t)m * p.Cout + n;
+      if (vec_b && n + 3 < p.Cout) {
+        vb = __ldg(reinterpret_cast<const float4*>(dr));
+      } else {
+        if (n + 0 < p.Cout) vb.x = __ldg(dr + 0);
+        if (n + 1 < p.Cout) vb.y = __ldg(dr + 1);
+        if (n + 2 < p.Cout) vb.z = __ldg(dr + 2);
+        if (n + 3 < p.Cout) vb.w = __ldg(dr + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(&As[pm][kq]) = make_float4(va[0], va[1], va[2], va[3]);
+    *reinterpret_cast<float4*>(&Bs[pm][nq]) = vb;
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < MS; ++mm) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
+      if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bsum[j] += bw[j];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+    const int tap = k / p.Cin, ci = k - tap * p.Cin;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co < p.Cout) atomicAdd(p.dw + (long long)co * p.s_co + (long long)ci * p.s_ci + (long long)tap * p.s_tap, acc[i][j]);
+    }
+  }
+  if (p.dbias && kt == 0 && ty == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co < p.Cout) atomicAdd(p.dbias + co, bsum[j]);
+    }
+  }
+}
+
+// Cout <= 4 layers (generator head 7x7 -> 1, PatchGAN heads 4x4 -> 1): dW[k][co] = sum_m A[m][k] * dy[m][co].
+// grid = (ceil(K / 256), B * chunks); each thread owns one k, walks the chunk's pixels (dy broadcast from shared memory).
+__global__ void __launch_bounds__(256) conv_wgrad_small_cout_kernel(const WgradParams p) {
+  __shared__ float s_scale[1024], s_shift[1024];
+  __shared__ float s_dy[256][4];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y / p.chunks_per_sample;
+  const int chunk = blockIdx.y - b * p.chunks_per_sample;
+  const int HWo = p.Ho * p.Wo;
+  const int m_begin = chunk * p.pix_per_chunk;
+  const int m_end = min(HWo, m_begin + p.pix_per_chunk);
+  const int K = p.kh * p.kw * p.Cin;
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  if (has_norm) nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
+  const int k = blockIdx.x * 256 + tid;
+  int ky = 0, kx = 0, c = -1;
+  if (k < K) { const int tap = k / p.Cin; c = k - tap * p.Cin; ky = tap / p.kw; kx = tap - ky * p.kw; }
+  __syncthreads();
+  const float a_s = (has_norm && c >= 0) ? s_scale[c] : 1.f, a_t = (has_norm && c >= 0) ? s_shift[c] : 0.f;
+  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+  const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int mb = m_begin; mb < m_end; mb += 256) {
+    const int mload = mb + tid;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_dy[tid][j] = (mload < m_end && j < p.Cout) ? __ldg(dyb + (size_t)mload * p.Cout + j) : 0.f;
+    __syncthreads();
+    const int cnt = min(256, m_end - mb);
+    if (c >= 0) {
+      int oy = mb / p.Wo, ox = mb - oy * p.Wo;
+      for (int t = 0; t < cnt; ++t) {
+        const int iy = in_coord(oy, ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+        const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+        if (iy >= 0 && ix >= 0) {
+          float v = __ldg(xb + ((size_t)iy * p.W + ix) * p.Cin + c);
+          if (has_norm) v = apply_act(fmaf(v, a_s, a_t), p.in.act);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, s_dy[t][j], acc[j]);
+        }
+        if (++ox == p.Wo) { ox = 0; ++oy; }
+      }
+    }
+    if (p.dbias && blockIdx.x == 0 && tid < 4) {
+      for (int t = 0; t < cnt; ++t) bsum[0] += s_dy[t][tid];
+    }
+    __syncthreads();
+  }
+  if (c >= 0) {
+    const int tap = k / p.Cin;
+    for (int j = 0; j < p.Cout; ++j) atomicAdd(p.dw + (long long)j * p.s_co + (long long)c * p.s_ci + (long long)tap * p.s_tap, acc[j]);
+  }
+  if (p.dbias && blockIdx.x == 0 && tid < p.Cout) atomicAdd(p.dbias + tid, bsum[0]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of v = act(norm(x)), norm = InstanceNorm2d(affine=False) (mode 0) or train-mode BatchNorm2d (mode 1):
+//   pre = (x - mean) * rstd * gamma + beta,  g = dv * act'(pre),  xhat = (x - mean) * rstd
+//   dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat))       (means over the plane / over batch x plane)
+// Pass 1 reduces (sum g, sum g*xhat) per (b, c); pass 2 applies.
+// ------------------------------------------------------------------------------------------------
+struct NormBwdParams {
+  const float* x; const float* dv; float* dx;
+  const double* stats; double count; float eps; int mode;
+  const float* gamma; const float* beta;
+  int act;
+  double* red;                 // [B][C][2]
+  float* dgamma; float* dbeta; // BatchNorm parameter gradients (accumulated), nullable
+  int B, HW, C, stats_B;       // stats_B: batch size the forward statistics were taken over (BatchNorm; >= B)
+};
+
+// mean / rstd (and the forward affine) of sample b into shared memory
+__device__ __forceinline__ void norm_bwd_coeffs(const NormBwdParams& p, int b, float* s_mean, float* s_rstd, float* s_gam, float* s_bet) {
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    double s = 0, q = 0, n = p.count;
+    if (p.mode == 0) { s = p.stats[2 * ((size_t)b * p.C + c)]; q = p.stats[2 * ((size_t)b * p.C + c) + 1]; }
+    else {
+      for (int bb = 0; bb < p.stats_B; ++bb) { s += p.stats[2 * ((size_t)bb * p.C + c)]; q += p.stats[2 * ((size_t)bb * p.C + c) + 1]; }
+      n = p.count * p.stats_B;
+    }
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[c] = (float)mean;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+    s_gam[c] = (p.mode == 1 && p.gamma) ? __ldg(p.gamma + c) : 1.f;
+    s_bet[c] = (p.mode == 1 && p.beta) ? __ldg(p.beta + c) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParams p) {
+  __shared__ float s_mean[1024], s_rstd[1024], s_gam[1024], s_bet[1024];
+  __shared__ float s_acc[2][1024];
+  const int b = blockIdx.y;
+  norm_bwd_coeffs(p, b, s_mean, s_rstd, s_gam, s_bet);
+  for (int c = threadIdx.x; c < p.C; c += 256) { s_acc[0][c] = 0.f; s_acc[1][c] = 0.f; }
+  __syncthreads();
+  const int groups = p.C / 4;                    // float4 channel groups; C <= 1024 -> groups <= 256
+  const int cg = threadIdx.x % groups, prow = threadIdx.x / groups, pstep = 256 / groups;
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (prow < pstep) {
+    const size_t base = (size_t)b * p.HW * p.C;
+    for (int pix = blockIdx.x * pstep + prow; pix < p.HW; pix += gridDim.x * pstep) {
+      const size_t e = base + (size_t)pix * p.C + cg * 4;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + e));
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + e));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = cg * 4 + u;
+        const float xhat = (xs[u] - s_mean[c]) * s_rstd[c];
+        const float g = ds[u] * act_grad_from_pre(fmaf(xhat, s_gam[c], s_bet[c]), p.act);
+        sg[u] += g; sq[u] += g * xhat;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { atomicAdd(&s_acc[0][cg * 4 + u], sg[u]); atomicAdd(&s_acc[1][cg * 4 + u], sq[u]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += 256) {
+    double* r = p.red + 2 * ((size_t)b * p.C + c);
+    atomicAdd(r, (double)s_acc[0][c]);
+    atomicAdd(r + 1, (double)s_acc[1][c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams p) {
+  __shared__ float s_mean[1024], s_rstd[1024], s_gam[1024], s_bet[1024];
+  __shared__ float s_mg[1024], s_mgx[1024];
+  const int b = blockIdx.y;
+  norm_bwd_coeffs(p, b, s_mean, s_rstd, s_gam, s_bet);
+  for (int c = threadIdx.x; c < p.C; c += 256) {
+    double sg = 0, sq = 0, n = p.count;
+    if (p.mode == 0) { sg = p.red[2 * ((size_t)b * p.C + c)]; sq = p.red[2 * ((size_t)b * p.C + c) + 1]; }
+    else {
+      for (int bb = 0; bb < p.B; ++bb) { sg += p.red[2 * ((size_t)bb * p.C + c)]; sq += p.red[2 * ((size_t)bb * p.C + c) + 1]; }
+      n = p.count * p.B;
+      if (blockIdx.x == 0 && b == 0) {
+        if (p.dgamma) atomicAdd(p.dgamma + c, (float)sq);
+        if (p.dbeta) atomicAdd(p.dbeta + c, (float)sg);
+      }
+    }
+    s_mg[c] = (float)(sg / n);
+    s_mgx[c] = (float)(sq / n);
+  }
+  __syncthreads();
+  const size_t per_sample4 = (size_t)p.HW * p.C / 4;
+  const size_t base = (size_t)b * p.HW * p.C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < per_sample4; i += (size_t)gridDim.x * 256) {
+    const size_t e = i * 4;
+    const int c0 = (int)(e % p.C);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + e));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + e));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u;
+      const float xhat = (xs[u] - s_mean[c]) * s_rstd[c];
+      const float g = ds[u] * act_grad_from_pre(fmaf(xhat, s_gam[c], s_bet[c]), p.act);
+      o[u] = s_gam[c] * s_rstd[c] * (g - s_mg[c] - xhat * s_mgx[c]);
+    }
+    *reinterpret_cast<float4*>(p.dx + base + e) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// g = dy * act'(y)  from the ACTIVATED value y (epilogue activations; also plain ReLU / LeakyReLU views)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g, size_t n, int act) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    g[i] = dy[i] * act_grad_from_out(y[i], act);
+}
+
+// y = a + b
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = a[i] + b[i];
+}
+
+// nn.ReflectionPad2d backward: dpad [B][H+2p][W+2p][C] -> dx [B][H][W][C] (every padded position has exactly one source)
+__global__ void reflect_fold_kernel(const float* __restrict__ dpad, float* __restrict__ dx, int B, int H, int W, int C, int pad) {
+  const size_t total = (size_t)B * H * W * C;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = iy;
+    if (iy >= 1 && iy <= pad) ys[ny++] = -iy;
+    if (H - 1 - iy >= 1 && H - 1 - iy <= pad) ys[ny++] = 2 * (H - 1) - iy;
+    xs[nx++] = ix;
+    if (ix >= 1 && ix <= pad) xs[nx++] = -ix;
+    if (W - 1 - ix >= 1 && W - 1 - ix <= pad) xs[nx++] = 2 * (W - 1) - ix;
+    float s = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int q = 0; q < nx; ++q) s += __ldg(dpad + (((size_t)b * Hp + ys[a] + pad) * Wp + xs[q] + pad) * C + c);
+    dx[i] = s;
+  }
+}
+
+// AvgPool2d(3, 2, 1, count_include_pad=False) backward
+__global__ void avgpool3s2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
+  const size_t total = (size_t)B * H * W * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    float s = 0.f;
+    for (int oy = (iy - 1 + 1) / 2; oy <= (iy + 1) / 2; ++oy) {      // windows [2oy-1, 2oy+1] containing iy
+      if (oy < 0 || oy >= Ho || 2 * oy - 1 > iy || 2 * oy + 1 < iy) continue;
+      const int ny = min(2 * oy + 1, H - 1) - max(2 * oy - 1, 0) + 1;
+      for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Wo || 2 * ox - 1 > ix || 2 * ox + 1 < ix) continue;
+        const int nx = min(2 * ox + 1, W - 1) - max(2 * ox - 1, 0) + 1;
+        s += __ldg(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c) / (float)(ny * nx);
+      }
+    }
+    dx[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BoTNet attention backward.  One CTA per (sample, head); K+emb, V and the column accumulators dV, dKp in shared
+// memory; one warp per query row recomputes the softmax row.  dqkv [B][L][3C]; demb_h / demb_w accumulated.
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  const float* qkv; const float* emb_h; const float* emb_w; const float* dout;
+  float* dqkv; float* demb_h; float* demb_w;
+  int B, Hh, Ww, heads, d; float scale;
+};
+
+template <int KPL>
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdParams p) {
+  extern __shared__ float sm[];
+  const int L = p.Hh * p.Ww, d = p.d, C = p.heads * d;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  float* Kp = sm;                        // [L][d+1]
+  float* V = Kp + (size_t)L * (d + 1);   // [L][d+1]
+  float* dKp = V + (size_t)L * (d + 1);  // [L][d]
+  float* dV = dKp + (size_t)L * d;       // [L][d]
+  float* rows = dV + (size_t)L * d;      // [8 warps][2][d]: scaled q row, dO row
+  const float* base = p.qkv + (size_t)b * L * 3 * C;
+  for (int i = threadIdx.x; i < L * d; i += 256) {
+    const int j = i / d, dd = i - j * d;
+    const int y = j / p.Ww, x = j - y * p.Ww;
+    const float* tok = base + (size_t)j * 3 * C + h * d + dd;
+    Kp[j * (d + 1) + dd] = __ldg(tok + C) + __ldg(p.emb_h + y * d + dd) + __ldg(p.emb_w + x * d + dd);
+    V[j * (d + 1) + dd] = __ldg(tok + 2 * C);
+    dKp[i] = 0.f; dV[i] = 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = rows + warp * 2 * d;
+  float* go = q + d;
+  const int dpl = d / 32;
+  for (int i = warp; i < L; i += 8) {
+    for (int dd = lane; dd < d; dd += 32) {
+      q[dd] = __ldg(base + (size_t)i * 3 * C + h * d + dd) * p.scale;
+      go[dd] = __ldg(p.dout + ((size_t)b * L + i) * C + h * d + dd);
+    }
+    __syncwarp();
+    float sc[KPL], dp[KPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+      const int j = lane + 32 * u;
+      float a = -INFINITY, t = 0.f;
+      if (j < L) {
+        a = 0.f;
+        const float* kr = Kp + j * (d + 1);
+        const float* vr = V + j * (d + 1);
+        for (int dd = 0; dd < d; ++dd) { a = fmaf(q[dd], kr[dd], a); t = fmaf(go[dd], vr[dd], t); }
+      }
+      sc[u] = a; dp[u] = t;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) { sc[u] = (lane + 32 * u < L) ? __expf(sc[u] - mx) : 0.f; sum += sc[u]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) { sc[u] *= inv; dot += sc[u] * dp[u]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    float ds[KPL];
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) ds[u] = sc[u] * (dp[u] - dot);
+    // dq_i = scale * sum_j ds_ij Kp_j ; dV_j += p_ij dO_i ; dKp_j += ds_ij q_i
+    float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+      for (int l = 0; l < 32; ++l) {
+        const int j = l + 32 * u;
+        if (j >= L) break;
+        const float pj = __shfl_sync(0xffffffffu, sc[u], l);
+        const float dj = __shfl_sync(0xffffffffu, ds[u], l);
+        for (int t = 0; t < dpl; ++t) {
+          const int dd = lane + 32 * t;
+          dq[t] = fmaf(dj, Kp[j * (d + 1) + dd], dq[t]);
+          atomicAdd(&dV[j * d + dd], pj * go[dd]);
+          atomicAdd(&dKp[j * d + dd], dj * q[dd]);
+        }
+      }
+    }
+    for (int t = 0; t < dpl; ++t) p.dqkv[((size_t)b * L + i) * 3 * C + h * d + lane + 32 * t] = dq[t] * p.scale;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * d; i += 256) {
+    const int j = i / d, dd = i - j * d;
+    float* tok = p.dqkv + ((size_t)b * L + j) * 3 * C + h * d + dd;
+    tok[C] = dKp[i];
+    tok[2 * C] = dV[i];
+    const int y = j / p.Ww, x = j - y * p.Ww;
+    if (p.demb_h) atomicAdd(p.demb_h + y * d + dd, dKp[i]);
+    if (p.demb_w) atomicAdd(p.demb_w + x * d + dd, dKp[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Losses.  Forward kernels add  coef * sum(...)  into a double slot; backward kernels write (or accumulate)
+// coef * (*gscale) * d/dx.  `gscale` is the upstream gradient of the 0-dim loss tensor (device scalar, nullable = 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v) {
+  __shared__ double s_part[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+  if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) t += s_part[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) mse_const_fwd_kernel(const float* __restrict__ x, size_t n, float target, double coef, double* slot) {
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) { const float e = x[i] - target; s = fmaf(e, e, s); }
+  const double t = block_sum_256((double)s);
+  if (threadIdx.x == 0) atomicAdd(slot, coef * t);
+}
+__global__ void mse_const_bwd_kernel(const float* __restrict__ x, size_t n, float target, float coef, const float* __restrict__ gscale,
+                                     float* __restrict__ g, int accumulate) {
+  const float k = 2.f * coef * (gscale ? __ldg(gscale) : 1.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = k * (x[i] - target);
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
+__global__ void __launch_bounds__(256) l1_pair_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double coef, double* slot) {
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s += fabsf(a[i] - b[i]);
+  const double t = block_sum_256((double)s);
+  if (threadIdx.x == 0) atomicAdd(slot, coef * t);
+}
+__global__ void l1_pair_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float coef, const float* __restrict__ gscale,
+                                   float* __restrict__ g, int accumulate) {
+  const float k = coef * (gscale ? __ldg(gscale) : 1.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float e = a[i] - b[i];
+    const float v = e > 0.f ? k : (e < 0.f ? -k : 0.f);
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ a, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (float)a[i];
+}
+
+// cat(lr, s, |s|*2 + lo) as NHWC [rows][nbins][3]   (lr rows may sit in a wider tensor: row stride in elements)
+__global__ void disc_input_fwd_kernel(const float* __restrict__ lr, int64_t lr_clip_stride, const float* __restrict__ s, float* __restrict__ out,
+                                      int64_t clips, int64_t per_clip, float lo) {
+  const size_t total = (size_t)clips * per_clip;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / per_clip, r = i - b * per_clip;
+    const float v = s[i];
+    out[3 * i + 0] = lr[b * lr_clip_stride + r];
+    out[3 * i + 1] = v;
+    out[3 * i + 2] = fabsf(v) * 2.f + lo;
+  }
+}
+// ds = g[.,1] + 2 sign(s) g[.,2]
+__global__ void disc_input_bwd_kernel(const float* __restrict__ g, const float* __restrict__ s, float* __restrict__ ds, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = s[i];
+    const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+    ds[i] = g[3 * i + 1] + 2.f * sg * g[3 * i + 2];
+  }
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
+struct AdamParams {
+  float* p; const float* g; float* m; float* v; size_t n;
+  float lr, beta1, beta2, eps, grad_scale, bias_c1, bias_c2_sqrt;
+  const long long* step_dev;   // optional: 1-based step counter in device memory (CUDA-graph replays), overrides bias_c*
+};
+__global__ void counter_inc_kernel(long long* c) { *c += 1; }
+__global__ void __launch_bounds__(256) adam_flat_kernel(AdamParams a) {
+  if (a.step_dev) {
+    const double t = (double)*a.step_dev;
+    a.bias_c1 = (float)(1.0 - pow((double)a.beta1, t));
+    a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, t));
+  }
+  const float step_size = a.lr / a.bias_c1;
+  const size_t n4 = a.n / 4;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 p = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g.x, g.y, g.z, g.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gr = gg[u] * a.grad_scale;
+      mm[u] = mm[u] + (gr - mm[u]) * (1.f - a.beta1);               // exp_avg.lerp_(grad, 1 - beta1)
+      vv[u] = vv[u] * a.beta2 + (1.f - a.beta2) * gr * gr;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(vv[u]) / a.bias_c2_sqrt + a.eps;
+      pp[u] = pp[u] - step_size * (mm[u] / denom);
+    }
+    reinterpret_cast<float4*>(a.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(a.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (size_t i = n4 * 4; i < a.n; ++i) {
+      const float gr = a.g[i] * a.grad_scale;
+      const float m = a.m[i] + (gr - a.m[i]) * (1.f - a.beta1);
+      const float v = a.v[i] * a.beta2 + (1.f - a.beta2) * gr * gr;
+      a.m[i] = m; a.v[i] = v;
+      a.p[i] = a.p[i] - step_size * (m / (sqrtf(v) / a.bias_c2_sqrt + a.eps));
+    }
+  }
+}
+
+}  // namespace trk

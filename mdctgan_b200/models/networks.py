@@ -39,7 +39,7 @@ class _PackedWeight:
         self._val = None
 
     def get(self, p: torch.Tensor, fn):
-        key = (p.data_ptr(), p._version, p.device)
+        key = (p.data_ptr(), p._version, getattr(p, "_version_bump", 0), p.device)   # _version_bump: FusedAdam.step (optim.py)
         if key != self._key:
             self._val = fn(p)
             self._key = key
@@ -72,7 +72,22 @@ class Conv2d(nn.Conv2d):
         if pad_reflect and self.padding[0]:
             raise RuntimeError("ReflectionPad2d in front of a zero-padded convolution is not a reference configuration")
         return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=pad, pad_mode=mode, act=act,
-                          want_stats=want_stats, w_umma=self.packed_umma())
+                          want_stats=want_stats, w_umma=self.packed_umma(), owner=self)
+
+    def packed_dgrad(self):
+        """(weights of the input-gradient convolution [kh*kw*Cout][Cin], their tcgen05 image or None, flipped).
+        stride 1: a plain convolution with the taps flipped; stride > 1: the transposed-geometry kernels."""
+        flipped = self.stride[0] == 1
+        if not hasattr(self, "_pkd"):
+            self._pkd, self._pkdu = _PackedWeight(), _PackedWeight()
+        if flipped:
+            wd = self._pkd.get(self.weight, lambda w: ops.pack_conv_weight(w.detach().permute(1, 0, 2, 3).flip(2, 3), False))
+        else:
+            wd = self._pkd.get(self.weight, lambda w: ops.pack_conv_weight(w, True))
+        wu = None
+        if ops.umma_supported(self.out_channels, self.in_channels):
+            wu = self._pkdu.get(self.weight, lambda w: ops.pack_conv_weight_umma(wd))
+        return wd, wu, flipped
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):
@@ -95,7 +110,18 @@ class ConvTranspose2d(nn.ConvTranspose2d):
         assert not pad_reflect
         kh, kw = self.kernel_size
         return ops.conv2d(f, self.packed(), self.bias, kh=kh, kw=kw, stride=self.stride[0], pad=self.padding[0], transposed=True,
-                          output_padding=self.output_padding[0], act=act, want_stats=want_stats, w_umma=self.packed_umma())
+                          output_padding=self.output_padding[0], act=act, want_stats=want_stats, w_umma=self.packed_umma(), owner=self)
+
+    def packed_dgrad(self):
+        """Input gradient of a ConvTranspose2d = plain strided convolution with the same weight tensor read as
+        [Cout_c = in_channels][Cin_c = out_channels][kh][kw]."""
+        if not hasattr(self, "_pkd"):
+            self._pkd, self._pkdu = _PackedWeight(), _PackedWeight()
+        wd = self._pkd.get(self.weight, lambda w: ops.pack_conv_weight(w, False))
+        wu = None
+        if ops.umma_supported(self.out_channels, self.in_channels):
+            wu = self._pkdu.get(self.weight, lambda w: ops.pack_conv_weight_umma(wd))
+        return wd, wu, False
 
 
 class InstanceNorm2d(nn.InstanceNorm2d):
@@ -459,6 +485,21 @@ class MultiscaleDiscriminator(nn.Module):
         if self.getIntermFeat:
             return [getattr(self, "scale" + str(i) + "_layer" + str(j)) for j in range(self.n_layers + 2)]
         return [getattr(self, "layer" + str(i))]
+
+    def run_features(self, f: Feat):
+        """Forward on a Feat (NHWC), as `forward` but staying on the device layout: list[num_D] of list[n_layers + 2]
+        Feats; the intermediate features are materialised (IN + LeakyReLU applied) because the feature-matching
+        loss reads them (pix2pixHD_model.py:447-451); the next stage still consumes the deferred view."""
+        result = []
+        for i in range(self.num_D):
+            outs, g = [], f
+            for st in self._stages(self.num_D - 1 - i):
+                g = run_layers(list(st), g)
+                outs.append(ops.materialize(g))
+            result.append(outs)
+            if i != self.num_D - 1:
+                f = ops.avgpool3s2(f)
+        return result
 
     def forward(self, input):
         with torch.no_grad(), ops.stats_pass(input.device):

@@ -200,7 +200,9 @@ class BaseModel(torch.nn.Module):
     def save_network(self, network, network_label, epoch_label, gpu_ids=None):
         """`<checkpoints_dir>/<name>/<epoch>_net_<label>.pth` = plain state_dict (base_model.py:43-46)."""
         os.makedirs(self.save_dir, exist_ok=True)
-        torch.save(network.state_dict(), os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label)))
+        # parameters are views into one flat buffer (optim.FlatBucket): clone so the file holds plain per-tensor storages
+        torch.save({k: v.detach().clone() for k, v in network.state_dict().items()},
+                   os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label)))
 
     def load_network(self, network, network_label, epoch_label, save_dir=""):
         """Three-level fallback of the reference (base_model.py:49-111): strict load -> keys present in the
@@ -234,9 +236,9 @@ class BaseModel(torch.nn.Module):
 
 
 class Pix2PixHDModel(BaseModel):
-    """Drop-in for the reference facade.  This round implements the inference graph (`inference`, and the
-    generator half of `forward`); the loss / optimiser half of `_forward` raises NotImplementedError
-    (DESIGN.md: next)."""
+    """Drop-in for the reference facade (models/pix2pixHD_model.py:203-714): `inference`, `forward`, `_forward` (the
+    four losses as differentiable 0-dim tensors), `optimizer_G` / `optimizer_D`, `save`, `update_learning_rate`;
+    plus `train_step` = the whole train.py:160-202 iteration as one call (what bench.py times)."""
 
     loss_names = ["G_GAN", "G_GAN_Feat", "D_real", "D_fake"]
 
@@ -267,6 +269,25 @@ class Pix2PixHDModel(BaseModel):
             if self.isTrain:
                 self.load_network(self.netD, "D", opt.which_epoch, pretrained_path)
         self._two_channel = bool(self.abs_spectro and self.arcsinh_transform)
+        if self.isTrain:
+            if opt.pool_size > 0 and len(self.gpu_ids) > 1:
+                raise NotImplementedError("Fake Pool Not Implemented for MultiGPU")
+            if opt.pool_size > 0:
+                raise NotImplementedError("--pool_size > 0 (image history buffer) is out of scope: identity at the reference default 0")
+            from ..optim import FlatBucket, FusedAdam
+
+            self.old_lr = opt.lr
+            self.limit_aux_loss = False
+            self.loss_names = [n for n in ["G_GAN", "G_GAN_Feat", "D_real", "D_fake"] if not (n == "G_GAN_Feat" and opt.no_ganFeat_loss)]
+            self.netG.to(self.device)
+            self.netD.to(self.device)
+            # every parameter becomes a view into one flat buffer per network; gradients likewise (the all-reduce bucket)
+            self.bucket_G, self.bucket_D = FlatBucket(self.netG), FlatBucket(self.netD)
+            if opt.niter_fix_global > 0:
+                raise NotImplementedError("--niter_fix_global > 0 (local-enhancer-only finetuning) is listed as next in DESIGN.md")
+            self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999))
+            self._graph = None
 
     # ---- generator graph ---------------------------------------------------------------------------------
     def _lr_input(self, lr_audio):
@@ -286,8 +307,72 @@ class Pix2PixHDModel(BaseModel):
         return sr_spectro, None, hr_spectro, hr_pha, hr_norm_param, lr_spectro, lr_pha, lr_norm_param
 
     def _forward(self, lr_audio, hr_audio, infer=False):
-        raise NotImplementedError("Pix2PixHDModel._forward (discriminator losses + backward) is not built in this round: "
-                                  "the sm_100a training kernels (dgrad / wgrad / norm backward / fused Adam) are next (DESIGN.md)")
+        """pix2pixHD_model.py:416-616: returns [[G_GAN, G_GAN_Feat, D_real, D_fake] (loss_filter order), sr_spectro or
+        None].  The losses are 0-dim CUDA tensors; `loss_G.backward()` / `loss_D.backward()` (train.py:185-201) run the
+        generator / discriminator backward sweeps of train_ops.GanGraph, which write straight into the flat gradient
+        buckets behind `optimizer_G` / `optimizer_D`."""
+        from .. import train_ops as T
+
+        if not self.isTrain:
+            raise RuntimeError("_forward needs a training model (opt.isTrain)")
+        graph = T.GanGraph(self)
+        with _ops.stats_pass(self.device):
+            graph.forward(lr_audio, hr_audio)
+        self._graph = graph
+        g_gan, g_feat, d_real, d_fake = T.loss_tensors(graph, self.bucket_G.params[0], self.bucket_D.params[0])
+        losses = [g_gan] + ([] if self.no_ganFeat_loss else [g_feat]) + [d_real, d_fake]
+        return [losses, None if not infer else graph.sr_spectro]
+
+    def train_step(self, lr_audio, hr_audio, world_size: int = 1, all_reduce=None):
+        """One whole iteration of train.py:160-202 without autograd in the loop: forward, generator sweep,
+        discriminator sweep, [ONE all-reduce over the two flat gradient buckets], both Adam steps.  Mathematically the
+        reference order (G step before D backward) because loss_D never depends on the updated G.
+        Returns the 4-element fp32 loss vector (device)."""
+        from .. import train_ops as T
+
+        graph = T.GanGraph(self)
+        with _ops.stats_pass(self.device):
+            self.optimizer_G.zero_grad()
+            self.optimizer_D.zero_grad()
+            losses = graph.forward(lr_audio, hr_audio)
+            graph.backward_G()
+            half = self._half_scalar()
+            graph.backward_D(half, half)
+            if all_reduce is not None:
+                all_reduce(self.bucket_G.grad, self.bucket_D.grad)
+            self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size
+            self.optimizer_G.step()
+            self.optimizer_D.step()
+        graph.release()
+        return losses
+
+    def _half_scalar(self):
+        if not hasattr(self, "_half"):
+            self._half = torch.full((), 0.5, dtype=torch.float32, device=self.device)
+        return self._half
+
+    def update_fixed_params(self):
+        raise NotImplementedError("--niter_fix_global > 0 is listed as next in DESIGN.md")
+
+    def update_learning_rate(self):
+        """Linear decay, pix2pixHD_model.py:664-673."""
+        lrd = self.lr / self.niter_decay
+        lr = self.old_lr - lrd
+        for opt_ in (self.optimizer_D, self.optimizer_G):
+            for g in opt_.param_groups:
+                g["lr"] = lr
+        if getattr(self, "verbose", False):
+            print("update learning rate: %f -> %f" % (self.old_lr, lr))
+        self.old_lr = lr
+
+    def get_current_visuals(self):
+        """Device references of the last step (the reference copies three tensors to the host EVERY step,
+        pix2pixHD_model.py:569-613; here they are materialised only when asked for)."""
+        g = getattr(self, "_graph", None)
+        if g is None:
+            return {}
+        return {"lable_spectro": g.lr_spectro[0, 0].detach().cpu().numpy(), "generated_spectro": g.sr_spectro[0, 0].detach().cpu().numpy(),
+                "real_spectro": g.hr_spectro[0, 0].detach().cpu().numpy()}
 
     @torch.no_grad()
     def inference(self, lr_audio):

@@ -57,6 +57,28 @@ def _L():
         L.mdctgan_avgpool3s2_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
         L.mdctgan_nchw_to_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
         L.mdctgan_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+        # train step
+        L.mdctgan_conv2d_wgrad.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_double, c_float, c_void_p, c_int64,
+                                           c_int64, c_int64, c_void_p, c_void_p]
+        L.mdctgan_norm_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_int, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+        L.mdctgan_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+        L.mdctgan_reflect_pad_bwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_avgpool3s2_bwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_attention_abs_pos_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                                    c_int, c_int, c_float, c_void_p]
+        L.mdctgan_mse_const_fwd.argtypes = [c_void_p, c_int64, c_float, c_double, c_void_p, c_void_p]
+        L.mdctgan_mse_const_bwd.argtypes = [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]
+        L.mdctgan_l1_pair_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]
+        L.mdctgan_l1_pair_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]
+        L.mdctgan_f64_to_f32.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+        L.mdctgan_disc_input_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p]
+        L.mdctgan_disc_input_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+        L.mdctgan_adam_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
+                                        c_void_p, c_void_p]
+        L.mdctgan_counter_inc.argtypes = [c_void_p, c_void_p]
         _bound = True
     return L
 
@@ -90,6 +112,7 @@ class Feat:
     norm_stats: Optional[torch.Tensor] = None
     norm_count: float = 0.0
     norm_eps: float = 1e-5
+    needs_grad: bool = True                  # False on data leaves: the tape skips the input gradient
 
     @property
     def shape(self):
@@ -168,7 +191,7 @@ def to_nhwc(x_nchw: torch.Tensor) -> Feat:
     if y.numel():
         with torch.cuda.device(x_nchw.device):
             _lib.check(_L().mdctgan_nchw_to_nhwc(x_nchw.data_ptr(), y.data_ptr(), B, C, H * W, _stream(y)))
-    return Feat(y)
+    return Feat(y, needs_grad=False)
 
 
 def to_nchw(f: Feat) -> torch.Tensor:
@@ -207,16 +230,19 @@ def pack_conv_weight_umma(w_kn: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1, pad: int = 0,
-           pad_mode: int = PAD_ZERO, transposed: bool = False, output_padding: int = 0, act: int = ACT_NONE,
-           want_stats: bool = False, w_umma: Optional[torch.Tensor] = None) -> Feat:
+def _conv_launch(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1, pad: int = 0,
+                 pad_mode: int = PAD_ZERO, transposed: bool = False, output_padding: int = 0, act: int = ACT_NONE,
+                 want_stats: bool = False, w_umma: Optional[torch.Tensor] = None, out_hw=None) -> Feat:
+    """One convolution launch (no tape).  `out_hw` forces the output size of a transposed convolution (dgrad)."""
     x = f.x
     _req(x, "conv2d input")
     B, H, W, Cin = x.shape
     K, Cout = w_packed.shape
     if K != kh * kw * Cin:
         raise RuntimeError(f"conv2d: packed weight has K={K}, expected {kh}*{kw}*{Cin}")
-    if transposed:
+    if out_hw is not None:
+        Ho, Wo = out_hw
+    elif transposed:
         Ho = (H - 1) * stride - 2 * pad + kh + output_padding
         Wo = (W - 1) * stride - 2 * pad + kw + output_padding
     else:
@@ -226,10 +252,6 @@ def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh:
         raise RuntimeError("conv2d: input still carries un-finalised statistics (missing norm layer?)")
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     stats = _new_stats(B, Cout, x.device) if want_stats else None
-    in_act = f.act
-    if not f.has_norm and f.act != ACT_NONE:
-        f = materialize(f)      # an activation without an affine in front of it: apply it for real
-        x, in_act = f.x, ACT_NONE
     use_umma = w_umma is not None and CONV_ENGINE != "direct"
     if use_umma and transposed and stride > 1 and (Ho % stride or Wo % stride or Cin % 32 or kh < stride or kw < stride):
         use_umma = False        # the tensor-core kernel runs strided transposed convolutions per output parity class only
@@ -238,14 +260,30 @@ def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh:
             if use_umma:
                 _lib.check(_L().mdctgan_conv2d_umma(x.data_ptr(), B, H, W, Cin, w_umma.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
                                                     kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
-                                                    1 if f.per_sample else 0, in_act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
+                                                    1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
                                                     act, _ptr(stats), 1 if CONV_ENGINE == "tf32" else 0, _stream(x)))
             else:
                 _lib.check(_L().mdctgan_conv2d_nhwc(x.data_ptr(), B, H, W, Cin, w_packed.data_ptr(), _ptr(bias), y.data_ptr(), Ho, Wo, Cout,
                                                     kh, kw, stride, pad, pad_mode, 1 if transposed else 0, _ptr(f.scale), _ptr(f.shift),
-                                                    1 if f.per_sample else 0, in_act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
+                                                    1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
                                                     act, _ptr(stats), _stream(x)))
     return Feat(y, stats=stats)
+
+
+def conv2d(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1, pad: int = 0,
+           pad_mode: int = PAD_ZERO, transposed: bool = False, output_padding: int = 0, act: int = ACT_NONE,
+           want_stats: bool = False, w_umma: Optional[torch.Tensor] = None, owner=None) -> Feat:
+    """nn.Conv2d / nn.ConvTranspose2d forward on a Feat.  Under `recording(tape)` the launch is also put on the tape
+    (`owner` = the parameter-holding module, needed for dgrad / wgrad)."""
+    if not f.has_norm and f.act != ACT_NONE:
+        f = materialize(f)      # an activation without an affine in front of it: apply it for real
+    out = _conv_launch(f, w_packed, bias, kh=kh, kw=kw, stride=stride, pad=pad, pad_mode=pad_mode, transposed=transposed,
+                       output_padding=output_padding, act=act, want_stats=want_stats, w_umma=w_umma)
+    if _tape is not None:
+        if owner is None:
+            raise RuntimeError("conv2d: recording a tape needs the owning module (dgrad / wgrad)")
+        _tape.ops.append(_ConvOp(f, out, owner, kh, kw, stride, pad, pad_mode, transposed, act))
+    return out
 
 
 def finalize_norm(f: Feat, *, eps: float = 1e-5, mode: int = 0, gamma=None, beta=None, running_mean=None, running_var=None,
@@ -257,8 +295,14 @@ def finalize_norm(f: Feat, *, eps: float = 1e-5, mode: int = 0, gamma=None, beta
     B, H, W, C = f.x.shape
     if mode != 2 and f.stats is None:
         raise RuntimeError("finalize_norm: the producer did not record statistics")
+    if _tape is not None and (mode == 2 or eager):
+        raise NotImplementedError("finalize_norm on a tape: eval-mode BatchNorm2d / eager InstanceNorm2d have no backward here "
+                                  "(call model.train() before a train step)")
     if mode == 0 and not eager:
-        return Feat(f.x, per_sample=True, act=ACT_NONE, norm_stats=f.stats, norm_count=float(H * W), norm_eps=float(eps))
+        out = Feat(f.x, per_sample=True, act=ACT_NONE, norm_stats=f.stats, norm_count=float(H * W), norm_eps=float(eps))
+        if _tape is not None:
+            _tape.ops.append(_ViewOp(f, out, "in", ACT_NONE, stats=f.stats, count=float(H * W), eps=float(eps)))
+        return out
     n = B * C if mode == 0 else C
     scale = torch.empty(n, dtype=torch.float32, device=f.x.device)
     shift = torch.empty(n, dtype=torch.float32, device=f.x.device)
@@ -267,13 +311,18 @@ def finalize_norm(f: Feat, *, eps: float = 1e-5, mode: int = 0, gamma=None, beta
             _lib.check(_L().mdctgan_norm_finalize(_ptr(f.stats), B, C, float(H * W), eps, mode, _ptr(gamma), _ptr(beta),
                                                   _ptr(running_mean), _ptr(running_var), momentum, scale.data_ptr(), shift.data_ptr(),
                                                   _stream(f.x)))
-    return Feat(f.x, scale=scale, shift=shift, per_sample=(mode == 0), act=ACT_NONE)
+    out = Feat(f.x, scale=scale, shift=shift, per_sample=(mode == 0), act=ACT_NONE)
+    if _tape is not None:
+        _tape.ops.append(_ViewOp(f, out, "bn", ACT_NONE, stats=f.stats, count=float(H * W), eps=float(eps), gamma=gamma, beta=beta))
+    return out
 
 
 def resolve_norm(f: Feat) -> Feat:
     """Turn a deferred InstanceNorm (raw statistics) into explicit scale / shift with the finalize kernel."""
     if f.norm_stats is None:
         return f
+    if _tape is not None:
+        raise NotImplementedError("resolve_norm on a tape")
     B, H, W, C = f.x.shape
     g = finalize_norm(Feat(f.x, stats=f.norm_stats), eps=f.norm_eps, mode=0, eager=True)
     return Feat(f.x, g.scale, g.shift, True, f.act)
@@ -282,7 +331,18 @@ def resolve_norm(f: Feat) -> Feat:
 def with_act(f: Feat, act: int) -> Feat:
     if f.act != ACT_NONE:
         f = materialize(f)
-    return Feat(f.x, f.scale, f.shift, f.per_sample, act, f.stats, f.norm_stats, f.norm_count, f.norm_eps)
+    out = Feat(f.x, f.scale, f.shift, f.per_sample, act, f.stats, f.norm_stats, f.norm_count, f.norm_eps, f.needs_grad)
+    if _tape is not None and act != ACT_NONE:
+        last = _tape.ops[-1] if _tape.ops else None
+        if isinstance(last, _ViewOp) and last.out is f and last.act == ACT_NONE:
+            last.out, last.act = out, act            # norm + activation: one backward
+        else:
+            if f.has_norm:
+                raise NotImplementedError("with_act on a tape: activation on a normalised view that is not the latest tape entry")
+            if act == ACT_TANH:
+                raise NotImplementedError("with_act on a tape: stand-alone tanh")
+            _tape.ops.append(_ViewOp(f, out, "act", act))
+    return out
 
 
 def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
@@ -304,7 +364,10 @@ def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
                                                1 if (b is not None and b.per_sample) else 0, b.act if b is not None else 0,
                                                _ptr(b.norm_stats) if b is not None else None, count, eps, y.data_ptr(), B, H * W, C, act_out,
                                                _stream(y)))
-    return Feat(y)
+    out = Feat(y)
+    if _tape is not None:
+        _tape.ops.append(_CombineOp(a, b, out, act_out))
+    return out
 
 
 def materialize(f: Feat) -> Feat:
@@ -321,7 +384,10 @@ def avgpool3s2(f: Feat) -> Feat:
     if y.numel():
         with torch.cuda.device(y.device):
             _lib.check(_L().mdctgan_avgpool3s2_nhwc(f.x.data_ptr(), y.data_ptr(), B, H, W, C, _stream(y)))
-    return Feat(y)
+    out = Feat(y, needs_grad=f.needs_grad)
+    if _tape is not None and f.needs_grad:
+        _tape.ops.append(_PoolOp(f, out))
+    return out
 
 
 def attention(qkv: Feat, emb_h: torch.Tensor, emb_w: torch.Tensor, heads: int, dim_head: int, scale: float,
@@ -338,7 +404,10 @@ def attention(qkv: Feat, emb_h: torch.Tensor, emb_w: torch.Tensor, heads: int, d
         with torch.cuda.device(out.device):
             _lib.check(_L().mdctgan_attention_abs_pos(qkv.x.data_ptr(), emb_h.data_ptr(), emb_w.data_ptr(), out.data_ptr(), B, H, W, heads,
                                                       dim_head, scale, _ptr(stats), _stream(out)))
-    return Feat(out, stats=stats)
+    res = Feat(out, stats=stats)
+    if _tape is not None:
+        _tape.ops.append(_AttnOp(qkv, res, emb_h, emb_w, heads, dim_head, scale))
+    return res
 
 
 def residual_scale_add(sr: torch.Tensor, lr: torch.Tensor, lr_bins: int, low_scale: float = 1e-3) -> torch.Tensor:
@@ -354,3 +423,225 @@ def residual_scale_add(sr: torch.Tensor, lr: torch.Tensor, lr_bins: int, low_sca
         with torch.cuda.device(sr.device):
             _lib.check(_L().mdctgan_residual_scale_add(sr.data_ptr(), lr.data_ptr(), N, y.data_ptr(), B * Fr, N, lr_bins, low_scale, _stream(sr)))
     return y
+
+
+# =====================================================================================================================
+# Tape: what torch autograd does for the reference's train step (train.py:175-202), written out over our own kernels.
+# Forward ops append an entry while `recording(tape)` is active; `Tape.backward(grads, ...)` walks the entries in
+# reverse.  Gradients are keyed by Feat object and are taken with respect to the VALUE a Feat stands for
+# (act(norm(x)) for a deferred view, x for a raw tensor).
+# =====================================================================================================================
+_tape = None
+
+
+class Tape:
+    def __init__(self):
+        self.ops = []
+
+    def backward(self, grads: "GradMap", wgrad: bool = True, nb: Optional[int] = None):
+        """`nb`: only the first nb samples of every saved tensor take part (the generator-loss sweep through the
+        discriminator runs on the fake half of the [fake ; real] batch).  `wgrad=False`: input gradients only."""
+        for op in reversed(self.ops):
+            op.backward(grads, wgrad, nb)
+
+
+class recording:
+    def __init__(self, tape: Tape):
+        self.tape = tape
+
+    def __enter__(self):
+        global _tape
+        self.prev, _tape = _tape, self.tape
+        return self.tape
+
+    def __exit__(self, *exc):
+        global _tape
+        _tape = self.prev
+
+
+class GradMap:
+    def __init__(self):
+        self.g = {}
+
+    def add(self, f: Feat, t: torch.Tensor):
+        if not f.needs_grad:
+            return
+        cur = self.g.get(id(f))
+        self.g[id(f)] = t if cur is None else add(cur, t)
+
+    def pop(self, f: Feat):
+        return self.g.pop(id(f), None)
+
+    def get(self, f: Feat):
+        return self.g.get(id(f))
+
+
+def _sl(t: Optional[torch.Tensor], nb: Optional[int]):
+    return t if (t is None or nb is None) else t[:nb]
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(a)
+    if y.numel():
+        with torch.cuda.device(a.device):
+            _lib.check(_L().mdctgan_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), y.numel(), _stream(a)))
+    return y
+
+
+def act_bwd(dy: torch.Tensor, y: torch.Tensor, act: int) -> torch.Tensor:
+    """dy * act'(.) evaluated from the activated value y (ReLU / LeakyReLU: the pre-activation works as well)."""
+    g = torch.empty_like(dy)
+    if g.numel():
+        with torch.cuda.device(dy.device):
+            _lib.check(_L().mdctgan_act_bwd(dy.data_ptr(), y.data_ptr(), g.data_ptr(), g.numel(), act, _stream(dy)))
+    return g
+
+
+def grad_of(p: torch.Tensor) -> torch.Tensor:
+    """The gradient buffer a backward kernel accumulates into (a view of the flat bucket once optim.flatten ran)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+def _view_feat(f: Feat, nb: Optional[int]) -> Feat:
+    """The first nb samples of a Feat (contiguous slices, no copies)."""
+    if nb is None:
+        return f
+    C = f.x.shape[-1]
+    sc = f.scale[:nb * C] if (f.scale is not None and f.per_sample) else f.scale
+    sh = f.shift[:nb * C] if (f.shift is not None and f.per_sample) else f.shift
+    return Feat(f.x[:nb], sc, sh, f.per_sample, f.act, None, _sl(f.norm_stats, nb), f.norm_count, f.norm_eps, f.needs_grad)
+
+
+class _ConvOp:
+    def __init__(self, f, out, owner, kh, kw, stride, pad, pad_mode, transposed, act):
+        self.f, self.out, self.owner = f, out, owner
+        self.kh, self.kw, self.stride, self.pad, self.pad_mode, self.transposed, self.act = kh, kw, stride, pad, pad_mode, transposed, act
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dy = G.pop(self.out)
+        if dy is None:
+            return
+        if self.act != ACT_NONE:
+            dy = act_bwd(dy, _sl(self.out.x, nb), self.act)
+        f = _view_feat(self.f, nb)
+        own = self.owner
+        B, H, W, Cin = f.x.shape
+        _, Ho, Wo, Cout = dy.shape
+        L = _L()
+        if wgrad and own.weight.requires_grad:
+            dw = grad_of(own.weight)
+            db = grad_of(own.bias) if (own.bias is not None and own.bias.requires_grad) else None
+            taps = self.kh * self.kw
+            s_co, s_ci = (taps, Cout * taps) if self.transposed else (Cin * taps, taps)
+            with torch.cuda.device(dy.device):
+                _lib.check(L.mdctgan_conv2d_wgrad(f.x.data_ptr(), B, H, W, Cin, dy.data_ptr(), Ho, Wo, Cout, self.kh, self.kw, self.stride,
+                                                  self.pad, self.pad_mode, 1 if self.transposed else 0, _ptr(f.scale), _ptr(f.shift),
+                                                  1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
+                                                  dw.data_ptr(), s_co, s_ci, 1, _ptr(db), _stream(dy)))
+        if not self.f.needs_grad:
+            return
+        # input gradient = the forward convolution on the transposed geometry with the same weights
+        wd, wd_umma, flipped = own.packed_dgrad()
+        g = Feat(dy)
+        if self.transposed:          # ConvTranspose2d: a plain strided convolution of dy
+            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=self.stride, pad=self.pad, w_umma=wd_umma).x
+            assert dv.shape[1:3] == (H, W)
+        elif flipped:                # stride 1: plain convolution with the taps flipped, pad' = k - 1 - pad
+            p_eff = 0 if self.pad_mode == PAD_REFLECT else self.pad
+            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=1, pad=self.kh - 1 - p_eff, w_umma=wd_umma).x
+        else:                        # strided nn.Conv2d: transposed convolution of dy, output size forced to the input's
+            p_eff = 0 if self.pad_mode == PAD_REFLECT else self.pad
+            hw = (H + 2 * self.pad, W + 2 * self.pad) if self.pad_mode == PAD_REFLECT else (H, W)
+            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=self.stride, pad=p_eff, transposed=True, w_umma=wd_umma,
+                              out_hw=hw).x
+        if self.pad_mode == PAD_REFLECT:
+            assert dv.shape[1:3] == (H + 2 * self.pad, W + 2 * self.pad), (dv.shape, H, W, self.pad)
+            dx = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dv.device)
+            with torch.cuda.device(dv.device):
+                _lib.check(L.mdctgan_reflect_pad_bwd(dv.data_ptr(), dx.data_ptr(), B, H, W, Cin, self.pad, _stream(dv)))
+            dv = dx
+        assert dv.shape == f.x.shape, (dv.shape, f.x.shape)
+        G.add(self.f, dv)
+
+
+class _ViewOp:
+    """out = act(norm(src)) as a deferred view: kind 'in' (InstanceNorm2d), 'bn' (train-mode BatchNorm2d), 'act'."""
+
+    def __init__(self, src, out, kind, act, stats=None, count=0.0, eps=1e-5, gamma=None, beta=None):
+        self.src, self.out, self.kind, self.act = src, out, kind, act
+        self.stats, self.count, self.eps, self.gamma, self.beta = stats, count, eps, gamma, beta
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dv = G.pop(self.out)
+        if dv is None:
+            return
+        x = _sl(self.src.x, nb)
+        if self.kind == "act":
+            G.add(self.src, act_bwd(dv, x, self.act))
+            return
+        if self.kind == "bn" and nb is not None:
+            raise NotImplementedError("BatchNorm2d backward on a batch slice")
+        B, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        red = _new_stats(B, C, x.device)     # zeroed (sum g, sum g*xhat) scratch
+        gam = self.gamma if self.kind == "bn" else None
+        bet = self.beta if self.kind == "bn" else None
+        dgam = grad_of(gam) if (gam is not None and wgrad and gam.requires_grad) else None
+        dbet = grad_of(bet) if (bet is not None and wgrad and bet.requires_grad) else None
+        with torch.cuda.device(x.device):
+            _lib.check(_L().mdctgan_norm_act_bwd(x.data_ptr(), dv.data_ptr(), dx.data_ptr(), _sl(self.stats, nb).data_ptr(), self.count, self.eps,
+                                                 0 if self.kind == "in" else 1, _ptr(gam), _ptr(bet), self.act, red.data_ptr(), _ptr(dgam),
+                                                 _ptr(dbet), B, H * W, C, _stream(x)))
+        G.add(self.src, dx)
+
+
+class _CombineOp:
+    def __init__(self, a, b, out, act_out):
+        self.a, self.b, self.out, self.act_out = a, b, out, act_out
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dy = G.pop(self.out)
+        if dy is None:
+            return
+        if self.act_out != ACT_NONE:
+            dy = act_bwd(dy, _sl(self.out.x, nb), self.act_out)
+        G.add(self.a, dy)
+        if self.b is not None:
+            G.add(self.b, dy)
+
+
+class _PoolOp:
+    def __init__(self, f, out):
+        self.f, self.out = f, out
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dy = G.pop(self.out)
+        if dy is None:
+            return
+        B, H, W, C = _sl(self.f.x, nb).shape
+        dx = torch.empty((B, H, W, C), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            _lib.check(_L().mdctgan_avgpool3s2_bwd(dy.data_ptr(), dx.data_ptr(), B, H, W, C, _stream(dy)))
+        G.add(self.f, dx)
+
+
+class _AttnOp:
+    def __init__(self, qkv, out, emb_h, emb_w, heads, d, scale):
+        self.qkv, self.out, self.emb_h, self.emb_w, self.heads, self.d, self.scale = qkv, out, emb_h, emb_w, heads, d, scale
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dout = G.pop(self.out)
+        if dout is None:
+            return
+        qkv = _sl(self.qkv.x, nb)
+        B, H, W, _ = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        dh = grad_of(self.emb_h) if (wgrad and self.emb_h.requires_grad) else None
+        dw = grad_of(self.emb_w) if (wgrad and self.emb_w.requires_grad) else None
+        with torch.cuda.device(qkv.device):
+            _lib.check(_L().mdctgan_attention_abs_pos_bwd(qkv.data_ptr(), self.emb_h.data_ptr(), self.emb_w.data_ptr(), dout.data_ptr(),
+                                                          dqkv.data_ptr(), _ptr(dh), _ptr(dw), B, H, W, self.heads, self.d, self.scale,
+                                                          _stream(qkv)))
+        G.add(self.qkv, dqkv)

@@ -1,0 +1,122 @@
+"""Flat parameter / gradient buckets and the fused Adam step.
+
+Reference: two `torch.optim.Adam(params, lr=opt.lr, betas=(opt.beta1, 0.999))` (models/pix2pixHD_model.py:350-364)
+stepped from train.py:185-202.  Here every parameter of a network is a view into ONE flat fp32 buffer (so are the
+gradients: that buffer is also the NCCL all-reduce bucket) and `step()` is one kernel launch
+(`mdctgan_adam_flat`) per contiguous run of trainable parameters.  The optimizer keeps the torch.optim.Optimizer
+surface train.py touches: `zero_grad()`, `step()`, `param_groups[i]['lr']`, `state_dict()`.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _lib
+from . import nn_ops as ops
+
+
+class FlatBucket:
+    """All parameters of `module` re-pointed into one flat buffer (16-byte aligned segments), with a matching flat
+    gradient buffer whose views are installed as `p.grad`."""
+
+    def __init__(self, module: torch.nn.Module):
+        params = [p for p in module.parameters()]
+        if not params:
+            raise ValueError("FlatBucket: module has no parameters")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatBucket: parameters must live on a CUDA device (no CPU path)")
+        self.params: List[torch.nn.Parameter] = params
+        self.offsets, off = [], 0
+        for p in params:
+            if p.dtype != torch.float32:
+                raise RuntimeError("FlatBucket: fp32 master parameters only")
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                self.flat[o:o + p.numel()].view_as(p).copy_(p)
+                p.data = self.flat[o:o + p.numel()].view_as(p)
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def trainable_runs(self):
+        """Maximal contiguous [begin, end) runs of the flat buffer whose parameters require grad."""
+        runs, cur = [], None
+        for p, o in zip(self.params, self.offsets):
+            end = o + (p.numel() + 3) // 4 * 4
+            if p.requires_grad:
+                cur = [o, end] if cur is None else [cur[0], end]
+            elif cur is not None:
+                runs.append(tuple(cur))
+                cur = None
+        if cur is not None:
+            runs.append(tuple(cur))
+        return runs
+
+    def reattach_grads(self):
+        """Re-install the gradient views (after something set p.grad = None)."""
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (no weight decay, no amsgrad) over a FlatBucket.  `grad_scale` multiplies the
+    gradient inside the kernel (1/world_size after a sum all-reduce)."""
+
+    def __init__(self, bucket: FlatBucket, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, graph_safe: bool = False):
+        trainable = [p for p in bucket.params if p.requires_grad]
+        super().__init__(trainable, dict(lr=lr, betas=betas, eps=eps))
+        self.bucket = bucket
+        self.exp_avg = torch.zeros_like(bucket.flat)
+        self.exp_avg_sq = torch.zeros_like(bucket.flat)
+        self.step_count = 0
+        self.grad_scale = 1.0
+        # a device-side step counter lets a captured CUDA graph of the step replay with the right bias corrections
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=bucket.flat.device) if graph_safe else None
+
+    def zero_grad(self, set_to_none: bool = True):
+        """One memset of the flat gradient bucket; the `p.grad` views stay installed (the backward kernels
+        accumulate straight into them)."""
+        self.bucket.grad.zero_()
+        for p in self.bucket.params:
+            if p.grad is None:
+                self.bucket.reattach_grads()
+                break
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedAdam.step(closure)")
+        g = self.param_groups[0]
+        b = self.bucket
+        self.step_count += 1
+        L = ops._L()
+        with torch.cuda.device(b.flat.device):
+            st = torch.cuda.current_stream(b.flat.device).cuda_stream
+            if self.step_dev is not None:
+                _lib.check(L.mdctgan_counter_inc(self.step_dev.data_ptr(), st))
+            for lo, hi in b.trainable_runs():
+                _lib.check(L.mdctgan_adam_flat(b.flat[lo:hi].data_ptr(), b.grad[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
+                                               self.exp_avg_sq[lo:hi].data_ptr(), hi - lo, float(g["lr"]), float(g["betas"][0]),
+                                               float(g["betas"][1]), float(g["eps"]), float(self.grad_scale), self.step_count,
+                                               self.step_dev.data_ptr() if self.step_dev is not None else None, st))
+        for p in b.params:          # kernel-side weight images (packed / tcgen05) are keyed on the version counter
+            p._version_bump = getattr(p, "_version_bump", 0) + 1
+        return None
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step_count)
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)

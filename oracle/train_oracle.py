@@ -1,0 +1,80 @@
+"""Oracle (CPU, torch autograd) for the GAN train step -- TEST INFRASTRUCTURE ONLY.
+
+Follows /root/reference/models/pix2pixHD_model.py:394-451 (forward, _forward: three discriminator passes, LSGAN
+and feature-matching losses, networks.py:97-137) and /root/reference/train.py:175-202 (loss_G / loss_D, two
+backward passes, two Adam steps, pix2pixHD_model.py:350-364) over reference-layout state_dicts, with
+oracle/mdct_oracle.py for the spectrograms and oracle/networks_oracle.py for G and D.
+Pinned against tests/golden/train_golden.npz (the reference's own create_model(opt)._forward / backward / Adam on
+seeded weights and audio, tests/golden/make_golden_nets.py train) by tests/test_oracle_train.py.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import mdct_oracle as MO
+from . import networks_oracle as NO
+
+
+def spectro(audio, gain=1000.0, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0)):
+    w = MO.kbdwin(512)
+    s, _, _, _ = MO.to_spectro(np.asarray(audio, dtype=np.float32), w, arcsinh_transform=True, arcsinh_gain=gain, abs_norm=True,
+                               src_range=src_range, norm_range=norm_range)
+    return torch.from_numpy(s)
+
+
+def losses(pG, pD, lr_spectro, hr_spectro, *, netG="local", n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128,
+           num_D=3, n_layers_D=3, lambda_feat=10.0, fit_residual=True, lo=-1.0, use_feat=True):
+    """The four loss tensors [G_GAN, G_GAN_Feat, D_real, D_fake] as autograd functions of the parameter dicts."""
+    x = torch.cat((lr_spectro, lr_spectro.abs() * 2 + lo), dim=1)
+    if netG == "global":
+        sr = NO.global_generator(pG, x, n_down, n_blocks_global, n_attn, heads, dim_head, training=True)
+    else:
+        sr = NO.local_enhancer(pG, x, n_down, n_blocks_global, n_blocks_local, n_attn, heads, dim_head, training=True)
+    if fit_residual:
+        sr = sr + lr_spectro
+    sr_in = torch.cat((sr, sr.abs() * 2 + lo), dim=1)
+    hr_in = torch.cat((hr_spectro, hr_spectro.abs() * 2 + lo), dim=1)
+    pred_fake_pool = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in.detach()), dim=1), num_D, n_layers_D)
+    pred_real = NO.multiscale_d(pD, torch.cat((lr_spectro, hr_in), dim=1), num_D, n_layers_D)
+    pred_fake = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in), dim=1), num_D, n_layers_D)
+    d_fake = sum(F.mse_loss(p[-1], torch.zeros_like(p[-1])) for p in pred_fake_pool)
+    d_real = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_real)
+    g_gan = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_fake)
+    g_feat = torch.zeros(())
+    if use_feat:
+        fw, dw = 4.0 / (n_layers_D + 1), 1.0 / num_D
+        for i in range(num_D):
+            for j in range(len(pred_fake[i]) - 1):
+                g_feat = g_feat + dw * fw * F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) * lambda_feat
+    return [g_gan, g_feat, d_real, d_fake], sr
+
+
+def train_step(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, steps=1, **cfg):
+    """`steps` iterations of train.py:160-202 on the same batch.  Returns per-step losses, the gradients of the
+    first step and the parameters after the last one."""
+    floatsG = {k for k, v in sdG.items() if v.dtype.is_floating_point and "running_" not in k}
+    pG = {k: (v.clone().requires_grad_(True) if k in floatsG else v.clone()) for k, v in sdG.items()}
+    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    optG = torch.optim.Adam([pG[k] for k in pG if k in floatsG], lr=lr, betas=(beta1, 0.999))
+    optD = torch.optim.Adam(list(pD.values()), lr=lr, betas=(beta1, 0.999))
+    ls, hs = spectro(lr_audio), spectro(hr_audio)
+    out = {"losses": []}
+    for it in range(steps):
+        (g_gan, g_feat, d_real, d_fake), sr = losses(pG, pD, ls, hs, **cfg)
+        out["losses"].append([float(g_gan), float(g_feat), float(d_real), float(d_fake)])
+        loss_D = (d_fake + d_real) * 0.5
+        loss_G = g_gan + g_feat
+        optG.zero_grad()
+        loss_G.backward()
+        if it == 0:
+            out["gradG"] = {k: pG[k].grad.detach().clone() for k in pG if k in floatsG and pG[k].grad is not None}
+            out["sr_spectro"] = sr.detach().clone()
+        optG.step()
+        optD.zero_grad()
+        loss_D.backward()
+        if it == 0:
+            out["gradD"] = {k: v.grad.detach().clone() for k, v in pD.items()}
+        optD.step()
+    out["paramsG"] = {k: v.detach().clone() for k, v in pG.items()}
+    out["paramsD"] = {k: v.detach().clone() for k, v in pD.items()}
+    return out

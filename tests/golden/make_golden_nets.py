@@ -127,5 +127,73 @@ def gen_infer():
     np.savez_compressed(path, **out)
 
 
+TRAIN_FLAGS = {
+    # BASELINE configs[3] per-GPU slice: LocalEnhancer + 2 attention layers, num_D 3, feature matching, --fit_residual (batch 2 here)
+    "tr_cfg4": (["--netG", "local", "--ngf", "32", "--n_downsample_global", "3", "--n_blocks_global", "9", "--n_blocks_attn_g", "2",
+                 "--heads_g", "4", "--dim_head_g", "64", "--n_blocks_local", "3", "--num_D", "3", "--segment_length", "7936",
+                 "--bins", "32", "--fit_residual"], 2, 7936, 5151),
+    "tr_small": (["--netG", "local", "--ngf", "8", "--n_downsample_global", "2", "--n_blocks_global", "2", "--n_blocks_attn_g", "1",
+                  "--heads_g", "2", "--dim_head_g", "32", "--n_blocks_local", "1", "--num_D", "2", "--n_layers_D", "2", "--ndf", "8",
+                  "--segment_length", "3840", "--bins", "16", "--fit_residual"], 3, 3840, 5152),
+}
+TRAIN_STEPS = 2
+
+
+def make_hr_audio(batch, T, seed):
+    rng = np.random.default_rng(seed + 17)
+    return torch.from_numpy((0.1 * rng.standard_normal((batch, T))).astype(np.float32))
+
+
 def gen_train():
-    raise SystemExit("train-step goldens: not generated in this round")
+    """create_model(opt) of the reference in training mode: _forward, loss_G / loss_D backward, both Adam steps
+    (train.py:160-202), TRAIN_STEPS iterations on one seeded batch."""
+    from make_golden import ref_opt
+    from models.models import create_model
+
+    out = {}
+    for name, (flags, batch, T, seed) in TRAIN_FLAGS.items():
+        opt = ref_opt(flags)
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = create_model(opt)
+        model.train()
+        lr, hr = make_lr_audio(batch, T, seed), make_hr_audio(batch, T, seed)
+        out[f"{name}_lr_audio"], out[f"{name}_hr_audio"] = lr.numpy(), hr.numpy()
+        out[f"{name}_G_cksum0"] = state_checksum(model.netG.state_dict())
+        out[f"{name}_D_cksum0"] = state_checksum(model.netD.state_dict())
+        losses_all = []
+        for it in range(TRAIN_STEPS):
+            losses, _ = model._forward(lr, hr)
+            d = dict(zip(model.loss_names, losses))
+            losses_all.append([float(d[k]) for k in ("G_GAN", "G_GAN_Feat", "D_real", "D_fake")])
+            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+            loss_G = d["G_GAN"] + d["G_GAN_Feat"]
+            model.optimizer_G.zero_grad()
+            loss_G.backward()
+            if it == 0:
+                gG = {k: p.grad for k, p in model.netG.named_parameters()}
+                out[f"{name}_gradG_keys"] = np.array(list(gG.keys()))
+                out[f"{name}_gradG_cksum"] = state_checksum(gG)
+                if name == "tr_small":
+                    for k, v in gG.items():
+                        out[f"{name}_gradG::{k}"] = v.numpy().copy()
+            model.optimizer_G.step()
+            model.optimizer_D.zero_grad()
+            loss_D.backward()
+            if it == 0:
+                gD = {k: p.grad for k, p in model.netD.named_parameters()}
+                out[f"{name}_gradD_keys"] = np.array(list(gD.keys()))
+                out[f"{name}_gradD_cksum"] = state_checksum(gD)
+                if name == "tr_small":
+                    for k, v in gD.items():
+                        out[f"{name}_gradD::{k}"] = v.numpy().copy()
+            model.optimizer_D.step()
+        out[f"{name}_losses"] = np.array(losses_all)
+        out[f"{name}_G_cksum_after"] = state_checksum(model.netG.state_dict())
+        out[f"{name}_D_cksum_after"] = state_checksum(model.netD.state_dict())
+        if name == "tr_small":
+            for k, v in model.netG.state_dict().items():
+                out[f"{name}_G_after::{k}"] = v.numpy().copy()
+        print(name, "done", losses_all)
+    np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
+    print("wrote train_golden.npz")
