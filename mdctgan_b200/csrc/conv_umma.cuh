@@ -186,7 +186,7 @@ struct Cfg {
   static constexpr int kStages = (192 * 1024 / kStageBytes) >= 8 ? 8 : ((192 * 1024 / kStageBytes) >= 4 ? 4 : 2);
   static constexpr int kPitch = BN + 4;                                   // staging row pitch (floats)
   static constexpr int kStagingBytes = ((kBM * kPitch * 4 + 1023) / 1024) * 1024;
-  static constexpr int kRedBytes = 2 * kProducerThreads * 4 * 4;          // [2][RP][BN] floats, RP*BN = 4 * producer threads
+  static constexpr int kRedBytes = 2 * kProducerThreads * 4 * 8;          // [2][RP][BN] doubles, RP*BN = 4 * producer threads
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kMaxCin * 4 + 256;
   static_assert(kStagingBytes + kRedBytes <= kStages * kStageBytes, "staging must fit in the pipeline buffers");
@@ -498,14 +498,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
 
   // ================= epilogue part 2: split-K reduction over DSMEM, bias, statistics, activation, store =======
   float* stage_out = reinterpret_cast<float*>(smem);
-  float* red = reinterpret_cast<float*>(smem + C::kStagingBytes);
+  double* red = reinterpret_cast<double*>(smem + C::kStagingBytes);   // fp64: E[x^2] - mean^2 must survive |mean| >> std
   constexpr int CQ = BN / 4;                  // float4 columns per row
   constexpr int RP = kProducerThreads / CQ;   // rows per pass over the producer threads
   constexpr int kRedHalf = kProducerThreads * 4;
   const int r_begin = kBM * split / p.splits, r_end = kBM * (split + 1) / p.splits;
   const int cq = tid % CQ, rg = tid / CQ;
   if (tid < kProducerThreads) {
-    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+    double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
     const int n = n0 + cq * 4;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -522,8 +522,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
       }
-      ssum.x += acc.x; ssq.x += acc.x * acc.x; ssum.y += acc.y; ssq.y += acc.y * acc.y;
-      ssum.z += acc.z; ssq.z += acc.z * acc.z; ssum.w += acc.w; ssq.w += acc.w * acc.w;
+      if (p.stats) {
+        const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
+        ssum[0] += a0; ssq[0] = fma(a0, a0, ssq[0]); ssum[1] += a1; ssq[1] = fma(a1, a1, ssq[1]);
+        ssum[2] += a2; ssq[2] = fma(a2, a2, ssq[2]); ssum[3] += a3; ssq[3] = fma(a3, a3, ssq[3]);
+      }
       acc.x = nnk::apply_act(acc.x, p.act); acc.y = nnk::apply_act(acc.y, p.act);
       acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
       const int oyc = pix / tg.woc;
@@ -531,20 +534,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       *reinterpret_cast<float4*>(p.y + (((size_t)b * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
     }
     if (p.stats) {
-      *reinterpret_cast<float4*>(red + rg * BN + cq * 4) = ssum;
-      *reinterpret_cast<float4*>(red + kRedHalf + rg * BN + cq * 4) = ssq;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { red[rg * BN + cq * 4 + u] = ssum[u]; red[kRedHalf + rg * BN + cq * 4 + u] = ssq[u]; }
     }
   }
   trace_mark(p, 8, tid == 0);
   if (p.stats) {        // block-uniform branch
     __syncthreads();
     if (tid < BN) {
-      float s = 0.f, q = 0.f;
+      double s = 0.0, q = 0.0;
 #pragma unroll 4
       for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
       double* st = p.stats + ((size_t)b * p.Cout + n0 + tid) * 2;
-      red_add_f64(st, (double)s);
-      red_add_f64(st + 1, (double)q);
+      red_add_f64(st, s);
+      red_add_f64(st + 1, q);
     }
   }
   trace_mark(p, 9, tid == 0);

@@ -212,9 +212,11 @@ __global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
   }
 
   // ---- epilogue: bias, activation, store, InstanceNorm / BatchNorm statistics
-  float csum[TN], csq[TN];
+  // fp64 partial sums: var = E[x^2] - mean^2 must survive planes with |mean| >> std (e.g. the PatchGAN layers behind the
+  // nearly constant |s|*2+lo input channel); torch's two-pass / Welford statistics do
+  double csum[TN], csq[TN];
 #pragma unroll
-  for (int jn = 0; jn < TN; ++jn) { csum[jn] = 0.f; csq[jn] = 0.f; }
+  for (int jn = 0; jn < TN; ++jn) { csum[jn] = 0.0; csq[jn] = 0.0; }
   float* yb = p.y + (size_t)b * HWo * p.Cout;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -224,26 +226,26 @@ __global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
       const int n = n0 + tx * TN + jn;
       if (m < HWo && n < p.Cout) {
         float v = acc[i][jn] + (p.bias ? __ldg(p.bias + n) : 0.f);
-        csum[jn] += v; csq[jn] += v * v;     // statistics are taken BEFORE the epilogue activation (norm follows conv)
+        if (p.stats) { csum[jn] += (double)v; csq[jn] = fma((double)v, (double)v, csq[jn]); }   // BEFORE the epilogue activation (norm follows conv)
         yb[(size_t)m * p.Cout + n] = apply_act(v, p.act);
       }
     }
   }
   if (p.stats) {
     // reduce over the 16 ty-rows of the CTA through shared memory, then one atomic per channel per CTA
-    __shared__ float red[2][16][BN];
+    __shared__ double red[2][16][BN];
 #pragma unroll
     for (int jn = 0; jn < TN; ++jn) { red[0][ty][tx * TN + jn] = csum[jn]; red[1][ty][tx * TN + jn] = csq[jn]; }
     __syncthreads();
     if (tid < BN) {
-      float s = 0.f, q = 0.f;
+      double s = 0.0, q = 0.0;
 #pragma unroll
       for (int r = 0; r < 16; ++r) { s += red[0][r][tid]; q += red[1][r][tid]; }
       const int n = n0 + tid;
       if (n < p.Cout) {
         double* st = p.stats + ((size_t)b * p.Cout + n) * 2;
-        atomicAdd(st, (double)s);
-        atomicAdd(st + 1, (double)q);
+        atomicAdd(st, s);
+        atomicAdd(st + 1, q);
       }
     }
   }
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(256) attention_abs_pos_kernel(const AttnParams
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* q = qrow + warp * d;
   const int dpl = d / 32;               // channels per lane (d % 32 == 0)
-  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = warp; i < L; i += 8) {
     for (int dd = lane; dd < d; dd += 32) q[dd] = __ldg(base + (size_t)i * 3 * C + h * d + dd) * p.scale;
     __syncwarp();
@@ -510,15 +512,15 @@ __global__ void __launch_bounds__(256) attention_abs_pos_kernel(const AttnParams
     for (int t = 0; t < dpl; ++t) {
       const float o = acc[t] * inv;
       p.out[((size_t)b * L + i) * C + h * d + lane + 32 * t] = o;
-      ssum[t] += o; ssq[t] += o * o;
+      ssum[t] += (double)o; ssq[t] = fma((double)o, (double)o, ssq[t]);
     }
     __syncwarp();
   }
   if (p.stats) {
     for (int t = 0; t < dpl; ++t) {
       double* st = p.stats + ((size_t)b * C + h * d + lane + 32 * t) * 2;
-      atomicAdd(st, (double)ssum[t]);
-      atomicAdd(st + 1, (double)ssq[t]);
+      atomicAdd(st, ssum[t]);
+      atomicAdd(st + 1, ssq[t]);
     }
   }
 }

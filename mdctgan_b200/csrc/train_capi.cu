@@ -1,5 +1,6 @@
 // train_capi.cu -- C ABI of the train-step kernels (include/mdctgan_b200.h, "train step").
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/mdctgan_b200.h"
 #include "train_kernels.cuh"
@@ -66,7 +67,7 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     p.pix_per_chunk = ((HWo + chunks - 1) / chunks + 15) / 16 * 16;
     p.chunks_per_sample = (HWo + p.pix_per_chunk - 1) / p.pix_per_chunk;
     if ((long long)B * p.chunks_per_sample > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
-    conv_wgrad_kernel<<<dim3(tiles, B * p.chunks_per_sample), 256, 0, st>>>(p);
+    conv_wgrad_kernel<float><<<dim3(tiles, B * p.chunks_per_sample), 256, 0, st>>>(p);
   }
   mdctgan_count_launch();
   CKT(cudaGetLastError());

@@ -57,6 +57,7 @@ struct WgradParams {
   int n_tiles, chunks_per_sample, pix_per_chunk;
 };
 
+template <typename AccT>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   constexpr int TK = 64, TN = 64, MS = 16;
   __shared__ __align__(16) float As[MS][TK + 4];
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   }
   const int nq = (tid & 15) * 4;
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
+  AccT acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int mb = m_begin; mb < m_end; mb += MS) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((AccT)av[i], (AccT)bw[j], acc[i][j]);
       if (ty == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) bsum[j] += bw[j];
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = n0 + tx * 4 + j;
-      if (co < p.Cout) atomicAdd(p.dw + (long long)co * p.s_co + (long long)ci * p.s_ci + (long long)tap * p.s_tap, acc[i][j]);
+      if (co < p.Cout) atomicAdd(p.dw + (long long)co * p.s_co + (long long)ci * p.s_ci + (long long)tap * p.s_tap, (float)acc[i][j]);
     }
   }
   if (p.dbias && kt == 0 && ty == 0) {
@@ -277,14 +278,14 @@ __device__ __forceinline__ void norm_bwd_coeffs(const NormBwdParams& p, int b, f
 
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParams p) {
   __shared__ float s_mean[1024], s_rstd[1024], s_gam[1024], s_bet[1024];
-  __shared__ float s_acc[2][1024];
+  __shared__ double s_acc[2][1024];   // fp64: the apply pass subtracts mean(g) from g, and g is often nearly constant over a plane
   const int b = blockIdx.y;
   norm_bwd_coeffs(p, b, s_mean, s_rstd, s_gam, s_bet);
-  for (int c = threadIdx.x; c < p.C; c += 256) { s_acc[0][c] = 0.f; s_acc[1][c] = 0.f; }
+  for (int c = threadIdx.x; c < p.C; c += 256) { s_acc[0][c] = 0.0; s_acc[1][c] = 0.0; }
   __syncthreads();
   const int groups = p.C / 4;                    // float4 channel groups; C <= 1024 -> groups <= 256
   const int cg = threadIdx.x % groups, prow = threadIdx.x / groups, pstep = 256 / groups;
-  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  double sg[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
   if (prow < pstep) {
     const size_t base = (size_t)b * p.HW * p.C;
     for (int pix = blockIdx.x * pstep + prow; pix < p.HW; pix += gridDim.x * pstep) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
         const int c = cg * 4 + u;
         const float xhat = (xs[u] - s_mean[c]) * s_rstd[c];
         const float g = ds[u] * act_grad_from_pre(fmaf(xhat, s_gam[c], s_bet[c]), p.act);
-        sg[u] += g; sq[u] += g * xhat;
+        sg[u] += (double)g; sq[u] = fma((double)g, (double)xhat, sq[u]);
       }
     }
 #pragma unroll
@@ -306,8 +307,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += 256) {
     double* r = p.red + 2 * ((size_t)b * p.C + c);
-    atomicAdd(r, (double)s_acc[0][c]);
-    atomicAdd(r + 1, (double)s_acc[1][c]);
+    atomicAdd(r, s_acc[0][c]);
+    atomicAdd(r + 1, s_acc[1][c]);
   }
 }
 

@@ -1,0 +1,312 @@
+"""GPU parity of the train step (mdctgan_b200/train_ops.py, csrc/train_kernels.cuh) through the C ABI.
+
+Layer level: our tape (forward kernels + dgrad / wgrad / norm-backward kernels) against torch-CPU autograd of the same
+layers (reference layers: models/networks.py:308-352 generator, :421-463 ResnetBlock, :649-670 PatchGAN,
+bottleneck_transformer_pytorch attention).  Step level: losses, gradients and post-Adam parameters against
+oracle/train_oracle.py (pinned to the reference by tests/test_oracle_train.py) and against the committed reference
+goldens directly (tests/golden/train_golden.npz).
+
+Tolerances: layer level 2e-4 rel-L2 per gradient tensor (measured: 1e-7 .. 2e-6: fp32 kernels, different summation order
+than torch-CPU).  Whole step: losses 5e-4 relative; gradients 2e-2 rel-L2 per tensor.  The whole-step gradient bar is NOT a
+precision bar: the graph holds ~10^5 ReLU / LeakyReLU masks and L1 signs, and a forward difference of 1e-6 (fp32 rounding)
+flips a few of them, each flip a finite jump of the gradient.  Measured on the oracle itself (tools/debug_train.py,
+"cond" rows): perturbing the discriminator input by 1e-6 relative moves its own weight gradients by 4e-4 .. 9e-4 rel-L2 on
+the coarse scale -- exactly the differences our kernels show against it -- while every layer in isolation agrees to 1e-6.
+The cfg4 network (9 residual blocks on 2x16-pixel planes, BatchNorm over a batch of 2) is chaotic at random init: the same 1e-6
+probe moves the ORACLE's generator gradients by 3e-3 (last layers) .. 6e-2 (first layers) (/tmp-style probe recorded in
+DESIGN.md section 5), which is the profile of our differences (3e-3 .. 7e-2, with either convolution engine and with the fp64
+transform), so tr_cfg4 is held to 0.25 (generator) / 5e-2 (discriminator) and tr_small to 2e-2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, GOLDEN)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+LAYER_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, reflect, transposed, norm_in ('in' | None), act_in
+    (2, 32, 8, 16, 64, 3, 1, 1, True, False, "in", 1),      # ResnetBlock conv (reflect) behind IN + ReLU
+    (3, 16, 8, 32, 32, 3, 2, 1, False, False, "in", 1),     # stride-2 downsample
+    (2, 64, 4, 8, 32, 3, 2, 1, False, True, "in", 1),       # ConvTranspose2d k3 s2 p1 op1
+    (2, 3, 9, 17, 16, 4, 2, 2, False, False, None, 0),      # PatchGAN first layer (Cin = 3)
+    (2, 16, 5, 9, 32, 4, 1, 2, False, False, "in", 2),      # PatchGAN stride-1 layer behind IN + LeakyReLU
+    (2, 32, 5, 9, 1, 4, 1, 2, False, False, "in", 2),       # PatchGAN head (Cout = 1)
+    (2, 8, 16, 32, 1, 7, 1, 3, True, False, "in", 1),       # generator head 7x7 reflect (Cout = 1)
+    (2, 2, 16, 32, 8, 7, 1, 3, True, False, None, 0),       # generator stem (Cin = 2)
+    (2, 64, 2, 16, 128, 1, 1, 0, False, False, None, 0),    # 1x1 (BottleStack)
+    (4, 256, 4, 32, 256, 3, 1, 1, True, False, "in", 1),    # cfg2 residual conv (tcgen05 path for forward / dgrad)
+]
+
+
+@pytest.mark.parametrize("engine", ["direct", "umma"])
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_conv_layer_backward_matches_torch(dev, case, engine, monkeypatch):
+    """x -> [IN -> act] -> conv -> loss = sum(y * r): dX, dW, dbias vs torch autograd."""
+    from mdctgan_b200 import nn_ops as ops
+    from mdctgan_b200.models import networks as N
+
+    monkeypatch.setattr(ops, "CONV_ENGINE", engine)
+    B, Cin, H, W, Cout, k, stride, pad, reflect, transposed, norm_in, act_in = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 2**31)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    if transposed:
+        layer = N.ConvTranspose2d(Cin, Cout, k, stride=stride, padding=pad, output_padding=1)
+    else:
+        layer = N.Conv2d(Cin, Cout, k, stride=stride, padding=0 if reflect else pad)
+    with torch.no_grad():
+        layer.weight.copy_(torch.randn(layer.weight.shape, generator=g) * 0.1)
+        layer.bias.copy_(torch.randn(Cout, generator=g))
+    # torch reference
+    xr = x.clone().requires_grad_(True)
+    wr, br = layer.weight.detach().clone().requires_grad_(True), layer.bias.detach().clone().requires_grad_(True)
+    v = xr
+    if norm_in:
+        v = F.instance_norm(v)
+        v = F.relu(v) if act_in == 1 else F.leaky_relu(v, 0.2)
+    if transposed:
+        y = F.conv_transpose2d(v, wr, br, stride=stride, padding=pad, output_padding=1)
+    elif reflect:
+        y = F.conv2d(F.pad(v, (pad,) * 4, mode="reflect"), wr, br, stride=stride)
+    else:
+        y = F.conv2d(v, wr, br, stride=stride, padding=pad)
+    r = torch.randn(y.shape, generator=g)
+    (y * r).sum().backward()
+    # ours: the raw tensor x plays the producer's conv output; its statistics come from a tiny helper conv-free path
+    layer = layer.to(dev)
+    tape = ops.Tape()
+    with ops.stats_pass(dev), ops.recording(tape):
+        raw = ops.Feat(_nhwc(x).to(dev))
+        f = raw
+        if norm_in:
+            xd = x.double()
+            st = torch.stack((xd.sum(dim=(2, 3)), (xd * xd).sum(dim=(2, 3))), dim=-1).to(dev)    # [B, C, 2] (sum, sumsq)
+            raw = ops.Feat(raw.x, stats=st)
+            f = ops.with_act(ops.finalize_norm(raw, eps=1e-5, mode=0), act_in)
+        out = layer.run(f, pad_reflect=pad if reflect else 0)
+    assert rel_l2(_nchw(out.x.cpu()).numpy(), y.detach().numpy()) < 2e-5
+    G = ops.GradMap()
+    G.add(out, _nhwc(r).to(dev))
+    tape.backward(G)
+    dx = G.pop(raw)
+    torch.cuda.synchronize()
+    e_w = rel_l2(layer.weight.grad.cpu().numpy(), wr.grad.numpy())
+    e_b = rel_l2(layer.bias.grad.cpu().numpy(), br.grad.numpy())
+    e_x = rel_l2(_nchw(dx.cpu()).numpy(), xr.grad.numpy())
+    print(f"layer {case} [{engine}]: dW {e_w:.2e} db {e_b:.2e} dX {e_x:.2e}")
+    assert e_w < 2e-4 and e_b < 2e-4 and e_x < 2e-4
+
+
+def test_resnet_block_and_pool_backward(dev):
+    """x -> avgpool -> ResnetBlock -> sum(y*r): exercises combine, deferred IN views with two consumers, pool backward."""
+    from mdctgan_b200 import nn_ops as ops
+    from mdctgan_b200.models import networks as N
+    from oracle import networks_oracle as NO
+
+    torch.manual_seed(3)
+    C = 32
+    blk = N.ResnetBlock(C, "reflect", N.get_norm_layer("instance"))
+    blk.apply(N.weights_init)
+    x = torch.randn(2, C, 16, 32)
+    sd = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    y = NO.resnet_block(sd, "b", NO.avgpool(xr))
+    r = torch.randn(y.shape)
+    (y * r).sum().backward()
+    blk = blk.to(dev)
+    tape = ops.Tape()
+    with ops.stats_pass(dev), ops.recording(tape):
+        leaf = ops.Feat(_nhwc(x).to(dev))
+        out = blk.run(ops.avgpool3s2(leaf))
+    G = ops.GradMap()
+    G.add(out, _nhwc(r).to(dev))
+    tape.backward(G)
+    assert rel_l2(_nchw(out.x.cpu()).numpy(), y.detach().numpy()) < 2e-5
+    assert rel_l2(_nchw(G.pop(leaf).cpu()).numpy(), xr.grad.numpy()) < 3e-4
+    for k, p in blk.named_parameters():
+        ref = sd["b." + k].grad
+        if k.endswith("bias"):     # bias in front of InstanceNorm: the true gradient is zero, both sides hold rounding noise
+            assert p.grad.abs().max().item() < 1e-3 * float(sd["b.conv_block.1.weight"].grad.abs().max())
+        else:
+            assert rel_l2(p.grad.cpu().numpy(), ref.numpy()) < 3e-4, k
+
+
+def test_bottlestack_backward(dev):
+    """BottleStack (1x1 convs, train-mode BatchNorm, attention with abs. position embedding, shortcut) vs torch autograd."""
+    from mdctgan_b200 import nn_ops as ops
+    from mdctgan_b200.models import networks as N
+    from mdctgan_b200.models.bottleneck import BottleStack
+    from oracle import networks_oracle as NO
+
+    torch.manual_seed(5)
+    dim, heads, dh, fmap = 64, 2, 32, (2, 16)
+    bs = BottleStack(dim=dim, fmap_size=fmap, dim_out=dim, num_layers=2, proj_factor=4, downsample=False, heads=heads, dim_head=dh,
+                     activation=N.ReLU(True), rel_pos_emb=False)
+    bs.apply(N.weights_init)
+    bs.train()
+    x = torch.randn(3, dim, *fmap)
+    sd = {"s." + k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+          for k, v in bs.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    y = NO.bottle_stack(sd, "s", xr, 2, heads, dh, training=True)
+    r = torch.randn(y.shape)
+    (y * r).sum().backward()
+    bs = bs.to(dev)
+    tape = ops.Tape()
+    with ops.stats_pass(dev), ops.recording(tape):
+        leaf = ops.Feat(_nhwc(x).to(dev))
+        out = bs.run(leaf)
+    G = ops.GradMap()
+    G.add(out, _nhwc(r).to(dev))
+    tape.backward(G)
+    assert rel_l2(_nchw(out.x.cpu()).numpy(), y.detach().numpy()) < 2e-5
+    assert rel_l2(_nchw(G.pop(leaf).cpu()).numpy(), xr.grad.numpy()) < 5e-4
+    for k, p in bs.named_parameters():
+        assert rel_l2(p.grad.cpu().numpy(), sd["s." + k].grad.numpy()) < 5e-4, k
+
+
+def test_fused_adam_matches_torch(dev):
+    from mdctgan_b200.optim import FlatBucket, FusedAdam
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3), torch.nn.Conv2d(5, 7, 1)).to(dev)
+    ref = [p.detach().cpu().clone().requires_grad_(True) for p in net.parameters()]
+    opt_ref = torch.optim.Adam(ref, lr=2e-4, betas=(0.5, 0.999))
+    bucket = FlatBucket(net)
+    opt = FusedAdam(bucket, lr=2e-4, betas=(0.5, 0.999))
+    for it in range(3):
+        opt.zero_grad()
+        for p, q in zip(net.parameters(), ref):
+            g = torch.randn(q.shape)
+            q.grad = g.clone()
+            p.grad.copy_(g)
+        opt.step()
+        opt_ref.step()
+    for p, q in zip(net.parameters(), ref):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().numpy(), rtol=0, atol=2e-7)
+
+
+def _build_model(flags, seed, dev):
+    from mdctgan_b200.models.models import create_model
+    from mdctgan_b200.options.train_options import TrainOptions
+
+    base = ["--name", "t", "--checkpoints_dir", "/tmp/mdctgan_test", "--gpu_ids", str(dev.index or 0), "--lr_sampling_rate", "12000",
+            "--sr_sampling_rate", "48000", "--arcsinh_transform", "--abs_spectro", "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1",
+            "--abs_norm", "--src_range", "-5", "5"]
+    opt = TrainOptions().parse(save=False, args=base + list(flags))
+    torch.manual_seed(seed)
+    model = create_model(opt)
+    model.train()
+    return model
+
+
+@pytest.mark.parametrize("name", ["tr_small", "tr_cfg4"])
+@pytest.mark.parametrize("api", ["autograd", "train_step"])
+def test_train_step_matches_oracle_and_reference(dev, name, api):
+    """Two iterations of train.py:160-202 on the reference's seeded batch: the four losses, every gradient tensor of the
+    first iteration and the parameters after the second, through (a) the reference-shaped API
+    (_forward -> loss.backward() -> optimizer.step()) and (b) model.train_step()."""
+    from make_golden_nets import TRAIN_FLAGS, TRAIN_STEPS
+    from oracle import train_oracle as TO
+    from test_oracle_train import flags_to_cfg
+
+    gold = dict(np.load(os.path.join(GOLDEN, "train_golden.npz")))
+    flags, batch, T, seed = TRAIN_FLAGS[name]
+    cfg = flags_to_cfg(flags)
+    from test_oracle_train import build_nets
+
+    model = _build_model(flags, seed, dev)
+    # the reference golden was made on CPU: same seeded CPU initialisation (weights_init on a CUDA module draws from the CUDA generator)
+    G0, D0 = build_nets(cfg, seed)
+    model.netG.load_state_dict(G0.state_dict())
+    model.netD.load_state_dict(D0.state_dict())
+    sdG = {k: v.detach().cpu().clone() for k, v in model.netG.state_dict().items()}
+    sdD = {k: v.detach().cpu().clone() for k, v in model.netD.state_dict().items()}
+    kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D",
+                              "fit_residual")}
+    lr_a, hr_a = gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"]
+    ref = TO.train_step(sdG, sdD, lr_a, hr_a, steps=TRAIN_STEPS, **kw)
+    lr_d, hr_d = torch.from_numpy(lr_a).to(dev), torch.from_numpy(hr_a).to(dev)
+    losses = []
+    for it in range(TRAIN_STEPS):
+        if api == "autograd":
+            ls, _ = model._forward(lr_d, hr_d)
+            d = dict(zip(model.loss_names, ls))
+            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+            loss_G = d["G_GAN"] + d["G_GAN_Feat"]
+            model.optimizer_G.zero_grad()
+            loss_G.backward()
+            if it == 0:
+                gG = {k: p.grad.detach().cpu().clone() for k, p in model.netG.named_parameters()}
+            model.optimizer_G.step()
+            model.optimizer_D.zero_grad()
+            loss_D.backward()
+            if it == 0:
+                gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
+            model.optimizer_D.step()
+            losses.append([float(d[k]) for k in ("G_GAN", "G_GAN_Feat", "D_real", "D_fake")])
+        else:
+            lv = model.train_step(lr_d, hr_d)
+            losses.append(lv.cpu().tolist())
+            if it == 0:
+                gG = {k: p.grad.detach().cpu().clone() for k, p in model.netG.named_parameters()}
+                gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
+    # iteration 1: same weights on both sides.  Iteration 2 sees one Adam step, which at step 1 is a pure sign update
+    # (m / sqrt(v) = g / |g|): elements whose gradient is below the fp32 noise floor move by +-lr on a coin flip, on any two
+    # implementations (the reference on CPU vs on GPU included), so the second-iteration losses are held to 1e-2.
+    np.testing.assert_allclose(np.array(losses)[0], np.array(ref["losses"])[0], rtol=5e-4)
+    np.testing.assert_allclose(np.array(losses)[0], gold[f"{name}_losses"][0], rtol=5e-4)       # the reference itself
+    rt2 = 5e-2 if name == "tr_cfg4" else 1e-2
+    np.testing.assert_allclose(np.array(losses)[1:], np.array(ref["losses"])[1:], rtol=rt2)
+    np.testing.assert_allclose(np.array(losses)[1:], gold[f"{name}_losses"][1:], rtol=rt2)
+    gmaxG = max(float(v.abs().max()) for v in ref["gradG"].values())
+    worst = 0.0
+    for k, v in ref["gradG"].items():
+        if float(v.abs().max()) < 1e-4 * gmaxG:      # zero-gradient tensors (biases in front of a norm): noise on both sides
+            assert float(gG[k].abs().max()) < 1e-3 * gmaxG, k
+            continue
+        e = rel_l2(gG[k].numpy(), v.numpy())
+        worst = max(worst, e)
+        assert e < (0.25 if name == "tr_cfg4" else 2e-2), (k, e)
+    gmaxD = max(float(v.abs().max()) for v in ref["gradD"].values())
+    for k, v in ref["gradD"].items():
+        if float(v.abs().max()) < 1e-4 * gmaxD:
+            assert float(gD[k].abs().max()) < 1e-3 * gmaxD, k
+            continue
+        e = rel_l2(gD[k].numpy(), v.numpy())
+        assert e < (5e-2 if name == "tr_cfg4" else 2e-2), (k, e)
+    # parameters after TRAIN_STEPS Adam steps: each element moves by ~lr per step in the direction of sign(gradient), so an element
+    # whose (tiny) gradient differs in sign between the two implementations ends 2*lr apart: with a fraction f of such elements the
+    # distance is ~2*sqrt(f) of the distance moved (random signs would give 1.41); 0.25 <=> f < 1.6 % of the elements
+    for k, v in ref["paramsG"].items():
+        if v.dim() >= 2:
+            got = model.netG.state_dict()[k].detach().cpu()
+            moved = (v - sdG[k]).norm().item()
+            assert (got - v).norm().item() < (1.0 if name == "tr_cfg4" else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
+    for k, v in ref["paramsD"].items():
+        if v.dim() >= 2:
+            got = model.netD.state_dict()[k].detach().cpu()
+            moved = (v - sdD[k]).norm().item()
+            assert (got - v).norm().item() < (1.0 if name == "tr_cfg4" else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
+    print(f"{name}/{api}: losses {losses[0]}, worst G-gradient rel-L2 {worst:.2e}")
