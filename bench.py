@@ -1,26 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- the MDCT -> generator -> IMDCT hot path on N B200s of one node.
+"""bench.py -- the GAN train step of the MDCT -> generator -> IMDCT hot path on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload = BASELINE.json configs[1]: GlobalGenerator only (n_blocks_attn_g = 0), 12 -> 48 kHz, ngf = 32,
-n_downsample_global = 3, 9 residual blocks, batch 4, fp32, segments of 7936 samples (= 32 frames: 8192
-samples give 33 frames, which the reference generator cannot process).  A "step" is one
-`model.inference(lr_audio)` pass over one batch: fused MDCT+arcsinh/abs-norm kernel -> generator kernels ->
---fit_residual -> fused denorm+IMDCT kernel.  (The train step of the BASELINE metric -- discriminator,
-losses, backward, Adam -- is not built in this round; DESIGN.md.)  Rank 0 prints ONE JSON line:
+Metric (BASELINE.json): train-step audio-seconds per second.  Workload = BASELINE configs[3] at its per-GPU slice:
+LocalEnhancer (ngf 32, 3 downsamplings, 9 global + 3 local residual blocks, 2 BottleStack attention layers with
+4 heads x 64) + MultiscaleDiscriminator (num_D 3, 3 layers, ndf 64) + LSGAN + feature matching + two Adams,
+--fit_residual, 12 -> 48 kHz, fp32, 4 segments of 7936 samples (32 frames; 8192 samples give 33 frames, which the
+reference generator cannot process) per GPU: global batch 4 N (32 at N = 8, the configuration the
+metric is quoted on), weak scaling, ONE NCCL all-reduce of the flat [grad_G | grad_D] bucket per step.
+A "step" = one iteration of train.py:160-202: 2 fused MDCT launches, G forward, D forward on [fake ; real], the
+four losses, generator sweep, discriminator sweep, all-reduce, both Adam steps.  Rank 0 prints ONE JSON line:
 
-  value        whole-job audio-seconds per second, batch resident in HBM, the captured CUDA graph of the step
-               replayed K times, CUDA events, max over ranks; N > 1 = N independent replicas (weak scaling,
-               no collective on this path)
-  e2e          same metric through the public API from pinned HOST audio: H2D copy, the step, D2H copy of
-               the reconstructed audio, every step
-  roofline     the dominant kernel of the step (the residual-block convolution), timed with CUDA events
-               around every launch of an eager pass inside bench.py
-  mdct         the transform half on its own at HBM-roofline scale (8192 clips x 8192 samples): GSamp/s and
-               achieved GB/s of the fused forward / inverse kernels vs MEASURED_PEAKS.json
-  cpu_baseline the reference's torch-CPU formulation of the same step (oracle/: torch_port + networks_oracle,
-               kind "port") on this box's cores
+  value        whole-job audio-s/s, batch resident in HBM, the step captured as a CUDA graph (runtime.GraphedTrainStep)
+               and replayed K times, CUDA events, max over ranks
+  e2e          same metric through the public API from pinned HOST audio: H2D of lr / hr audio, the step, D2H of the
+               four losses, every step, stream-synchronised
+  roofline     the kernel with the largest share of the step, timed with CUDA events around every C-ABI launch of an
+               eager pass inside bench.py
+  mdct         the transform half at HBM-roofline scale (8192 clips x 8192 samples): GSamp/s and achieved GB/s of the
+               fused forward / inverse kernels vs MEASURED_PEAKS.json (the metric's second clause)
+  cpu_baseline the reference's torch-CPU formulation of the same step (oracle/train_oracle.py: complex128 FFT
+               transform, F.conv2d / instance_norm graph, torch autograd, torch.optim.Adam; kind "port") on this box
 """
 import argparse
 import json
@@ -39,12 +40,14 @@ SEG = 7936             # samples per segment (32 frames)
 BATCH = 4
 N_FFT, HOP, NBINS = 512, 256, 256
 GAIN, SRC, RNG = 1000.0, (-5.0, 5.0), (-1.0, 1.0)
-G_KW = dict(ngf=32, n_down=3, n_blocks=9)
-METRIC, UNIT = "inference-step audio-sec/sec (cfg2: MDCT4 -> GlobalGenerator ngf32 -> IMDCT4, batch 4 x 7936 samples, fp32)", "audio-s/s"
+NET_KW = dict(netG="local", n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=2, heads=4, dim_head=64, num_D=3, n_layers_D=3,
+              fit_residual=True)
+METRIC, UNIT = "train-step audio-sec/sec (cfg4 per-GPU slice: LocalEnhancer+2 attn, num_D 3, feat-match, 2x Adam, batch 4 x 7936 samples per GPU, fp32)", "audio-s/s"
 OPT_ARGS = ["--name", "bench", "--lr_sampling_rate", "12000", "--sr_sampling_rate", "48000", "--arcsinh_transform", "--abs_spectro",
-            "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1", "--abs_norm", "--src_range", "-5", "5", "--netG", "global",
-            "--ngf", "32", "--n_downsample_global", "3", "--n_blocks_global", "9", "--n_blocks_attn_g", "0", "--segment_length", str(SEG),
-            "--bins", "32", "--fit_residual", "--num_D", "1"]
+            "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1", "--abs_norm", "--src_range", "-5", "5", "--netG", "local",
+            "--ngf", "32", "--n_downsample_global", "3", "--n_blocks_global", "9", "--n_blocks_attn_g", "2", "--heads_g", "4",
+            "--dim_head_g", "64", "--n_blocks_local", "3", "--num_D", "3", "--n_layers_D", "3", "--ndf", "64", "--lambda_feat", "10",
+            "--segment_length", str(SEG), "--bins", "32", "--fit_residual", "--lr", "0.0002", "--beta1", "0.5"]
 
 
 def peaks():
@@ -58,12 +61,14 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"
 
 
-def workload_config():
-    return {"workload": "cfg2 (BASELINE configs[1]): GlobalGenerator only, ngf 32, 3 downsamplings, 9 residual blocks, no attention, "
-                        "12->48 kHz, --fit_residual, batch 4 segments x 7936 samples (32 frames x 256 bins), fp32; inference step",
-            "batch_per_gpu": BATCH, "samples_per_segment": SEG, "n_fft": N_FFT, "hop": HOP,
-            "l2": "working set (46 MB of weights + 20 MB of activations) is smaller than L2 by construction of the reference config; "
-                  "the `mdct` sub-benchmark uses inputs larger than L2 (268 MB audio)"}
+def workload_config(world=1):
+    return {"workload": "cfg4 (BASELINE configs[3]) per-GPU slice: full GAN train step, LocalEnhancer ngf 32 / 3 down / 9+3 blocks / 2 attention "
+                        "layers (4 heads x 64) + MultiscaleDiscriminator num_D 3 + LSGAN + feature matching (lambda 10) + 2x Adam(2e-4, 0.5), "
+                        "--fit_residual, 12->48 kHz, fp32, 4 segments x 7936 samples (32 frames x 256 bins) per GPU",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * world, "samples_per_segment": SEG, "n_fft": N_FFT, "hop": HOP,
+            "parallelism": f"dp{world}: batch-sharded, one all-reduce of the flat 54.7 M-element gradient bucket per step",
+            "l2": "per step the kernels stream 219 MB of weights, 219 MB of gradients and 438 MB of Adam state (larger than the 126 MB L2) "
+                  "plus ~60 MB of activations; the `mdct` sub-benchmark uses 268 MB of audio"}
 
 
 class ClockSampler(threading.Thread):
@@ -127,32 +132,27 @@ def make_lr_audio(batch, T, seed):
     return torch.from_numpy(np.fft.irfft(X, n=T, axis=-1).astype(np.float32))
 
 
+def make_hr_audio(batch, T, seed):
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(seed + 17)
+    return torch.from_numpy((0.1 * rng.standard_normal((batch, T))).astype(np.float32))
+
+
 def cpu_port_run(seconds_budget=None, steps=None, warmup=1):
-    """The reference's torch-CPU formulation of the step: oracle/torch_port.py (transform, complex128 FFT) +
-    oracle/networks_oracle.py (the same F.conv2d / instance_norm calls the reference's modules make)."""
+    """The reference's torch-CPU formulation of the train step: oracle/train_oracle.py (make_stepper)."""
     import torch
 
     from mdctgan_b200.models import networks
-    from oracle import networks_oracle as NO
-    from oracle import torch_port as P
+    from oracle import train_oracle as TO
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
-    net = networks.define_G(2, 1, 32, "global", 3, 9, norm="instance", input_size=(32, 256))   # parameter holder only
-    sd = net.state_dict()
-    x = make_lr_audio(BATCH, SEG, 7)
-    a2m = P.Audio2MDCTPort(GAIN, SRC, RNG, N_FFT, HOP)
-
-    def step():
-        with torch.no_grad():
-            s, pha, prm = a2m.to_spectro(x)
-            inp = torch.cat((s, s.abs() * 2 + RNG[0]), dim=1)
-            sr = NO.global_generator(sd, inp, 3, 9)
-            sr[..., :64] *= 1e-3
-            sr = sr + s
-            return a2m.to_audio(sr, prm, pha)
-
+    G = networks.define_G(2, 1, 32, "local", 3, 9, 1, 3, "instance", input_size=(32, 256), n_attn_g=2, heads_g=4, dim_head_g=64)  # parameter holders
+    D = networks.define_D(3, 64, 3, "instance", False, 3, True)
+    step = TO.make_stepper(G.state_dict(), D.state_dict(), make_lr_audio(BATCH, SEG, 42), make_hr_audio(BATCH, SEG, 42), **NET_KW)
     for _ in range(warmup):
         step()
     times = []
@@ -167,19 +167,19 @@ def cpu_port_run(seconds_budget=None, steps=None, warmup=1):
             break
     total = sum(times)
     return {"value": BATCH * SEG / SR * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"the same step (batch {BATCH} x {SEG} samples), {len(times)} steps, torch-CPU {torch.get_num_threads()} threads, fp32 "
-                      f"network + complex128 transform (oracle/torch_port.py + oracle/networks_oracle.py)",
+            "sample": f"the same train step (batch {BATCH} x {SEG} samples), {len(times)} steps, torch-CPU {torch.get_num_threads()} threads, fp32 "
+                      f"networks + complex128 transform, torch autograd + torch.optim.Adam (oracle/train_oracle.py)",
             "ms_per_step": 1e3 * total / len(times)}
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = min(args.steps, 40)
-    r = cpu_port_run(steps=steps, warmup=min(args.warmup, 3))
+    steps = min(args.steps, 30)
+    r = cpu_port_run(steps=steps, warmup=min(args.warmup, 2))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 network / f64 transform (reference dtypes)", "data": "synthetic", "config": workload_config(),
+            "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 networks / f64 transform (reference dtypes)", "data": "synthetic", "config": workload_config(1),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -230,25 +230,30 @@ def bench_mdct(dev, steps, hbm_peak):
 
 
 # ---------------------------------------------------------------------------------------------- per-launch profile
+KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_wgrad", "mdctgan_norm_finalize", "mdctgan_norm_apply",
+                  "mdctgan_norm_act_bwd", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_avgpool3s2_nhwc",
+                  "mdctgan_avgpool3s2_bwd", "mdctgan_attention_abs_pos", "mdctgan_attention_abs_pos_bwd", "mdctgan_mse_const_fwd",
+                  "mdctgan_mse_const_bwd", "mdctgan_l1_pair_fwd", "mdctgan_l1_pair_bwd", "mdctgan_f64_to_f32", "mdctgan_disc_input_fwd",
+                  "mdctgan_disc_input_bwd", "mdctgan_adam_flat", "mdctgan_counter_inc", "mdctgan_conv2d_umma_pack_weight",
+                  "mdctgan_nchw_to_nhwc", "mdctgan_nhwc_to_nchw", "mdctgan_residual_scale_add", "mdctgan_audio2mdct_forward",
+                  "mdctgan_mdct2audio_inverse"]
+
+
 class LaunchProfiler:
     """CUDA events around every C-ABI launch of an eager pass (bench-only instrumentation)."""
 
     def __init__(self, dev):
         import torch
 
-        from mdctgan_b200 import _lib, nn_ops
+        from mdctgan_b200 import nn_ops
 
         self.torch, self.dev = torch, dev
         self.L = nn_ops._L()
-        self.names = [n for n in dir(self.L) if n.startswith("mdctgan_")] or []
-        self.names = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_norm_finalize", "mdctgan_norm_apply", "mdctgan_attention_abs_pos",
-                      "mdctgan_avgpool3s2_nhwc", "mdctgan_nchw_to_nhwc", "mdctgan_nhwc_to_nchw", "mdctgan_residual_scale_add",
-                      "mdctgan_audio2mdct_forward", "mdctgan_mdct2audio_inverse"]
         self.orig, self.records = {}, []
 
     def __enter__(self):
         torch = self.torch
-        for n in self.names:
+        for n in KERNEL_ENTRIES:
             if not hasattr(self.L, n):
                 continue
             f = getattr(self.L, n)
@@ -260,15 +265,23 @@ class LaunchProfiler:
                 e0.record(st)
                 rc = _f(*a)
                 e1.record(st)
-                tag = _n
+                tag, flops, nbytes = _n.replace("mdctgan_", ""), 0.0, 0.0
                 if _n in ("mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma"):
-                    B, H, W, Cin, Cout, kh, stride, transposed = a[1], a[2], a[3], a[4], a[10], a[11], a[13], a[16]
-                    Ho, Wo = a[8], a[9]
-                    eng = "umma" if _n.endswith("umma") else "direct"
-                    tag = f"conv[{eng}] k{kh} s{stride}{' T' if transposed else ''} {Cin}->{Cout} @{Ho}x{Wo}"
-                    self.records.append((tag, e0, e1, 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)))
-                else:
-                    self.records.append((tag, e0, e1, 0.0))
+                    B, H, W, Cin, Ho, Wo, Cout, kh, stride, transposed = a[1], a[2], a[3], a[4], a[8], a[9], a[10], a[11], a[13], a[16]
+                    eng = "tcgen05" if _n.endswith("umma") else "fp32"
+                    tag = f"conv[{eng}] k{kh} s{stride}{'T' if transposed else ''} {Cin}->{Cout} B{B} @{Ho}x{Wo}"
+                    flops = 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)
+                elif _n == "mdctgan_conv2d_wgrad":
+                    B, Cin, Ho, Wo, Cout, kh, stride, transposed = a[1], a[4], a[6], a[7], a[8], a[9], a[11], a[14]
+                    tag = f"wgrad[fp32] k{kh} s{stride}{'T' if transposed else ''} {Cin}->{Cout} B{B} @{Ho}x{Wo}"
+                    flops = 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)
+                elif _n == "mdctgan_adam_flat":
+                    nbytes = 28.0 * a[4]          # p, g, m, v read (16 B) + p, m, v written (12 B) per parameter
+                elif _n == "mdctgan_norm_act_bwd":
+                    nbytes = 4.0 * a[13] * a[14] * a[15] * 5   # x, dv read twice + dx written
+                elif _n == "mdctgan_norm_apply":
+                    nbytes = 4.0 * a[15] * a[16] * a[17] * (3 if a[6] else 2)
+                self.records.append((tag, _n, e0, e1, flops, nbytes))
                 return rc
 
             setattr(self.L, n, wrap)
@@ -279,13 +292,13 @@ class LaunchProfiler:
             setattr(self.L, n, f)
 
     def table(self):
+        """tag -> [launches, total ms, flops per launch, bytes per launch, entry point]"""
         self.torch.cuda.synchronize(self.dev)
         agg = {}
-        for tag, e0, e1, flops in self.records:
-            t = e0.elapsed_time(e1)
-            a = agg.setdefault(tag, [0, 0.0, flops])
+        for tag, entry, e0, e1, flops, nbytes in self.records:
+            a = agg.setdefault(tag, [0, 0.0, flops, nbytes, entry])
             a[0] += 1
-            a[1] += t
+            a[1] += e0.elapsed_time(e1)
         return agg
 
 
@@ -297,7 +310,7 @@ def run_ours(args):
     import mdctgan_b200
     from mdctgan_b200.models.models import create_model
     from mdctgan_b200.options.train_options import TrainOptions
-    from mdctgan_b200.runtime import GraphedInference
+    from mdctgan_b200.runtime import GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -311,72 +324,105 @@ def run_ours(args):
 
     opt = TrainOptions().parse(save=False, args=OPT_ARGS + ["--gpu_ids", str(local)])
     opt.checkpoints_dir = "/tmp/mdctgan_bench"
-    torch.manual_seed(1234)                      # identical weights on every rank
+    torch.manual_seed(1234)                      # identical initial weights on every rank
+    torch.cuda.manual_seed(1234)
     model = create_model(opt)
-    model.eval()
-    lr = make_lr_audio(BATCH, SEG, 42 + rank).to(dev)
+    model.train()
+    lr = make_lr_audio(BATCH, SEG, 42 + rank).to(dev)      # a different batch per rank
+    hr = make_hr_audio(BATCH, SEG, 42 + rank).to(dev)
     warm = max(args.warmup, 3)
+
+    def all_reduce(flat):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- eager warm-up + correctness guard against the CPU oracle (outside every timed region)
-    for _ in range(warm):
-        out = model.inference(lr)
+    # ---- correctness guard against the CPU oracle (rank 0, world-size-1 math, outside every timed region): the four losses
+    # of the first iteration on the initial weights
+    err = None
     if rank == 0:
-        from oracle import model_oracle as MOD
+        from oracle import train_oracle as TO
 
-        sd = {k: v.cpu() for k, v in model.netG.state_dict().items()}
-        _, ref_audio, _ = MOD.inference(sd, lr.cpu().numpy(), netG="global", n_down=3, n_blocks_global=9, fit_residual=True, up_ratio=4.0)
-        err = float(((out[1].cpu().double().numpy() - ref_audio) ** 2).sum() ** 0.5 / (ref_audio ** 2).sum() ** 0.5)
-        assert err < 1e-3, f"waveform rel-L2 vs oracle {err} breaks the 1e-3 bar"
-    else:
-        err = None
+        sdG = {k: v.detach().cpu().clone() for k, v in model.netG.state_dict().items()}
+        sdD = {k: v.detach().cpu().clone() for k, v in model.netD.state_dict().items()}
+        ls, hs = TO.spectro(lr.cpu().numpy()), TO.spectro(hr.cpu().numpy())
+        with torch.no_grad():
+            ref_losses, _ = TO.losses(sdG, sdD, ls, hs, **NET_KW)
+        ref_losses = [float(v) for v in ref_losses]
+    # ---- eager steps: launches per step, per-kernel table (CUDA events around every C-ABI launch)
+    first = model.train_step(lr, hr, world, all_reduce if world > 1 else None).cpu().tolist()
+    if rank == 0:
+        err = max(abs(a - b) / abs(b) for a, b in zip(first, ref_losses))
+        assert err < 2e-3, f"train-step losses {first} vs oracle {ref_losses}"
+    for _ in range(2):
+        model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+    n0 = mdctgan_b200.launch_count()
+    model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+    launches_per_step = mdctgan_b200.launch_count() - n0
+    with LaunchProfiler(dev) as prof:
+        for _ in range(3):
+            model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+    table = prof.table()
+    tot_ms = sum(v[1] for v in table.values())
 
     # ---- timed region: the step as a CUDA graph, K replays
-    gi = GraphedInference(model, BATCH, SEG, warmup=2)
-    gi.static_in.copy_(lr)
+    gts = GraphedTrainStep(model, BATCH, SEG, world, all_reduce if world > 1 else None, warmup=2)
+    gts.lr_in.copy_(lr)
+    gts.hr_in.copy_(hr)
+    gts.recapture()
     st = torch.cuda.current_stream(dev)
     for _ in range(warm):
-        gi.replay()
+        gts.replay()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(args.steps):
-        gi.replay()
+        gts.replay()
     e1.record(st)
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
+    last_losses = gts.losses.cpu().tolist()
 
-    # ---- launches per step + per-kernel table from an eager, event-instrumented pass
-    n0 = mdctgan_b200.launch_count()
-    model.inference(lr)
-    launches_per_step = mdctgan_b200.launch_count() - n0
-    with LaunchProfiler(dev) as prof:
-        for _ in range(5):
-            model.inference(lr)
-    table = prof.table()
-    tot_ms = sum(v[1] for v in table.values())
-    dom_tag, dom = max(((k, v) for k, v in table.items() if k.startswith("conv")), key=lambda kv: kv[1][1])
-    dom_ms = dom[1] / dom[0]
-    kernel_table = {k: {"launches_per_step": v[0] // 5, "ms_per_step": v[1] / 5, "share": v[1] / tot_ms} for k, v in
-                    sorted(table.items(), key=lambda kv: -kv[1][1])[:8]}
-
-    # ---- e2e: pinned host audio -> H2D -> graph replay -> D2H of the reconstructed audio, every step
-    xh = lr.cpu().pin_memory()
-    yh = torch.empty(BATCH, 1, 1, SEG, dtype=torch.float32).pin_memory()
+    # ---- e2e: pinned host audio -> H2D -> graph replay -> D2H of the four losses, every step
+    lr_h, hr_h = lr.cpu().pin_memory(), hr.cpu().pin_memory()
+    loss_h = torch.empty(4, dtype=torch.float32).pin_memory()
     for _ in range(3):
-        yh.copy_(gi(xh)[1], non_blocking=True)
+        loss_h.copy_(gts(lr_h, hr_h), non_blocking=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        yh.copy_(gi(xh)[1], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()     # the caller consumes each result before submitting the next batch
+        loss_h.copy_(gts(lr_h, hr_h), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()     # the training loop reads the losses of a step before the next one
+    barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+
+    # ---- the reference-shaped API (train.py:160-202 verbatim: _forward, two backward(), two optimizer.step()), eager, for the record
+    def api_step():
+        ls_, _ = model._forward(lr, hr)
+        d = dict(zip(model.loss_names, ls_))
+        loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+        loss_G = d["G_GAN"] + d["G_GAN_Feat"]
+        model.optimizer_G.zero_grad()
+        loss_G.backward()
+        model.optimizer_G.step()
+        model.optimizer_D.zero_grad()
+        loss_D.backward()
+        model.optimizer_D.step()
+
+    for _ in range(2):
+        api_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    n_api = max(5, min(args.steps, 30))
+    for _ in range(n_api):
+        api_step()
+    torch.cuda.synchronize(dev)
+    api_ms = 1e3 * (time.perf_counter() - t0) / n_api
     clocks = sampler.stop()
 
     mdct = bench_mdct(dev, 50, hbm_peak) if rank == 0 else None
@@ -389,26 +435,43 @@ def run_ours(args):
     if rank == 0:
         audio_s = world * BATCH * SEG / SR
         cpu = cpu_port_run(seconds_budget=args.cpu_seconds, warmup=1)
-        flops = dom[2]
+        dom_tag, dom = max(table.items(), key=lambda kv: kv[1][1])
+        dom_ms = dom[1] / dom[0]
+        if dom[2] > 0:
+            roof = {"bound": "tensor", "kernel": dom_tag, "achieved": dom[2] / (dom_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": dom[2] / (dom_ms * 1e-3) / 1e12 / bf16_peak, "traffic": None, "algorithmic_flops_per_launch": dom[2],
+                    "note": "algorithmic flops = 2*M*N*K of the layer; peak = measured dense bf16 cuBLAS burst (MEASURED_PEAKS.json)"}
+        else:
+            roof = {"bound": "hbm", "kernel": dom_tag, "achieved": dom[3] / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dom[3] / (dom_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": dom[3]}
+        roof.update({"peak_source": peak_src, "avg_launch_ms": dom_ms, "launches_per_step": dom[0] // 3, "share_of_step": dom[1] / tot_ms})
+        by_entry = {}
+        for tag, v in table.items():
+            e = by_entry.setdefault(v[4].replace("mdctgan_", ""), [0, 0.0])
+            e[0] += v[0] // 3
+            e[1] += v[1] / 3
+        kernel_table = {k: {"launches_per_step": v[0] // 3, "ms_per_step": round(v[1] / 3, 4), "share": round(v[1] / tot_ms, 4),
+                            **({"tflops": round(v[2] / (v[1] / v[0] * 1e-3) / 1e12, 2)} if v[2] else {})}
+                        for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:12]}
         line = {
             "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(),
-            "roofline": {"bound": "tensor", "kernel": f"{'conv2d_umma_kernel<64,true> (tcgen05 kind::tf32, 3xTF32 split, cluster split-K)' if 'umma' in dom_tag else 'conv2d_nhwc_kernel (fp32 FFMA)'}: {dom_tag}",
-                         "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
-                         "frac": flops / (dom_ms * 1e-3) / 1e12 / bf16_peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": dom_ms, "share_of_step": dom[1] / tot_ms,
-                         "note": "algorithmic flops = 2*M*N*K of the convolution (the 3xTF32 split issues 3x that on the tensor pipe); "
-                                 "peak = measured dense bf16 cuBLAS burst; at batch 4 x 4x32 pixels the layer is 0.6 GFLOP over 2.4 MB of "
-                                 "weights: latency / weight-bandwidth bound, not tensor bound (DESIGN.md)"},
+            "config": workload_config(world),
+            "roofline": roof,
             "kernel_table": kernel_table,
+            "entry_point_table": {k: {"launches_per_step": v[0], "ms_per_step": round(v[1], 4)} for k, v in
+                                  sorted(by_entry.items(), key=lambda kv: -kv[1][1])},
+            "eager_sum_of_kernels_ms": tot_ms / 3,
             "mdct": mdct,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": BATCH * SEG * 4, "d2h_bytes_per_step": BATCH * SEG * 4,
-                    "ms_per_step": e2e_ms, "api": "GraphedInference(model)(pinned lr_audio) -> sr_audio copied to pinned host memory, "
-                                                  "stream-synchronised every step"},
+            "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SEG * 4, "d2h_bytes_per_step": 16,
+                    "ms_per_step": e2e_ms, "api": "runtime.GraphedTrainStep(model)(pinned lr_audio, pinned hr_audio) -> 4 losses copied to "
+                                                  "pinned host memory, stream-synchronised every step"},
+            "reference_api": {"value": audio_s / world / (api_ms * 1e-3), "ms_per_step": api_ms, "n_gpus": 1,
+                              "api": "train.py:160-202 verbatim on rank 0: model._forward -> loss_G.backward() -> optimizer_G.step() -> "
+                                     "loss_D.backward() -> optimizer_D.step(), eager (host-launch bound), no all-reduce"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
-            "waveform_rel_l2_vs_oracle": err,
+            "losses_first_step_rel_err_vs_oracle": err, "losses_last_step": last_losses,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -418,7 +481,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -191,6 +191,18 @@ int mdctgan_disc_input_bwd(const float* g, const float* s, float* ds, int64_t n,
 int mdctgan_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                       float grad_scale, int64_t step, const int64_t* step_dev, void* stream);
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream);
+/* Kernel-side weight images of every convolution of a model in ONE launch (run after each optimiser step; replaces the
+ * per-layer host-side re-layouts).  Element (k, n) of descriptor d: tap = k / Kch, kc = k % Kch, value =
+ * src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)]; written to dst_kn[k*N + n] (nullable) and / or as TF32 hi|lo into the
+ * tcgen05 image dst_umma (nullable; layout of mdctgan_conv2d_umma_pack_weight, kchunks*2*N*32 floats, rows k >= K zero).
+ * work_begin = prefix sum of kchunks*32*N.  `descs_dev`: device array of n_desc descriptors. */
+typedef struct mdctgan_pack_desc {
+  const float* src; float* dst_kn; float* dst_umma;
+  int32_t K, N, Kch, taps, flip, kchunks;
+  int64_t s_kch, s_n;
+  int64_t work_begin;
+} mdctgan_pack_desc;
+int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_work, void* stream);
 
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);

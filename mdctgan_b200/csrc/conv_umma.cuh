@@ -218,7 +218,8 @@ __device__ __forceinline__ TileGeom make_geom(const ConvUmmaParams& p, int cls) 
     const int nky = (p.kh - g.py + g.cs - 1) / g.cs;
     g.nkx = (p.kw - g.px + g.cs - 1) / g.cs;
     g.cpt = p.Cin / kKC;
-    g.woc = p.Wo / g.cs; g.hw = (p.Ho / g.cs) * g.woc;
+    // ragged classes (Ho or Wo not a multiple of the stride): class (py, px) owns the outputs oy = offy + cs*i < Ho, ox = offx + cs*j < Wo
+    g.woc = (p.Wo - g.offx + g.cs - 1) / g.cs; g.hw = ((p.Ho - g.offy + g.cs - 1) / g.cs) * g.woc;
     g.ntaps = nky * g.nkx;
     g.kchunks = g.ntaps * g.cpt;
     g.sgn = -1; g.mul = 1; g.addy = (g.offy + p.pad - g.py) / g.cs; g.addx = (g.offx + p.pad - g.px) / g.cs;

@@ -285,14 +285,15 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   int min_kchunks = p.kchunks;
   // ConvTranspose2d: tiles per output parity class, K loop over the live taps only (conv_umma.cuh TileGeom)
   p.classes = 1;
-  if (transposed && stride > 1 && Ho % stride == 0 && Wo % stride == 0 && Cin % umma::kKC == 0 && kh >= stride && kw >= stride) {
+  int hw_class = Ho * Wo;
+  if (transposed && stride > 1 && Cin % umma::kKC == 0 && kh >= stride && kw >= stride && Ho >= stride && Wo >= stride) {
     p.classes = stride * stride;
     min_kchunks = (kh / stride) * (kw / stride) * (Cin / umma::kKC);
+    hw_class = ((Ho + stride - 1) / stride) * ((Wo + stride - 1) / stride);   // the largest class (classes are ragged for odd sizes)
   }
   else if (transposed && stride > 1)
-    return mdctgan_set_error(-2, "conv2d_umma: ConvTranspose2d stride %d needs Ho, Wo %% stride == 0, Cin %% 32 == 0, k >= stride", stride);
+    return mdctgan_set_error(-2, "conv2d_umma: ConvTranspose2d stride %d needs Cin %% 32 == 0, k >= stride, Ho, Wo >= stride", stride);
   if (transposed && pad_mode == kPadReflect) return mdctgan_set_error(-1, "conv2d_umma: reflection padding on a transposed convolution");
-  const int hw_class = (Ho * Wo) / p.classes;
   p.m_tiles = (hw_class + umma::kBM - 1) / umma::kBM;     // tiles never span samples
   if (in_stats) {
     if (in_scale) return mdctgan_set_error(-1, "conv2d_umma: pass either in_scale/in_shift or in_stats");

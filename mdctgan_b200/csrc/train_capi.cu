@@ -48,7 +48,7 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout <= 4) {
     const int kblocks = (K + 255) / 256;
-    int chunks = (296 + kblocks * B - 1) / (kblocks * B);
+    int chunks = (1184 + kblocks * B - 1) / (kblocks * B);
     const int max_chunks = (HWo + 255) / 256;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -66,8 +66,13 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     if (chunks < 1) chunks = 1;
     p.pix_per_chunk = ((HWo + chunks - 1) / chunks + 15) / 16 * 16;
     p.chunks_per_sample = (HWo + p.pix_per_chunk - 1) / p.pix_per_chunk;
-    if ((long long)B * p.chunks_per_sample > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
-    conv_wgrad_kernel<float><<<dim3(tiles, B * p.chunks_per_sample), 256, 0, st>>>(p);
+    // work items = (sample, chunk); a CTA takes a contiguous run of them so that ~2 waves of CTAs cover the device
+    const int items = B * p.chunks_per_sample;
+    int gy = (296 + tiles - 1) / tiles;
+    if (gy > items) gy = items;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
+    conv_wgrad_kernel<float><<<dim3(tiles, gy), 256, 0, st>>>(p);
   }
   mdctgan_count_launch();
   CKT(cudaGetLastError());
@@ -250,6 +255,17 @@ int mdctgan_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, f
   }
   const int grid = grid_for((size_t)n / 4 + 1, 256);
   adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_work, void* stream) {
+  if (!descs_dev) return mdctgan_set_error(-1, "pack_weights_multi: NULL descriptor table");
+  if (n_desc <= 0 || total_work <= 0) return 0;
+  static_assert(sizeof(PackDesc) == sizeof(mdctgan_pack_desc), "descriptor layout");
+  pack_weights_multi_kernel<<<grid_for((size_t)total_work, 256 * 8), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, n_desc,
+                                                                                                      (long long)total_work);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;

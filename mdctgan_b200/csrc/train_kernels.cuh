@@ -65,20 +65,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   __shared__ float s_scale[1024], s_shift[1024];
   const int tid = threadIdx.x;
   const int kt = blockIdx.x / p.n_tiles, nt = blockIdx.x - kt * p.n_tiles;
-  const int b = blockIdx.y / p.chunks_per_sample;
-  const int chunk = blockIdx.y - b * p.chunks_per_sample;
   const int HWo = p.Ho * p.Wo;
-  const int m_begin = chunk * p.pix_per_chunk;
-  const int m_end = min(HWo, m_begin + p.pix_per_chunk);
   const int K = p.kh * p.kw * p.Cin;
   const int k0 = kt * TK, n0 = nt * TN;
   const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
-  if (has_norm) nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
-  __syncthreads();
-  if (m_begin >= m_end) return;
-
-  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
-  const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
+  // work items (sample, pixel chunk) of this CTA: a contiguous range, so the per-sample normalisation is reloaded rarely
+  const int items = p.B * p.chunks_per_sample;
+  const int item_begin = (int)((long long)items * blockIdx.y / gridDim.y), item_end = (int)((long long)items * (blockIdx.y + 1) / gridDim.y);
   const bool vec_a = (p.Cin % 4) == 0;
   const bool vec_b = (p.Cout % 4) == 0;
   // A-load role: pixel slot pm, 4 consecutive k starting at kq (loop invariant -> tap decode hoisted)
@@ -103,6 +96,20 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
+  int b_loaded = -1;
+  for (int item = item_begin; item < item_end; ++item) {
+  const int b = item / p.chunks_per_sample;
+  const int chunk = item - b * p.chunks_per_sample;
+  const int m_begin = chunk * p.pix_per_chunk;
+  const int m_end = min(HWo, m_begin + p.pix_per_chunk);
+  if (has_norm && b != b_loaded) {
+    __syncthreads();
+    nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
+    __syncthreads();
+    b_loaded = b;
+  }
+  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+  const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
   for (int mb = m_begin; mb < m_end; mb += MS) {
     const int m = mb + pm;
     float va[4] = {0.f, 0.f, 0.f, 0.f};
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
     }
     __syncthreads();
   }
+  }   // work items
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + ty * 4 + i;
@@ -580,6 +588,61 @@ __global__ void disc_input_bwd_kernel(const float* __restrict__ g, const float* 
     const float v = s[i];
     const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
     ds[i] = g[3 * i + 1] + 2.f * sg * g[3 * i + 2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-side weight images of EVERY convolution of a model in ONE launch (after each optimiser step): from the
+// parameter's own layout to  [K][N] (direct kernels)  and / or the tcgen05 kernel's pre-swizzled TF32 hi|lo image
+// (conv_umma.cuh), for the forward GEMM and for the input-gradient GEMM (transposed geometry / flipped taps).
+//   element (k, n):  tap = k / Kch, kc = k % Kch;  src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)]
+// ------------------------------------------------------------------------------------------------
+struct PackDesc {
+  const float* src; float* dst_kn; float* dst_umma;
+  int K, N, Kch, taps, flip, kchunks;
+  long long s_kch, s_n;
+  long long work_begin;          // prefix sum of kchunks*32*N over the descriptors
+};
+constexpr unsigned kTf32MaskPack = 0xFFFFE000u;
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n_desc, long long total) {
+  constexpr int kPer = 8;                       // a block walks 256*8 consecutive elements: the descriptor lookup is reused
+  PackDesc d;
+  long long d_end = -1;                         // [d.work_begin, d_end) = range of the cached descriptor
+  d.work_begin = 0;
+  for (long long c0 = (long long)blockIdx.x * 256 * kPer; c0 < total; c0 += (long long)gridDim.x * 256 * kPer) {
+#pragma unroll 1
+    for (int jj = 0; jj < kPer; ++jj) {
+      const long long i = c0 + threadIdx.x + 256 * jj;
+      if (i >= total) break;
+      if (i >= d_end || i < d.work_begin) {
+        int lo = 0, hi = n_desc - 1;
+        while (lo < hi) {                       // last descriptor with work_begin <= i
+          const int mid = (lo + hi + 1) >> 1;
+          if (descs[mid].work_begin <= i) lo = mid; else hi = mid - 1;
+        }
+        d = descs[lo];
+        d_end = d.work_begin + (long long)d.kchunks * 32 * d.N;
+      }
+      const long long r = i - d.work_begin;
+      const int n = (int)(r % d.N);
+      const int k = (int)(r / d.N);
+      float v = 0.f;
+      if (k < d.K) {
+        const int tap = k / d.Kch, kc = k - tap * d.Kch;
+        v = __ldg(d.src + kc * d.s_kch + n * d.s_n + (d.flip ? d.taps - 1 - tap : tap));
+        if (d.dst_kn) d.dst_kn[(size_t)k * d.N + n] = v;
+      }
+      if (d.dst_umma) {
+        const float hi_v = __uint_as_float(__float_as_uint(v) & kTf32MaskPack);
+        const float lo_v = __uint_as_float((__float_as_uint(v - hi_v) + 0x1000u) & kTf32MaskPack);   // nearest TF32 of the remainder
+        const int kcn = k >> 5, kk = k & 31;
+        const int piece = (kk >> 2) ^ (n & 7);
+        const size_t dst = (((size_t)kcn * 2) * d.N + n) * 32 + piece * 4 + (kk & 3);
+        d.dst_umma[dst] = hi_v;
+        d.dst_umma[dst + (size_t)d.N * 32] = lo_v;
+      }
+    }
   }
 }
 

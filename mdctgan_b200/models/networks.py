@@ -53,6 +53,9 @@ class Conv2d(nn.Conv2d):
         raise RuntimeError(_NO_DIRECT)
 
     def packed(self):
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None:
+            return sp["fwd"][0]
         if not hasattr(self, "_pk"):
             self._pk = _PackedWeight()
         return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, False))
@@ -61,6 +64,9 @@ class Conv2d(nn.Conv2d):
         """tcgen05 kernel's weight image, or None for the shapes that stay on the direct kernels."""
         if not ops.umma_supported(self.in_channels, self.out_channels):
             return None
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None:
+            return sp["fwd"][1]
         if not hasattr(self, "_pku"):
             self._pku = _PackedWeight()
         return self._pku.get(self.weight, lambda w: ops.pack_conv_weight_umma(self.packed()))
@@ -78,6 +84,10 @@ class Conv2d(nn.Conv2d):
         """(weights of the input-gradient convolution [kh*kw*Cout][Cin], their tcgen05 image or None, flipped).
         stride 1: a plain convolution with the taps flipped; stride > 1: the transposed-geometry kernels."""
         flipped = self.stride[0] == 1
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None and "dgrad" in sp:
+            kn, um, fl = sp["dgrad"]
+            return kn, (um if ops.CONV_ENGINE != "direct" else None), fl
         if not hasattr(self, "_pkd"):
             self._pkd, self._pkdu = _PackedWeight(), _PackedWeight()
         if flipped:
@@ -95,6 +105,9 @@ class ConvTranspose2d(nn.ConvTranspose2d):
         raise RuntimeError(_NO_DIRECT)
 
     def packed(self):
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None:
+            return sp["fwd"][0]
         if not hasattr(self, "_pk"):
             self._pk = _PackedWeight()
         return self._pk.get(self.weight, lambda w: ops.pack_conv_weight(w, True))
@@ -102,6 +115,9 @@ class ConvTranspose2d(nn.ConvTranspose2d):
     def packed_umma(self):
         if not ops.umma_supported(self.in_channels, self.out_channels):
             return None
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None:
+            return sp["fwd"][1]
         if not hasattr(self, "_pku"):
             self._pku = _PackedWeight()
         return self._pku.get(self.weight, lambda w: ops.pack_conv_weight_umma(self.packed()))
@@ -115,6 +131,10 @@ class ConvTranspose2d(nn.ConvTranspose2d):
     def packed_dgrad(self):
         """Input gradient of a ConvTranspose2d = plain strided convolution with the same weight tensor read as
         [Cout_c = in_channels][Cin_c = out_channels][kh][kw]."""
+        sp = self.__dict__.get("_static_pack")
+        if sp is not None and "dgrad" in sp:
+            kn, um, fl = sp["dgrad"]
+            return kn, (um if ops.CONV_ENGINE != "direct" else None), fl
         if not hasattr(self, "_pkd"):
             self._pkd, self._pkdu = _PackedWeight(), _PackedWeight()
         wd = self._pkd.get(self.weight, lambda w: ops.pack_conv_weight(w, False))

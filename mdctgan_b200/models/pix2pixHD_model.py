@@ -282,12 +282,21 @@ class Pix2PixHDModel(BaseModel):
             self.netG.to(self.device)
             self.netD.to(self.device)
             # every parameter becomes a view into one flat buffer per network; gradients likewise (the all-reduce bucket)
-            self.bucket_G, self.bucket_D = FlatBucket(self.netG), FlatBucket(self.netD)
+            nG, nD = FlatBucket.padded_numel(self.netG), FlatBucket.padded_numel(self.netD)
+            self.grad_all = torch.zeros(nG + nD, dtype=torch.float32, device=self.device)     # [grad_G | grad_D]: THE all-reduce bucket
+            self.bucket_G = FlatBucket(self.netG, self.grad_all[:nG])
+            self.bucket_D = FlatBucket(self.netD, self.grad_all[nG:])
             if opt.niter_fix_global > 0:
                 raise NotImplementedError("--niter_fix_global > 0 (local-enhancer-only finetuning) is listed as next in DESIGN.md")
-            self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999))
-            self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999))
+            graph_safe = bool(getattr(opt, "graph_safe_adam", True))
+            self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
+            self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
             self._graph = None
+            from ..packing import WeightPacker
+
+            # all kernel-side weight images (forward + input-gradient, direct + tcgen05) in one buffer, refreshed by one launch
+            self.packer = WeightPacker(self.netG, self.netD)
+            self._packed_at = (0, 0)
 
     # ---- generator graph ---------------------------------------------------------------------------------
     def _lr_input(self, lr_audio):
@@ -306,6 +315,13 @@ class Pix2PixHDModel(BaseModel):
             sr_spectro = _ops.residual_scale_add(sr_spectro, lr_spectro, 0, 1.0)
         return sr_spectro, None, hr_spectro, hr_pha, hr_norm_param, lr_spectro, lr_pha, lr_norm_param
 
+    def _refresh_weight_images(self):
+        """Re-pack after optimiser steps / load_state_dict (keyed on the optimisers' step counts and the parameter versions)."""
+        key = (self.optimizer_G.step_count, self.optimizer_D.step_count, self.bucket_G.params[0]._version, self.bucket_D.params[0]._version)
+        if key != self._packed_at:
+            self.packer.refresh()
+            self._packed_at = key
+
     def _forward(self, lr_audio, hr_audio, infer=False):
         """pix2pixHD_model.py:416-616: returns [[G_GAN, G_GAN_Feat, D_real, D_fake] (loss_filter order), sr_spectro or
         None].  The losses are 0-dim CUDA tensors; `loss_G.backward()` / `loss_D.backward()` (train.py:185-201) run the
@@ -316,6 +332,7 @@ class Pix2PixHDModel(BaseModel):
         if not self.isTrain:
             raise RuntimeError("_forward needs a training model (opt.isTrain)")
         graph = T.GanGraph(self)
+        self._refresh_weight_images()
         with _ops.stats_pass(self.device):
             graph.forward(lr_audio, hr_audio)
         self._graph = graph
@@ -331,18 +348,21 @@ class Pix2PixHDModel(BaseModel):
         from .. import train_ops as T
 
         graph = T.GanGraph(self)
+        self._refresh_weight_images()
         with _ops.stats_pass(self.device):
-            self.optimizer_G.zero_grad()
-            self.optimizer_D.zero_grad()
+            self.grad_all.zero_()                          # one memset for both buckets
             losses = graph.forward(lr_audio, hr_audio)
             graph.backward_G()
             half = self._half_scalar()
             graph.backward_D(half, half)
             if all_reduce is not None:
-                all_reduce(self.bucket_G.grad, self.bucket_D.grad)
+                all_reduce(self.grad_all)                  # ONE collective per step
             self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size
             self.optimizer_G.step()
             self.optimizer_D.step()
+            self.packer.refresh()                          # the next forward (and a CUDA-graph replay) sees the updated weights
+            self._packed_at = (self.optimizer_G.step_count, self.optimizer_D.step_count, self.bucket_G.params[0]._version,
+                               self.bucket_D.params[0]._version)
         graph.release()
         return losses
 
@@ -377,6 +397,8 @@ class Pix2PixHDModel(BaseModel):
     @torch.no_grad()
     def inference(self, lr_audio):
         """pix2pixHD_model.py:618-638 -> (sr_spectro, sr_audio, lr_pha, lr_norm_param, lr_spectro)."""
+        if getattr(self, "packer", None) is not None:
+            self._refresh_weight_images()
         lr_spectro, lr_input, lr_pha, lr_norm_param = self._lr_input(lr_audio)
         sr_spectro = self.netG.forward(lr_input)
         if self.fit_residual:

@@ -253,7 +253,7 @@ def _conv_launch(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], 
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     stats = _new_stats(B, Cout, x.device) if want_stats else None
     use_umma = w_umma is not None and CONV_ENGINE != "direct"
-    if use_umma and transposed and stride > 1 and (Ho % stride or Wo % stride or Cin % 32 or kh < stride or kw < stride):
+    if use_umma and transposed and stride > 1 and (Ho < stride or Wo < stride or Cin % 32 or kh < stride or kw < stride):
         use_umma = False        # the tensor-core kernel runs strided transposed convolutions per output parity class only
     if B:
         with torch.cuda.device(x.device):

@@ -20,7 +20,13 @@ class FlatBucket:
     """All parameters of `module` re-pointed into one flat buffer (16-byte aligned segments), with a matching flat
     gradient buffer whose views are installed as `p.grad`."""
 
-    def __init__(self, module: torch.nn.Module):
+    @staticmethod
+    def padded_numel(module: torch.nn.Module) -> int:
+        return sum((p.numel() + 3) // 4 * 4 for p in module.parameters())
+
+    def __init__(self, module: torch.nn.Module, grad_storage: torch.Tensor = None):
+        """`grad_storage`: an existing flat fp32 tensor of padded_numel(module) elements to hold the gradients (lets
+        several buckets share ONE buffer = one all-reduce per step)."""
         params = [p for p in module.parameters()]
         if not params:
             raise ValueError("FlatBucket: module has no parameters")
@@ -36,7 +42,10 @@ class FlatBucket:
             off += (p.numel() + 3) // 4 * 4
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        if grad_storage is None:
+            grad_storage = torch.zeros(off, dtype=torch.float32, device=dev)
+        assert grad_storage.numel() == off and grad_storage.dtype == torch.float32 and grad_storage.is_contiguous()
+        self.grad = grad_storage
         with torch.no_grad():
             for p, o in zip(params, self.offsets):
                 self.flat[o:o + p.numel()].view_as(p).copy_(p)

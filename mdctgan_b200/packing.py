@@ -1,0 +1,99 @@
+"""Kernel-side weight images for a whole model, refreshed by ONE kernel launch per optimiser step.
+
+The convolution kernels read their weights as [kh*kw*Cin][Cout] (direct fp32 kernels) or as the pre-swizzled TF32
+hi|lo shared-memory image of the tcgen05 kernel (csrc/conv_umma.cuh); the input-gradient convolutions need the same
+weights on the transposed geometry.  At inference the images are cached per weight version (models/networks.py
+_PackedWeight); in training the weights change every step, so `WeightPacker` lays all images of all layers out in one
+buffer, installs views of it on the layers, and `refresh()` rewrites everything from the flat parameter buffer with
+`mdctgan_pack_weights_multi` (one launch, ~25 bytes of traffic per parameter)."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int32, c_int64, c_void_p
+
+import torch
+
+from . import _lib
+from . import nn_ops as ops
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst_kn", c_void_p), ("dst_umma", c_void_p), ("K", c_int32), ("N", c_int32), ("Kch", c_int32),
+                ("taps", c_int32), ("flip", c_int32), ("kchunks", c_int32), ("s_kch", c_int64), ("s_n", c_int64), ("work_begin", c_int64)]
+
+
+class WeightPacker:
+    def __init__(self, *modules: torch.nn.Module, dgrad: bool = True):
+        from .models.networks import Conv2d, ConvTranspose2d
+
+        L = ops._L()
+        L.mdctgan_pack_weights_multi.argtypes = [c_void_p, ctypes.c_int, c_int64, c_void_p]
+        layers = [m for mod in modules for m in mod.modules() if isinstance(m, (Conv2d, ConvTranspose2d))]
+        layers = list(dict.fromkeys(layers))
+        if not layers:
+            raise ValueError("WeightPacker: no convolution layers")
+        dev = layers[0].weight.device
+        plans, total_floats = [], 0
+
+        def plan(layer, role, K, N, Kch, taps, flip, s_kch, s_n):
+            nonlocal total_floats
+            kchunks = (K + 31) // 32
+            use_umma = bool(L.mdctgan_conv2d_umma_supported(Kch, N))
+            off_kn = total_floats
+            total_floats += (K * N + 3) // 4 * 4
+            off_um = None
+            if use_umma:
+                total_floats = (total_floats + 31) // 32 * 32          # 128-byte aligned: the image is fetched by TMA bulk copies
+                off_um = total_floats
+                total_floats += kchunks * 2 * N * 32
+            plans.append(dict(layer=layer, role=role, K=K, N=N, Kch=Kch, taps=taps, flip=flip, s_kch=s_kch, s_n=s_n, kchunks=kchunks,
+                              off_kn=off_kn, off_um=off_um))
+
+        for m in layers:
+            kh, kw = m.kernel_size
+            taps = kh * kw
+            ci, co = m.in_channels, m.out_channels
+            if isinstance(m, ConvTranspose2d):      # weight [Cin][Cout][kh][kw]
+                plan(m, "fwd", taps * ci, co, ci, taps, 0, co * taps, taps)
+                if dgrad:
+                    plan(m, "dgrad", taps * co, ci, co, taps, 0, taps, co * taps)
+            else:                                   # weight [Cout][Cin][kh][kw]
+                plan(m, "fwd", taps * ci, co, ci, taps, 0, taps, ci * taps)
+                if dgrad:
+                    plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, ci * taps, taps)
+        self.buf = torch.zeros(total_floats + 32, dtype=torch.float32, device=dev)
+        base_off = (-(self.buf.data_ptr() // 4)) % 32                     # align the buffer itself to 128 bytes
+        descs = (_Desc * len(plans))()
+        work = 0
+        for i, p in enumerate(plans):
+            m = p["layer"]
+            kn = self.buf[base_off + p["off_kn"]: base_off + p["off_kn"] + p["K"] * p["N"]].view(p["K"], p["N"])
+            um = None
+            if p["off_um"] is not None:
+                n_um = p["kchunks"] * 2 * p["N"] * 32
+                um = self.buf[base_off + p["off_um"]: base_off + p["off_um"] + n_um]
+                assert um.data_ptr() % 128 == 0
+            descs[i] = _Desc(m.weight.data_ptr(), kn.data_ptr(), um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],
+                             p["taps"], p["flip"], p["kchunks"], p["s_kch"], p["s_n"], work)
+            work += p["kchunks"] * 32 * p["N"]
+            st = m.__dict__.setdefault("_static_pack", {})
+            st[p["role"]] = (kn, um, bool(p["flip"]))
+        self.total_work, self.n_desc = work, len(plans)
+        self.layers = layers
+        self._ptrs = [m.weight.data_ptr() for m in layers]
+        raw = bytes(descs)
+        self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.refresh()
+
+    def refresh(self):
+        """Rewrite every image from the current parameter values (one launch on the current stream)."""
+        for m, ptr in zip(self.layers, self._ptrs):
+            if m.weight.data_ptr() != ptr:
+                raise RuntimeError("WeightPacker: a parameter was re-allocated after the packer was built (call it after FlatBucket)")
+        with torch.cuda.device(self.buf.device):
+            _lib.check(ops._L().mdctgan_pack_weights_multi(self.descs.data_ptr(), self.n_desc, self.total_work,
+                                                            torch.cuda.current_stream(self.buf.device).cuda_stream))
+
+    def detach(self):
+        for m in self.layers:
+            m.__dict__.pop("_static_pack", None)

@@ -78,3 +78,33 @@ def train_step(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, steps=1, **c
     out["paramsG"] = {k: v.detach().clone() for k, v in pG.items()}
     out["paramsD"] = {k: v.detach().clone() for k, v in pD.items()}
     return out
+
+
+def make_stepper(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, **cfg):
+    """A closure running one full iteration of train.py:160-202 per call (spectrograms included), for the timed CPU
+    baseline of bench.py; returns the four loss values of the iteration."""
+    floatsG = {k for k, v in sdG.items() if v.dtype.is_floating_point and "running_" not in k}
+    pG = {k: (v.clone().requires_grad_(True) if k in floatsG else v.clone()) for k, v in sdG.items()}
+    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    optG = torch.optim.Adam([pG[k] for k in pG if k in floatsG], lr=lr, betas=(beta1, 0.999))
+    optD = torch.optim.Adam(list(pD.values()), lr=lr, betas=(beta1, 0.999))
+    from . import torch_port as P
+
+    a2m = P.Audio2MDCTPort(1000.0, (-5.0, 5.0), (-1.0, 1.0), 512, 256)
+    lr_t, hr_t = torch.as_tensor(lr_audio), torch.as_tensor(hr_audio)
+
+    def step():
+        with torch.no_grad():
+            ls, hs = a2m.to_spectro(lr_t)[0], a2m.to_spectro(hr_t)[0]      # the reference's complex128 512-pt FFT formulation
+        (g_gan, g_feat, d_real, d_fake), _ = losses(pG, pD, ls, hs, **cfg)
+        loss_D = (d_fake + d_real) * 0.5
+        loss_G = g_gan + g_feat
+        optG.zero_grad()
+        loss_G.backward()
+        optG.step()
+        optD.zero_grad()
+        loss_D.backward()
+        optD.step()
+        return [float(g_gan.detach()), float(g_feat.detach()), float(d_real.detach()), float(d_fake.detach())]
+
+    return step

@@ -41,6 +41,8 @@ UMMA_CASES = [
     (4, 128, 8, 64, 256, 3, 2, 1, False, False),
     (2, 64, 8, 16, 32, 3, 2, 1, False, True),      # ConvTranspose2d k3 s2 p1 op1, Cout = 32 (BN = 32)
     (4, 256, 4, 32, 128, 3, 2, 1, False, True),
+    (2, 64, 5, 9, 32, 4, 2, 2, False, True),       # transposed k4 s2 p2 op1 -> 9x17: odd output, ragged parity classes (PatchGAN dgrad)
+    (3, 128, 3, 17, 64, 4, 2, 2, False, True),     # 5x33 output
     (2, 64, 9, 17, 128, 4, 1, 2, False, False),    # PatchGAN 4x4 s1 p2, odd plane (M = 2*12*20 = 480: partial tile)
     (2, 64, 17, 33, 128, 4, 2, 2, False, False),   # PatchGAN 4x4 s2 p2
     (2, 128, 5, 9, 96, 1, 1, 0, False, False),     # 1x1 (BottleStack), Cout % 64 != 0, K = 128 (4 chunks)

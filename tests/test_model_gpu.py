@@ -93,5 +93,6 @@ def test_checkpoint_round_trip(tmp_path):
     m2 = create_model(opt)
     for k, v in m.netG.state_dict().items():
         assert torch.equal(v, m2.netG.state_dict()[k])
-    with pytest.raises(NotImplementedError):
-        m._forward(torch.zeros(1, 3840).cuda(), torch.zeros(1, 3840).cuda())
+    m.train()
+    losses, _ = m._forward(0.1 * torch.randn(2, 3840).cuda(), 0.1 * torch.randn(2, 3840).cuda())
+    assert len(losses) == len(m.loss_names) == 4 and all(torch.isfinite(v).item() and v.dim() == 0 for v in losses)
