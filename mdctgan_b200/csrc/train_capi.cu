@@ -57,7 +57,7 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     if ((long long)B * p.chunks_per_sample > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
     conv_wgrad_small_cout_kernel<<<dim3(kblocks, B * p.chunks_per_sample), 256, 0, st>>>(p);
   } else {
-    const int k_tiles = (K + 63) / 64;
+    const int k_tiles = (K + 127) / 128;
     p.n_tiles = (Cout + 63) / 64;
     const int tiles = k_tiles * p.n_tiles;
     int chunks = (296 + tiles * B - 1) / (tiles * B);
@@ -81,7 +81,7 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
 
 int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
                          const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int HW, int C, void* stream) {
-  if (!x || !dv || !dx || !stats || !red) return mdctgan_set_error(-1, "norm_act_bwd: NULL buffer");
+  if (!x || !dv || !dx || !stats) return mdctgan_set_error(-1, "norm_act_bwd: NULL buffer");
   if (mode != 0 && mode != 1) return mdctgan_set_error(-1, "norm_act_bwd: mode %d (0 InstanceNorm2d, 1 train-mode BatchNorm2d)", mode);
   if (C % 4 || C > 1024) return mdctgan_set_error(-2, "norm_act_bwd: C %d must be a multiple of 4, <= 1024", C);
   if (act == kActTanh) return mdctgan_set_error(-2, "norm_act_bwd: tanh after a normalisation is not a reference configuration");
@@ -89,6 +89,13 @@ int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const doubl
   if (B > 65535) return mdctgan_set_error(-2, "norm_act_bwd: batch %d > 65535", B);
   NormBwdParams p{x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, C, B};
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0 && C % 8 == 0 && C / 8 <= 65535) {      // InstanceNorm2d: one launch, no scratch
+    instnorm_bwd_fused_kernel<<<dim3(C / 8, B), 256, 0, st>>>(p);
+    mdctgan_count_launch();
+    CKT(cudaGetLastError());
+    return 0;
+  }
+  if (!red) return mdctgan_set_error(-1, "norm_act_bwd: NULL reduction scratch");
   const int groups = C / 4, pstep = 256 / groups;
   int chunks = (HW + pstep - 1) / pstep;
   const int cap = (148 * 4 + B - 1) / B;

@@ -57,11 +57,64 @@ struct WgradParams {
   int n_tiles, chunks_per_sample, pix_per_chunk;
 };
 
+// CTA tile 128 (k) x 64 (co), 8 x 4 outputs per thread; the pixel (reduction) dimension is walked 16 at a time through a
+// double-buffered shared-memory stage: the global gather of step i+1 is in flight while step i is multiplied.
+struct WgradALoad {            // one float4 slot of the A stage: 4 consecutive k of one pixel row
+  int ky[4], kx[4], c[4];      // tap / channel of each k (c < 0: beyond K)
+};
+
+__device__ __forceinline__ void wgrad_decode(const WgradParams& p, int K, int kbase, WgradALoad& a) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = kbase + u;
+    if (k < K) {
+      const int tap = k / p.Cin;
+      a.c[u] = k - tap * p.Cin;
+      a.ky[u] = tap / p.kw;
+      a.kx[u] = tap - a.ky[u] * p.kw;
+    } else { a.c[u] = -1; a.ky[u] = 0; a.kx[u] = 0; }
+  }
+}
+
+__device__ __forceinline__ float4 wgrad_gather(const WgradParams& p, const float* xb, const WgradALoad& a, int oy, int ox, bool vec_a, bool has_norm,
+                                                const float* s_scale, const float* s_shift) {
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec_a) {
+    if (a.c[0] >= 0) {
+      const int iy = in_coord(oy, a.ky[0], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+      const int ix = in_coord(ox, a.kx[0], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+      if (iy >= 0 && ix >= 0) {
+        const int c = a.c[0];
+        const float4 q = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix) * p.Cin + c));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        if (has_norm) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = apply_act(fmaf(v[u], s_scale[c + u], s_shift[c + u]), p.in.act);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (a.c[u] >= 0) {
+        const int iy = in_coord(oy, a.ky[u], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+        const int ix = in_coord(ox, a.kx[u], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+        if (iy >= 0 && ix >= 0) {
+          float t = __ldg(xb + ((size_t)iy * p.W + ix) * p.Cin + a.c[u]);
+          if (has_norm) t = apply_act(fmaf(t, s_scale[a.c[u]], s_shift[a.c[u]]), p.in.act);
+          v[u] = t;
+        }
+      }
+    }
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <typename AccT>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
-  constexpr int TK = 64, TN = 64, MS = 16;
-  __shared__ __align__(16) float As[MS][TK + 4];
-  __shared__ __align__(16) float Bs[MS][TN];
+  constexpr int TK = 128, TN = 64, MS = 16;
+  __shared__ __align__(16) float As[2][MS][TK + 4];
+  __shared__ __align__(16) float Bs[2][MS][TN];
   __shared__ float s_scale[1024], s_shift[1024];
   const int tid = threadIdx.x;
   const int kt = blockIdx.x / p.n_tiles, nt = blockIdx.x - kt * p.n_tiles;
@@ -74,116 +127,100 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   const int item_begin = (int)((long long)items * blockIdx.y / gridDim.y), item_end = (int)((long long)items * (blockIdx.y + 1) / gridDim.y);
   const bool vec_a = (p.Cin % 4) == 0;
   const bool vec_b = (p.Cout % 4) == 0;
-  // A-load role: pixel slot pm, 4 consecutive k starting at kq (loop invariant -> tap decode hoisted)
-  const int pm = tid >> 4, kq = (tid & 15) * 4;
-  int a_ky[4], a_kx[4], a_c[4];
+  // load roles: pixel slot pm; A: two float4 slots (k offsets kq, kq + 64); B: one float4 slot (co offset nq)
+  const int pm = tid >> 4, kq = (tid & 15) * 4, nq = (tid & 15) * 4;
+  WgradALoad a0, a1;
+  wgrad_decode(p, K, k0 + kq, a0);
+  wgrad_decode(p, K, k0 + kq + 64, a1);
+  const int ty = tid >> 4, tx = tid & 15;        // outputs: k rows ty*4 + {0..3} and 64 + ty*4 + {0..3}; co columns tx*4 + {0..3}
+  AccT acc[8][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = k0 + kq + u;
-    if (k < K) {
-      const int tap = k / p.Cin;
-      a_c[u] = k - tap * p.Cin;
-      a_ky[u] = tap / p.kw;
-      a_kx[u] = tap - a_ky[u] * p.kw;
-    } else { a_c[u] = -1; a_ky[u] = 0; a_kx[u] = 0; }
-  }
-  const int nq = (tid & 15) * 4;
-  const int ty = tid >> 4, tx = tid & 15;
-  AccT acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
   int b_loaded = -1;
   for (int item = item_begin; item < item_end; ++item) {
-  const int b = item / p.chunks_per_sample;
-  const int chunk = item - b * p.chunks_per_sample;
-  const int m_begin = chunk * p.pix_per_chunk;
-  const int m_end = min(HWo, m_begin + p.pix_per_chunk);
-  if (has_norm && b != b_loaded) {
-    __syncthreads();
-    nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
-    __syncthreads();
-    b_loaded = b;
-  }
-  const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
-  const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
-  for (int mb = m_begin; mb < m_end; mb += MS) {
-    const int m = mb + pm;
-    float va[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < m_end) {
-      const int oy = m / p.Wo, ox = m - oy * p.Wo;
-      if (vec_a) {
-        if (a_c[0] >= 0) {
-          const int iy = in_coord(oy, a_ky[0], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
-          const int ix = in_coord(ox, a_kx[0], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
-          if (iy >= 0 && ix >= 0) {
-            const int c = a_c[0];
-            const float4 q = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)iy * p.W + ix) * p.Cin + c));
-            va[0] = q.x; va[1] = q.y; va[2] = q.z; va[3] = q.w;
-            if (has_norm) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) va[u] = apply_act(fmaf(va[u], s_scale[c + u], s_shift[c + u]), p.in.act);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (a_c[u] >= 0) {
-            const int iy = in_coord(oy, a_ky[u], p.H, p.stride, p.pad, p.pad_mode, p.transposed);
-            const int ix = in_coord(ox, a_kx[u], p.W, p.stride, p.pad, p.pad_mode, p.transposed);
-            if (iy >= 0 && ix >= 0) {
-              float t = __ldg(xb + ((size_t)iy * p.W + ix) * p.Cin + a_c[u]);
-              if (has_norm) t = apply_act(fmaf(t, s_scale[a_c[u]], s_shift[a_c[u]]), p.in.act);
-              va[u] = t;
-            }
-          }
+    const int b = item / p.chunks_per_sample;
+    const int chunk = item - b * p.chunks_per_sample;
+    const int m_begin = chunk * p.pix_per_chunk;
+    const int m_end = min(HWo, m_begin + p.pix_per_chunk);
+    if (m_begin >= m_end) continue;
+    if (has_norm && b != b_loaded) {
+      __syncthreads();
+      nnk::norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, tid, 256);
+      b_loaded = b;
+    }
+    __syncthreads();                                  // scale / shift visible; the stage buffers of the previous item are free
+    const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+    const float* dyb = p.dy + (size_t)b * HWo * p.Cout;
+
+    auto load_stage = [&](int mb, float4& ra0, float4& ra1, float4& rb) {
+      const int m = mb + pm;
+      ra0 = ra1 = rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m_end) {
+        const int oy = m / p.Wo, ox = m - oy * p.Wo;
+        ra0 = wgrad_gather(p, xb, a0, oy, ox, vec_a, has_norm, s_scale, s_shift);
+        ra1 = wgrad_gather(p, xb, a1, oy, ox, vec_a, has_norm, s_scale, s_shift);
+        const int n = n0 + nq;
+        const float* dr = dyb + (size_t)m * p.Cout + n;
+        if (vec_b && n + 3 < p.Cout) {
+          rb = __ldg(reinterpret_cast<const float4*>(dr));
+        } else {
+          if (n + 0 < p.Cout) rb.x = __ldg(dr + 0);
+          if (n + 1 < p.Cout) rb.y = __ldg(dr + 1);
+          if (n + 2 < p.Cout) rb.z = __ldg(dr + 2);
+          if (n + 3 < p.Cout) rb.w = __ldg(dr + 3);
         }
       }
-      const int n = n0 + nq;
-      const float* dr = dyb + (size_t)m * p.Cout + n;
-      if (vec_b && n + 3 < p.Cout) {
-        vb = __ldg(reinterpret_cast<const float4*>(dr));
-      } else {
-        if (n + 0 < p.Cout) vb.x = __ldg(dr + 0);
-        if (n + 1 < p.Cout) vb.y = __ldg(dr + 1);
-        if (n + 2 < p.Cout) vb.z = __ldg(dr + 2);
-        if (n + 3 < p.Cout) vb.w = __ldg(dr + 3);
-      }
-    }
-    *reinterpret_cast<float4*>(&As[pm][kq]) = make_float4(va[0], va[1], va[2], va[3]);
-    *reinterpret_cast<float4*>(&Bs[pm][nq]) = vb;
+    };
+    float4 ra0, ra1, rb;
+    load_stage(m_begin, ra0, ra1, rb);
+    *reinterpret_cast<float4*>(&As[0][pm][kq]) = ra0;
+    *reinterpret_cast<float4*>(&As[0][pm][kq + 64]) = ra1;
+    *reinterpret_cast<float4*>(&Bs[0][pm][nq]) = rb;
     __syncthreads();
+    int buf = 0;
+    for (int mb = m_begin; mb < m_end; mb += MS) {
+      const bool more = mb + MS < m_end;
+      if (more) load_stage(mb + MS, ra0, ra1, rb);   // in flight while this stage is multiplied
 #pragma unroll
-    for (int mm = 0; mm < MS; ++mm) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+      for (int mm = 0; mm < MS; ++mm) {
+        const float4 al = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 4]);
+        const float4 ah = *reinterpret_cast<const float4*>(&As[buf][mm][64 + ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 4]);
+        const float av[8] = {al.x, al.y, al.z, al.w, ah.x, ah.y, ah.z, ah.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma((AccT)av[i], (AccT)bw[j], acc[i][j]);
-      if (ty == 0) {
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma((AccT)av[i], (AccT)bw[j], acc[i][j]);
+        if (ty == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bsum[j] += bw[j];
+          for (int j = 0; j < 4; ++j) bsum[j] += bw[j];
+        }
       }
+      if (more) {
+        *reinterpret_cast<float4*>(&As[buf ^ 1][pm][kq]) = ra0;
+        *reinterpret_cast<float4*>(&As[buf ^ 1][pm][kq + 64]) = ra1;
+        *reinterpret_cast<float4*>(&Bs[buf ^ 1][pm][nq]) = rb;
+      }
+      __syncthreads();
+      buf ^= 1;
     }
-    __syncthreads();
-  }
   }   // work items
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (k >= K) continue;
     const int tap = k / p.Cin, ci = k - tap * p.Cin;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = n0 + tx * 4 + j;
-      if (co < p.Cout) atomicAdd(p.dw + (long long)co * p.s_co + (long long)ci * p.s_ci + (long long)tap * p.s_tap, (float)acc[i][j]);
+      if (co < p.Cout) {
+        float* dst = p.dw + (long long)co * p.s_co + (long long)ci * p.s_ci + (long long)tap * p.s_tap;
+        atomicAdd(dst, (float)acc[i][j]);   // fire-and-forget reduction at L2 (a read-modify-write of these scattered addresses is slower)
+      }
     }
   }
   if (p.dbias && kt == 0 && ty == 0) {
@@ -357,6 +394,74 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams
       o[u] = s_gam[c] * s_rstd[c] * (g - s_mg[c] - xhat * s_mgx[c]);
     }
     *reinterpret_cast<float4*>(p.dx + base + e) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// InstanceNorm2d backward in ONE launch: a CTA owns 8 channels of one sample (one 32-byte sector per pixel), reduces
+// (sum g, sum g*xhat) over the plane, then applies -- the second read of x / dv hits L1 / L2.  grid = (C / 8, B).
+__global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const NormBwdParams p) {
+  __shared__ double s_red[8][2][8];     // [warp][sum g | sum g*xhat][channel of the group]
+  __shared__ float s_m[2][8];
+  const int b = blockIdx.y, c0 = blockIdx.x * 8;
+  const int cl = threadIdx.x & 1, pl = threadIdx.x >> 1;          // float4 half of the group, pixel lane
+  const int cb = c0 + cl * 4;
+  float mean[4], rstd[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const double s = p.stats[2 * ((size_t)b * p.C + cb + u)], q = p.stats[2 * ((size_t)b * p.C + cb + u) + 1];
+    const double m = s / p.count;
+    double var = q / p.count - m * m;
+    if (var < 0) var = 0;
+    mean[u] = (float)m;
+    rstd[u] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  const size_t base = (size_t)b * p.HW * p.C + cb;
+  double sg[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int pix = pl; pix < p.HW; pix += 128) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + (size_t)pix * p.C));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + (size_t)pix * p.C));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xhat = (xs[u] - mean[u]) * rstd[u];
+      const float g = ds[u] * act_grad_from_pre(xhat, p.act);
+      sg[u] += (double)g; sq[u] = fma((double)g, (double)xhat, sq[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+#pragma unroll
+    for (int o = 16; o >= 2; o >>= 1) { sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o); sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o); }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 2) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s_red[warp][0][lane * 4 + u] = sg[u]; s_red[warp][1][lane * 4 + u] = sq[u]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, ch = threadIdx.x & 7;
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][which][ch];
+    s_m[which][ch] = (float)(t / p.count);
+  }
+  __syncthreads();
+  float mg[4], mgx[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { mg[u] = s_m[0][cl * 4 + u]; mgx[u] = s_m[1][cl * 4 + u]; }
+  for (int pix = pl; pix < p.HW; pix += 128) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + (size_t)pix * p.C));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + (size_t)pix * p.C));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xhat = (xs[u] - mean[u]) * rstd[u];
+      const float g = ds[u] * act_grad_from_pre(xhat, p.act);
+      o[u] = rstd[u] * (g - mg[u] - xhat * mgx[u]);
+    }
+    *reinterpret_cast<float4*>(p.dx + base + (size_t)pix * p.C) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -625,8 +730,16 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc*
         d_end = d.work_begin + (long long)d.kchunks * 32 * d.N;
       }
       const long long r = i - d.work_begin;
-      const int n = (int)(r % d.N);
-      const int k = (int)(r / d.N);
+      int n, k;
+      if (d.dst_umma && !d.dst_kn) {            // tcgen05 image only: a warp writes one 128-byte row (32 consecutive k of one n)
+        const int kk = (int)(r & 31);
+        const long long q = r >> 5;
+        n = (int)(q % d.N);
+        k = (int)(q / d.N) * 32 + kk;
+      } else {                                  // [K][N] image: n fastest
+        n = (int)(r % d.N);
+        k = (int)(r / d.N);
+      }
       float v = 0.f;
       if (k < d.K) {
         const int tap = k / d.Kch, kc = k - tap * d.Kch;

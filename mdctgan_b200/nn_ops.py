@@ -255,6 +255,8 @@ def _conv_launch(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], 
     use_umma = w_umma is not None and CONV_ENGINE != "direct"
     if use_umma and transposed and stride > 1 and (Ho < stride or Wo < stride or Cin % 32 or kh < stride or kw < stride):
         use_umma = False        # the tensor-core kernel runs strided transposed convolutions per output parity class only
+    if not use_umma and w_packed.stride(0) == 0:
+        raise RuntimeError("conv2d: this layer only has a tcgen05 weight image (packing.WeightPacker) but the direct kernel was selected")
     if B:
         with torch.cuda.device(x.device):
             if use_umma:

@@ -35,12 +35,18 @@ class WeightPacker:
         dev = layers[0].weight.device
         plans, total_floats = [], 0
 
-        def plan(layer, role, K, N, Kch, taps, flip, s_kch, s_n):
+        def plan(layer, role, K, N, Kch, taps, flip, s_kch, s_n, strided_transposed=False):
             nonlocal total_floats
             kchunks = (K + 31) // 32
             use_umma = bool(L.mdctgan_conv2d_umma_supported(Kch, N))
-            off_kn = total_floats
-            total_floats += (K * N + 3) // 4 * 4
+            if strided_transposed and (Kch % 32 or min(layer.kernel_size) < layer.stride[0]):
+                use_umma = False                    # the tensor-core kernel runs strided transposed geometry per parity class only
+            # the [K][N] image is only read by the direct fp32 kernels: skip it where the tcgen05 kernel runs the layer
+            want_kn = (not use_umma) or ops.CONV_ENGINE == "direct"
+            off_kn = None
+            if want_kn:
+                off_kn = total_floats
+                total_floats += (K * N + 3) // 4 * 4
             off_um = None
             if use_umma:
                 total_floats = (total_floats + 31) // 32 * 32          # 128-byte aligned: the image is fetched by TMA bulk copies
@@ -54,26 +60,31 @@ class WeightPacker:
             taps = kh * kw
             ci, co = m.in_channels, m.out_channels
             if isinstance(m, ConvTranspose2d):      # weight [Cin][Cout][kh][kw]
-                plan(m, "fwd", taps * ci, co, ci, taps, 0, co * taps, taps)
+                plan(m, "fwd", taps * ci, co, ci, taps, 0, co * taps, taps, strided_transposed=m.stride[0] > 1)
                 if dgrad:
                     plan(m, "dgrad", taps * co, ci, co, taps, 0, taps, co * taps)
             else:                                   # weight [Cout][Cin][kh][kw]
                 plan(m, "fwd", taps * ci, co, ci, taps, 0, taps, ci * taps)
                 if dgrad:
-                    plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, ci * taps, taps)
+                    plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, ci * taps, taps, strided_transposed=m.stride[0] > 1)
         self.buf = torch.zeros(total_floats + 32, dtype=torch.float32, device=dev)
         base_off = (-(self.buf.data_ptr() // 4)) % 32                     # align the buffer itself to 128 bytes
         descs = (_Desc * len(plans))()
         work = 0
         for i, p in enumerate(plans):
             m = p["layer"]
-            kn = self.buf[base_off + p["off_kn"]: base_off + p["off_kn"] + p["K"] * p["N"]].view(p["K"], p["N"])
+            if p["off_kn"] is not None:
+                kn = self.buf[base_off + p["off_kn"]: base_off + p["off_kn"] + p["K"] * p["N"]].view(p["K"], p["N"])
+                kn_ptr = kn.data_ptr()
+            else:                                   # shape-only placeholder (stride 0): never dereferenced, _conv_launch checks
+                kn = self.buf[:1].as_strided((p["K"], p["N"]), (0, 0))
+                kn_ptr = None
             um = None
             if p["off_um"] is not None:
                 n_um = p["kchunks"] * 2 * p["N"] * 32
                 um = self.buf[base_off + p["off_um"]: base_off + p["off_um"] + n_um]
                 assert um.data_ptr() % 128 == 0
-            descs[i] = _Desc(m.weight.data_ptr(), kn.data_ptr(), um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],
+            descs[i] = _Desc(m.weight.data_ptr(), kn_ptr, um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],
                              p["taps"], p["flip"], p["kchunks"], p["s_kch"], p["s_n"], work)
             work += p["kchunks"] * 32 * p["N"]
             st = m.__dict__.setdefault("_static_pack", {})
