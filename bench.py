@@ -332,8 +332,10 @@ def run_ours(args):
     hr = make_hr_audio(BATCH, SEG, 42 + rank).to(dev)
     warm = max(args.warmup, 3)
 
-    def all_reduce(flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    from mdctgan_b200.parallel import GradExchange, broadcast_flat
+
+    all_reduce = GradExchange() if world > 1 else None      # ONE sum all-reduce of the flat [grad_G | grad_D] bucket per step
+    broadcast_flat([model.bucket_G.flat, model.bucket_D.flat])
 
     def barrier():
         if world > 1:
@@ -353,23 +355,23 @@ def run_ours(args):
             ref_losses, _ = TO.losses(sdG, sdD, ls, hs, **NET_KW)
         ref_losses = [float(v) for v in ref_losses]
     # ---- eager steps: launches per step, per-kernel table (CUDA events around every C-ABI launch)
-    first = model.train_step(lr, hr, world, all_reduce if world > 1 else None).cpu().tolist()
+    first = model.train_step(lr, hr, world, all_reduce).cpu().tolist()
     if rank == 0:
         err = max(abs(a - b) / abs(b) for a, b in zip(first, ref_losses))
         assert err < 2e-3, f"train-step losses {first} vs oracle {ref_losses}"
     for _ in range(2):
-        model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+        model.train_step(lr, hr, world, all_reduce)
     n0 = mdctgan_b200.launch_count()
-    model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+    model.train_step(lr, hr, world, all_reduce)
     launches_per_step = mdctgan_b200.launch_count() - n0
     with LaunchProfiler(dev) as prof:
         for _ in range(3):
-            model.train_step(lr, hr, world, all_reduce if world > 1 else None)
+            model.train_step(lr, hr, world, all_reduce)
     table = prof.table()
     tot_ms = sum(v[1] for v in table.values())
 
     # ---- timed region: the step as a CUDA graph, K replays
-    gts = GraphedTrainStep(model, BATCH, SEG, world, all_reduce if world > 1 else None, warmup=2)
+    gts = GraphedTrainStep(model, BATCH, SEG, world, all_reduce, warmup=2)
     gts.lr_in.copy_(lr)
     gts.hr_in.copy_(hr)
     gts.recapture()
@@ -431,6 +433,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     step_ms, e2e_ms = vals.tolist()
+    if world > 1:
+        # No collective follows.  Leave without the NCCL / CUDA-graph teardown: destroying a communicator that a live captured
+        # graph still references can block forever (seen on the 2-GPU run), and the driver waits for every rank to exit.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        if rank != 0:
+            sys.stdout.flush()
+            os._exit(0)
 
     if rank == 0:
         audio_s = world * BATCH * SEG / SR
@@ -475,7 +485,9 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -61,14 +61,16 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     p.n_tiles = (Cout + 63) / 64;
     const int tiles = k_tiles * p.n_tiles;
     int chunks = (296 + tiles * B - 1) / (tiles * B);
-    const int max_chunks = (HWo + 63) / 64;
+    const int max_chunks = (HWo + 127) / 128;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     p.pix_per_chunk = ((HWo + chunks - 1) / chunks + 15) / 16 * 16;
     p.chunks_per_sample = (HWo + p.pix_per_chunk - 1) / p.pix_per_chunk;
     // work items = (sample, chunk); a CTA takes a contiguous run of them so that ~2 waves of CTAs cover the device
     const int items = B * p.chunks_per_sample;
-    int gy = (296 + tiles - 1) / tiles;
+    // every extra CTA along y costs a full set of output atomics (the epilogue is what bounds the small-plane layers): split the
+    // reduction only while the tile grid alone leaves SMs idle
+    int gy = tiles >= 148 ? 1 : (296 + tiles - 1) / tiles;
     if (gy > items) gy = items;
     if (gy < 1) gy = 1;
     if (gy > 65535) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
