@@ -229,6 +229,43 @@ def bench_mdct(dev, steps, hbm_peak):
             "round_trip_rel_l2": rt, "hbm_peak_gbs": hbm_peak}
 
 
+# ---------------------------------------------------------------------------------------------- long-form sub-benchmark
+def bench_longform(dev, reps=3):
+    """BASELINE configs[4]: generate_audio.py on a 60 s clip, 16 -> 48 kHz, 32512-sample segments (128 frames), gen_overlap 256,
+    LocalEnhancer + 2 attention layers: pinned host clip -> H2D -> on-device segmentation -> batched inference (CUDA graphs) ->
+    on-device overlap-add -> D2H.  Real-time factor = clip seconds / wall seconds (host clock around synchronised calls)."""
+    import torch
+
+    from mdctgan_b200.longform import LongFormGenerator
+    from mdctgan_b200.models.models import create_model
+    from mdctgan_b200.options.train_options import TrainOptions
+
+    seg, ov, secs = 32512, 256, 60
+    args = [a for a in OPT_ARGS]
+    for k, v in (("--segment_length", str(seg)), ("--bins", "128"), ("--lr_sampling_rate", "16000")):
+        args[args.index(k) + 1] = v
+    opt = TrainOptions().parse(save=False, args=args + ["--gpu_ids", str(dev.index), "--gen_overlap", str(ov)])
+    opt.checkpoints_dir = "/tmp/mdctgan_bench"
+    torch.manual_seed(99)
+    model = create_model(opt)
+    model.eval()
+    clip = make_lr_audio(1, secs * SR, 5).pin_memory()
+    gen = LongFormGenerator(model, batch_size=16)
+    out = gen(clip.to(dev, non_blocking=True), seg, ov)            # captures the two batch shapes
+    out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = gen(clip.to(dev, non_blocking=True), seg, ov)
+        out_h.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / reps
+    del gen, model
+    return {"workload": f"{secs} s clip @48 kHz -> {int((secs * SR + seg - 1) // seg)} x {seg}-sample segments, gen_overlap {ov}, LocalEnhancer+2 attn at 128 frames, "
+                        "batches of 16, fp32", "seconds_per_clip": dt, "real_time_factor": secs / dt, "audio_sec_per_sec": out.shape[-1] / SR / dt,
+            "output_samples": int(out.shape[-1]), "h2d_bytes": clip.numel() * 4, "d2h_bytes": out.numel() * out.element_size()}
+
+
 # ---------------------------------------------------------------------------------------------- per-launch profile
 KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_wgrad", "mdctgan_norm_finalize", "mdctgan_norm_apply",
                   "mdctgan_norm_act_bwd", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_avgpool3s2_nhwc",
@@ -428,6 +465,12 @@ def run_ours(args):
     clocks = sampler.stop()
 
     mdct = bench_mdct(dev, 50, hbm_peak) if rank == 0 else None
+    longform = None
+    if rank == 0 and world == 1 and not args.no_longform:
+        try:
+            longform = bench_longform(dev)
+        except Exception as e:  # noqa: BLE001  (a sub-benchmark must not take the headline line down)
+            longform = {"error": repr(e)[:300]}
 
     vals = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -473,6 +516,7 @@ def run_ours(args):
                                   sorted(by_entry.items(), key=lambda kv: -kv[1][1])},
             "eager_sum_of_kernels_ms": tot_ms / 3,
             "mdct": mdct,
+            "longform": longform,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SEG * 4, "d2h_bytes_per_step": 16,
                     "ms_per_step": e2e_ms, "api": "runtime.GraphedTrainStep(model)(pinned lr_audio, pinned hr_audio) -> 4 losses copied to "
@@ -497,6 +541,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-longform", dest="no_longform", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -204,6 +204,17 @@ typedef struct mdctgan_pack_desc {
 } mdctgan_pack_desc;
 int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_work, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Long-form generation (generate_audio.py:29-53).
+ */
+/* number of segments AudioTestDataset.seg_pad_audio (data/audio_dataset.py:153-167) produces for an L-sample clip */
+int64_t mdctgan_segment_count(int64_t L, int seg, int ov);
+/* seg_pad_audio: clip [L] fp32 -> [n_seg, seg] (zero-pad (ov, seg*ceil(L/seg) - L + ov), unfold(size seg, step seg - ov)) */
+int mdctgan_segment_gather(const float* audio_dev, int64_t L, float* out_dev, int64_t n_seg, int seg, int ov, void* stream);
+/* generate_audio.py:40-53: halve the first / last ov samples of each segment, fold(stride seg - ov), crop ov at both ends;
+ * [n_seg, seg] -> [(n_seg-1)*(seg-ov) + seg - 2*ov]; ov = 0 is the plain concatenation.  precision: MDCTGAN_F32 / _F64 (in and out). */
+int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream);
+
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);
 

@@ -280,6 +280,39 @@ int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_
   return 0;
 }
 
+int64_t mdctgan_segment_count(int64_t L, int seg, int ov) {
+  if (L < seg) return 1;
+  const int64_t nfull = (L + seg - 1) / seg;
+  const int64_t padded = seg * nfull + 2 * (int64_t)ov;     // ov + L + (seg*nfull - L + ov)
+  return (padded - seg) / (seg - ov) + 1;
+}
+
+int mdctgan_segment_gather(const float* audio_dev, int64_t L, float* out_dev, int64_t n_seg, int seg, int ov, void* stream) {
+  if (!audio_dev || !out_dev) return mdctgan_set_error(-1, "segment_gather: NULL buffer");
+  if (seg <= 0 || ov < 0 || ov >= seg || L <= 0 || n_seg <= 0) return mdctgan_set_error(-1, "segment_gather: bad shape");
+  // a clip shorter than one segment is padded at the end only (audio_dataset.py:163-166)
+  const int ov_eff = L < seg ? 0 : ov;
+  segment_gather_kernel<<<grid_for((size_t)(n_seg * seg), 256), 256, 0, (cudaStream_t)stream>>>(audio_dev, L, out_dev, n_seg, seg, seg - ov_eff, ov_eff);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream) {
+  if (!seg_dev || !out_dev) return mdctgan_set_error(-1, "segment_ola: NULL buffer");
+  if (seg <= 0 || ov < 0 || 2 * ov > seg || n_seg <= 0) return mdctgan_set_error(-1, "segment_ola: bad shape (0 <= 2*overlap <= segment)");
+  const int step = seg - ov;
+  const int64_t out_len = (n_seg - 1) * step + seg - 2 * (int64_t)ov;
+  if (out_len <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MDCTGAN_F64) segment_ola_kernel<double><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const double*)seg_dev, (double*)out_dev, out_len, n_seg, seg, step, ov);
+  else if (precision == MDCTGAN_F32) segment_ola_kernel<float><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const float*)seg_dev, (float*)out_dev, out_len, n_seg, seg, step, ov);
+  else return mdctgan_set_error(-1, "segment_ola: precision %d", precision);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
   if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
   counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);

@@ -759,6 +759,42 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long-form generation (generate_audio.py): segmenting a whole clip and overlap-adding the generated segments.
+//   segment_gather: AudioTestDataset.seg_pad_audio (data/audio_dataset.py:153-167): zero-pad (ov, seg*ceil(L/seg) - L + ov),
+//                   unfold(size = seg, step = seg - ov)
+//   segment_ola:    generate_audio.py:40-53: halve the first / last ov samples of every segment, fold with stride seg - ov,
+//                   crop ov at both ends (ov = 0: plain concatenation)
+// ------------------------------------------------------------------------------------------------
+__global__ void segment_gather_kernel(const float* __restrict__ audio, long long L, float* __restrict__ out, long long n_seg, int seg, int step,
+                                      int ov) {
+  const long long total = n_seg * seg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / seg;
+    const int j = (int)(i - s * seg);
+    const long long t = s * step + j - ov;          // position in the un-padded clip
+    out[i] = (t >= 0 && t < L) ? audio[t] : 0.f;
+  }
+}
+
+template <typename T>
+__global__ void segment_ola_kernel(const T* __restrict__ x, T* __restrict__ out, long long out_len, long long n_seg, int seg, int step, int ov) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < out_len; t += (long long)gridDim.x * blockDim.x) {
+    const long long q = t + ov;                     // position in the folded signal
+    long long s_hi = q / step;
+    if (s_hi >= n_seg) s_hi = n_seg - 1;
+    T acc = (T)0;
+    for (long long s = s_hi; s >= 0; --s) {         // segments covering q, in fold order (ascending s summed last-to-first is the same sum of <= 2 terms)
+      const long long j = q - s * step;
+      if (j >= seg) break;
+      T v = x[s * seg + j];
+      if (ov > 0 && (j < ov || j >= seg - ov)) v *= (T)0.5;
+      acc += v;
+    }
+    out[t] = acc;
+  }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;

@@ -63,6 +63,49 @@ def ref_opt(extra=()):
     return opt
 
 
+LONGFORM_CASES = [(100000, 7936, 0), (100000, 7936, 256), (50000, 32512, 4096), (5000, 7936, 0), (5000, 7936, 256), (63488, 7936, 0),
+                  (63488, 7936, 512), (9000, 3840, 128), (2880000, 32512, 256)]
+LONGFORM_FULL = {(5000, 7936, 256), (9000, 3840, 128)}      # cases whose full outputs are stored (the others: checksums + probes)
+
+
+def longform_clip(L, seg, ov):
+    torch.manual_seed(L + seg + ov)
+    return 0.1 * torch.randn(1, L)
+
+
+def gen_longform():
+    """AudioTestDataset.seg_pad_audio of the reference itself (data/audio_dataset.py:153-167) on seeded clips; the overlap-add
+    block of generate_audio.py:40-53 is script-level code, so it is run through its restatement (oracle/longform_oracle.py)."""
+    import torchaudio
+
+    if not hasattr(torchaudio, "set_audio_backend"):
+        torchaudio.set_audio_backend = lambda *a, **k: None      # removed API, called at import time (audio_dataset.py:9)
+    from data.audio_dataset import AudioTestDataset
+
+    from oracle import longform_oracle as LO
+
+    out = {}
+    for (L, seg, ov) in LONGFORM_CASES:
+        clip = longform_clip(L, seg, ov)
+        ds = object.__new__(AudioTestDataset)
+        ds.segment_length, ds.overlap = seg, ov
+        segs = ds.seg_pad_audio(clip.clone())
+        assert torch.equal(segs, LO.seg_pad_audio(clip.clone(), seg, ov))
+        key = f"{L}_{seg}_{ov}"
+        ola = LO.overlap_add(segs.double().reshape(-1, 1, 1, seg), seg, ov)
+        out[f"segshape_{key}"] = np.array(segs.shape)
+        out[f"segck_{key}"] = np.array([float(segs.double().sum()), float((segs.double() ** 2).sum())])
+        out[f"olashape_{key}"] = np.array(ola.shape)
+        out[f"olack_{key}"] = np.array([float(ola.sum()), float((ola ** 2).sum())])
+        idx = np.linspace(0, ola.shape[-1] - 1, 257).astype(np.int64)
+        out[f"olaprobe_{key}"] = ola[0, idx].numpy()
+        if (L, seg, ov) in LONGFORM_FULL:
+            out[f"seg_{key}"] = segs.numpy()
+            out[f"ola_{key}"] = ola.numpy()
+        print(key, tuple(segs.shape), tuple(ola.shape))
+    np.savez_compressed(os.path.join(HERE, "longform_golden.npz"), **out)
+
+
 def gen_mdct():
     from models.mdct import IMDCT4, MDCT4
     from models.pix2pixHD_model import Audio2MDCT
@@ -159,6 +202,8 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["mdct"]
     if "mdct" in what:
         gen_mdct()
+    if "longform" in what:
+        gen_longform()
     if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 
