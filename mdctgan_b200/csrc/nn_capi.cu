@@ -48,14 +48,21 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
   p.act = act; p.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   const int HWo = Ho * Wo;
-  if (Cout == 1) {
-    if (stats) return mdctgan_set_error(-2, "conv2d: statistics of a 1-channel output are not supported");
+  if (Cout <= 4 && !stats) {
     const int bps = (HWo + 31) / 32;
-    const size_t smem = ((size_t)kh * kw * Cin + 2 * (size_t)Cin) * sizeof(float);
-    if (smem > 200 * 1024) return mdctgan_set_error(-2, "conv2d: Cout=1 kernel needs %zu bytes of shared memory", smem);
-    static bool attr_set = false;   // once, outside any stream capture in practice (first eager call)
-    if (!attr_set) { CKN(cudaFuncSetAttribute(conv2d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
-    conv2d_cout1_kernel<<<B * bps, 256, smem, st>>>(p);
+    const size_t smem = ((size_t)kh * kw * Cin * Cout + 2 * (size_t)Cin) * sizeof(float);
+    if (smem > 200 * 1024) return mdctgan_set_error(-2, "conv2d: Cout<=4 kernel needs %zu bytes of shared memory", smem);
+#define LAUNCH_SMALL(CO)                                                                                                       \
+    do {                                                                                                                       \
+      static bool attr_set = false;   /* once, outside any stream capture in practice (first eager call) */                    \
+      if (!attr_set) { CKN(cudaFuncSetAttribute(conv2d_cout_small_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; } \
+      conv2d_cout_small_kernel<CO><<<B * bps, 256, smem, st>>>(p);                                                             \
+    } while (0)
+    if (Cout == 1) LAUNCH_SMALL(1);
+    else if (Cout == 2) LAUNCH_SMALL(2);
+    else if (Cout == 3) LAUNCH_SMALL(3);
+    else LAUNCH_SMALL(4);
+#undef LAUNCH_SMALL
   } else {
     const int bn = Cout >= 64 ? 64 : 32;
     int bm = 64;

@@ -252,14 +252,15 @@ __global__ void __launch_bounds__(256) conv2d_nhwc_kernel(const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cout = 1 convolution (generator head 7x7 -> tanh, discriminator head 4x4): 8 lanes per output pixel,
-// lanes split the channels in float4, shuffle-reduce.  Optional residual add after the activation
-// (fit_residual: sr = tanh(conv) ... + lr handled by the caller) is not fused here.
+// Cout <= 4 convolution (generator head 7x7 -> 1 + tanh, PatchGAN heads 4x4 -> 1, input gradient of the first PatchGAN
+// layer 64 -> 3): 8 lanes per output pixel, lanes split the channels in float4, shuffle-reduce.  Dead taps of a
+// transposed / strided geometry are skipped per pixel.  Weights [kh*kw*Cin][COUT] in shared memory.
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
-  extern __shared__ float s_w[];   // [kh*kw*Cin] weights, then scale/shift [Cin] x2 when normalising
+template <int COUT>
+__global__ void __launch_bounds__(256) conv2d_cout_small_kernel(const ConvParams p) {
+  extern __shared__ float s_w[];   // [kh*kw*Cin][COUT] weights, then scale/shift [Cin] x2 when normalising
   const int K = p.kh * p.kw * p.Cin;
-  float* s_scale = s_w + K;
+  float* s_scale = s_w + K * COUT;
   float* s_shift = s_scale + p.Cin;
   const int HWo = p.Ho * p.Wo;
   const int groups_per_block = 256 / 8;
@@ -267,11 +268,13 @@ static __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvPara
   const int b = blockIdx.x / blocks_per_sample;
   const int m = (blockIdx.x - b * blocks_per_sample) * groups_per_block + threadIdx.x / 8;
   const int l8 = threadIdx.x % 8;
-  for (int i = threadIdx.x; i < K; i += 256) s_w[i] = __ldg(p.w + i);
+  for (int i = threadIdx.x; i < K * COUT; i += 256) s_w[i] = __ldg(p.w + i);
   const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
   if (has_norm) norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, threadIdx.x, 256);
   __syncthreads();
-  float acc = 0.f;
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
   if (m < HWo) {
     const int oy = m / p.Wo, ox = m - oy * p.Wo;
     const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
@@ -282,7 +285,7 @@ static __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvPara
         const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
         if (ix < 0) continue;
         const float* px = xb + ((size_t)iy * p.W + ix) * p.Cin;
-        const float* wt = s_w + (ky * p.kw + kx) * p.Cin;
+        const float* wt = s_w + (size_t)(ky * p.kw + kx) * p.Cin * COUT;
         for (int c = l8 * 4; c < p.Cin; c += 32) {
           if (c + 3 < p.Cin && (p.Cin % 4) == 0) {
             float4 q = __ldg(reinterpret_cast<const float4*>(px + c));
@@ -290,26 +293,34 @@ static __global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvPara
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (has_norm) v[u] = apply_act(fmaf(v[u], s_scale[c + u], s_shift[c + u]), p.in.act);
-              acc = fmaf(v[u], wt[c + u], acc);
+#pragma unroll
+              for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v[u], wt[(c + u) * COUT + j], acc[j]);
             }
           } else {
             for (int u = 0; u < 4 && c + u < p.Cin; ++u) {
               float v = __ldg(px + c + u);
               if (has_norm) v = apply_act(fmaf(v, s_scale[c + u], s_shift[c + u]), p.in.act);
-              acc = fmaf(v, wt[c + u], acc);
+#pragma unroll
+              for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v, wt[(c + u) * COUT + j], acc[j]);
             }
           }
         }
       }
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+  }
   if (m < HWo && l8 == 0) {
-    const float v = acc + (p.bias ? __ldg(p.bias) : 0.f);
-    p.y[(size_t)b * HWo + m] = apply_act(v, p.act);
-    // (no statistics: the reference never normalises a 1-channel map)
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+      const float v = acc[j] + (p.bias ? __ldg(p.bias + j) : 0.f);
+      p.y[((size_t)b * HWo + m) * COUT + j] = apply_act(v, p.act);
+    }
+    // (no statistics: the reference never normalises these maps)
   }
 }
 

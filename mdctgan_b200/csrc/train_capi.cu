@@ -91,7 +91,8 @@ int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const doubl
   if (B > 65535) return mdctgan_set_error(-2, "norm_act_bwd: batch %d > 65535", B);
   NormBwdParams p{x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, C, B};
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == 0 && C % 8 == 0 && C / 8 <= 65535) {      // InstanceNorm2d: one launch, no scratch
+  if (mode == 0 && C % 8 == 0 && C / 8 <= 65535 && (long long)B * (C / 8) * 256 >= (long long)HW * 2) {
+    // InstanceNorm2d, one launch, no scratch: when the (sample, 8-channel) groups alone give enough CTAs for the plane size
     instnorm_bwd_fused_kernel<<<dim3(C / 8, B), 256, 0, st>>>(p);
     mdctgan_count_launch();
     CKT(cudaGetLastError());

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
     for (int mb = m_begin; mb < m_end; mb += MS) {
       const bool more = mb + MS < m_end;
       if (more) load_stage(mb + MS, ra0, ra1, rb);   // in flight while this stage is multiplied
-#pragma unroll
+#pragma unroll 4
       for (int mm = 0; mm < MS; ++mm) {
         const float4 al = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 4]);
         const float4 ah = *reinterpret_cast<const float4*>(&As[buf][mm][64 + ty * 4]);

@@ -352,9 +352,10 @@ class Pix2PixHDModel(BaseModel):
         with _ops.stats_pass(self.device):
             self.grad_all.zero_()                          # one memset for both buckets
             losses = graph.forward(lr_audio, hr_audio)
-            graph.backward_G()
+            graph.backward_G(join=False)                  # weight-gradient kernels keep running on the side stream ...
             half = self._half_scalar()
-            graph.backward_D(half, half)
+            graph.backward_D(half, half, join=False)
+            _ops.join_side_work(self.device)              # ... until here: the exchange / optimiser read the gradients
             if all_reduce is not None:
                 all_reduce(self.grad_all)                  # ONE collective per step
             self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size

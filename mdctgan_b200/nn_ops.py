@@ -10,6 +10,7 @@ them (and the ReLU / LeakyReLU) while it gathers its input.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from ctypes import c_double, c_float, c_int, c_int64, c_void_p
 from dataclasses import dataclass
@@ -436,15 +437,62 @@ def residual_scale_add(sr: torch.Tensor, lr: torch.Tensor, lr_bins: int, low_sca
 _tape = None
 
 
+class _SideWork:
+    """A second CUDA stream for work whose results are only needed at the end of the step (weight gradients)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.keep = []          # tensors read on the side stream: kept alive until join() so the allocator cannot recycle them
+        self.active = False
+
+
+_side = {}
+SIDE_STREAM_WGRAD = os.environ.get("MDCTGAN_SIDE_WGRAD", "1") != "0"
+
+
+def _side_stream(dy: torch.Tensor):
+    """Fork: make the side stream wait for everything issued so far on the current stream; returns it (or None when disabled)."""
+    if not SIDE_STREAM_WGRAD:
+        return None
+    key = dy.device.index
+    sw = _side.get(key)
+    if sw is None:
+        sw = _side[key] = _SideWork(dy.device)
+    main = torch.cuda.current_stream(dy.device)
+    if main == sw.stream:
+        return None
+    ev = torch.cuda.Event()
+    ev.record(main)
+    sw.stream.wait_event(ev)
+    sw.keep.append(dy)
+    sw.active = True
+    return sw.stream
+
+
+def join_side_work(device) -> None:
+    """Join: the current stream waits for the side stream (call before anything reads the weight gradients)."""
+    sw = _side.get(torch.device(device).index)
+    if sw is None or not sw.active:
+        return
+    torch.cuda.current_stream(sw.device).wait_stream(sw.stream)
+    sw.keep.clear()
+    sw.active = False
+
+
 class Tape:
     def __init__(self):
         self.ops = []
 
-    def backward(self, grads: "GradMap", wgrad: bool = True, nb: Optional[int] = None):
+    def backward(self, grads: "GradMap", wgrad: bool = True, nb: Optional[int] = None, join: bool = True):
         """`nb`: only the first nb samples of every saved tensor take part (the generator-loss sweep through the
-        discriminator runs on the fake half of the [fake ; real] batch).  `wgrad=False`: input gradients only."""
+        discriminator runs on the fake half of the [fake ; real] batch).  `wgrad=False`: input gradients only.
+        `join=False` leaves the weight-gradient kernels running on the side stream (the caller joins later)."""
         for op in reversed(self.ops):
             op.backward(grads, wgrad, nb)
+        if join:
+            for sw in list(_side.values()):
+                join_side_work(sw.device)
 
 
 class recording:
@@ -516,6 +564,25 @@ def _view_feat(f: Feat, nb: Optional[int]) -> Feat:
     return Feat(f.x[:nb], sc, sh, f.per_sample, f.act, None, _sl(f.norm_stats, nb), f.norm_count, f.norm_eps, f.needs_grad)
 
 
+def _explicit_norm(f: Feat, cache_on: Optional[Feat]) -> Feat:
+    """A deferred InstanceNorm (raw statistics) as explicit fp32 scale / shift: one tiny finalize launch instead of every CTA
+    of the weight-gradient kernel re-deriving rstd in fp64 for every sample it visits.  Cached on the tape's Feat."""
+    if f.norm_stats is None:
+        return f
+    cached = getattr(cache_on, "_explicit", None) if cache_on is not None else None
+    if cached is None:
+        B, H, W, C = f.x.shape
+        scale = torch.empty(B * C, dtype=torch.float32, device=f.x.device)
+        shift = torch.empty(B * C, dtype=torch.float32, device=f.x.device)
+        with torch.cuda.device(f.x.device):
+            _lib.check(_L().mdctgan_norm_finalize(f.norm_stats.data_ptr(), B, C, f.norm_count, f.norm_eps, 0, None, None, None, None, 0.0,
+                                                  scale.data_ptr(), shift.data_ptr(), _stream(f.x)))
+        cached = (scale, shift)
+        if cache_on is not None:
+            cache_on._explicit = cached
+    return Feat(f.x, cached[0], cached[1], True, f.act, None, None, 0.0, f.norm_eps, f.needs_grad)
+
+
 class _ConvOp:
     def __init__(self, f, out, owner, kh, kw, stride, pad, pad_mode, transposed, act):
         self.f, self.out, self.owner = f, out, owner
@@ -527,7 +594,7 @@ class _ConvOp:
             return
         if self.act != ACT_NONE:
             dy = act_bwd(dy, _sl(self.out.x, nb), self.act)
-        f = _view_feat(self.f, nb)
+        f = _explicit_norm(_view_feat(self.f, nb), self.f if nb is None else None)
         own = self.owner
         B, H, W, Cin = f.x.shape
         _, Ho, Wo, Cout = dy.shape
@@ -537,7 +604,10 @@ class _ConvOp:
             db = grad_of(own.bias) if (own.bias is not None and own.bias.requires_grad) else None
             taps = self.kh * self.kw
             s_co, s_ci = (taps, Cout * taps) if self.transposed else (Cin * taps, taps)
-            with torch.cuda.device(dy.device):
+            # nothing reads a weight gradient before the optimiser step: the wgrad kernels run on a side stream, concurrently with
+            # the dgrad / norm-backward chain of the main stream (most kernels of this step fill a fraction of the 148 SMs)
+            side = _side_stream(dy)
+            with torch.cuda.device(dy.device), (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 _lib.check(L.mdctgan_conv2d_wgrad(f.x.data_ptr(), B, H, W, Cin, dy.data_ptr(), Ho, Wo, Cout, self.kh, self.kw, self.stride,
                                                   self.pad, self.pad_mode, 1 if self.transposed else 0, _ptr(f.scale), _ptr(f.shift),
                                                   1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,

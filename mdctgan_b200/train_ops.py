@@ -95,7 +95,7 @@ class GanGraph:
 
     # ------------------------------------------------------------------ backward sweeps
     @torch.no_grad()
-    def backward_G(self, g_gan: Optional[torch.Tensor] = None, g_feat: Optional[torch.Tensor] = None, use_gan=True, use_feat=True):
+    def backward_G(self, g_gan: Optional[torch.Tensor] = None, g_feat: Optional[torch.Tensor] = None, use_gan=True, use_feat=True, join=True):
         """d(g_gan * G_GAN + g_feat * G_GAN_Feat) / d(G parameters) accumulated into their .grad (the flat bucket).
         g_*: 0-dim CUDA tensors (upstream gradients of the loss tensors) or None = 1."""
         m, B = self.m, self.B
@@ -116,16 +116,18 @@ class GanGraph:
                         _lib.check(L.mdctgan_l1_pair_bwd(f.x.data_ptr(), f.x[B:].data_ptr(), n, self.feat_coef / n, ops._ptr(g_feat),
                                                          g.data_ptr(), 0, _st(g)))
                         G.add(f, g)
-            self.tapeD.backward(G, wgrad=False, nb=B)
+            self.tapeD.backward(G, wgrad=False, nb=B, join=False)
             gin = G.pop(self.din)                                         # [B,F,N,3]
             dsr = torch.empty((B, self.Fr, self.N, 1), dtype=torch.float32, device=m.device)
             _lib.check(L.mdctgan_disc_input_bwd(gin.data_ptr(), self.sr_spectro.data_ptr(), dsr.data_ptr(), dsr.numel(), _st(dsr)))
             GG = ops.GradMap()
             GG.add(self.g_out, dsr)                                       # fit_residual's "+ lr" passes the gradient through
-            self.tapeG.backward(GG, wgrad=True, nb=None)
+            self.tapeG.backward(GG, wgrad=True, nb=None, join=False)
+            if join:
+                ops.join_side_work(m.device)
 
     @torch.no_grad()
-    def backward_D(self, g_real: Optional[torch.Tensor] = None, g_fake: Optional[torch.Tensor] = None):
+    def backward_D(self, g_real: Optional[torch.Tensor] = None, g_fake: Optional[torch.Tensor] = None, join=True):
         """d(g_real * D_real + g_fake * D_fake) / d(D parameters) accumulated into their .grad."""
         m, B = self.m, self.B
         L = ops._L()
@@ -140,7 +142,9 @@ class GanGraph:
                     _lib.check(L.mdctgan_mse_const_bwd(pred.x.data_ptr(), n, 0.0, 1.0 / n, ops._ptr(g_fake), g.data_ptr(), 0, _st(g)))
                     _lib.check(L.mdctgan_mse_const_bwd(pred.x[B:].data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_real), g[B:].data_ptr(), 0, _st(g)))
                     G.add(pred, g)
-                self.tapeD.backward(G, wgrad=True, nb=None)
+                self.tapeD.backward(G, wgrad=True, nb=None, join=False)
+                if join:
+                    ops.join_side_work(m.device)
         finally:
             self.din.needs_grad = True
 
