@@ -292,8 +292,8 @@ class LaunchProfiler:
         torch = self.torch
         from mdctgan_b200 import nn_ops
 
-        self._side = nn_ops.SIDE_STREAM_WGRAD
-        nn_ops.SIDE_STREAM_WGRAD = False        # per-kernel times are taken with everything serialised on one stream
+        self._side, self._par = nn_ops.SIDE_STREAM_WGRAD, nn_ops.PARALLEL_BRANCHES
+        nn_ops.SIDE_STREAM_WGRAD = nn_ops.PARALLEL_BRANCHES = False        # per-kernel times: everything serialised on one stream
         for n in KERNEL_ENTRIES:
             if not hasattr(self.L, n):
                 continue
@@ -331,7 +331,7 @@ class LaunchProfiler:
     def __exit__(self, *exc):
         from mdctgan_b200 import nn_ops
 
-        nn_ops.SIDE_STREAM_WGRAD = self._side
+        nn_ops.SIDE_STREAM_WGRAD, nn_ops.PARALLEL_BRANCHES = self._side, self._par
         for n, f in self.orig.items():
             setattr(self.L, n, f)
 

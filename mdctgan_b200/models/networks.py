@@ -510,16 +510,21 @@ class MultiscaleDiscriminator(nn.Module):
         """Forward on a Feat (NHWC), as `forward` but staying on the device layout: list[num_D] of list[n_layers + 2]
         Feats; the intermediate features are materialised (IN + LeakyReLU applied) because the feature-matching
         loss reads them (pix2pixHD_model.py:447-451); the next stage still consumes the deferred view."""
-        result = []
-        for i in range(self.num_D):
-            outs, g = [], f
-            for st in self._stages(self.num_D - 1 - i):
-                g = run_layers(list(st), g)
-                outs.append(ops.materialize(g))
-            result.append(outs)
-            if i != self.num_D - 1:
-                f = ops.avgpool3s2(f)
-        return result
+        pyramid = [f]
+        for i in range(self.num_D - 1):
+            pyramid.append(ops.avgpool3s2(pyramid[-1]))
+
+        def scale(i):
+            def run():
+                outs, g = [], pyramid[i]
+                for st in self._stages(self.num_D - 1 - i):
+                    g = run_layers(list(st), g)
+                    outs.append(ops.materialize(g))
+                return outs
+            return run
+
+        # the scales are independent given the pyramid: one CUDA stream each (forward and both backward sweeps)
+        return ops.run_branches([scale(i) for i in range(self.num_D)], f.x.device)
 
     def forward(self, input):
         with torch.no_grad(), ops.stats_pass(input.device):

@@ -352,10 +352,21 @@ class Pix2PixHDModel(BaseModel):
         with _ops.stats_pass(self.device):
             self.grad_all.zero_()                          # one memset for both buckets
             losses = graph.forward(lr_audio, hr_audio)
-            graph.backward_G(join=False)                  # weight-gradient kernels keep running on the side stream ...
+            # the two sweeps only read the tapes and write disjoint gradients: the discriminator sweep runs on its own stream,
+            # concurrently with the generator sweep; weight-gradient kernels of both go to the side stream
             half = self._half_scalar()
-            graph.backward_D(half, half, join=False)
-            _ops.join_side_work(self.device)              # ... until here: the exchange / optimiser read the gradients
+            main = torch.cuda.current_stream(self.device)
+            if _ops.PARALLEL_BRANCHES:
+                sD = _ops.aux_stream(self.device, "sweep_D")
+                sD.wait_stream(main)
+                with torch.cuda.stream(sD):
+                    graph.backward_D(half, half, join=False)
+                graph.backward_G(join=False)
+                main.wait_stream(sD)
+            else:
+                graph.backward_G(join=False)
+                graph.backward_D(half, half, join=False)
+            _ops.join_side_work(self.device)              # the exchange / optimiser read the gradients from here on
             if all_reduce is not None:
                 all_reduce(self.grad_all)                  # ONE collective per step
             self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size

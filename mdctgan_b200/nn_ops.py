@@ -480,6 +480,74 @@ def join_side_work(device) -> None:
     sw.active = False
 
 
+_branch_streams = {}
+PARALLEL_BRANCHES = os.environ.get("MDCTGAN_PARALLEL_BRANCHES", "1") != "0"
+
+
+def _branch_stream(device, i: int, parent=None):
+    """Stream of branch i forked from `parent` (default: the current stream): every parent has its own set, so two sweeps
+    running on different streams do not serialise on shared branch streams."""
+    parent = parent if parent is not None else torch.cuda.current_stream(device)
+    key = (torch.device(device).index, parent.cuda_stream, i)
+    if key not in _branch_streams:
+        _branch_streams[key] = torch.cuda.Stream(device)
+    return _branch_streams[key]
+
+
+def aux_stream(device, name: str):
+    """A named long-lived stream (e.g. the discriminator sweep of the train step)."""
+    key = (torch.device(device).index, name)
+    if key not in _branch_streams:
+        _branch_streams[key] = torch.cuda.Stream(device)
+    return _branch_streams[key]
+
+
+def run_branches(fns, device):
+    """Independent sub-graphs (the PatchGAN scales of the multiscale discriminator) on their own CUDA streams: each branch is
+    forked from the current stream, records into its own tape, and the current stream joins them all afterwards.  The backward
+    of the group forks / joins the same way (`_ParallelOp`).  Most kernels of one branch fill a fraction of the 148 SMs."""
+    main = torch.cuda.current_stream(device)
+    use_streams = PARALLEL_BRANCHES and len(fns) > 1
+    results, tapes = [], []
+    ev = torch.cuda.Event()
+    ev.record(main)
+    outer = _tape
+    for i, fn in enumerate(fns):
+        sub = Tape() if outer is not None else None
+        st = _branch_stream(device, i, main) if use_streams else main
+        if use_streams:
+            st.wait_event(ev)
+        with torch.cuda.stream(st), (recording(sub) if sub is not None else contextlib.nullcontext()):
+            results.append(fn())
+        tapes.append(sub)
+    if use_streams:
+        for i in range(len(fns)):
+            main.wait_stream(_branch_stream(device, i, main))
+    if outer is not None:
+        outer.ops.append(_ParallelOp(tapes, device))
+    return results
+
+
+class _ParallelOp:
+    def __init__(self, tapes, device):
+        self.tapes, self.device = tapes, device
+
+    def backward(self, G, wgrad, nb):
+        main = torch.cuda.current_stream(self.device)
+        use_streams = PARALLEL_BRANCHES and len(self.tapes) > 1
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for i, t in enumerate(self.tapes):
+            st = _branch_stream(self.device, i, main) if use_streams else main
+            if use_streams:
+                st.wait_event(ev)
+            with torch.cuda.stream(st):
+                t.backward(G, wgrad, nb, join=False)
+        if use_streams:
+            for i in range(len(self.tapes)):
+                main.wait_stream(_branch_stream(self.device, i, main))
+
+
 class Tape:
     def __init__(self):
         self.ops = []
