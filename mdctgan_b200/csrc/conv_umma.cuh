@@ -183,7 +183,7 @@ struct Cfg {
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-  static constexpr int kStages = (192 * 1024 / kStageBytes) >= 8 ? 8 : ((192 * 1024 / kStageBytes) >= 4 ? 4 : 2);
+  static constexpr int kStages = (192 * 1024 / kStageBytes) >= 8 ? 8 : (192 * 1024 / kStageBytes);   // 3 for BN = 128 with the hi/lo split
   static constexpr int kPitch = BN + 4;                                   // staging row pitch (floats)
   static constexpr int kStagingBytes = ((kBM * kPitch * 4 + 1023) / 1024) * 1024;
   static constexpr int kRedBytes = 2 * kProducerThreads * 4 * 8;          // [2][RP][BN] doubles, RP*BN = 4 * producer threads
@@ -250,8 +250,7 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmmaParams p) {
   using C = Cfg<BN, SPLIT3>;
-  static_assert((C::kStages & (C::kStages - 1)) == 0, "stage count must be a power of two");
-  constexpr int kStageMask = C::kStages - 1;
+  static_assert(C::kStages >= 2 && C::kStages <= 8, "stage count");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t smem_a = smem_u32(smem);
@@ -357,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         if (it < nk) cp_async_wait<kAhead - 1>(); else cp_async_wait<0>();
         const int newer = (it < nk ? it : nk) - 1 - q;          // chunks issued after q
         const uint32_t ok2 = (okq >> (2 * newer)) & 3u;
-        const int s = q & kStageMask;
+        const int s = q % C::kStages;
         const uint32_t a_hi = smem_a + s * C::kStageBytes + row_off;
         const float4 sc = *reinterpret_cast<const float4*>(s_scale + c2);
         const float4 sh = *reinterpret_cast<const float4*>(s_shift + c2);
@@ -386,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       }
       if (it < nk) {
         // ---- issue chunk it
-        const int s = it & kStageMask;
+        const int s = it % C::kStages;
         mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
         if (tap_dirty) {
           tap_dirty = false;
@@ -443,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       constexpr uint32_t idesc = make_idesc_tf32(BN);
 #pragma unroll 1
       for (int it = 0; it < nk; ++it) {
-        const int s = it & kStageMask;
+        const int s = it % C::kStages;
         mbar_wait(&full[s], (uint32_t)(it / C::kStages) & 1u);
         tc_fence_after();
         const uint32_t a_hi = smem_a + s * C::kStageBytes;
@@ -470,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     if (lane == 0) {
 #pragma unroll 1
       for (int it = 0; it < nk; ++it) {
-        const int s = it & kStageMask;
+        const int s = it % C::kStages;
         mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&full[s], (uint32_t)(C::kParts * C::kBBytes));
         uint8_t* b_hi = smem + s * C::kStageBytes + C::kParts * C::kABytes;

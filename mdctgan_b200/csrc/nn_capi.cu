@@ -309,7 +309,13 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   }
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
+  // BN = 128 halves the shared-memory traffic per output (the K loop of this kernel is shared-memory-bandwidth bound: the A tile
+  // is re-read by every MMA) -- taken when the 128-wide tiles, split over K, still give about a wave of CTAs
+  const long long tiles128 = (long long)p.m_tiles * B * p.classes * (Cout / 128);
+  const int max_split = min_kchunks < 8 ? min_kchunks : 8;
+  if (Cout % 128 == 0 && (tiles128 >= 74 || tiles128 * max_split >= 96))
+    rc = precision == 0 ? launch_umma<128, true>(p, Cout / 128, min_kchunks, st) : launch_umma<128, false>(p, Cout / 128, min_kchunks, st);
+  else if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
   else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, min_kchunks, st) : launch_umma<32, false>(p, Cout / 32, min_kchunks, st);
   if (rc) return rc;
   mdctgan_count_launch();

@@ -48,6 +48,9 @@ UMMA_CASES = [
     (2, 128, 5, 9, 96, 1, 1, 0, False, False),     # 1x1 (BottleStack), Cout % 64 != 0, K = 128 (4 chunks)
     (1, 40, 7, 5, 32, 5, 1, 2, False, False),      # Cin % 32 != 0: K chunks straddle taps, K = 1000 padded to 1024
     (5, 32, 32, 256, 32, 3, 1, 1, True, False),    # many tiles (320), no split
+    (4, 512, 2, 16, 512, 3, 1, 1, True, False),    # cfg4 bottleneck: BN = 128 tiles, 3-stage ring, cluster of 8
+    (2, 128, 16, 64, 128, 3, 1, 1, True, False),   # BN = 128, 8 M-tiles per sample
+    (2, 256, 5, 33, 512, 4, 1, 2, False, False),   # PatchGAN 4x4 s1 -> 512 channels (BN = 128), ragged last tile
 ]
 
 

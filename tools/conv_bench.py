@@ -19,6 +19,7 @@ LAYERS = [
     ("res 512->512 @2x16 b8", 8, 512, 2, 16, 512, 3, 1, 1, True, False),
     ("res 64->64 @16x128 b8", 8, 64, 16, 128, 64, 3, 1, 1, True, False),
     ("D 64->128 k4 s2 @17x129", 4, 64, 17, 129, 128, 4, 2, 2, False, False),
+    ("res 512->512 @2x16 b4 (cfg4 bottleneck)", 4, 512, 2, 16, 512, 3, 1, 1, True, False),
 ]
 
 

@@ -46,6 +46,6 @@ def trace(dev, spec, engine="umma"):
 
 if __name__ == "__main__":
     dev = torch.device("cuda:0")
-    for idx in (0, 1, 6):
+    for idx in (int(a) for a in sys.argv[1:]) if len(sys.argv) > 1 else (0, 1, 6):
         trace(dev, LAYERS[idx])
         trace(dev, LAYERS[idx], "tf32")
