@@ -267,6 +267,14 @@ def bench_longform(dev, reps=3):
 
 
 # ---------------------------------------------------------------------------------------------- per-launch profile
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same workload (profiles/, gpurun s5f / s5m)
+NCU_TRAFFIC = {
+    "wgrad[fp32] k3 s1 512->512 B4 @2x16": (10.08e6, "profiles/r01_train_ncu_full_wgrad.txt: 10.06-10.10 MB read, 0 B written back within the "
+                                                     "kernel (the 9.4 MB of gradient atomics resolve in L2); algorithmic minimum 9.4 MB (dW) + 0.5 MB"),
+    "conv[tcgen05] k3 s1 512->512 B4 @2x16": (19.2e6, "profiles/r01_train_ncu_full_wgrad_umma.txt: 19.2 MB read = the TF32 hi|lo weight image (2 x 9.4 MB)"),
+    "conv[tcgen05] k3 s1 512->512 B4 @4x18": (19.2e6, "profiles/r01_train_ncu_full_wgrad_umma.txt: 19.2 MB read = the TF32 hi|lo weight image (2 x 9.4 MB)"),
+}
+
 KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_wgrad", "mdctgan_norm_finalize", "mdctgan_norm_apply",
                   "mdctgan_norm_act_bwd", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_avgpool3s2_nhwc",
                   "mdctgan_avgpool3s2_bwd", "mdctgan_attention_abs_pos", "mdctgan_attention_abs_pos_bwd", "mdctgan_mse_const_fwd",
@@ -504,6 +512,8 @@ def run_ours(args):
         else:
             roof = {"bound": "hbm", "kernel": dom_tag, "achieved": dom[3] / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": dom[3] / (dom_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": dom[3]}
+        if dom_tag in NCU_TRAFFIC:
+            roof["traffic"], roof["traffic_source"] = NCU_TRAFFIC[dom_tag]
         roof.update({"peak_source": peak_src, "avg_launch_ms": dom_ms, "launches_per_step": dom[0] // 3, "share_of_step": dom[1] / tot_ms})
         by_entry = {}
         for tag, v in table.items():
