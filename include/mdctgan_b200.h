@@ -215,6 +215,18 @@ int mdctgan_segment_gather(const float* audio_dev, int64_t L, float* out_dev, in
  * [n_seg, seg] -> [(n_seg-1)*(seg-ov) + seg - 2*ov]; ov = 0 is the plain concatenation.  precision: MDCTGAN_F32 / _F64 (in and out). */
 int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics (util/util.py:132-177 compute_matrics; callers train.py:116-117, generate_audio.py:59-60).
+ */
+/* per row r of [rows, T]: rows_out[3r..] += (sum (sr-hr)^2, sum hr^2, sum (lr-hr)^2) in double (zero it first): MSE and the SNRs */
+int mdctgan_metrics_rows(const float* hr, const float* lr, const float* sr, int64_t rows, int64_t T, double* rows_out, void* stream);
+/* frames of aF.spectrogram(n_fft, hop, center) */
+int64_t mdctgan_lsd_frame_count(int64_t T, int n_fft, int hop, int center);
+/* *acc += sum over rows and frames of sqrt(mean_k (log10(|STFT hr|^2 + 1e-6) - log10(|STFT sr|^2 + 1e-6))^2): the LSD of
+ * util/util.py:170-175 is *acc / (rows * frames).  window_dev: n_fft fp32 values (kbdwin(2*win)); n_fft 512 / 1024 / 2048. */
+int mdctgan_lsd_frames(const float* hr, const float* sr, int64_t rows, int64_t T, int n_fft, int hop, const float* window_dev, int center,
+                       double* acc, void* stream);
+
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);
 

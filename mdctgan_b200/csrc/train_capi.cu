@@ -314,6 +314,41 @@ int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int s
   return 0;
 }
 
+int mdctgan_metrics_rows(const float* hr, const float* lr, const float* sr, int64_t rows, int64_t T, double* rows_out, void* stream) {
+  if (!hr || !lr || !sr || !rows_out) return mdctgan_set_error(-1, "metrics_rows: NULL buffer");
+  if (rows <= 0 || T <= 0) return 0;
+  if (rows > 65535) return mdctgan_set_error(-2, "metrics_rows: %lld rows > 65535", (long long)rows);
+  int gx = (int)((T + 256 * 16 - 1) / (256 * 16));
+  if (gx > 148 * 4) gx = 148 * 4;
+  metrics_rows_kernel<<<dim3(gx, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(hr, lr, sr, T, rows_out);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int64_t mdctgan_lsd_frame_count(int64_t T, int n_fft, int hop, int center) {
+  if (center) return T / hop + 1;
+  return T < n_fft ? 0 : (T - n_fft) / hop + 1;
+}
+
+int mdctgan_lsd_frames(const float* hr, const float* sr, int64_t rows, int64_t T, int n_fft, int hop, const float* window_dev, int center,
+                       double* acc, void* stream) {
+  if (!hr || !sr || !window_dev || !acc) return mdctgan_set_error(-1, "lsd_frames: NULL buffer");
+  if (n_fft != 1024 && n_fft != 512 && n_fft != 2048) return mdctgan_set_error(-2, "lsd_frames: n_fft %d (512, 1024 or 2048)", n_fft);
+  if (center && T <= n_fft / 2) return mdctgan_set_error(-1, "lsd_frames: reflect padding needs T > n_fft/2");
+  const int64_t frames = mdctgan_lsd_frame_count(T, n_fft, hop, center);
+  if (rows <= 0 || frames <= 0) return 0;
+  if (rows > 65535) return mdctgan_set_error(-2, "lsd_frames: %lld rows > 65535", (long long)rows);
+  dim3 grid((unsigned)frames, (unsigned)rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_fft == 1024) lsd_frames_kernel<1024><<<grid, 256, 0, st>>>(hr, sr, T, hop, (int)frames, window_dev, center, acc);
+  else if (n_fft == 512) lsd_frames_kernel<512><<<grid, 256, 0, st>>>(hr, sr, T, hop, (int)frames, window_dev, center, acc);
+  else lsd_frames_kernel<2048><<<grid, 256, 0, st>>>(hr, sr, T, hop, (int)frames, window_dev, center, acc);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
   if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
   counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);

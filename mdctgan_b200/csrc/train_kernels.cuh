@@ -795,6 +795,81 @@ __global__ void segment_ola_kernel(const T* __restrict__ x, T* __restrict__ out,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation metrics (util/util.py:132-177 compute_matrics): MSE, SNR of sr and lr against hr, and the log-spectral distance
+// over a 2*n_fft STFT with the kbdwin(2*win) window (torchaudio.functional.spectrogram, power 2, centre = reflect padding).
+//   metrics_rows_kernel: per row (last dim) sums  sum (sr-hr)^2, sum hr^2, sum (lr-hr)^2      -> rows[r][3] (double)
+//   lsd_frames_kernel:   one CTA per (row, frame): hr and sr frames go through ONE complex FFT (z = hr + i sr, the two real
+//                        spectra are separated afterwards), |X|^2 -> log10(. + 1e-6) -> sqrt(mean_k diff^2) -> acc += (double)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) metrics_rows_kernel(const float* __restrict__ hr, const float* __restrict__ lr, const float* __restrict__ sr,
+                                                           long long T, double* __restrict__ rows) {
+  const long long r = blockIdx.y;
+  const float* h = hr + r * T; const float* l = lr + r * T; const float* s = sr + r * T;
+  double a = 0, b = 0, c = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < T; i += (long long)gridDim.x * 256) {
+    const double hv = h[i], d1 = (double)s[i] - hv, d2 = (double)l[i] - hv;
+    a = fma(d1, d1, a); b = fma(hv, hv, b); c = fma(d2, d2, c);
+  }
+  const double ta = block_sum_256(a);
+  __syncthreads();
+  const double tb = block_sum_256(b);
+  __syncthreads();
+  const double tc = block_sum_256(c);
+  if (threadIdx.x == 0) { atomicAdd(rows + 3 * r, ta); atomicAdd(rows + 3 * r + 1, tb); atomicAdd(rows + 3 * r + 2, tc); }
+}
+
+template <int NF>      // FFT size (2 * n_fft of the model: 1024)
+__global__ void __launch_bounds__(256) lsd_frames_kernel(const float* __restrict__ hr, const float* __restrict__ sr, long long T, int hop, int frames,
+                                                         const float* __restrict__ window, int center, double* __restrict__ acc) {
+  __shared__ float2 z[NF];
+  __shared__ float2 tw[NF / 2];
+  const int row = blockIdx.y, fr = blockIdx.x;
+  const float* h = hr + (long long)row * T; const float* s = sr + (long long)row * T;
+  const long long start = (long long)fr * hop - (center ? NF / 2 : 0);
+  constexpr int LOG = NF == 2048 ? 11 : (NF == 1024 ? 10 : (NF == 512 ? 9 : 8));
+  for (int i = threadIdx.x; i < NF / 2; i += 256) {
+    float sn, cs;
+    sincospif(-2.f * (float)i / (float)NF, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  for (int i = threadIdx.x; i < NF; i += 256) {       // bit-reversed load of the windowed, reflect-padded frames
+    long long t = start + i;
+    if (t < 0) t = -t;
+    if (t >= T) t = 2 * (T - 1) - t;
+    const float w = __ldg(window + i);
+    const unsigned j = __brev((unsigned)i) >> (32 - LOG);
+    z[j] = make_float2(w * __ldg(h + t), w * __ldg(s + t));
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int st = 0; st < LOG; ++st) {
+    const int half = 1 << st;
+    for (int bfly = threadIdx.x; bfly < NF / 2; bfly += 256) {
+      const int grp = bfly >> st, pos = bfly & (half - 1);
+      const int i0 = (grp << (st + 1)) + pos, i1 = i0 + half;
+      const float2 w = tw[pos << (LOG - 1 - st)];
+      const float2 a = z[i0], b = z[i1];
+      const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+      z[i0] = make_float2(a.x + t.x, a.y + t.y);
+      z[i1] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
+  }
+  float part = 0.f;
+  for (int k = threadIdx.x; k <= NF / 2; k += 256) {
+    const float2 a = z[k], b = z[(NF - k) & (NF - 1)];
+    // X_hr = (Z[k] + conj(Z[N-k])) / 2,  X_sr = (Z[k] - conj(Z[N-k])) / (2i)
+    const float hre = 0.5f * (a.x + b.x), him = 0.5f * (a.y - b.y);
+    const float sre = 0.5f * (a.y + b.y), sim = -0.5f * (a.x - b.x);
+    const float ph = hre * hre + him * him, ps = sre * sre + sim * sim;
+    const float d = log10f(ph + 1e-6f) - log10f(ps + 1e-6f);
+    part = fmaf(d, d, part);
+  }
+  const double tot = block_sum_256((double)part);
+  if (threadIdx.x == 0) atomicAdd(acc, sqrt(tot / (double)(NF / 2 + 1)));
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;

@@ -106,6 +106,32 @@ def gen_longform():
     np.savez_compressed(os.path.join(HERE, "longform_golden.npz"), **out)
 
 
+METRIC_CASES = [(1, 20000, True, 3), (4, 7936, True, 4), (2, 32512, False, 5), (1, 2870528 // 8, True, 6)]
+
+
+def metric_signals(rows, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    hr = 0.1 * torch.randn(rows, T, generator=g)
+    lr = hr + 0.05 * torch.randn(rows, T, generator=g)
+    sr = hr + 0.01 * torch.randn(rows, T, generator=g)
+    return hr, lr, sr
+
+
+def gen_metrics():
+    """compute_matrics of the reference itself (util/util.py:132-177)."""
+    from types import SimpleNamespace
+
+    from util.util import compute_matrics
+
+    out = {}
+    for (rows, T, center, seed) in METRIC_CASES:
+        hr, lr, sr = metric_signals(rows, T, seed)
+        opt = SimpleNamespace(n_fft=512, hop_length=256, win_length=512, center=center, hr_sampling_rate=48000)
+        out[f"m_{rows}_{T}_{int(center)}"] = np.array(compute_matrics(hr, lr, sr, opt), dtype=np.float64)
+        print(rows, T, center, out[f"m_{rows}_{T}_{int(center)}"])
+    np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)
+
+
 def gen_mdct():
     from models.mdct import IMDCT4, MDCT4
     from models.pix2pixHD_model import Audio2MDCT
@@ -204,6 +230,8 @@ if __name__ == "__main__":
         gen_mdct()
     if "longform" in what:
         gen_longform()
+    if "metrics" in what:
+        gen_metrics()
     if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 
