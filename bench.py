@@ -280,6 +280,7 @@ KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_
                   "mdctgan_avgpool3s2_bwd", "mdctgan_attention_abs_pos", "mdctgan_attention_abs_pos_bwd", "mdctgan_mse_const_fwd",
                   "mdctgan_mse_const_bwd", "mdctgan_l1_pair_fwd", "mdctgan_l1_pair_bwd", "mdctgan_f64_to_f32", "mdctgan_disc_input_fwd",
                   "mdctgan_disc_input_bwd", "mdctgan_adam_flat", "mdctgan_counter_inc", "mdctgan_conv2d_umma_pack_weight",
+                  "mdctgan_pack_weights_multi", "mdctgan_pack_weights_tiled",
                   "mdctgan_nchw_to_nhwc", "mdctgan_nhwc_to_nchw", "mdctgan_residual_scale_add", "mdctgan_audio2mdct_forward",
                   "mdctgan_mdct2audio_inverse"]
 

@@ -203,6 +203,9 @@ typedef struct mdctgan_pack_desc {
   int64_t work_begin;
 } mdctgan_pack_desc;
 int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_work, void* stream);
+/* The same for descriptors with dst_kn == NULL, Kch % 32 == 0, N % 32 == 0, taps <= 49, as a shared-memory tiled transpose (every
+ * global access coalesced): tile_begin_dev[i] = prefix sum of (N/32)*(Kch/32); max_taps = largest taps in the table. */
+int mdctgan_pack_weights_tiled(const void* descs_dev, const int64_t* tile_begin_dev, int n_desc, int64_t total_tiles, int max_taps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Long-form generation (generate_audio.py:29-53).

@@ -349,6 +349,23 @@ int mdctgan_lsd_frames(const float* hr, const float* sr, int64_t rows, int64_t T
   return 0;
 }
 
+int mdctgan_pack_weights_tiled(const void* descs_dev, const int64_t* tile_begin_dev, int n_desc, int64_t total_tiles, int max_taps, void* stream) {
+  if (!descs_dev || !tile_begin_dev) return mdctgan_set_error(-1, "pack_weights_tiled: NULL table");
+  if (n_desc <= 0 || total_tiles <= 0) return 0;
+  if (max_taps <= 0 || max_taps > kPackMaxTaps) return mdctgan_set_error(-2, "pack_weights_tiled: %d taps (max %d)", max_taps, kPackMaxTaps);
+  if (total_tiles > 0x7fffffffLL) return mdctgan_set_error(-2, "pack_weights_tiled: too many tiles");
+  const size_t smem = (size_t)max_taps * 32 * 33 * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    CKT(cudaFuncSetAttribute(pack_weights_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackMaxTaps * 32 * 33 * sizeof(float))));
+    attr_smem = kPackMaxTaps * 32 * 33 * sizeof(float);
+  }
+  pack_weights_tiled_kernel<<<(unsigned)total_tiles, 256, smem, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, (const long long*)tile_begin_dev, n_desc);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
   if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
   counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);

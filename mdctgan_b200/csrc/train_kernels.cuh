@@ -870,6 +870,54 @@ __global__ void __launch_bounds__(256) lsd_frames_kernel(const float* __restrict
   if (threadIdx.x == 0) atomicAdd(acc, sqrt(tot / (double)(NF / 2 + 1)));
 }
 
+// Tiled form for the tensor-core images of layers with Kch % 32 == 0 and N % 32 == 0 (almost all parameters): a CTA takes a
+// 32 (n) x 32 (channel) x taps block of one descriptor, reads it in contiguous runs of the parameter layout, transposes through
+// shared memory and writes whole 128-byte rows of the image (hi and lo) -- every global access coalesced.
+// tile_begin = prefix sum of (N/32)*(Kch/32) over the descriptors.
+constexpr int kPackMaxTaps = 49;
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc* __restrict__ descs, const long long* __restrict__ tile_begin,
+                                                                 int n_desc) {
+  extern __shared__ float sm_pack[];            // [taps][32 (kc)][33]
+  const long long tile = blockIdx.x;
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_begin[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  const PackDesc d = descs[lo];
+  const int t = (int)(tile - tile_begin[lo]);
+  const int kc_blocks = d.Kch / 32;
+  const int nb = t / kc_blocks, kb = t - nb * kc_blocks;
+  const int n0 = nb * 32, kc0 = kb * 32;
+  const int taps = d.taps;
+  const int total = 32 * 32 * taps;
+  const bool n_outer = d.s_n > d.s_kch;         // which of (n, kc) has the larger stride in the parameter layout
+  for (int idx = threadIdx.x; idx < total; idx += 256) {
+    const int tap = idx % taps;
+    const int ab = idx / taps;
+    const int inner = ab & 31, outer = ab >> 5;
+    const int n = n_outer ? outer : inner, kc = n_outer ? inner : outer;
+    const float v = __ldg(d.src + (long long)(kc0 + kc) * d.s_kch + (long long)(n0 + n) * d.s_n + tap);
+    sm_pack[(tap * 32 + kc) * 33 + n] = v;
+  }
+  __syncthreads();
+  // rows of the image: (tap_dst, n) -> 32 consecutive k = tap_dst*Kch + kc0 .. +31; a warp writes one row (lane = kc)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < taps * 32; r += 8) {
+    const int tap_dst = r >> 5, n = r & 31;
+    const int tap_src = d.flip ? taps - 1 - tap_dst : tap_dst;
+    const float v = sm_pack[(tap_src * 32 + lane) * 33 + n];
+    const float hi_v = __uint_as_float(__float_as_uint(v) & kTf32MaskPack);
+    const float lo_v = __uint_as_float((__float_as_uint(v - hi_v) + 0x1000u) & kTf32MaskPack);
+    const int k = tap_dst * d.Kch + kc0 + lane;
+    const int kcn = k >> 5, kk = k & 31, ng = n0 + n;
+    const int piece = (kk >> 2) ^ (ng & 7);
+    const size_t dst = (((size_t)kcn * 2) * d.N + ng) * 32 + piece * 4 + (kk & 3);
+    d.dst_umma[dst] = hi_v;
+    d.dst_umma[dst + (size_t)d.N * 32] = lo_v;
+  }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;

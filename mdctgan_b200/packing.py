@@ -28,6 +28,7 @@ class WeightPacker:
 
         L = ops._L()
         L.mdctgan_pack_weights_multi.argtypes = [c_void_p, ctypes.c_int, c_int64, c_void_p]
+        L.mdctgan_pack_weights_tiled.argtypes = [c_void_p, c_void_p, ctypes.c_int, c_int64, ctypes.c_int, c_void_p]
         layers = [m for mod in modules for m in mod.modules() if isinstance(m, (Conv2d, ConvTranspose2d))]
         layers = list(dict.fromkeys(layers))
         if not layers:
@@ -69,6 +70,11 @@ class WeightPacker:
                     plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, ci * taps, taps, strided_transposed=m.stride[0] > 1)
         self.buf = torch.zeros(total_floats + 32, dtype=torch.float32, device=dev)
         base_off = (-(self.buf.data_ptr() // 4)) % 32                     # align the buffer itself to 128 bytes
+        # descriptors that qualify for the tiled (coalesced) kernel: tensor-core image only, 32-aligned channel counts
+        def tiled_ok(p):
+            return p["off_um"] is not None and p["off_kn"] is None and p["Kch"] % 32 == 0 and p["N"] % 32 == 0 and p["taps"] <= 49
+        plans = [p for p in plans if not tiled_ok(p)] + [p for p in plans if tiled_ok(p)]
+        n_generic = sum(0 if tiled_ok(p) else 1 for p in plans)
         descs = (_Desc * len(plans))()
         work = 0
         for i, p in enumerate(plans):
@@ -87,9 +93,23 @@ class WeightPacker:
             descs[i] = _Desc(m.weight.data_ptr(), kn_ptr, um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],
                              p["taps"], p["flip"], p["kchunks"], p["s_kch"], p["s_n"], work)
             work += p["kchunks"] * 32 * p["N"]
+            if i == n_generic - 1:
+                self.total_work = work                                    # the generic kernel stops here
             st = m.__dict__.setdefault("_static_pack", {})
             st[p["role"]] = (kn, um, bool(p["flip"]))
-        self.total_work, self.n_desc = work, len(plans)
+        self.n_desc = n_generic
+        if n_generic == 0:
+            self.total_work = 0
+        tiled = plans[n_generic:]
+        self.n_tiled = len(tiled)
+        tb, acc_t = [], 0
+        for p in tiled:
+            tb.append(acc_t)
+            acc_t += (p["N"] // 32) * (p["Kch"] // 32)
+        self.total_tiles = acc_t
+        self.max_taps = max([p["taps"] for p in tiled], default=1)
+        self.tile_begin = torch.tensor(tb if tb else [0], dtype=torch.int64, device=dev)
+        self._desc_size = ctypes.sizeof(_Desc)
         self.layers = layers
         self._ptrs = [m.weight.data_ptr() for m in layers]
         raw = bytes(descs)
@@ -102,8 +122,12 @@ class WeightPacker:
             if m.weight.data_ptr() != ptr:
                 raise RuntimeError("WeightPacker: a parameter was re-allocated after the packer was built (call it after FlatBucket)")
         with torch.cuda.device(self.buf.device):
-            _lib.check(ops._L().mdctgan_pack_weights_multi(self.descs.data_ptr(), self.n_desc, self.total_work,
-                                                            torch.cuda.current_stream(self.buf.device).cuda_stream))
+            st = torch.cuda.current_stream(self.buf.device).cuda_stream
+            if self.n_desc:
+                _lib.check(ops._L().mdctgan_pack_weights_multi(self.descs.data_ptr(), self.n_desc, self.total_work, st))
+            if self.n_tiled:
+                _lib.check(ops._L().mdctgan_pack_weights_tiled(self.descs.data_ptr() + self.n_desc * self._desc_size, self.tile_begin.data_ptr(),
+                                                               self.n_tiled, self.total_tiles, self.max_taps, st))
 
     def detach(self):
         for m in self.layers:

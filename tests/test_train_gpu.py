@@ -310,3 +310,47 @@ def test_train_step_matches_oracle_and_reference(dev, name, api):
             moved = (v - sdD[k]).norm().item()
             assert (got - v).norm().item() < (1.0 if name == "tr_cfg4" else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
     print(f"{name}/{api}: losses {losses[0]}, worst G-gradient rel-L2 {worst:.2e}")
+
+
+def test_weight_packer_matches_per_layer_packing(dev):
+    """packing.WeightPacker (one / two launches for a whole model: generic + tiled kernels) writes exactly the images the per-layer
+    path builds (nn_ops.pack_conv_weight + pack_conv_weight_umma), for the forward and the input-gradient geometry."""
+    from mdctgan_b200 import nn_ops as ops
+    from mdctgan_b200.models import networks as N
+    from mdctgan_b200.packing import WeightPacker
+
+    torch.manual_seed(9)
+    layers = torch.nn.ModuleList([
+        N.Conv2d(64, 128, 3, padding=0), N.Conv2d(32, 64, 3, stride=2, padding=1), N.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1),
+        N.Conv2d(3, 64, 4, stride=2, padding=2), N.Conv2d(128, 384, 1, bias=False), N.Conv2d(64, 1, 4, padding=2), N.Conv2d(2, 32, 7),
+        N.Conv2d(256, 512, 4, stride=1, padding=2), N.Conv2d(40, 32, 5, padding=2), N.ConvTranspose2d(128, 64, 3, stride=2, padding=1, output_padding=1),
+    ]).to(dev)
+    ref = []
+    for m in layers:                     # per-layer path first (no packer attached yet)
+        kn, um = m.packed().clone(), m.packed_umma()
+        dkn, dum, fl = m.packed_dgrad()
+        ref.append((kn, None if um is None else um.clone(), dkn.clone(), None if dum is None else dum.clone(), fl))
+    packer = WeightPacker(layers)
+    assert packer.n_tiled > 0 and packer.n_desc > 0
+    torch.cuda.synchronize()
+    for m, (kn, um, dkn, dum, fl) in zip(layers, ref):
+        sp = m._static_pack
+        f_kn, f_um, _ = sp["fwd"]
+        d_kn, d_um, d_fl = sp["dgrad"]
+        assert d_fl == fl
+        if f_kn.stride(0) != 0:
+            assert torch.equal(f_kn, kn), type(m).__name__
+        if um is not None and f_um is not None:
+            assert torch.equal(f_um, um), (type(m).__name__, m.in_channels, m.out_channels)
+        if d_kn.stride(0) != 0:
+            assert torch.equal(d_kn, dkn)
+        if dum is not None and d_um is not None:
+            assert torch.equal(d_um, dum), (type(m).__name__, m.in_channels, m.out_channels, "dgrad")
+    # and after a weight change + refresh
+    with torch.no_grad():
+        for m in layers:
+            m.weight.mul_(1.5)
+    packer.refresh()
+    m = layers[0]
+    packer.detach()
+    assert torch.equal(m.packed_umma(), ops.pack_conv_weight_umma(ops.pack_conv_weight(m.weight, False)))
