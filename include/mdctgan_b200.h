@@ -169,6 +169,12 @@ int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const doubl
 /* g = dy * act'(y) from the activated value y (epilogue LeakyReLU / tanh, plain ReLU views) */
 int mdctgan_act_bwd(const float* dy, const float* y, float* g, int64_t n, int act, void* stream);
 int mdctgan_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+/* (sum, sumsq) per (sample, channel) of a materialised NHWC tensor -> stats [B][C][2] (+=): the branch sums of ConvResBlock /
+ * InterpolateUpsample (networks.py:387-417) are followed by an InstanceNorm2d */
+int mdctgan_plane_stats(const float* x, int B, int HW, int C, double* stats, void* stream);
+/* F.interpolate(scale_factor=2.0, mode="nearest") (networks.py:396): x [B,H,W,C] -> y [B,2H,2W,C]; backward = 1: x = dy [B,2H,2W,C] ->
+ * y = dx [B,H,W,C] (H, W always the SMALL size) */
+int mdctgan_upsample_nearest2x(const float* x, float* y, int B, int H, int W, int C, int backward, void* stream);
 /* nn.ReflectionPad2d backward: dpad [B,H+2p,W+2p,C] -> dx [B,H,W,C] */
 int mdctgan_reflect_pad_bwd(const float* dpad, float* dx, int B, int H, int W, int C, int pad, void* stream);
 int mdctgan_avgpool3s2_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);

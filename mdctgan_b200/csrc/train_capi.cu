@@ -161,25 +161,30 @@ int mdctgan_attention_abs_pos_bwd(const float* qkv, const float* emb_h, const fl
   const int L = Hh * Ww;
   if (d % 32 || d > 128) return mdctgan_set_error(-2, "attention_bwd: dim_head %d must be a multiple of 32, <= 128", d);
   if (L > 256) return mdctgan_set_error(-2, "attention_bwd: %d tokens > 256 unsupported", L);
-  const size_t smem = (2 * (size_t)L * (d + 1) + 2 * (size_t)L * d + 16 * (size_t)d) * sizeof(float);
+  size_t smem = (2 * (size_t)L * (d + 1) + 2 * (size_t)L * d + 16 * (size_t)d) * sizeof(float);
+  int npass = 1;
+  if (smem > 227 * 1024 && (d / 32) % 2 == 0) { npass = 2; smem = (2 * (size_t)L * (d + 1) + (size_t)L * d + 16 * (size_t)d) * sizeof(float); }
+  if (smem > 227 * 1024 && (d / 32) % 4 == 0) { npass = 4; smem = (2 * (size_t)L * (d + 1) + (size_t)L * d / 2 + 16 * (size_t)d) * sizeof(float); }
   if (smem > 227 * 1024) return mdctgan_set_error(-2, "attention_bwd: %zu bytes of shared memory needed (L=%d, d=%d)", smem, L, d);
   if (B == 0) return 0;
   AttnBwdParams p{qkv, emb_h, emb_w, dout, dqkv, demb_h, demb_w, B, Hh, Ww, heads, d, scale};
   cudaStream_t st = (cudaStream_t)stream;
   const int kpl = (L + 31) / 32;
-#define LAUNCH_ATTN_BWD(K)                                                                                             \
+#define LAUNCH_ATTN_BWD2(K, G)                                                                                         \
   do {                                                                                                                 \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
-      CKT(cudaFuncSetAttribute(attention_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
+      CKT(cudaFuncSetAttribute(attention_bwd_kernel<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    attention_bwd_kernel<K><<<B * heads, 256, smem, st>>>(p);                                                          \
+    attention_bwd_kernel<K, G><<<B * heads, 256, smem, st>>>(p);                                                       \
   } while (0)
+#define LAUNCH_ATTN_BWD(K) do { if (npass == 1) LAUNCH_ATTN_BWD2(K, 1); else if (npass == 2) LAUNCH_ATTN_BWD2(K, 2); else LAUNCH_ATTN_BWD2(K, 4); } while (0)
   if (kpl <= 1) LAUNCH_ATTN_BWD(1);
   else if (kpl <= 2) LAUNCH_ATTN_BWD(2);
   else if (kpl <= 4) LAUNCH_ATTN_BWD(4);
   else LAUNCH_ATTN_BWD(8);
+#undef LAUNCH_ATTN_BWD2
 #undef LAUNCH_ATTN_BWD
   mdctgan_count_launch();
   CKT(cudaGetLastError());
@@ -361,6 +366,34 @@ int mdctgan_pack_weights_tiled(const void* descs_dev, const int64_t* tile_begin_
     attr_smem = kPackMaxTaps * 32 * 33 * sizeof(float);
   }
   pack_weights_tiled_kernel<<<(unsigned)total_tiles, 256, smem, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, (const long long*)tile_begin_dev, n_desc);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_plane_stats(const float* x, int B, int HW, int C, double* stats, void* stream) {
+  if (!x || !stats) return mdctgan_set_error(-1, "plane_stats: NULL buffer");
+  if (C % 4 || C > 1024) return mdctgan_set_error(-2, "plane_stats: C %d must be a multiple of 4, <= 1024", C);
+  if (B <= 0 || HW <= 0) return 0;
+  if (B > 65535) return mdctgan_set_error(-2, "plane_stats: batch %d > 65535", B);
+  const int pstep = 256 / (C / 4);
+  int chunks = (HW + pstep * 8 - 1) / (pstep * 8);
+  const int cap = (148 * 4 + B - 1) / B;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  plane_stats_kernel<<<dim3(chunks, B), 256, 0, (cudaStream_t)stream>>>(x, HW, C, stats);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_upsample_nearest2x(const float* x, float* y, int B, int H, int W, int C, int backward, void* stream) {
+  if (!x || !y) return mdctgan_set_error(-1, "upsample_nearest2x: NULL buffer");
+  if (C % 4) return mdctgan_set_error(-2, "upsample_nearest2x: C %d must be a multiple of 4", C);
+  const size_t total = (size_t)B * H * W * (C / 4) * (backward ? 1 : 4);
+  if (!total) return 0;
+  if (backward) upsample_nearest2x_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
+  else upsample_nearest2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;

@@ -465,6 +465,62 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const NormBwdPa
   }
 }
 
+// (sum, sumsq) per (sample, channel) of a materialised NHWC tensor (the sum of the two branches of ConvResBlock /
+// InterpolateUpsample, networks.py:387-417, which an InstanceNorm2d follows).  grid = (chunks, B); stats += (zero it first).
+__global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ x, int HW, int C, double* __restrict__ stats) {
+  __shared__ double s_acc[2][1024];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) { s_acc[0][c] = 0.0; s_acc[1][c] = 0.0; }
+  __syncthreads();
+  const int groups = C / 4;
+  const int cg = threadIdx.x % groups, prow = threadIdx.x / groups, pstep = 256 / groups;
+  double sg[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+  if (prow < pstep) {
+    const size_t base = (size_t)b * HW * C;
+    for (int pix = blockIdx.x * pstep + prow; pix < HW; pix += gridDim.x * pstep) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + (size_t)pix * C + cg * 4));
+      const double vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sg[u] += vs[u]; sq[u] = fma(vs[u], vs[u], sq[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { atomicAdd(&s_acc[0][cg * 4 + u], sg[u]); atomicAdd(&s_acc[1][cg * 4 + u], sq[u]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double* r = stats + 2 * ((size_t)b * C + c);
+    atomicAdd(r, s_acc[0][c]);
+    atomicAdd(r + 1, s_acc[1][c]);
+  }
+}
+
+// F.interpolate(scale_factor=2.0, mode="nearest") on NHWC (networks.py:396) and its backward (sum of the 2x2 block)
+__global__ void upsample_nearest2x_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C4) {
+  const size_t total = (size_t)B * 2 * H * 2 * W * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int ox = (int)(r % (2 * W)); r /= 2 * W;
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    reinterpret_cast<float4*>(y)[i] = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c);
+  }
+}
+__global__ void upsample_nearest2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C4) {
+  const size_t total = (size_t)B * H * W * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    const float4* src = reinterpret_cast<const float4*>(dy);
+    const size_t row0 = (((size_t)b * 2 * H + 2 * iy) * 2 * W + 2 * ix) * C4 + c, row1 = row0 + (size_t)2 * W * C4;
+    const float4 a = __ldg(src + row0), b4 = __ldg(src + row0 + C4), c4 = __ldg(src + row1), d4 = __ldg(src + row1 + C4);
+    reinterpret_cast<float4*>(dx)[i] = make_float4(a.x + b4.x + c4.x + d4.x, a.y + b4.y + c4.y + d4.y, a.z + b4.z + c4.z + d4.z, a.w + b4.w + c4.w + d4.w);
+  }
+}
+
 // g = dy * act'(y)  from the ACTIVATED value y (epilogue activations; also plain ReLU / LeakyReLU views)
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ g, size_t n, int act) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -533,16 +589,19 @@ struct AttnBwdParams {
   int B, Hh, Ww, heads, d; float scale;
 };
 
-template <int KPL>
+// NPASS: when the column accumulators dKp / dV do not fit in shared memory next to K and V (128 tokens x 128 channels), the head
+// dimension is covered in NPASS slices: every pass recomputes the softmax rows (cheap) and accumulates d / NPASS channels.
+template <int KPL, int NPASS>
 __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdParams p) {
   extern __shared__ float sm[];
   const int L = p.Hh * p.Ww, d = p.d, C = p.heads * d;
+  const int dslice = d / NPASS;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
-  float* Kp = sm;                        // [L][d+1]
-  float* V = Kp + (size_t)L * (d + 1);   // [L][d+1]
-  float* dKp = V + (size_t)L * (d + 1);  // [L][d]
-  float* dV = dKp + (size_t)L * d;       // [L][d]
-  float* rows = dV + (size_t)L * d;      // [8 warps][2][d]: scaled q row, dO row
+  float* Kp = sm;                             // [L][d+1]
+  float* V = Kp + (size_t)L * (d + 1);        // [L][d+1]
+  float* dKp = V + (size_t)L * (d + 1);       // [L][dslice]
+  float* dV = dKp + (size_t)L * dslice;       // [L][dslice]
+  float* rows = dV + (size_t)L * dslice;      // [8 warps][2][d]: scaled q row, dO row
   const float* base = p.qkv + (size_t)b * L * 3 * C;
   for (int i = threadIdx.x; i < L * d; i += 256) {
     const int j = i / d, dd = i - j * d;
@@ -550,79 +609,90 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const AttnBwdParams 
     const float* tok = base + (size_t)j * 3 * C + h * d + dd;
     Kp[j * (d + 1) + dd] = __ldg(tok + C) + __ldg(p.emb_h + y * d + dd) + __ldg(p.emb_w + x * d + dd);
     V[j * (d + 1) + dd] = __ldg(tok + 2 * C);
-    dKp[i] = 0.f; dV[i] = 0.f;
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* q = rows + warp * 2 * d;
   float* go = q + d;
-  const int dpl = d / 32;
-  for (int i = warp; i < L; i += 8) {
-    for (int dd = lane; dd < d; dd += 32) {
-      q[dd] = __ldg(base + (size_t)i * 3 * C + h * d + dd) * p.scale;
-      go[dd] = __ldg(p.dout + ((size_t)b * L + i) * C + h * d + dd);
-    }
-    __syncwarp();
-    float sc[KPL], dp[KPL];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < KPL; ++u) {
-      const int j = lane + 32 * u;
-      float a = -INFINITY, t = 0.f;
-      if (j < L) {
-        a = 0.f;
-        const float* kr = Kp + j * (d + 1);
-        const float* vr = V + j * (d + 1);
-        for (int dd = 0; dd < d; ++dd) { a = fmaf(q[dd], kr[dd], a); t = fmaf(go[dd], vr[dd], t); }
+  const int dpl = d / 32;                     // channels per lane
+  const int tpp = dpl / NPASS;                // ... handled per pass (host guarantees dpl % NPASS == 0)
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+    __syncthreads();                          // K / V staged (pass 0); previous pass written out
+    for (int i = threadIdx.x; i < L * dslice; i += 256) { dKp[i] = 0.f; dV[i] = 0.f; }
+    __syncthreads();
+    for (int i = warp; i < L; i += 8) {
+      for (int dd = lane; dd < d; dd += 32) {
+        q[dd] = __ldg(base + (size_t)i * 3 * C + h * d + dd) * p.scale;
+        go[dd] = __ldg(p.dout + ((size_t)b * L + i) * C + h * d + dd);
       }
-      sc[u] = a; dp[u] = t;
-      mx = fmaxf(mx, a);
-    }
+      __syncwarp();
+      float sc[KPL], dp[KPL];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
+      for (int u = 0; u < KPL; ++u) {
+        const int j = lane + 32 * u;
+        float a = -INFINITY, t = 0.f;
+        if (j < L) {
+          a = 0.f;
+          const float* kr = Kp + j * (d + 1);
+          const float* vr = V + j * (d + 1);
+          for (int dd = 0; dd < d; ++dd) { a = fmaf(q[dd], kr[dd], a); t = fmaf(go[dd], vr[dd], t); }
+        }
+        sc[u] = a; dp[u] = t;
+        mx = fmaxf(mx, a);
+      }
 #pragma unroll
-    for (int u = 0; u < KPL; ++u) { sc[u] = (lane + 32 * u < L) ? __expf(sc[u] - mx) : 0.f; sum += sc[u]; }
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.f / sum;
-    float dot = 0.f;
+      for (int u = 0; u < KPL; ++u) { sc[u] = (lane + 32 * u < L) ? __expf(sc[u] - mx) : 0.f; sum += sc[u]; }
 #pragma unroll
-    for (int u = 0; u < KPL; ++u) { sc[u] *= inv; dot += sc[u] * dp[u]; }
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+      float dot = 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    float ds[KPL];
+      for (int u = 0; u < KPL; ++u) { sc[u] *= inv; dot += sc[u] * dp[u]; }
 #pragma unroll
-    for (int u = 0; u < KPL; ++u) ds[u] = sc[u] * (dp[u] - dot);
-    // dq_i = scale * sum_j ds_ij Kp_j ; dV_j += p_ij dO_i ; dKp_j += ds_ij q_i
-    float dq[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      float ds[KPL];
 #pragma unroll
-    for (int u = 0; u < KPL; ++u) {
-      for (int l = 0; l < 32; ++l) {
-        const int j = l + 32 * u;
-        if (j >= L) break;
-        const float pj = __shfl_sync(0xffffffffu, sc[u], l);
-        const float dj = __shfl_sync(0xffffffffu, ds[u], l);
-        for (int t = 0; t < dpl; ++t) {
-          const int dd = lane + 32 * t;
-          dq[t] = fmaf(dj, Kp[j * (d + 1) + dd], dq[t]);
-          atomicAdd(&dV[j * d + dd], pj * go[dd]);
-          atomicAdd(&dKp[j * d + dd], dj * q[dd]);
+      for (int u = 0; u < KPL; ++u) ds[u] = sc[u] * (dp[u] - dot);
+      // dq_i = scale * sum_j ds_ij Kp_j (pass 0, all channels) ; dV_j += p_ij dO_i ; dKp_j += ds_ij q_i (this pass's channel slice)
+      float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < KPL; ++u) {
+        for (int l = 0; l < 32; ++l) {
+          const int j = l + 32 * u;
+          if (j >= L) break;
+          const float pj = __shfl_sync(0xffffffffu, sc[u], l);
+          const float dj = __shfl_sync(0xffffffffu, ds[u], l);
+          if (pass == 0) {
+            for (int t = 0; t < dpl; ++t) dq[t] = fmaf(dj, Kp[j * (d + 1) + lane + 32 * t], dq[t]);
+          }
+          for (int t = 0; t < tpp; ++t) {
+            const int dd = lane + 32 * (pass * tpp + t);       // channel of the head
+            const int ds_i = lane + 32 * t;                    // ... within this pass's slice
+            atomicAdd(&dV[j * dslice + ds_i], pj * go[dd]);
+            atomicAdd(&dKp[j * dslice + ds_i], dj * q[dd]);
+          }
         }
       }
+      if (pass == 0) {
+        for (int t = 0; t < dpl; ++t) p.dqkv[((size_t)b * L + i) * 3 * C + h * d + lane + 32 * t] = dq[t] * p.scale;
+      }
+      __syncwarp();
     }
-    for (int t = 0; t < dpl; ++t) p.dqkv[((size_t)b * L + i) * 3 * C + h * d + lane + 32 * t] = dq[t] * p.scale;
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < L * d; i += 256) {
-    const int j = i / d, dd = i - j * d;
-    float* tok = p.dqkv + ((size_t)b * L + j) * 3 * C + h * d + dd;
-    tok[C] = dKp[i];
-    tok[2 * C] = dV[i];
-    const int y = j / p.Ww, x = j - y * p.Ww;
-    if (p.demb_h) atomicAdd(p.demb_h + y * d + dd, dKp[i]);
-    if (p.demb_w) atomicAdd(p.demb_w + x * d + dd, dKp[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * dslice; i += 256) {
+      const int j = i / dslice, si = i - j * dslice;
+      const int dd = (si & 31) + 32 * (pass * tpp + (si >> 5));
+      float* tok = p.dqkv + ((size_t)b * L + j) * 3 * C + h * d + dd;
+      tok[C] = dKp[i];
+      tok[2 * C] = dV[i];
+      const int y = j / p.Ww, x = j - y * p.Ww;
+      if (p.demb_h) atomicAdd(p.demb_h + y * d + dd, dKp[i]);
+      if (p.demb_w) atomicAdd(p.demb_w + x * d + dd, dKp[i]);
+    }
   }
 }
 

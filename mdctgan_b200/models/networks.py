@@ -12,9 +12,8 @@ into: one convolution launch (reflection handled by its gather, (sum, sumsq) tak
 tiny statistics->scale/shift launch, and nothing else -- the normalisation and the activation are applied
 by whichever kernel reads the tensor next (nn_ops.Feat).
 
-Forward only in this round: the layers run under no_grad (the reference's `inference()` path,
-pix2pixHD_model.py:618-638); the training kernels (dgrad / wgrad / norm backward / Adam) are listed as next
-in DESIGN.md.
+`module.forward(x)` is the inference path (no_grad, NCHW in / out).  Training runs the same layers through `run()` while an
+`nn_ops.Tape` records them; the backward sweeps (dgrad / wgrad / norm backward) are driven by train_ops.GanGraph.
 """
 from __future__ import annotations
 
@@ -203,7 +202,7 @@ def run_layers(layers: Sequence[nn.Module], f: Feat) -> Feat:
         if isinstance(L, ReflectionPad2d):
             pad_reflect = L.padding
             i += 1
-        elif isinstance(L, (Conv2d, ConvTranspose2d)):
+        elif isinstance(L, (Conv2d, ConvTranspose2d, ConvResBlock, InterpolateUpsample)):
             want_stats = isinstance(nxt, (InstanceNorm2d, BatchNorm2d))
             act, skip = ops.ACT_NONE, 0
             if not want_stats and nxt is not None and _act_of(nxt) is not None:
@@ -300,16 +299,49 @@ class ConvResBlock(nn.Module):
         self.conv_res = Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
 
     def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
+        assert not pad_reflect
         x = self.conv1.run(f)
-        y = ops.combine(self.conv2.run(x), self.conv_res.run(x))
-        if act != ops.ACT_NONE:
-            y = ops.with_act(y, act)
-        if want_stats:
-            raise NotImplementedError("ConvResBlock followed by a norm layer needs a statistics pass (DESIGN.md: next)")
+        y = ops.combine(self.conv2.run(x), self.conv_res.run(x), act_out=act, want_stats=want_stats)
         return y
 
 
+class InterpolateUpsample(nn.Module):
+    """upsample_type='interpolate' (networks.py:375-400): nearest x2, then conv1 5x5 p1 -> conv2 3x3 p2, plus conv_res 3x3 p1."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels = kwargs["in_channels"], kwargs["out_channels"]
+        self.conv1 = Conv2d(self.in_channels, self.out_channels, 5, padding=1)
+        self.conv2 = Conv2d(self.out_channels, self.out_channels, 3, padding=2)
+        self.conv_res = Conv2d(self.in_channels, self.out_channels, 3, padding=1)
+
+    def run(self, f: Feat, pad_reflect: int = 0, act: int = ops.ACT_NONE, want_stats: bool = False) -> Feat:
+        assert not pad_reflect
+        assert f.x.shape[-1] == self.in_channels
+        x = ops.upsample_nearest2x(f)
+        res = self.conv_res.run(x)
+        y = self.conv2.run(self.conv1.run(x))
+        return ops.combine(y, res, act_out=act, want_stats=want_stats)
+
+
 # ------------------------------------------------------------------------------------------- generators
+def _sampling_layers(downsample_type, upsample_type):
+    """networks.py:189-205, :311-325"""
+    if downsample_type == "conv":
+        down = Conv2d
+    elif downsample_type == "resconv":
+        down = ConvResBlock
+    else:
+        raise NotImplementedError("downsample layer [{:s}] is not found".format(downsample_type))
+    if upsample_type == "transconv":
+        up = ConvTranspose2d
+    elif upsample_type == "interpolate":
+        up = InterpolateUpsample
+    else:
+        raise NotImplementedError("upsample layer [{:s}] is not found".format(upsample_type))
+    return down, up
+
+
 class GlobalGenerator(nn.Module):
     def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=3, n_blocks=9, norm_layer=None, padding_type="reflect",
                  upsample_type="transconv", downsample_type="conv", n_attn_g=0, input_size=(128, 256), proj_factor_g=4, heads_g=4,
@@ -318,12 +350,11 @@ class GlobalGenerator(nn.Module):
         super().__init__()
         norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
         activation = ReLU(True)   # ONE shared instance, as in the reference (keeps the positional state_dict keys)
-        if downsample_type != "conv" or upsample_type != "transconv":
-            raise NotImplementedError("downsample_type='resconv' / upsample_type='interpolate' are listed as next in DESIGN.md")
+        downsample_layer, upsample_layer = _sampling_layers(downsample_type, upsample_type)
         model: List[nn.Module] = [ReflectionPad2d(3), Conv2d(input_nc, ngf, kernel_size=7, padding=0), norm_layer(ngf), activation]
         for i in range(n_downsampling):
             mult = 2 ** i
-            model += [Conv2d(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf * mult * 2), activation]
+            model += [downsample_layer(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf * mult * 2), activation]
         mult = 2 ** n_downsampling
         bottle_neck: List[nn.Module] = [ResnetBlock(ngf * mult, padding_type=padding_type, activation=activation, norm_layer=norm_layer)
                                         for _ in range(n_blocks)]
@@ -337,8 +368,8 @@ class GlobalGenerator(nn.Module):
         model += bottle_neck
         for i in range(n_downsampling):
             mult = 2 ** (n_downsampling - i)
-            model += [ConvTranspose2d(in_channels=ngf * mult, out_channels=int(ngf * mult / 2), kernel_size=3, stride=2, padding=1,
-                                      output_padding=1), norm_layer(int(ngf * mult / 2)), activation]
+            model += [upsample_layer(in_channels=ngf * mult, out_channels=int(ngf * mult / 2), kernel_size=3, stride=2, padding=1,
+                                     output_padding=1), norm_layer(int(ngf * mult / 2)), activation]
         model += [ReflectionPad2d(3), Conv2d(ngf, output_nc, kernel_size=7, padding=0), Tanh()]
         self.model = nn.Sequential(*model)
         self.freeze = False
@@ -372,8 +403,7 @@ class LocalEnhancer(nn.Module):
         self.n_local_enhancers = n_local_enhancers
         if n_attn_l > 0:
             raise NotImplementedError("n_attn_l > 0 (local attention sandwich, networks.py:218-237) is listed as next in DESIGN.md")
-        if downsample_type != "conv" or upsample_type != "transconv":
-            raise NotImplementedError("downsample_type='resconv' / upsample_type='interpolate' are listed as next in DESIGN.md")
+        downsample_layer, upsample_layer = _sampling_layers(downsample_type, upsample_type)
         ngf_global = ngf * (2 ** n_local_enhancers)
         g = GlobalGenerator(input_nc, output_nc, ngf_global, n_downsample_global, n_blocks_global, norm_layer,
                             downsample_type=downsample_type, upsample_type=upsample_type, input_size=tuple(s // 2 for s in input_size),
@@ -381,11 +411,11 @@ class LocalEnhancer(nn.Module):
         self.model = nn.Sequential(*[g[i] for i in range(len(g) - 3)])       # drop ReflPad, Conv7x7, Tanh
         ngf_global = ngf * (2 ** (n_local_enhancers - 1))
         model_downsample = [ReflectionPad2d(3), Conv2d(input_nc, ngf_global, kernel_size=7, padding=0), norm_layer(ngf_global), ReLU(True),
-                            Conv2d(ngf_global, ngf_global * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global * 2), ReLU(True)]
+                            downsample_layer(ngf_global, ngf_global * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global * 2), ReLU(True)]
         model_upsample: List[nn.Module] = [ResnetBlock(ngf_global * 2, padding_type=padding_type, norm_layer=norm_layer)
                                            for _ in range(n_blocks_local)]
-        model_upsample += [ConvTranspose2d(in_channels=ngf_global * 2, out_channels=ngf_global, kernel_size=3, stride=2, padding=1,
-                                           output_padding=1), norm_layer(ngf_global), ReLU(True)]
+        model_upsample += [upsample_layer(in_channels=ngf_global * 2, out_channels=ngf_global, kernel_size=3, stride=2, padding=1,
+                                          output_padding=1), norm_layer(ngf_global), ReLU(True)]
         model_upsample += [ReflectionPad2d(3), Conv2d(ngf, output_nc, kernel_size=7, padding=0), Tanh()]
         self.model1_1 = nn.Sequential(*model_downsample)
         self.model1_2 = nn.Sequential(*model_upsample)

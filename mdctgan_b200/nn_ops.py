@@ -80,6 +80,8 @@ def _L():
         L.mdctgan_adam_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
                                         c_void_p, c_void_p]
         L.mdctgan_counter_inc.argtypes = [c_void_p, c_void_p]
+        L.mdctgan_plane_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+        L.mdctgan_upsample_nearest2x.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         _bound = True
     return L
 
@@ -348,8 +350,9 @@ def with_act(f: Feat, act: int) -> Feat:
     return out
 
 
-def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
-    """act_out( act_a(a*sa+ta) [+ act_b(b*sb+tb)] ) materialised as a plain NHWC tensor."""
+def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE, want_stats: bool = False) -> Feat:
+    """act_out( act_a(a*sa+ta) [+ act_b(b*sb+tb)] ) materialised as a plain NHWC tensor.  `want_stats`: also take the
+    per-(sample, channel) (sum, sumsq) of the result for a normalisation layer that follows (one more small launch)."""
     B, H, W, C = a.x.shape
     if b is not None and b.x.shape != a.x.shape:
         raise RuntimeError(f"combine: shape mismatch {tuple(a.x.shape)} vs {tuple(b.x.shape)}")
@@ -367,9 +370,29 @@ def combine(a: Feat, b: Optional[Feat] = None, act_out: int = ACT_NONE) -> Feat:
                                                1 if (b is not None and b.per_sample) else 0, b.act if b is not None else 0,
                                                _ptr(b.norm_stats) if b is not None else None, count, eps, y.data_ptr(), B, H * W, C, act_out,
                                                _stream(y)))
-    out = Feat(y)
+    stats = None
+    if want_stats:
+        stats = _new_stats(B, C, y.device)
+        if y.numel():
+            with torch.cuda.device(y.device):
+                _lib.check(_L().mdctgan_plane_stats(y.data_ptr(), B, H * W, C, stats.data_ptr(), _stream(y)))
+    out = Feat(y, stats=stats)
     if _tape is not None:
         _tape.ops.append(_CombineOp(a, b, out, act_out))
+    return out
+
+
+def upsample_nearest2x(f: Feat) -> Feat:
+    """F.interpolate(scale_factor=2.0, mode="nearest") (networks.py:396) on the materialised value of f."""
+    f = materialize(f)
+    B, H, W, C = f.x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=f.x.device)
+    if y.numel():
+        with torch.cuda.device(y.device):
+            _lib.check(_L().mdctgan_upsample_nearest2x(f.x.data_ptr(), y.data_ptr(), B, H, W, C, 0, _stream(y)))
+    out = Feat(y, needs_grad=f.needs_grad)
+    if _tape is not None and f.needs_grad:
+        _tape.ops.append(_UpsampleOp(f, out))
     return out
 
 
@@ -764,6 +787,21 @@ class _PoolOp:
         dx = torch.empty((B, H, W, C), dtype=torch.float32, device=dy.device)
         with torch.cuda.device(dy.device):
             _lib.check(_L().mdctgan_avgpool3s2_bwd(dy.data_ptr(), dx.data_ptr(), B, H, W, C, _stream(dy)))
+        G.add(self.f, dx)
+
+
+class _UpsampleOp:
+    def __init__(self, f, out):
+        self.f, self.out = f, out
+
+    def backward(self, G: GradMap, wgrad: bool, nb):
+        dy = G.pop(self.out)
+        if dy is None:
+            return
+        B, H, W, C = _sl(self.f.x, nb).shape
+        dx = torch.empty((B, H, W, C), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            _lib.check(_L().mdctgan_upsample_nearest2x(dy.data_ptr(), dx.data_ptr(), B, H, W, C, 1, _stream(dy)))
         G.add(self.f, dx)
 
 

@@ -31,6 +31,26 @@ def _convt(sd, key, x):
     return F.conv_transpose2d(x, sd[key + ".weight"], sd.get(key + ".bias"), stride=2, padding=1, output_padding=1)
 
 
+def conv_res_block(sd, key, x):
+    """ConvResBlock.forward (networks.py:403-417) as the stride-2 downsampling layer (kernel 3, stride 2, padding 1)."""
+    x = _conv(sd, key + ".conv1", x, stride=2, padding=1)
+    return _conv(sd, key + ".conv2", x, padding=2) + _conv(sd, key + ".conv_res", x, padding=1)
+
+
+def interpolate_upsample(sd, key, x):
+    """InterpolateUpsample.forward (networks.py:394-400)."""
+    x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    return _conv(sd, key + ".conv2", _conv(sd, key + ".conv1", x, padding=1), padding=2) + _conv(sd, key + ".conv_res", x, padding=1)
+
+
+def _down(sd, key, x, kind):
+    return conv_res_block(sd, key, x) if kind == "resconv" else _conv(sd, key, x, stride=2, padding=1)
+
+
+def _up(sd, key, x, kind):
+    return interpolate_upsample(sd, key, x) if kind == "interpolate" else _convt(sd, key, x)
+
+
 def resnet_block(sd, prefix, x):
     h = F.relu(_in(_conv(sd, prefix + ".conv_block.1", x, reflect=1)))
     return x + _in(_conv(sd, prefix + ".conv_block.5", h, reflect=1))
@@ -67,12 +87,13 @@ def bottle_stack(sd, prefix, x, num_layers, heads, dim_head, training=False):
     return x
 
 
-def _global_trunk(sd, prefix, x, n_down, n_blocks, n_attn=0, heads=4, dim_head=128, training=False, with_head=True):
+def _global_trunk(sd, prefix, x, n_down, n_blocks, n_attn=0, heads=4, dim_head=128, training=False, with_head=True, down="conv",
+                  up="transconv"):
     i = 1
     x = F.relu(_in(_conv(sd, f"{prefix}.{i}", x, reflect=3)))
     i = 4
     for _ in range(n_down):
-        x = F.relu(_in(_conv(sd, f"{prefix}.{i}", x, stride=2, padding=1)))
+        x = F.relu(_in(_down(sd, f"{prefix}.{i}", x, down)))
         i += 3
     for blk in range(n_blocks + (1 if n_attn else 0)):
         if n_attn and blk == n_blocks // 2:
@@ -81,30 +102,32 @@ def _global_trunk(sd, prefix, x, n_down, n_blocks, n_attn=0, heads=4, dim_head=1
             x = resnet_block(sd, f"{prefix}.{i}", x)
         i += 1
     for _ in range(n_down):
-        x = F.relu(_in(_convt(sd, f"{prefix}.{i}", x)))
+        x = F.relu(_in(_up(sd, f"{prefix}.{i}", x, up)))
         i += 3
     if with_head:
         x = torch.tanh(_conv(sd, f"{prefix}.{i + 1}", x, reflect=3))
     return x
 
 
-def global_generator(sd, x, n_down=3, n_blocks=9, n_attn=0, heads=4, dim_head=128, training=False):
-    return _global_trunk(sd, "model", x, n_down, n_blocks, n_attn, heads, dim_head, training)
+def global_generator(sd, x, n_down=3, n_blocks=9, n_attn=0, heads=4, dim_head=128, training=False, down="conv", up="transconv"):
+    return _global_trunk(sd, "model", x, n_down, n_blocks, n_attn, heads, dim_head, training, down=down, up=up)
 
 
 def avgpool(x):
     return F.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False)
 
 
-def local_enhancer(sd, x, n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128, training=False):
-    coarse = _global_trunk(sd, "model", avgpool(x), n_down, n_blocks_global, n_attn, heads, dim_head, training, with_head=False)
+def local_enhancer(sd, x, n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128, training=False, down="conv",
+                   up="transconv"):
+    coarse = _global_trunk(sd, "model", avgpool(x), n_down, n_blocks_global, n_attn, heads, dim_head, training, with_head=False, down=down,
+                           up=up)
     h = F.relu(_in(_conv(sd, "model1_1.1", x, reflect=3)))
-    h = F.relu(_in(_conv(sd, "model1_1.4", h, stride=2, padding=1)))
+    h = F.relu(_in(_down(sd, "model1_1.4", h, down)))
     h = h + coarse
     for b in range(n_blocks_local):
         h = resnet_block(sd, f"model1_2.{b}", h)
     i = n_blocks_local
-    h = F.relu(_in(_convt(sd, f"model1_2.{i}", h)))
+    h = F.relu(_in(_up(sd, f"model1_2.{i}", h, up)))
     return torch.tanh(_conv(sd, f"model1_2.{i + 4}", h, reflect=3))
 
 

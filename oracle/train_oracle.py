@@ -23,13 +23,13 @@ def spectro(audio, gain=1000.0, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0)):
 
 
 def losses(pG, pD, lr_spectro, hr_spectro, *, netG="local", n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128,
-           num_D=3, n_layers_D=3, lambda_feat=10.0, fit_residual=True, lo=-1.0, use_feat=True):
+           num_D=3, n_layers_D=3, lambda_feat=10.0, fit_residual=True, lo=-1.0, use_feat=True, down="conv", up="transconv"):
     """The four loss tensors [G_GAN, G_GAN_Feat, D_real, D_fake] as autograd functions of the parameter dicts."""
     x = torch.cat((lr_spectro, lr_spectro.abs() * 2 + lo), dim=1)
     if netG == "global":
-        sr = NO.global_generator(pG, x, n_down, n_blocks_global, n_attn, heads, dim_head, training=True)
+        sr = NO.global_generator(pG, x, n_down, n_blocks_global, n_attn, heads, dim_head, training=True, down=down, up=up)
     else:
-        sr = NO.local_enhancer(pG, x, n_down, n_blocks_global, n_blocks_local, n_attn, heads, dim_head, training=True)
+        sr = NO.local_enhancer(pG, x, n_down, n_blocks_global, n_blocks_local, n_attn, heads, dim_head, training=True, down=down, up=up)
     if fit_residual:
         sr = sr + lr_spectro
     sr_in = torch.cat((sr, sr.abs() * 2 + lo), dim=1)

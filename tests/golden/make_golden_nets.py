@@ -29,6 +29,12 @@ NET_CASES = {
              (2, 2, 32, 256), 78),
     "l_small": ("G", dict(input_nc=2, output_nc=1, ngf=8, netG="local", n_downsample_global=2, n_blocks_global=2, n_local_enhancers=1,
                           n_blocks_local=1, norm="instance", input_size=(16, 64)), (2, 2, 16, 64), 12),
+    # the reference's shipped training recipe (train.sh): resconv down / interpolate up, ngf 56, 3 attention layers (6 heads x 128)
+    "trainsh": ("G", dict(input_nc=2, output_nc=1, ngf=56, netG="local", n_downsample_global=3, n_blocks_global=4, n_local_enhancers=1,
+                          n_blocks_local=3, norm="instance", input_size=(128, 256), n_attn_g=3, heads_g=6, dim_head_g=128, proj_factor_g=4,
+                          upsample_type="interpolate", downsample_type="resconv"), (1, 2, 128, 256), 79),
+    "g_small_rc": ("G", dict(input_nc=2, output_nc=1, ngf=8, netG="global", n_downsample_global=2, n_blocks_global=2, norm="instance",
+                             input_size=(16, 64), upsample_type="interpolate", downsample_type="resconv"), (3, 2, 16, 64), 14),
     "d3": ("D", dict(input_nc=3, ndf=64, n_layers_D=3, norm="instance", use_sigmoid=False, num_D=3, getIntermFeat=True),
            (2, 3, 32, 256), 99),
     "d_small": ("D", dict(input_nc=3, ndf=8, n_layers_D=2, norm="instance", use_sigmoid=False, num_D=2, getIntermFeat=True),
@@ -136,6 +142,7 @@ TRAIN_FLAGS = {
                   "--heads_g", "2", "--dim_head_g", "32", "--n_blocks_local", "1", "--num_D", "2", "--n_layers_D", "2", "--ndf", "8",
                   "--segment_length", "3840", "--bins", "16", "--fit_residual"], 3, 3840, 5152),
 }
+TRAIN_FLAGS["tr_small_rc"] = (TRAIN_FLAGS["tr_small"][0] + ["--upsample_type", "interpolate", "--downsample_type", "resconv"], 2, 3840, 5153)
 TRAIN_STEPS = 2
 
 
@@ -174,9 +181,10 @@ def gen_train():
                 gG = {k: p.grad for k, p in model.netG.named_parameters()}
                 out[f"{name}_gradG_keys"] = np.array(list(gG.keys()))
                 out[f"{name}_gradG_cksum"] = state_checksum(gG)
-                if name == "tr_small":
+                if name.startswith("tr_small"):
                     for k, v in gG.items():
-                        out[f"{name}_gradG::{k}"] = v.numpy().copy()
+                        if name == "tr_small" or v.numel() <= 2500:
+                            out[f"{name}_gradG::{k}"] = v.numpy().copy()
             model.optimizer_G.step()
             model.optimizer_D.zero_grad()
             loss_D.backward()

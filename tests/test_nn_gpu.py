@@ -155,7 +155,7 @@ def _build(kind, kw, seed, dev):
     return net.to(dev)
 
 
-@pytest.mark.parametrize("name", ["g_small", "l_small", "cfg2", "local_noattn", "cfg3"])
+@pytest.mark.parametrize("name", ["g_small", "l_small", "cfg2", "local_noattn", "cfg3", "g_small_rc", "trainsh"])
 def test_generator_matches_reference_output(dev, nets_golden, name):
     import mdctgan_b200
 

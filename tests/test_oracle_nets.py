@@ -37,12 +37,13 @@ def test_state_dict_layout_and_seeded_init_match_reference(nets_golden, name):
     np.testing.assert_allclose(state_checksum(sd), nets_golden[f"{name}_cksum"], rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["g_small", "l_small", "cfg2", "local_noattn", "cfg3"])
+@pytest.mark.parametrize("name", ["g_small", "l_small", "cfg2", "local_noattn", "cfg3", "g_small_rc", "trainsh"])
 def test_generator_oracle_matches_reference(nets_golden, name):
     kind, kw, shape, seed = NET_CASES[name]
     sd = build_ours(kind, kw, seed).state_dict()
     x = make_input(shape, seed)
-    common = dict(n_attn=kw.get("n_attn_g", 0), heads=kw.get("heads_g", 4), dim_head=kw.get("dim_head_g", 128))
+    common = dict(n_attn=kw.get("n_attn_g", 0), heads=kw.get("heads_g", 4), dim_head=kw.get("dim_head_g", 128),
+                  down=kw.get("downsample_type", "conv"), up=kw.get("upsample_type", "transconv"))
     with torch.no_grad():
         if kw["netG"] == "global":
             y = NO.global_generator(sd, x, kw["n_downsample_global"], kw["n_blocks_global"], **common)

@@ -221,7 +221,7 @@ def _build_model(flags, seed, dev):
     return model
 
 
-@pytest.mark.parametrize("name", ["tr_small", "tr_cfg4"])
+@pytest.mark.parametrize("name", ["tr_small", "tr_cfg4", "tr_small_rc"])
 @pytest.mark.parametrize("api", ["autograd", "train_step"])
 def test_train_step_matches_oracle_and_reference(dev, name, api):
     """Two iterations of train.py:160-202 on the reference's seeded batch: the four losses, every gradient tensor of the
@@ -244,7 +244,7 @@ def test_train_step_matches_oracle_and_reference(dev, name, api):
     sdG = {k: v.detach().cpu().clone() for k, v in model.netG.state_dict().items()}
     sdD = {k: v.detach().cpu().clone() for k, v in model.netD.state_dict().items()}
     kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D",
-                              "fit_residual")}
+                              "fit_residual", "down", "up")}
     lr_a, hr_a = gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"]
     ref = TO.train_step(sdG, sdD, lr_a, hr_a, steps=TRAIN_STEPS, **kw)
     lr_d, hr_d = torch.from_numpy(lr_a).to(dev), torch.from_numpy(hr_a).to(dev)
@@ -303,12 +303,12 @@ def test_train_step_matches_oracle_and_reference(dev, name, api):
         if v.dim() >= 2:
             got = model.netG.state_dict()[k].detach().cpu()
             moved = (v - sdG[k]).norm().item()
-            assert (got - v).norm().item() < (1.0 if name == "tr_cfg4" else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
+            assert (got - v).norm().item() < (1.0 if name in ("tr_cfg4", "tr_small_rc") else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
     for k, v in ref["paramsD"].items():
         if v.dim() >= 2:
             got = model.netD.state_dict()[k].detach().cpu()
             moved = (v - sdD[k]).norm().item()
-            assert (got - v).norm().item() < (1.0 if name == "tr_cfg4" else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
+            assert (got - v).norm().item() < (1.0 if name in ("tr_cfg4", "tr_small_rc") else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
     print(f"{name}/{api}: losses {losses[0]}, worst G-gradient rel-L2 {worst:.2e}")
 
 

@@ -16,11 +16,12 @@ cfg = flags_to_cfg(flags)
 model = _build_model(list(flags) + ["--mdct_precision", os.environ.get("MDCT_PREC", "fp32")], seed, dev)
 G0, D0 = build_nets(cfg, seed)
 model.netG.load_state_dict(G0.state_dict()); model.netD.load_state_dict(D0.state_dict())
-kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D", "fit_residual")}
+kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D", "fit_residual", "down", "up")}
 ref = TO.train_step(G0.state_dict(), D0.state_dict(), gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"], steps=1, **kw)
 lr_d, hr_d = torch.from_numpy(gold[f"{name}_lr_audio"]).to(dev), torch.from_numpy(gold[f"{name}_hr_audio"]).to(dev)
 from mdctgan_b200 import train_ops as T, nn_ops as ops
 model.optimizer_G.zero_grad(); model.optimizer_D.zero_grad()
+model._refresh_weight_images()      # load_state_dict above changed the weights behind the packer
 graph = T.GanGraph(model)
 with ops.stats_pass(dev):
     graph.forward(lr_d, hr_d)
@@ -72,3 +73,18 @@ fo = NO.multiscale_d(sd, din, cfg["num_D"], cfg["n_layers_D"])
 for i, sc in enumerate(graph.feats):
     for j, f in enumerate(sc):
         print("feat", i, j, rl(f.x.permute(0, 3, 1, 2).cpu(), fo[i][j].detach()))
+# ---- generator forward on OUR network input, against the oracle generator (isolates G from the transform)
+with torch.no_grad():
+    lr_spectro, lr_input, _, _ = model._lr_input(lr_d)
+    xin = lr_input.cpu()
+    fn = NO.global_generator if cfg["netG"] == "global" else NO.local_enhancer
+    args = (cfg["n_down"], cfg["n_blocks_global"]) + (() if cfg["netG"] == "global" else (cfg["n_blocks_local"],))
+    y_or = fn(G0.state_dict(), xin, *args, cfg["n_attn"], cfg["heads"], cfg["dim_head"], training=True, down=cfg["down"], up=cfg["up"])
+    with ops.stats_pass(dev):
+        y_run = model.netG.run(ops.to_nhwc(lr_input)).x.reshape(y_or.shape).cpu()
+    print("G forward (train-mode BN) on our input vs oracle:", rl(y_run, y_or))
+    for k, v in G0.state_dict().items():
+        w = model.netG.state_dict()[k].cpu()
+        if not torch.equal(w, v) and v.dtype.is_floating_point and "running" not in k and "num_batches" not in k:
+            print("  weight differs from the seeded CPU init:", k, rl(w, v))
+            break
