@@ -152,7 +152,8 @@ def test_resnet_block_and_pool_backward(dev):
             assert rel_l2(p.grad.cpu().numpy(), ref.numpy()) < 3e-4, k
 
 
-def test_bottlestack_backward(dev):
+@pytest.mark.parametrize("dim,heads,dh,fmap", [(64, 2, 32, (2, 16)), (128, 2, 128, (8, 16))])   # second: 128 tokens x 128 channels -> the
+def test_bottlestack_backward(dev, dim, heads, dh, fmap):                                         # two-pass attention backward (train.sh shape)
     """BottleStack (1x1 convs, train-mode BatchNorm, attention with abs. position embedding, shortcut) vs torch autograd."""
     from mdctgan_b200 import nn_ops as ops
     from mdctgan_b200.models import networks as N
@@ -160,7 +161,6 @@ def test_bottlestack_backward(dev):
     from oracle import networks_oracle as NO
 
     torch.manual_seed(5)
-    dim, heads, dh, fmap = 64, 2, 32, (2, 16)
     bs = BottleStack(dim=dim, fmap_size=fmap, dim_out=dim, num_layers=2, proj_factor=4, downsample=False, heads=heads, dim_head=dh,
                      activation=N.ReLU(True), rel_pos_emb=False)
     bs.apply(N.weights_init)
