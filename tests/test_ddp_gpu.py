@@ -1,0 +1,90 @@
+"""2 GPUs, NCCL: the batch-sharded train step (one all-reduce of the flat [grad_G | grad_D] bucket, 1/world folded into Adam)
+computes the gradient of the global batch.  A configuration without BatchNorm is used (InstanceNorm only: per-sample
+statistics, so sharding the batch changes no forward value and the comparison is tight); with BottleStack attention the
+BatchNorm statistics are per rank by design (the reference has no multi-GPU semantics to match).
+Skipped on boxes with fewer than 2 GPUs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FLAGS = ["--name", "ddp", "--checkpoints_dir", "/tmp/mdctgan_ddp", "--lr_sampling_rate", "12000", "--sr_sampling_rate", "48000",
+         "--arcsinh_transform", "--abs_spectro", "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1", "--abs_norm",
+         "--src_range", "-5", "5", "--netG", "local", "--ngf", "16", "--n_downsample_global", "2", "--n_blocks_global", "2",
+         "--n_blocks_attn_g", "0", "--n_blocks_local", "1", "--num_D", "2", "--n_layers_D", "2", "--ndf", "16", "--segment_length", "3840",
+         "--bins", "16", "--fit_residual"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from mdctgan_b200.models.models import create_model
+    from mdctgan_b200.options.train_options import TrainOptions
+    from mdctgan_b200.parallel import GradExchange, broadcast_flat, check_replicas_in_sync, shard_range
+
+    def build():
+        opt = TrainOptions().parse(save=False, args=FLAGS + ["--gpu_ids", str(rank)])
+        torch.manual_seed(77 + rank)                       # deliberately different: broadcast_flat must equalise
+        m = create_model(opt)
+        m.train()
+        return m
+
+    g = torch.Generator().manual_seed(5)
+    lr_all, hr_all = 0.05 * torch.randn(4, 3840, generator=g), 0.1 * torch.randn(4, 3840, generator=g)
+    model = build()
+    broadcast_flat([model.bucket_G.flat, model.bucket_D.flat])
+    w0 = (model.bucket_G.flat.clone(), model.bucket_D.flat.clone())
+    mine = shard_range(4, world, rank)
+    ex = GradExchange()
+    losses = model.train_step(lr_all[mine.start:mine.stop].to(dev), hr_all[mine.start:mine.stop].to(dev), world, ex)
+    grads_dp = model.grad_all.clone() / world
+    model.train_step(lr_all[mine.start:mine.stop].to(dev), hr_all[mine.start:mine.stop].to(dev), world, ex)
+    in_sync = check_replicas_in_sync(model.bucket_G.flat) and check_replicas_in_sync(model.bucket_D.flat)
+    res = dict(in_sync=in_sync, calls=ex.calls)
+    if rank == 0:                                          # the same two steps by ONE process on the global batch
+        single = build()
+        single.bucket_G.flat.copy_(w0[0])
+        single.bucket_D.flat.copy_(w0[1])
+        single._refresh_weight_images()
+        single.train_step(lr_all.to(dev), hr_all.to(dev))
+        grads_1 = single.grad_all.clone()
+        res["grad_rel"] = float((grads_dp - grads_1).norm() / grads_1.norm())
+        single.train_step(lr_all.to(dev), hr_all.to(dev))
+        moved = float((single.bucket_G.flat - w0[0]).norm())
+        res["param_rel_to_move"] = float((single.bucket_G.flat - model.bucket_G.flat).norm()) / moved
+    out[rank] = res
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_step_equals_global_batch_step():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0]["in_sync"] and out[1]["in_sync"]
+    assert out[0]["calls"] == 2                      # ONE collective per step
+    assert out[0]["grad_rel"] < 1e-4, out[0]
+    assert out[0]["param_rel_to_move"] < 0.05, out[0]
