@@ -79,6 +79,11 @@ int mdctgan_mdct2audio_inverse(const mdctgan_plan* plan, const float* spectro_de
                                const mdctgan_norm* norm, void* audio_dev, int64_t audio_stride, int64_t out_len,
                                int precision, void* stream);
 
+/* Audio2MDCT.normalize / denormalize on an existing spectrogram (pix2pixHD_model.py:83-137; arcsinh / raw with abs_norm), computed
+ * in fp64 like the reference.  normalize: x, y fp32 or fp64 per `precision`; denormalize: s fp32 or fp64 per `precision`, y fp64. */
+int mdctgan_spectro_normalize(const void* x, void* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream);
+int mdctgan_spectro_denormalize(const void* s, double* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream);
+
 /* Host-buffer forms of the four calls above (the end-to-end path a non-torch caller uses): inputs and
  * outputs are HOST arrays, densely packed; clips are streamed host->device->host in chunks over three
  * CUDA streams so copies overlap the kernels.  They synchronise before returning.  Scratch device

@@ -399,6 +399,40 @@ int mdctgan_upsample_nearest2x(const float* x, float* y, int B, int H, int W, in
   return 0;
 }
 
+static int spec_norm_of(const mdctgan_norm* n, SpecNorm* o) {
+  if (!n) return mdctgan_set_error(-1, "norm is NULL");
+  if (n->mode != MDCTGAN_MODE_RAW && n->mode != MDCTGAN_MODE_ARCSINH) return mdctgan_set_error(-2, "unsupported norm mode %d", n->mode);
+  if (!(n->src_hi > n->src_lo) || !(n->norm_hi > n->norm_lo)) return mdctgan_set_error(-1, "empty src_range / norm_range");
+  *o = SpecNorm{n->mode, (double)n->gain, (double)n->src_lo, (double)n->src_hi, (double)n->norm_lo, (double)n->norm_hi};
+  return 0;
+}
+
+int mdctgan_spectro_normalize(const void* x, void* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream) {
+  if (!x || !y) return mdctgan_set_error(-1, "spectro_normalize: NULL buffer");
+  SpecNorm p; if (int rc = spec_norm_of(norm, &p)) return rc;
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MDCTGAN_F64) spectro_normalize_kernel<double, double><<<grid_for((size_t)n, 256), 256, 0, st>>>((const double*)x, (double*)y, (size_t)n, p);
+  else if (precision == MDCTGAN_F32) spectro_normalize_kernel<float, float><<<grid_for((size_t)n, 256), 256, 0, st>>>((const float*)x, (float*)y, (size_t)n, p);
+  else return mdctgan_set_error(-1, "spectro_normalize: precision %d", precision);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_spectro_denormalize(const void* s, double* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream) {
+  if (!s || !y) return mdctgan_set_error(-1, "spectro_denormalize: NULL buffer");
+  SpecNorm p; if (int rc = spec_norm_of(norm, &p)) return rc;
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MDCTGAN_F64) spectro_denormalize_kernel<double><<<grid_for((size_t)n, 256), 256, 0, st>>>((const double*)s, y, (size_t)n, p);
+  else if (precision == MDCTGAN_F32) spectro_denormalize_kernel<float><<<grid_for((size_t)n, 256), 256, 0, st>>>((const float*)s, y, (size_t)n, p);
+  else return mdctgan_set_error(-1, "spectro_denormalize: precision %d", precision);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
   if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
   counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);

@@ -988,6 +988,32 @@ __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Audio2MDCT.normalize / denormalize as stand-alone calls (pix2pixHD_model.py:83-137, arcsinh / raw branch with abs_norm): the
+// fused transform kernels do this in their epilogue / prologue; these serve callers that hold a spectrogram already.
+// Computed in fp64 like the reference (its spectrograms are fp64); ln10 is the fp32 constant of :100,133.
+// ------------------------------------------------------------------------------------------------
+struct SpecNorm { int mode; double gain, src_lo, src_hi, norm_lo, norm_hi; };
+template <typename TI, typename TO>
+__global__ void spectro_normalize_kernel(const TI* __restrict__ x, TO* __restrict__ y, size_t n, SpecNorm p) {
+  const double ln10 = 2.3025851249694824;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = (double)x[i];
+    if (p.mode == 1) s = asinh(p.gain * s) / ln10;
+    s = (s - p.src_lo) / (p.src_hi - p.src_lo);
+    y[i] = (TO)(s * (p.norm_hi - p.norm_lo) + p.norm_lo);
+  }
+}
+template <typename TI>
+__global__ void spectro_denormalize_kernel(const TI* __restrict__ x, double* __restrict__ y, size_t n, SpecNorm p) {
+  const double ln10 = 2.3025851249694824;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = ((double)x[i] - p.norm_lo) / (p.norm_hi - p.norm_lo);
+    s = s * (p.src_hi - p.src_lo) + p.src_lo;
+    y[i] = p.mode == 1 ? sinh(s * ln10) / p.gain : s;
+  }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;

@@ -168,11 +168,45 @@ class Audio2MDCT(torch.nn.Module):
     # ------------------------------------------------------------------ un-fused pieces (API parity)
     @torch.no_grad()
     def normalize(self, spectro: torch.Tensor):
-        raise NotImplementedError("normalize() is fused into to_spectro(); call to_spectro(audio)")
+        """pix2pixHD_model.py:83-125 on an existing spectrogram (arcsinh / raw branch, abs_norm): returns
+        (log_spectro, audio_max, audio_min, mean, std) with the spectrogram's dtype (the reference's is fp64); `mean` / `std`
+        are None (computed and never consumed in the reference)."""
+        from ctypes import c_int, c_int64, c_void_p, POINTER
+
+        _require_cuda(spectro, "Audio2MDCT.normalize")
+        x = spectro.contiguous()
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float32)
+        y = torch.empty_like(x)
+        L = _lib.lib()
+        L.mdctgan_spectro_normalize.argtypes = [c_void_p, c_void_p, c_int64, POINTER(_lib._Norm), c_int, c_void_p]
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.check(L.mdctgan_spectro_normalize(x.data_ptr(), y.data_ptr(), x.numel(), self._cnorm,
+                                                       _lib.F64 if x.dtype == torch.float64 else _lib.F32, _stream_ptr(x.device)))
+        lo, hi = self._src_minmax(x.device)
+        return y, hi, lo, None, None
 
     @torch.no_grad()
     def denormalize(self, log_spectro: torch.Tensor, min: torch.Tensor, max: torch.Tensor):
-        raise NotImplementedError("denormalize() is fused into to_audio(); call to_audio(log_spectro, norm_param, pha)")
+        """pix2pixHD_model.py:127-137: normalised spectrogram -> fp64 MDCT coefficients (arcsinh / raw branch)."""
+        from ctypes import c_int, c_int64, c_void_p, POINTER
+
+        _require_cuda(log_spectro, "Audio2MDCT.denormalize")
+        self._check_norm_param({"min": min, "max": max})
+        lo_v, hi_v = float(torch.as_tensor(min).reshape(-1)[0]), float(torch.as_tensor(max).reshape(-1)[0])
+        cn = _lib.NormSpec(self._norm.mode, self._norm.gain, (lo_v, hi_v), self._norm.norm_range).c()
+        x = log_spectro.contiguous()
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float32)
+        y = torch.empty(x.shape, dtype=torch.float64, device=x.device)
+        L = _lib.lib()
+        L.mdctgan_spectro_denormalize.argtypes = [c_void_p, c_void_p, c_int64, POINTER(_lib._Norm), c_int, c_void_p]
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.check(L.mdctgan_spectro_denormalize(x.data_ptr(), y.data_ptr(), x.numel(), cn,
+                                                         _lib.F64 if x.dtype == torch.float64 else _lib.F32, _stream_ptr(x.device)))
+        return y
 
 
 # =====================================================================================================
@@ -286,10 +320,13 @@ class Pix2PixHDModel(BaseModel):
             self.grad_all = torch.zeros(nG + nD, dtype=torch.float32, device=self.device)     # [grad_G | grad_D]: THE all-reduce bucket
             self.bucket_G = FlatBucket(self.netG, self.grad_all[:nG])
             self.bucket_D = FlatBucket(self.netD, self.grad_all[nG:])
-            if opt.niter_fix_global > 0:
-                raise NotImplementedError("--niter_fix_global > 0 (local-enhancer-only finetuning) is listed as next in DESIGN.md")
             graph_safe = bool(getattr(opt, "graph_safe_adam", True))
-            self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
+            params_G = None
+            if opt.niter_fix_global > 0:      # only the local enhancer trains at first (pix2pixHD_model.py:333-347)
+                prefix = "model" + str(opt.n_local_enhancers)
+                params_G = [p for k, p in self.netG.named_parameters() if k.startswith(prefix)]
+                print("------------- Only training the local enhancer network (for %d epochs) ------------" % opt.niter_fix_global)
+            self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe, params=params_G)
             self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
             self._graph = None
             from ..packing import WeightPacker
@@ -384,7 +421,13 @@ class Pix2PixHDModel(BaseModel):
         return self._half
 
     def update_fixed_params(self):
-        raise NotImplementedError("--niter_fix_global > 0 is listed as next in DESIGN.md")
+        """After --niter_fix_global epochs also finetune the global generator: a fresh Adam over all of G, like the reference
+        (pix2pixHD_model.py:654-662)."""
+        from ..optim import FusedAdam
+
+        self.optimizer_G = FusedAdam(self.bucket_G, lr=self.lr, betas=(self.beta1, 0.999), graph_safe=self.optimizer_G.step_dev is not None)
+        if getattr(self, "verbose", False):
+            print("------------ Now also finetuning global generator -----------")
 
     def update_learning_rate(self):
         """Linear decay, pix2pixHD_model.py:664-673."""

@@ -52,12 +52,13 @@ class FlatBucket:
                 p.data = self.flat[o:o + p.numel()].view_as(p)
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
 
-    def trainable_runs(self):
-        """Maximal contiguous [begin, end) runs of the flat buffer whose parameters require grad."""
+    def trainable_runs(self, subset=None):
+        """Maximal contiguous [begin, end) runs of the flat buffer whose parameters require grad (and are in `subset`, a set of
+        parameter ids, when given)."""
         runs, cur = [], None
         for p, o in zip(self.params, self.offsets):
             end = o + (p.numel() + 3) // 4 * 4
-            if p.requires_grad:
+            if p.requires_grad and (subset is None or id(p) in subset):
                 cur = [o, end] if cur is None else [cur[0], end]
             elif cur is not None:
                 runs.append(tuple(cur))
@@ -76,8 +77,11 @@ class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (no weight decay, no amsgrad) over a FlatBucket.  `grad_scale` multiplies the
     gradient inside the kernel (1/world_size after a sum all-reduce)."""
 
-    def __init__(self, bucket: FlatBucket, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, graph_safe: bool = False):
-        trainable = [p for p in bucket.params if p.requires_grad]
+    def __init__(self, bucket: FlatBucket, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, graph_safe: bool = False, params=None):
+        """`params`: optional subset of the bucket's parameters to optimise (the reference's --niter_fix_global phase trains
+        only the local enhancer, pix2pixHD_model.py:333-347); the others keep receiving gradients but are not stepped."""
+        self._subset = None if params is None else {id(p) for p in params}
+        trainable = [p for p in bucket.params if p.requires_grad and (self._subset is None or id(p) in self._subset)]
         super().__init__(trainable, dict(lr=lr, betas=betas, eps=eps))
         self.bucket = bucket
         self.exp_avg = torch.zeros_like(bucket.flat)
@@ -108,7 +112,7 @@ class FusedAdam(torch.optim.Optimizer):
             st = torch.cuda.current_stream(b.flat.device).cuda_stream
             if self.step_dev is not None:
                 _lib.check(L.mdctgan_counter_inc(self.step_dev.data_ptr(), st))
-            for lo, hi in b.trainable_runs():
+            for lo, hi in b.trainable_runs(self._subset):
                 _lib.check(L.mdctgan_adam_flat(b.flat[lo:hi].data_ptr(), b.grad[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
                                                self.exp_avg_sq[lo:hi].data_ptr(), hi - lo, float(g["lr"]), float(g["betas"][0]),
                                                float(g["betas"][1]), float(g["eps"]), float(self.grad_scale), self.step_count,

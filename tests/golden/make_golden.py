@@ -132,6 +132,28 @@ def gen_metrics():
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)
 
 
+def gen_normalize():
+    """Audio2MDCT.normalize / denormalize of the reference itself (pix2pixHD_model.py:83-137), arcsinh and raw branches, abs_norm."""
+    from models.pix2pixHD_model import Audio2MDCT
+
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    spectro = 0.02 * torch.randn(1, 1, 4, 256, generator=g, dtype=torch.float64)
+    logs = (torch.rand(1, 1, 4, 256, generator=g) * 2 - 1).float()
+    out["spectro"], out["log_spectro"] = spectro.numpy(), logs.numpy()
+    for tag, extra in (("arcsinh", []), ("raw", ["--raw_mdct"])):
+        flags = ["--segment_length", "7936", "--bins", "32"] + extra
+        opt = ref_opt(flags)
+        if tag == "raw":
+            opt.arcsinh_transform = False
+        a2m = Audio2MDCT(opt)
+        y, mx, mn, mean, std = a2m.normalize(spectro.clone())
+        out[f"{tag}_norm"] = y.numpy()
+        out[f"{tag}_denorm"] = a2m.denormalize(logs.clone(), mn, mx).numpy()
+        print(tag, y.dtype, out[f"{tag}_denorm"].dtype)
+    np.savez_compressed(os.path.join(HERE, "normalize_golden.npz"), **out)
+
+
 def gen_mdct():
     from models.mdct import IMDCT4, MDCT4
     from models.pix2pixHD_model import Audio2MDCT
@@ -232,6 +254,8 @@ if __name__ == "__main__":
         gen_longform()
     if "metrics" in what:
         gen_metrics()
+    if "normalize" in what:
+        gen_normalize()
     if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 

@@ -313,3 +313,26 @@ def test_full_size_properties(dev, W):
     # (6) batch independence: clip i alone == clip i inside the batch (bit-exact)
     assert torch.equal(fwd(x[1234:1235])[0], spec[1234:1235])
     assert torch.equal(inv(spec[77:78])[0].reshape(-1), y[77])
+
+
+@pytest.mark.parametrize("tag", ["arcsinh", "raw"])
+def test_normalize_denormalize_standalone_match_reference(tag):
+    """Audio2MDCT.normalize / denormalize as stand-alone calls (pix2pixHD_model.py:83-137) against the reference's own outputs
+    (tests/golden/normalize_golden.npz): fp64 arithmetic on both sides, 1e-12 relative."""
+    import os
+
+    import numpy as np
+
+    from conftest import GOLDEN
+    from mdctgan_b200.models.pix2pixHD_model import Audio2MDCT, default_audio_opt
+
+    gold = dict(np.load(os.path.join(GOLDEN, "normalize_golden.npz")))
+    dev = torch.device("cuda:0")
+    opt = default_audio_opt(arcsinh_gain=1000.0, norm_range=(-1.0, 1.0), arcsinh_transform=(tag == "arcsinh"), raw_mdct=(tag == "raw"))
+    a2m = Audio2MDCT(opt, device=dev)
+    y, mx, mn, mean, std = a2m.normalize(torch.from_numpy(gold["spectro"]).to(dev))
+    assert y.dtype == torch.float64 and mean is None and std is None
+    np.testing.assert_allclose(y.cpu().numpy(), gold[f"{tag}_norm"], rtol=1e-12, atol=1e-14)
+    d = a2m.denormalize(torch.from_numpy(gold["log_spectro"]).to(dev), mn, mx)
+    assert d.dtype == torch.float64
+    np.testing.assert_allclose(d.cpu().numpy(), gold[f"{tag}_denorm"], rtol=1e-12, atol=1e-300)

@@ -96,3 +96,24 @@ def test_checkpoint_round_trip(tmp_path):
     m.train()
     losses, _ = m._forward(0.1 * torch.randn(2, 3840).cuda(), 0.1 * torch.randn(2, 3840).cuda())
     assert len(losses) == len(m.loss_names) == 4 and all(torch.isfinite(v).item() and v.dim() == 0 for v in losses)
+
+
+def test_niter_fix_global_trains_local_enhancer_only(tmp_path):
+    """--niter_fix_global > 0 (pix2pixHD_model.py:333-347): optimizer_G steps only the `model1_*` parameters until
+    update_fixed_params() (:654-662) replaces it by an Adam over the whole generator."""
+    from mdctgan_b200.models.models import create_model
+
+    opt = our_opt("inf_small", gpu="0")
+    opt.checkpoints_dir, opt.name, opt.niter_fix_global = str(tmp_path), "fix", 2
+    torch.manual_seed(4)
+    m = create_model(opt)
+    m.train()
+    before = {k: v.detach().clone() for k, v in m.netG.named_parameters()}
+    x, y = 0.05 * torch.randn(2, 3840).cuda(), 0.1 * torch.randn(2, 3840).cuda()
+    m.train_step(x, y)
+    moved = {k: not torch.equal(v, before[k]) for k, v in m.netG.named_parameters()}
+    assert all(moved[k] for k in moved if k.startswith("model1") and k.endswith("weight"))
+    assert not any(moved[k] for k in moved if not k.startswith("model1"))
+    m.update_fixed_params()
+    m.train_step(x, y)
+    assert any(not torch.equal(v, before[k]) for k, v in m.netG.named_parameters() if not k.startswith("model1"))
