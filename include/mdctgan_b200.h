@@ -241,6 +241,14 @@ int64_t mdctgan_lsd_frame_count(int64_t T, int n_fft, int hop, int center);
 int mdctgan_lsd_frames(const float* hr, const float* sr, int64_t rows, int64_t T, int n_fft, int hop, const float* window_dev, int center,
                        double* acc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data preparation in front of the path: torchaudio.functional.resample (sinc_interp_hann) as the reference calls it
+ * (data/audio_dataset.py:66-71, :169-177).  `table`: [nw][K] polyphase FIR (K = 2*width + orig; orig / nw = the two rates
+ * divided by their gcd); x [rows, L] -> y [rows, target], target = ceil(nw * L / orig).
+ */
+int mdctgan_resample_fir(const float* x, int rows, int64_t L, const float* table, int K, int orig, int nw, int width, float* y,
+                         int64_t target, void* stream);
+
 /* Introspection for tests / bench: number of kernels this library has launched in this process. */
 int64_t mdctgan_launch_count(void);
 

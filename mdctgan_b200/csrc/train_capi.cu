@@ -433,6 +433,20 @@ int mdctgan_spectro_denormalize(const void* s, double* y, int64_t n, const mdctg
   return 0;
 }
 
+int mdctgan_resample_fir(const float* x, int rows, int64_t L, const float* table, int K, int orig, int nw, int width, float* y,
+                         int64_t target, void* stream) {
+  if (!x || !table || !y) return mdctgan_set_error(-1, "resample_fir: NULL buffer");
+  if (rows <= 0 || L <= 0 || target <= 0) return 0;
+  if (K != 2 * width + orig || orig <= 0 || nw <= 0) return mdctgan_set_error(-1, "resample_fir: K %d != 2*width + orig (%d, %d)", K, width, orig);
+  const size_t smem = (size_t)nw * K * sizeof(float);
+  const int in_smem = smem <= 48 * 1024;
+  resample_fir_kernel<<<grid_for((size_t)rows * (size_t)target, 256), 256, in_smem ? smem : 0, (cudaStream_t)stream>>>(
+      x, L, table, K, orig, nw, width, y, target, rows, in_smem);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream) {
   if (!counter_dev) return mdctgan_set_error(-1, "counter_inc: NULL buffer");
   counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter_dev);

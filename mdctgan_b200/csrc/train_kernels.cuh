@@ -1014,6 +1014,38 @@ __global__ void spectro_denormalize_kernel(const TI* __restrict__ x, double* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// torchaudio.functional.resample (sinc_interp_hann polyphase FIR), the data-preparation step in front of the hot path
+// (data/audio_dataset.py:66-71: HR -> LR -> HR on CPU workers in the reference):
+//   y[r][q*new + ph] = sum_k x_pad[r][q*orig + k] * table[ph][k],  x_pad = x zero-padded by `width` on the left, width + orig right
+// One thread per output sample; the [new][K] table sits in shared memory when it fits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resample_fir_kernel(const float* __restrict__ x, long long L, const float* __restrict__ table, int K,
+                                                           int orig, int nw, int width, float* __restrict__ y, long long target, int rows,
+                                                           int table_in_smem) {
+  extern __shared__ float s_tab[];
+  if (table_in_smem) {
+    for (int i = threadIdx.x; i < nw * K; i += 256) s_tab[i] = __ldg(table + i);
+    __syncthreads();
+  }
+  const float* tab = table_in_smem ? s_tab : table;
+  const long long total = (long long)rows * target;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / target, j = i - r * target;
+    const long long q = j / nw;
+    const int ph = (int)(j - q * nw);
+    const float* xr = x + r * L;
+    const long long base = q * orig - width;
+    const float* t = tab + (size_t)ph * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const long long xi = base + k;
+      if (xi >= 0 && xi < L) acc = fmaf(__ldg(xr + xi), t[k], acc);
+    }
+    y[i] = acc;
+  }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;

@@ -132,6 +132,26 @@ def gen_metrics():
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)
 
 
+RESAMPLE_CASES = [(48000, 12000, 4001), (12000, 48000, 1000), (48000, 16000, 4000), (16000, 48000, 1333), (44100, 48000, 2205),
+                  (48000, 8000, 3000)]
+
+
+def resample_wave(L, seed):
+    g = torch.Generator().manual_seed(seed)
+    return 0.1 * torch.randn(2, L, generator=g)
+
+
+def gen_resample():
+    """torchaudio.functional.resample -- the function the reference calls (data/audio_dataset.py:66-71) -- on seeded waveforms."""
+    import torchaudio.functional as aF
+
+    out = {}
+    for i, (o, n, L) in enumerate(RESAMPLE_CASES):
+        out[f"r_{o}_{n}_{L}"] = aF.resample(resample_wave(L, 300 + i), o, n).numpy()
+        print(o, n, L, out[f"r_{o}_{n}_{L}"].shape)
+    np.savez_compressed(os.path.join(HERE, "resample_golden.npz"), **out)
+
+
 def gen_normalize():
     """Audio2MDCT.normalize / denormalize of the reference itself (pix2pixHD_model.py:83-137), arcsinh and raw branches, abs_norm."""
     from models.pix2pixHD_model import Audio2MDCT
@@ -256,6 +276,8 @@ if __name__ == "__main__":
         gen_metrics()
     if "normalize" in what:
         gen_normalize()
+    if "resample" in what:
+        gen_resample()
     if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 
