@@ -426,8 +426,10 @@ class LocalEnhancer(nn.Module):
         pyramid = [f]
         for _ in range(self.n_local_enhancers):
             pyramid.append(ops.avgpool3s2(pyramid[-1]))
-        coarse = run_layers(list(self.model), pyramid[-1])
-        fine = run_layers(list(self.model1_1), pyramid[0])
+        # the global trunk (on the pooled input) and the local down-sampling branch are independent until their sum: two streams,
+        # forward and backward (nn_ops.run_branches)
+        coarse, fine = ops.run_branches([lambda: run_layers(list(self.model), pyramid[-1]),
+                                         lambda: run_layers(list(self.model1_1), pyramid[0])], f.x.device)
         return run_layers(list(self.model1_2), ops.combine(fine, coarse))   # only one enhancer level runs (networks.py:260-267)
 
     def forward(self, input):
