@@ -117,3 +117,63 @@ def test_niter_fix_global_trains_local_enhancer_only(tmp_path):
     m.update_fixed_params()
     m.train_step(x, y)
     assert any(not torch.equal(v, before[k]) for k, v in m.netG.named_parameters() if not k.startswith("model1"))
+
+
+def test_train_py_fp16_sequence_with_gradscaler(tmp_path):
+    """train.py:160-202 with --fp16 verbatim (autocast around _forward, ONE GradScaler, scaler.scale(loss).backward(),
+    scaler.step(optimizer), one scaler.update()): the loss scale reaches our backward kernels as the upstream gradient of the loss
+    tensors, GradScaler unscales the flat-bucket views in place and steps FusedAdam.  The kernels compute in fp32 either way, and the
+    scale is a power of two, so the unscaled gradients equal the plain run's."""
+    from torch.cuda.amp import GradScaler, autocast
+
+    from mdctgan_b200.models.models import create_model
+
+    def build():
+        opt = our_opt("inf_small", gpu="0")
+        opt.checkpoints_dir, opt.name, opt.fp16 = str(tmp_path), "amp", True
+        torch.manual_seed(8)
+        torch.cuda.manual_seed(8)
+        m = create_model(opt)
+        m.train()
+        return m
+
+    g = torch.Generator().manual_seed(1)
+    lr_a, hr_a = (0.05 * torch.randn(2, 3840, generator=g)).cuda(), (0.1 * torch.randn(2, 3840, generator=g)).cuda()
+    m_amp, m_ref = build(), build()
+    m_ref.bucket_G.flat.copy_(m_amp.bucket_G.flat)
+    m_ref.bucket_D.flat.copy_(m_amp.bucket_D.flat)
+    m_ref._refresh_weight_images()
+    # ---- train.py --fp16
+    scaler = GradScaler()
+    optimizer_G, optimizer_D = m_amp.optimizer_G, m_amp.optimizer_D
+    with autocast():
+        losses, _ = m_amp._forward(lr_a, hr_a, infer=False)
+    losses = [torch.mean(x) if not isinstance(x, int) else x for x in losses]
+    loss_dict = dict(zip(m_amp.loss_names, losses))
+    loss_D = (loss_dict["D_fake"] + loss_dict["D_real"]) * 0.5
+    loss_G = loss_dict["G_GAN"] + loss_dict.get("G_GAN_Feat", 0)
+    optimizer_G.zero_grad()
+    scaler.scale(loss_G).backward()
+    scaler.step(optimizer_G)
+    gG_amp = m_amp.bucket_G.grad.clone()
+    optimizer_D.zero_grad()
+    scaler.scale(loss_D).backward()
+    scaler.step(optimizer_D)
+    scaler.update()
+    gD_amp = m_amp.bucket_D.grad.clone()
+    # ---- plain sequence on the same weights
+    ls, _ = m_ref._forward(lr_a, hr_a)
+    d = dict(zip(m_ref.loss_names, ls))
+    m_ref.optimizer_G.zero_grad()
+    (d["G_GAN"] + d["G_GAN_Feat"]).backward()
+    gG = m_ref.bucket_G.grad.clone()
+    m_ref.optimizer_G.step()
+    m_ref.optimizer_D.zero_grad()
+    ((d["D_fake"] + d["D_real"]) * 0.5).backward()
+    gD = m_ref.bucket_D.grad.clone()
+    m_ref.optimizer_D.step()
+    assert torch.allclose(torch.stack([x.detach() for x in losses]), torch.stack([x.detach() for x in ls]), rtol=1e-6)
+    assert float((gG_amp - gG).norm() / gG.norm()) < 1e-4 and float((gD_amp - gD).norm() / gD.norm()) < 1e-4
+    assert m_amp.optimizer_G.step_count == 1 and m_amp.optimizer_D.step_count == 1
+    moved = float((m_ref.bucket_G.flat - m_amp.bucket_G.flat).norm()) / float(2e-4 * m_ref.bucket_G.flat.numel() ** 0.5)
+    assert moved < 0.2, moved
