@@ -471,6 +471,7 @@ class _SideWork:
 
 
 _side = {}
+_wgrad_hooks = {}       # id(module) -> callable(stream the module's weight-gradient kernel was enqueued on)
 SIDE_STREAM_WGRAD = os.environ.get("MDCTGAN_SIDE_WGRAD", "1") != "0"
 
 
@@ -703,6 +704,9 @@ class _ConvOp:
                                                   self.pad, self.pad_mode, 1 if self.transposed else 0, _ptr(f.scale), _ptr(f.shift),
                                                   1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
                                                   dw.data_ptr(), s_co, s_ci, 1, _ptr(db), _stream(dy)))
+            hook = _wgrad_hooks.get(id(own))
+            if hook is not None:      # e.g. "every gradient of this all-reduce bucket has been enqueued" (bucketed exchange)
+                hook(side if side is not None else torch.cuda.current_stream(dy.device))
         if not self.f.needs_grad:
             return
         # input gradient = the forward convolution on the transposed geometry with the same weights
