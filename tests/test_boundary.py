@@ -107,3 +107,26 @@ def test_kbdwin_bits(mdct_golden):
 
     for n in (64, 512, 1024):
         assert np.array_equal(kbdwin(n).numpy(), mdct_golden[f"kbdwin{n}"])
+
+
+def test_host_side_shape_functions(lib):
+    """Pure host arithmetic of the C ABI (no kernel launch): segment count of seg_pad_audio (data/audio_dataset.py:153-167) and frame
+    count of the LSD spectrogram (util/util.py:170-171) against the oracle restatements."""
+    import ctypes
+
+    import torch
+
+    from oracle import longform_oracle as LO
+
+    lib.mdctgan_segment_count.restype = ctypes.c_int64
+    lib.mdctgan_segment_count.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    for L in (1, 100, 3839, 3840, 3841, 7936, 20000, 100000, 2880000):
+        for seg, ov in ((3840, 0), (3840, 128), (7936, 256), (32512, 0), (32512, 4096)):
+            want = LO.seg_pad_audio(torch.zeros(1, L), seg, ov).shape[0]
+            assert lib.mdctgan_segment_count(L, seg, ov) == want, (L, seg, ov)
+    lib.mdctgan_lsd_frame_count.restype = ctypes.c_int64
+    lib.mdctgan_lsd_frame_count.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    for T in (1024, 4000, 7936, 32512):
+        for center in (0, 1):
+            z = torch.stft(torch.zeros(T), 1024, 512, 1024, window=torch.ones(1024), center=bool(center), return_complex=True)
+            assert lib.mdctgan_lsd_frame_count(T, 1024, 512, center) == z.shape[-1], (T, center)
