@@ -1,6 +1,6 @@
 """Per-tensor gradient error of the CUDA train step vs oracle/train_oracle.py (debug aid; run on the GPU box)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np, torch
 from oracle import train_oracle as TO

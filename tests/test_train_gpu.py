@@ -9,7 +9,7 @@ goldens directly (tests/golden/train_golden.npz).
 Tolerances: layer level 2e-4 rel-L2 per gradient tensor (measured: 1e-7 .. 2e-6: fp32 kernels, different summation order
 than torch-CPU).  Whole step: losses 5e-4 relative; gradients 2e-2 rel-L2 per tensor.  The whole-step gradient bar is NOT a
 precision bar: the graph holds ~10^5 ReLU / LeakyReLU masks and L1 signs, and a forward difference of 1e-6 (fp32 rounding)
-flips a few of them, each flip a finite jump of the gradient.  Measured on the oracle itself (tools/debug_train.py,
+flips a few of them, each flip a finite jump of the gradient.  Measured on the oracle itself (tests/debug/debug_train.py,
 "cond" rows): perturbing the discriminator input by 1e-6 relative moves its own weight gradients by 4e-4 .. 9e-4 rel-L2 on
 the coarse scale -- exactly the differences our kernels show against it -- while every layer in isolation agrees to 1e-6.
 The cfg4 network (9 residual blocks on 2x16-pixel planes, BatchNorm over a batch of 2) is chaotic at random init: the same 1e-6
