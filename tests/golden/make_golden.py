@@ -152,6 +152,27 @@ def gen_resample():
     np.savez_compressed(os.path.join(HERE, "resample_golden.npz"), **out)
 
 
+OPTION_ARGV = [[], ["--netG", "local", "--ngf", "56", "--fp16", "--batchSize", "20", "--lr", "1.5e-4", "--upsample_type", "interpolate",
+                     "--downsample_type", "resconv", "--n_blocks_attn_g", "3", "--heads_g", "6", "--niter", "60", "--niter_decay", "60",
+                     "--num_D", "3", "--fit_residual", "--param_key_map", "model.1:2,model.4:5", "--gen_overlap", "256", "--phase", "test"]]
+
+
+def gen_options():
+    """The Namespace TrainOptions().parse() of the reference returns (options/base_options.py, train_options.py) for the default
+    command line of ref_opt() and for the train.sh one: the flag surface create_model(opt) consumes."""
+    import json
+
+    out = []
+    for extra in OPTION_ARGV:
+        opt = ref_opt(extra)
+        d = {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in vars(opt).items() if k != "checkpoints_dir"}
+        d = {k: (v if isinstance(v, (int, float, str, bool, list, dict, type(None))) else str(v)) for k, v in d.items()}
+        out.append(d)
+    with open(os.path.join(HERE, "options_golden.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print("options:", len(out[0]), "fields")
+
+
 def gen_normalize():
     """Audio2MDCT.normalize / denormalize of the reference itself (pix2pixHD_model.py:83-137), arcsinh and raw branches, abs_norm."""
     from models.pix2pixHD_model import Audio2MDCT
@@ -278,6 +299,8 @@ if __name__ == "__main__":
         gen_normalize()
     if "resample" in what:
         gen_resample()
+    if "options" in what:
+        gen_options()
     if "nets" in what or "train" in what or "infer" in what:
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 

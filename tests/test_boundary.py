@@ -130,3 +130,33 @@ def test_host_side_shape_functions(lib):
         for center in (0, 1):
             z = torch.stft(torch.zeros(T), 1024, 512, 1024, window=torch.ones(1024), center=bool(center), return_complex=True)
             assert lib.mdctgan_lsd_frame_count(T, 1024, 512, center) == z.shape[-1], (T, center)
+
+
+def test_option_surface_matches_reference():
+    """TrainOptions().parse() returns the same Namespace as the reference's (options/base_options.py:11-127, train_options.py:5-73) for
+    the default and the train.sh command lines (tests/golden/options_golden.json, generated from the reference); our only extra field
+    is `mdct_precision`."""
+    import json
+    import os
+    import sys
+
+    from conftest import GOLDEN
+    from mdctgan_b200.options.train_options import TrainOptions
+
+    sys.path.insert(0, GOLDEN)
+    from make_golden import OPTION_ARGV
+
+    gold = json.load(open(os.path.join(GOLDEN, "options_golden.json")))
+    base = ["--name", "g", "--checkpoints_dir", "/tmp/x", "--gpu_ids", "-1", "--lr_sampling_rate", "12000", "--sr_sampling_rate", "48000",
+            "--arcsinh_transform", "--abs_spectro", "--arcsinh_gain", "1000", "--center", "--norm_range", "-1", "1", "--abs_norm",
+            "--src_range", "-5", "5"]
+    for extra, ref in zip(OPTION_ARGV, gold):
+        ours = vars(TrainOptions().parse(save=False, args=base + list(extra)))
+        assert set(ours) - set(ref) == {"mdct_precision", "checkpoints_dir"}
+        assert set(ref) <= set(ours)
+        for k, v in ref.items():
+            o = ours[k]
+            o = list(o) if isinstance(o, (list, tuple)) else o
+            if isinstance(v, float) and v != v:
+                continue
+            assert o == v or str(o) == v, (k, o, v)
