@@ -359,11 +359,11 @@ int mdctgan_pack_weights_tiled(const void* descs_dev, const int64_t* tile_begin_
   if (n_desc <= 0 || total_tiles <= 0) return 0;
   if (max_taps <= 0 || max_taps > kPackMaxTaps) return mdctgan_set_error(-2, "pack_weights_tiled: %d taps (max %d)", max_taps, kPackMaxTaps);
   if (total_tiles > 0x7fffffffLL) return mdctgan_set_error(-2, "pack_weights_tiled: too many tiles");
-  const size_t smem = (size_t)max_taps * 32 * 33 * sizeof(float);
+  const size_t smem = (size_t)max_taps * kPackTapStride * sizeof(float);
   static size_t attr_smem = 0;
   if (smem > 48 * 1024 && smem > attr_smem) {
-    CKT(cudaFuncSetAttribute(pack_weights_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackMaxTaps * 32 * 33 * sizeof(float))));
-    attr_smem = kPackMaxTaps * 32 * 33 * sizeof(float);
+    CKT(cudaFuncSetAttribute(pack_weights_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackMaxTaps * kPackTapStride * sizeof(float))));
+    attr_smem = kPackMaxTaps * kPackTapStride * sizeof(float);
   }
   pack_weights_tiled_kernel<<<(unsigned)total_tiles, 256, smem, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, (const long long*)tile_begin_dev, n_desc);
   mdctgan_count_launch();

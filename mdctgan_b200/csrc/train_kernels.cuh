@@ -945,9 +945,10 @@ __global__ void __launch_bounds__(256) lsd_frames_kernel(const float* __restrict
 // shared memory and writes whole 128-byte rows of the image (hi and lo) -- every global access coalesced.
 // tile_begin = prefix sum of (N/32)*(Kch/32) over the descriptors.
 constexpr int kPackMaxTaps = 49;
+constexpr int kPackTapStride = 32 * 33 + 1;   // [tap][kc][33] with the tap stride odd: the 9 taps of one (n, kc) land in different banks
 __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc* __restrict__ descs, const long long* __restrict__ tile_begin,
                                                                  int n_desc) {
-  extern __shared__ float sm_pack[];            // [taps][32 (kc)][33]
+  extern __shared__ float sm_pack[];            // [taps][32 (kc)][33] (+1 per tap)
   const long long tile = blockIdx.x;
   int lo = 0, hi = n_desc - 1;
   while (lo < hi) {
@@ -968,7 +969,7 @@ __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc*
     const int inner = ab & 31, outer = ab >> 5;
     const int n = n_outer ? outer : inner, kc = n_outer ? inner : outer;
     const float v = __ldg(d.src + (long long)(kc0 + kc) * d.s_kch + (long long)(n0 + n) * d.s_n + tap);
-    sm_pack[(tap * 32 + kc) * 33 + n] = v;
+    sm_pack[tap * kPackTapStride + kc * 33 + n] = v;
   }
   __syncthreads();
   // rows of the image: (tap_dst, n) -> 32 consecutive k = tap_dst*Kch + kc0 .. +31; a warp writes one row (lane = kc)
@@ -976,7 +977,7 @@ __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc*
   for (int r = warp; r < taps * 32; r += 8) {
     const int tap_dst = r >> 5, n = r & 31;
     const int tap_src = d.flip ? taps - 1 - tap_dst : tap_dst;
-    const float v = sm_pack[(tap_src * 32 + lane) * 33 + n];
+    const float v = sm_pack[tap_src * kPackTapStride + lane * 33 + n];
     const float hi_v = __uint_as_float(__float_as_uint(v) & kTf32MaskPack);
     const float lo_v = __uint_as_float((__float_as_uint(v - hi_v) + 0x1000u) & kTf32MaskPack);
     const int k = tap_dst * d.Kch + kc0 + lane;
