@@ -18,10 +18,16 @@ four losses, generator sweep, discriminator sweep, all-reduce, both Adam steps. 
                four losses, every step, stream-synchronised
   roofline     the kernel with the largest share of the step, timed with CUDA events around every C-ABI launch of an
                eager pass inside bench.py
-  mdct         the transform half at HBM-roofline scale (8192 clips x 8192 samples): GSamp/s and achieved GB/s of the
-               fused forward / inverse kernels vs MEASURED_PEAKS.json (the metric's second clause)
-  cpu_baseline the reference's torch-CPU formulation of the same step (oracle/train_oracle.py: complex128 FFT
-               transform, F.conv2d / instance_norm graph, torch autograd, torch.optim.Adam; kind "port") on this box
+  strong       the same step at the FIXED global batch 32 (SURVEY.md 8d cfg4 "report both"): 32 / N segments per GPU
+  mdct         the transform half at HBM-roofline scale (8192 clips x 8192 samples per GPU, and the README shape
+               [64, 32512]): GSamp/s and achieved GB/s of the raw MDCT4 / IMDCT4 kernels and of the fused
+               (compress + abs-norm) ones vs MEASURED_PEAKS.json, for the flavour that passes the 2-ulp round-trip bar
+               ("mixed": fp64 butterflies on fp32 tensors; checked in-line) and for the all-fp32 one
+  longform     BASELINE configs[4]: generate_audio.py on a 60 s clip, its segments sharded over the N ranks
+  configs      cfg2 / cfg3 generator inference steps and the train.sh recipe train step (ngf 56, 128 frames, batch 20)
+  gpu_baseline the reference's own code (baseline/_ref, torch eager, cuDNN / cuFFT) on the SAME GPU: the kernel to beat
+  cpu_baseline the reference's own code on this box's host cores (kind "reference"; "port" = oracle/train_oracle.py
+               when baseline/_ref is absent)
 """
 import argparse
 import json
@@ -143,7 +149,7 @@ def make_hr_audio(batch, T, seed):
 def cpu_port_run(seconds_budget=None, steps=None, warmup=1, init=None):
     """The reference's torch-CPU formulation of the train step: oracle/train_oracle.py (make_stepper).  `init` = (state_dict G,
     state_dict D) to start from (the GPU arm passes its own initial weights, so the first CPU step doubles as a cross-check of the
-    four losses); the losses of the first step come back as "first_losses"."""
+    four losses); the losses of the first step come back as "first_losses".  Used only where baseline/_ref is absent."""
     import torch
 
     from mdctgan_b200.models import networks
@@ -157,6 +163,33 @@ def cpu_port_run(seconds_budget=None, steps=None, warmup=1, init=None):
         D = networks.define_D(3, 64, 3, "instance", False, 3, True)
         init = (G.state_dict(), D.state_dict())
     step = TO.make_stepper(init[0], init[1], make_lr_audio(BATCH, SEG, 42), make_hr_audio(BATCH, SEG, 42), **NET_KW)
+    return _time_cpu_steps(step, seconds_budget, steps, warmup, "port",
+                           "torch-CPU {t} threads, fp32 networks + complex128 transform, torch autograd + torch.optim.Adam "
+                           "(oracle/train_oracle.py: the reference's formulation restated; baseline/_ref absent)")
+
+
+def cpu_reference_run(seconds_budget=None, steps=None, warmup=1, init=None):
+    """The UNMODIFIED reference (baseline/_ref: create_model(TrainOptions().parse()) + the train.py:160-202 loop) on the host
+    cores, all threads.  `init`: the GPU arm's initial state_dicts, loaded into the reference's own modules (same keys), so the
+    first step doubles as a cross-check of the four losses against the real reference."""
+    import torch
+
+    from baseline import ref_runner as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, model = R.make_stepper(OPT_ARGS, make_lr_audio(BATCH, SEG, 42), make_hr_audio(BATCH, SEG, 42), device="cpu", seed=1234)
+    if init is not None:
+        model.netG.load_state_dict(init[0])
+        model.netD.load_state_dict(init[1])
+    return _time_cpu_steps(step, seconds_budget, steps, warmup, "reference",
+                           "torch-CPU {t} threads: the reference's own create_model / Pix2PixHDModel._forward / torch autograd / "
+                           "torch.optim.Adam (baseline/_ref, unmodified), fp32 networks + complex128 transform")
+
+
+def _time_cpu_steps(step, seconds_budget, steps, warmup, kind, how):
+    import torch
+
     first_losses = None
     for _ in range(max(warmup, 1)):
         out = step()
@@ -169,22 +202,29 @@ def cpu_port_run(seconds_budget=None, steps=None, warmup=1, init=None):
         times.append(time.perf_counter() - t0)
         if steps is not None and len(times) >= steps:
             break
-        if steps is None and (time.perf_counter() - t_start) >= seconds_budget:
+        if seconds_budget is not None and (time.perf_counter() - t_start) >= seconds_budget:
             break
     total = sum(times)
-    return {"value": BATCH * SEG / SR * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"the same train step (batch {BATCH} x {SEG} samples), {len(times)} steps, torch-CPU {torch.get_num_threads()} threads, fp32 "
-                      f"networks + complex128 transform, torch autograd + torch.optim.Adam (oracle/train_oracle.py)",
-            "ms_per_step": 1e3 * total / len(times), "first_losses": first_losses}
+    return {"value": BATCH * SEG / SR * len(times) / total, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": f"the same train step (batch {BATCH} x {SEG} samples), {len(times)} steps, " + how.format(t=torch.get_num_threads()),
+            "ms_per_step": 1e3 * total / len(times), "first_losses": first_losses, "steps": len(times)}
+
+
+def cpu_baseline_run(**kw):
+    from baseline import ref_runner as R
+
+    return cpu_reference_run(**kw) if R.available() else cpu_port_run(**kw)
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the step on this box's host cores (rank 0 only), same
+    warm-up count as the GPU arm, every step a full train-step on the arm's own batch; bounded to ~150 s of timed work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = min(args.steps, 30)
-    r = cpu_port_run(steps=steps, warmup=min(args.warmup, 2))
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    warm = max(args.warmup, 3)
+    r = cpu_baseline_run(steps=args.steps, seconds_budget=150.0, warmup=warm)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 networks / f64 transform (reference dtypes)", "data": "synthetic", "config": workload_config(1),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -193,53 +233,86 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- transform sub-benchmark
 def bench_mdct(dev, steps, hbm_peak):
-    """The transform half at roofline scale: 8192 clips x 8192 samples, fused forward (2-channel spectrogram) + fused inverse."""
+    """The transform half at roofline scale, per GPU: 8192 clips x 8192 samples (268 MB of audio, > L2) and the README shape
+    [64, 32512] (README.md:102-109).  For each arithmetic flavour: the raw MDCT4 / IMDCT4 kernels (fp32 coefficients) and the
+    fused ones (compress + abs-norm, 2-channel forward).  The 2-ulp round-trip bar of north_star is checked here on the raw pair
+    of the quoted flavour, over every clip."""
     import torch
 
     import mdctgan_b200
+    from mdctgan_b200.models.mdct import IMDCT4, MDCT4
     from mdctgan_b200.models.pix2pixHD_model import Audio2MDCT, default_audio_opt
+    from mdctgan_b200.util.util import kbdwin
 
-    B, T = 8192, 8192
-    F = T // HOP + 1
-    a2m = Audio2MDCT(default_audio_opt(arcsinh_gain=GAIN, src_range=SRC, norm_range=RNG, gpu_ids=[dev.index]), device=dev)
-    x = 0.1 * torch.randn(B, T, device=dev)
-    spec = torch.empty(B, 2, F, NBINS, device=dev)
+    EPS = 2.0 ** -23
     st = torch.cuda.current_stream(dev)
-    for _ in range(5):
-        a2m.to_spectro(x, channels=2, out=spec)
-        y = a2m.to_audio(spec[:, 0])
-    torch.cuda.synchronize(dev)
+    w = kbdwin(N_FFT)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    def entry(kernel, ms, nbytes, n):
+        return {"kernel": kernel, "avg_launch_ms": ms, "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "gsamp_per_s": n / (ms * 1e-3) / 1e9}
+
+    out = {"quoted_flavour": "mixed", "hbm_peak_gbs": hbm_peak, "shapes": {}}
     n0 = mdctgan_b200.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    for k in range(steps):
-        evs[k][0].record(st)
-        a2m.to_spectro(x, channels=2, out=spec)
-        evs[k][1].record(st)
-        y = a2m.to_audio(spec[:, 0])
-        evs[k][2].record(st)
-    torch.cuda.synchronize(dev)
-    total = evs[0][0].elapsed_time(evs[-1][2]) / steps
-    fwd = statistics.fmean(e[0].elapsed_time(e[1]) for e in evs)
-    inv = statistics.fmean(e[1].elapsed_time(e[2]) for e in evs)
-    rt = ((y.reshape(B, T)[:64].double() - x[:64].double()).norm() / x[:64].double().norm()).item()
-    assert rt < 1e-3, rt
-    fb, ib = B * (4 * T + 8 * F * NBINS), B * (4 * F * NBINS + 4 * T)
-    return {"workload": f"{B} clips x {T} samples, fused MDCT4+arcsinh/abs-norm (2-channel fp32 spectrogram) -> fused denorm+IMDCT4",
-            "gsamp_per_s_round_trip": B * T / (total * 1e-3) / 1e9, "ms_per_round_trip": total, "launches": mdctgan_b200.launch_count() - n0,
-            "forward": {"kernel": "mdct4_fwd_kernel<float,1>", "avg_launch_ms": fwd, "algorithmic_bytes_per_launch": fb,
-                        "achieved_gbs": fb / (fwd * 1e-3) / 1e9, "frac_of_hbm_peak": fb / (fwd * 1e-3) / 1e9 / hbm_peak,
-                        "gsamp_per_s": B * T / (fwd * 1e-3) / 1e9},
-            "inverse": {"kernel": "imdct4_inv_kernel<float,float,float,1>", "avg_launch_ms": inv, "algorithmic_bytes_per_launch": ib,
-                        "achieved_gbs": ib / (inv * 1e-3) / 1e9, "frac_of_hbm_peak": ib / (inv * 1e-3) / 1e9 / hbm_peak,
-                        "gsamp_per_s": B * T / (inv * 1e-3) / 1e9},
-            "round_trip_rel_l2": rt, "hbm_peak_gbs": hbm_peak}
+    for (B, T) in ((8192, 8192), (64, 32512)):
+        F = T // HOP + 1
+        torch.manual_seed(7)
+        x = 0.1 * torch.randn(B, T, device=dev)
+        spec2 = torch.empty(B, 2, F, NBINS, device=dev)
+        n = B * T
+        shape = {}
+        for prec in ("mixed", "fp32"):
+            fwd, inv = MDCT4(N_FFT, HOP, N_FFT, w, device=dev, precision=prec), IMDCT4(N_FFT, HOP, N_FFT, w, device=dev, precision=prec)
+            a2m = Audio2MDCT(default_audio_opt(arcsinh_gain=GAIN, src_range=SRC, norm_range=RNG, gpu_ids=[dev.index]), device=dev, precision=prec)
+            spec = fwd(x)[0]
+            y = inv(spec)[0].reshape(B, -1)
+            err = ((y.double() - x[:, :y.shape[1]].double()).abs().amax(dim=1) / x.abs().amax(dim=1).double()).max().item() / EPS
+            if prec == "mixed":
+                assert err <= 2.0, f"MDCT4 -> IMDCT4 round trip {err} eps*peak breaks the 2-ulp bar"
+            core = "double" if prec == "mixed" else "float"
+            t_f, t_i = timed(lambda: fwd(x)), timed(lambda: inv(spec))
+            t_ff = timed(lambda: a2m.to_spectro(x, channels=2, out=spec2))
+            s1 = spec2[:, 0].contiguous()
+            t_fi = timed(lambda: a2m.to_audio(s1))
+            ya = a2m.to_audio(s1).reshape(B, -1)
+            rt = ((ya[:64].double() - x[:64, :ya.shape[1]].double()).norm() / x[:64].double().norm()).item()
+            assert rt < 1e-3, rt
+            shape[prec] = {
+                "round_trip_max_abs_err_in_eps_peak": err, "passes_2ulp": bool(err <= 2.0),
+                "raw_forward": entry(f"mdct4_fwd_kernel<{core},0,float>", t_f, 4 * n + 4 * B * F * NBINS, n),
+                "raw_inverse": entry(f"imdct4_inv_kernel<{core},float,float,0>", t_i, 4 * B * F * NBINS + 4 * n, n),
+                "raw_round_trip_gsamp_per_s": n / ((t_f + t_i) * 1e-3) / 1e9,
+                "fused_forward_2ch": entry(f"mdct4_fwd_kernel<{core},1,float>", t_ff, 4 * n + 8 * B * F * NBINS, n),
+                "fused_inverse": entry(f"imdct4_inv_kernel<{core},float,float,1>", t_fi, 4 * B * F * NBINS + 4 * n, n),
+                "fused_round_trip_rel_l2": rt}
+            del spec, y, s1, ya
+        out["shapes"][f"{B}x{T}"] = shape
+        del x, spec2
+    out["launches"] = mdctgan_b200.launch_count() - n0
+    q = out["shapes"]["8192x8192"]["mixed"]
+    out.update({"workload": "8192 clips x 8192 samples per GPU; raw = MDCT4 / IMDCT4 on fp32 tensors, fused = + arcsinh/abs-norm (2-channel forward)",
+                "gsamp_per_s_round_trip": q["raw_round_trip_gsamp_per_s"], "forward": q["raw_forward"], "inverse": q["raw_inverse"]})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- long-form sub-benchmark
-def bench_longform(dev, reps=3):
+def bench_longform(dev, rank=0, world=1, reps=3):
     """BASELINE configs[4]: generate_audio.py on a 60 s clip, 16 -> 48 kHz, 32512-sample segments (128 frames), gen_overlap 256,
     LocalEnhancer + 2 attention layers: pinned host clip -> H2D -> on-device segmentation -> batched inference (CUDA graphs) ->
-    on-device overlap-add -> D2H.  Real-time factor = clip seconds / wall seconds (host clock around synchronised calls)."""
+    on-device overlap-add -> D2H.  With N ranks every rank takes a contiguous run of the segments (parallel.shard_range, no
+    collective; the shard outputs overlap by gen_overlap samples and are summed by whoever assembles them).  Returns this rank's
+    seconds per clip; the caller takes the max over ranks."""
     import torch
 
     from mdctgan_b200.longform import LongFormGenerator
@@ -257,19 +330,184 @@ def bench_longform(dev, reps=3):
     model.eval()
     clip = make_lr_audio(1, secs * SR, 5).pin_memory()
     gen = LongFormGenerator(model, batch_size=16)
-    out = gen(clip.to(dev, non_blocking=True), seg, ov)            # captures the two batch shapes
+    out, _ = gen.generate_shard(clip.to(dev, non_blocking=True), seg, ov, rank, world)          # captures the batch shapes
     out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(reps):
-        out = gen(clip.to(dev, non_blocking=True), seg, ov)
+        out, _ = gen.generate_shard(clip.to(dev, non_blocking=True), seg, ov, rank, world)
         out_h.copy_(out, non_blocking=True)
         torch.cuda.synchronize(dev)
     dt = (time.perf_counter() - t0) / reps
+    n_seg = gen.last_segments
     del gen, model
-    return {"workload": f"{secs} s clip @48 kHz -> {int((secs * SR + seg - 1) // seg)} x {seg}-sample segments, gen_overlap {ov}, LocalEnhancer+2 attn at 128 frames, "
-                        "batches of 16, fp32", "seconds_per_clip": dt, "real_time_factor": secs / dt, "audio_sec_per_sec": out.shape[-1] / SR / dt,
-            "output_samples": int(out.shape[-1]), "h2d_bytes": clip.numel() * 4, "d2h_bytes": out.numel() * out.element_size()}
+    return {"workload": f"{secs} s clip @48 kHz -> {n_seg[1]} x {seg}-sample segments, gen_overlap {ov}, LocalEnhancer+2 attn at 128 frames, "
+                        f"batches of 16, fp32; {world} rank(s), contiguous segment runs, no collective", "seconds_per_clip": dt,
+            "segments_this_rank": n_seg[0], "clip_seconds": secs, "h2d_bytes": clip.numel() * 4, "d2h_bytes": out.numel() * out.element_size()}
+
+
+# ---------------------------------------------------------------------------------------------- other BASELINE configs
+def _build_model(extra, dev, seed=1234):
+    import torch
+
+    from mdctgan_b200.models.models import create_model
+    from mdctgan_b200.options.train_options import TrainOptions
+
+    args = [a for a in OPT_ARGS]
+    flags = []
+    for k, v in extra:
+        if v is None:
+            flags.append(k)
+        elif k in args:
+            args[args.index(k) + 1] = v
+        else:
+            flags += [k, v]
+    opt = TrainOptions().parse(save=False, args=args + flags + ["--gpu_ids", str(dev.index)])
+    opt.checkpoints_dir = "/tmp/mdctgan_bench"
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    return create_model(opt)
+
+
+def _graph_time(replay, steps, dev):
+    import torch
+
+    st = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        replay()
+    e1.record(st)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_configs(dev, steps, bf16_peak):
+    """The BASELINE configs that are not the headline: cfg2 (GlobalGenerator inference, batch 4), cfg3 (LocalEnhancer + 2 attention
+    layers inference, batch 8; the bf16 engine is not built: run by the fp32-class 3xTF32 engine and by the single-pass TF32 one)
+    and the train step of the reference's shipped recipe train.sh (ngf 56, resconv / interpolate, 3 attention layers of 6 x 128,
+    128 frames, batch 20).  Each: a CUDA-graph replay of the step, CUDA events; tensor-roofline fraction = algorithmic conv+matmul
+    FLOPs of the step (probed with torch's flop counter) / time / measured dense bf16 peak."""
+    import torch
+
+    from mdctgan_b200 import nn_ops
+    from mdctgan_b200.runtime import GraphedInference, GraphedTrainStep
+
+    res = {}
+
+    def infer_line(name, extra, batch, T, gflop_per_sample, engines):
+        model = _build_model(extra, dev)
+        model.eval()
+        lr = make_lr_audio(batch, T, 3).to(dev)
+        for eng in engines:
+            prev = nn_ops.CONV_ENGINE
+            nn_ops.CONV_ENGINE = eng
+            try:
+                gi = GraphedInference(model, batch, T, warmup=2)
+                gi.static_in.copy_(lr)
+                ms = _graph_time(gi.replay, steps, dev)
+            finally:
+                nn_ops.CONV_ENGINE = prev
+            fl = gflop_per_sample * 1e9 * batch
+            res[f"{name}[{eng}]"] = {"step": "model.inference: fused MDCT -> generator -> fused IMDCT, CUDA-graph replay", "batch": batch, "samples": T,
+                                     "engine": "3xTF32 (fp32-class)" if eng == "umma" else "single-pass TF32", "ms_per_step": ms,
+                                     "audio_sec_per_sec": batch * T / SR / (ms * 1e-3), "algorithmic_gflop_per_step": fl / 1e9,
+                                     "tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / bf16_peak}
+            del gi
+        del model
+
+    infer_line("cfg2_global_generator_fwd_b4", [("--netG", "global"), ("--n_blocks_attn_g", "0")], 4, SEG, 3.25, ("umma",))
+    infer_line("cfg3_local_enhancer_attn_fwd_b8", [], 8, SEG, 4.37, ("umma", "tf32"))
+    # train.sh: the reference's shipped recipe (train.sh:3-17)
+    try:
+        extra = [("--ngf", "56"), ("--n_blocks_global", "4"), ("--n_blocks_attn_g", "3"), ("--heads_g", "6"), ("--dim_head_g", "128"),
+                 ("--segment_length", "32512"), ("--bins", "128"), ("--lr_sampling_rate", "16000"), ("--upsample_type", "interpolate"),
+                 ("--downsample_type", "resconv"), ("--lr", "0.00015")]
+        model = _build_model(extra, dev)
+        model.train()
+        b, T = 20, 32512
+        gts = GraphedTrainStep(model, b, T, 1, None, warmup=2)
+        gts.lr_in.copy_(make_lr_audio(b, T, 11).to(dev))
+        gts.hr_in.copy_(make_hr_audio(b, T, 11).to(dev))
+        ms = _graph_time(gts.replay, max(3, min(steps, 10)), dev)
+        fl = (3 * 103.5 + 9 * 5.20) * 1e9 * b          # 3 G_fwd + 9 D_fwd per sample (SURVEY.md 8d), F = 128
+        res["train_sh_recipe_step_b20"] = {"step": "train.sh recipe: ngf 56, resconv/interpolate, 3 attn x (6 heads x 128), 128 frames x 256 bins, batch 20, "
+                                                   "num_D 3, full GAN train step, CUDA-graph replay", "batch": b, "samples": T, "ms_per_step": ms,
+                                           "audio_sec_per_sec": b * T / SR / (ms * 1e-3), "algorithmic_gflop_per_step": fl / 1e9,
+                                           "tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / bf16_peak,
+                                           "losses": [float(v) for v in gts.losses.cpu()]}
+        del gts, model
+    except Exception as e:  # noqa: BLE001
+        res["train_sh_recipe_step_b20"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- the GPU kernel to beat
+def bench_gpu_baseline(dev, sd0, lr, hr, steps):
+    """The same train step by the reference's OWN code on this GPU ("the bar on B200 is torch-eager"):
+      reference_eager_*   baseline/_ref create_model(opt) with --gpu_ids 0 + the verbatim train.py:160-202 loop, torch eager,
+                          cudnn.benchmark = True like train.py:26, weights = the GPU arm's initial weights; with torch's default
+                          TF32 policy (cuDNN convolutions TF32, matmul fp32) and with TF32 off (true fp32)
+      port_cuda_graph_*   oracle/train_oracle.py (the same torch ops, functional) captured whole in ONE torch CUDA graph with
+                          capturable Adam: the reference's kernels without its Python / launch overhead and without its per-step
+                          .cpu() snapshots -- the strongest torch baseline available here
+    CUDA events around `steps` iterations after 5 warm-up iterations (cuDNN autotuning included in the warm-up)."""
+    import torch
+
+    from baseline import ref_runner as R
+    from oracle import train_oracle as TO
+
+    out = {}
+    st = torch.cuda.current_stream(dev)
+    audio_s = BATCH * SEG / SR
+
+    def time_steps(step, n, warm=5):
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(st)
+        for _ in range(n):
+            step()
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        wall = (time.perf_counter() - t0) / n * 1e3
+        return max(e0.elapsed_time(e1) / n, wall)
+
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, tf32 in (("tf32_default", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            if R.available():
+                try:
+                    step, model = R.make_stepper(OPT_ARGS, lr.cpu(), hr.cpu(), device=dev, seed=1234)
+                    model.netG.load_state_dict(sd0[0])
+                    model.netD.load_state_dict(sd0[1])
+                    first = step()
+                    ms = time_steps(lambda: step(False), steps)
+                    out[f"reference_eager_{name}"] = {"ms_per_step": ms, "audio_sec_per_sec": audio_s / (ms * 1e-3), "first_losses": first,
+                                                      "what": "baseline/_ref (unmodified reference) on cuda, torch eager, train.py:160-202 verbatim"}
+                    del step, model
+                except Exception as e:  # noqa: BLE001
+                    out[f"reference_eager_{name}"] = {"error": repr(e)[:300]}
+            try:
+                replay = TO.make_stepper(sd0[0], sd0[1], lr, hr, device=dev, cuda_graph=True, **NET_KW)
+                ms = time_steps(replay, steps, warm=3)
+                out[f"port_cuda_graph_{name}"] = {"ms_per_step": ms, "audio_sec_per_sec": audio_s / (ms * 1e-3),
+                                                  "what": "oracle/train_oracle.py on cuda, whole step in one torch CUDA graph (capturable Adam)"}
+                del replay
+            except Exception as e:  # noqa: BLE001
+                out[f"port_cuda_graph_{name}"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- per-launch profile
@@ -477,18 +715,48 @@ def run_ours(args):
     api_ms = 1e3 * (time.perf_counter() - t0) / n_api
     clocks = sampler.stop()
 
-    mdct = bench_mdct(dev, 50, hbm_peak) if rank == 0 else None
+    # ---- strong scaling (SURVEY.md 8d cfg4 "report both"): the FIXED global batch 32, 32 / N segments per GPU
+    strong = None
+    G_BATCH = 32
+    if G_BATCH % world == 0 and not args.no_strong:
+        bs = G_BATCH // world
+        if bs == BATCH:
+            strong = {"global_batch": G_BATCH, "batch_per_gpu": bs, "ms_per_step": step_ms, "note": "same shape as the weak leg at this N"}
+        else:
+            del gts
+            torch.cuda.empty_cache()
+            lr_s, hr_s = make_lr_audio(bs, SEG, 142 + rank).to(dev), make_hr_audio(bs, SEG, 142 + rank).to(dev)
+            gs = GraphedTrainStep(model, bs, SEG, world, all_reduce, warmup=2)
+            gs.lr_in.copy_(lr_s)
+            gs.hr_in.copy_(hr_s)
+            for _ in range(3):
+                gs.replay()
+            n_s = max(5, min(args.steps, 30))
+            barrier()
+            e0.record(st)
+            for _ in range(n_s):
+                gs.replay()
+            e1.record(st)
+            barrier()
+            strong = {"global_batch": G_BATCH, "batch_per_gpu": bs, "ms_per_step": e0.elapsed_time(e1) / n_s, "steps": n_s}
+            del gs
+            torch.cuda.empty_cache()
+
+    # ---- transform and long-form sub-benchmarks: every rank runs its shard (no collective), max over ranks below
+    mdct = bench_mdct(dev, 30, hbm_peak)
     longform = None
-    if rank == 0 and world == 1 and not args.no_longform:
+    if not args.no_longform:
         try:
-            longform = bench_longform(dev)
+            longform = bench_longform(dev, rank, world)
         except Exception as e:  # noqa: BLE001  (a sub-benchmark must not take the headline line down)
             longform = {"error": repr(e)[:300]}
-
-    vals = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
+    lf_s = longform["seconds_per_clip"] if (longform and "seconds_per_clip" in longform) else 0.0
+    sh = mdct["shapes"]["8192x8192"]["mixed"]
+    vals = torch.tensor([step_ms, e2e_ms, strong["ms_per_step"] if strong else 0.0, lf_s, sh["raw_forward"]["avg_launch_ms"],
+                         sh["raw_inverse"]["avg_launch_ms"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms = vals.tolist()
+    step_ms, e2e_ms, strong_ms, lf_s, mf_ms, mi_ms = vals.tolist()
     if world > 1:
         # No collective follows.  Leave without the NCCL / CUDA-graph teardown: destroying a communicator that a live captured
         # graph still references can block forever (seen on the 2-GPU run), and the driver waits for every rank to exit.
@@ -500,7 +768,27 @@ def run_ours(args):
 
     if rank == 0:
         audio_s = world * BATCH * SEG / SR
-        cpu = cpu_port_run(seconds_budget=args.cpu_seconds, warmup=1, init=sd0)
+        if strong:
+            strong.update({"ms_per_step": strong_ms, "value": G_BATCH * SEG / SR / (strong_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                           "n_gpus": world})
+        if longform and "seconds_per_clip" in longform:
+            longform.update({"seconds_per_clip": lf_s, "real_time_factor": longform["clip_seconds"] / lf_s,
+                             "audio_sec_per_sec": longform["clip_seconds"] / lf_s, "n_gpus": world})
+        nsamp = 8192 * 8192
+        mdct["aggregate"] = {"n_gpus": world, "scaling": "weak (8192 x 8192 samples per GPU, no collective)",
+                             "raw_forward_gsamp_per_s": world * nsamp / (mf_ms * 1e-3) / 1e9, "raw_inverse_gsamp_per_s": world * nsamp / (mi_ms * 1e-3) / 1e9,
+                             "raw_round_trip_gsamp_per_s": world * nsamp / ((mf_ms + mi_ms) * 1e-3) / 1e9}
+        configs = gpu_base = None
+        if world == 1 and not args.no_extras:
+            try:
+                configs = bench_configs(dev, max(5, min(args.steps, 30)), bf16_peak)
+            except Exception as e:  # noqa: BLE001
+                configs = {"error": repr(e)[:300]}
+            try:
+                gpu_base = bench_gpu_baseline(dev, sd0, lr, hr, max(5, min(args.steps, 20)))
+            except Exception as e:  # noqa: BLE001
+                gpu_base = {"error": repr(e)[:300]}
+        cpu = cpu_baseline_run(seconds_budget=args.cpu_seconds, warmup=1, init=sd0)
         # world 1: the GPU's first step and the CPU baseline's first step saw the same weights and the same batch
         err = max(abs(a - b) / abs(b) for a, b in zip(first, cpu["first_losses"])) if world == 1 else None
         if err is not None:
@@ -525,17 +813,25 @@ def run_ours(args):
         kernel_table = {k: {"launches_per_step": v[0] // 3, "ms_per_step": round(v[1] / 3, 4), "share": round(v[1] / tot_ms, 4),
                             **({"tflops": round(v[2] / (v[1] / v[0] * 1e-3) / 1e12, 2)} if v[2] else {})}
                         for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:60]}
+        step_flops = 28.9e9 * BATCH       # 3 G_fwd + 9 D_fwd per sample at F = 32
         line = {
             "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "roofline": roof,
+            "step_roofline": {"algorithmic_gflop_per_gpu_step": step_flops / 1e9, "tflops": step_flops / (step_ms * 1e-3) / 1e12,
+                              "frac_of_bf16_peak": step_flops / (step_ms * 1e-3) / 1e12 / bf16_peak,
+                              "hbm_floor_ms": 3.8e9 / (hbm_peak * 1e9) * 1e3, "note": "whole step: conv+matmul flops / step time; HBM floor = "
+                              "weights + gradients + Adam state streamed once (DESIGN.md 5)"},
             "kernel_table": kernel_table,
             "entry_point_table": {k: {"launches_per_step": v[0], "ms_per_step": round(v[1], 4)} for k, v in
                                   sorted(by_entry.items(), key=lambda kv: -kv[1][1])},
             "eager_sum_of_kernels_ms": tot_ms / 3,
+            "strong": strong,
             "mdct": mdct,
             "longform": longform,
+            "configs": configs,
+            "gpu_baseline": gpu_base,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SEG * 4, "d2h_bytes_per_step": 16,
                     "ms_per_step": e2e_ms, "api": "runtime.GraphedTrainStep(model)(pinned lr_audio, pinned hr_audio) -> 4 losses copied to "
@@ -561,6 +857,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-longform", dest="no_longform", action="store_true")
+    ap.add_argument("--no-strong", dest="no_strong", action="store_true")
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the cfg2 / cfg3 / train.sh lines and the gpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

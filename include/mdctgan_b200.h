@@ -27,6 +27,8 @@ extern "C" {
 /* arithmetic flavour of the transform core */
 #define MDCTGAN_F32 0 /* fp32 butterflies, fp32 I/O  (fast path; ~1.2e-7 rel-L2 vs the reference)          */
 #define MDCTGAN_F64 1 /* fp64 butterflies, fp64 coefficient / audio I/O (reference dtypes, mdct.py:387-390) */
+#define MDCTGAN_MIXED 2 /* fp64 butterflies on fp32 I/O: the fp32 tensors of F32 with the accuracy of the fp64 core
+                         * (MDCT4 -> IMDCT4 round trip 0.3 eps*peak, inside the 2-ulp bar; F32 is at 2-2.8) */
 
 /* spectrogram encodings of Audio2MDCT.normalize (pix2pixHD_model.py:83-125) handled in-kernel */
 #define MDCTGAN_MODE_RAW 0     /* --raw_mdct         :102-103 */
@@ -228,6 +230,12 @@ int mdctgan_segment_gather(const float* audio_dev, int64_t L, float* out_dev, in
 /* generate_audio.py:40-53: halve the first / last ov samples of each segment, fold(stride seg - ov), crop ov at both ends;
  * [n_seg, seg] -> [(n_seg-1)*(seg-ov) + seg - 2*ov]; ov = 0 is the plain concatenation.  precision: MDCTGAN_F32 / _F64 (in and out). */
 int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream);
+/* The same fold over a contiguous RUN of segments (multi-GPU long-form generation: every rank folds its own run):
+ * crops crop_begin / crop_end (each in [0, ov]) samples instead of ov -- 0 at an interior shard edge, where the ov half-weighted
+ * samples that overlap the neighbouring run are kept and summed by whoever assembles the shards.
+ * [n_seg, seg] -> [(n_seg-1)*(seg-ov) + seg - crop_begin - crop_end] */
+int mdctgan_segment_ola_part(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int crop_begin, int crop_end,
+                             int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Evaluation metrics (util/util.py:132-177 compute_matrics; callers train.py:116-117, generate_audio.py:59-60).

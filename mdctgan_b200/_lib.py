@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libmdctgan_b200.so"
 _lib = None
 
-F32, F64 = 0, 1
+F32, F64, MIXED = 0, 1, 2     # MIXED: fp64 butterflies on fp32 tensors
 MODE_RAW, MODE_ARCSINH = 0, 1
 
 

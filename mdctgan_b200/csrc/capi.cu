@@ -65,8 +65,8 @@ struct mdctgan_plan {
   float* window = nullptr;       // the reference's synthesis window (= analysis window), fp64 flavour
   float* window_syn = nullptr;   // TDAC-exact synthesis window of the fp32 flavour (mdct_plan_tables.h)
   // occupancy-derived persistent grid sizes, indexed by kernel variant and frames-per-tile (ft = 4, 8, 12, 16)
-  int grid_fwd[4][4] = {};   // [f32 raw, f32 fused, f64 raw, f64 fused][ft/4 - 1]
-  int grid_inv[4][4] = {};   // [f32 raw, f64 raw, f32 fused, f64 fused][ft/4 - 1]
+  int grid_fwd[6][4] = {};   // [f32 raw, f32 fused, f64 raw, f64 fused, mixed raw, mixed fused][ft/4 - 1]
+  int grid_inv[6][4] = {};   // [f32 raw, f64 raw, f32 fused, f64 fused, mixed raw, mixed fused][ft/4 - 1]
   // host-API scratch
   cudaStream_t streams[kNumStreams] = {nullptr, nullptr, nullptr};
   void* scratch_in[kNumStreams] = {nullptr, nullptr, nullptr};
@@ -126,7 +126,7 @@ int check_norm(const mdctgan_norm* n) {
   return 0;
 }
 
-template <typename R, int EPI>
+template <typename R, int EPI, typename OutT, bool EXACT>
 int launch_fwd(const mdctgan_plan* pl, FwdParams& p, const int* grid_cap, cudaStream_t st) {
   p.ft = pick_ft(p.F, 0);
   p.tiles_per_clip = (p.F + p.ft - 1) / p.ft;
@@ -135,13 +135,13 @@ int launch_fwd(const mdctgan_plan* pl, FwdParams& p, const int* grid_cap, cudaSt
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
   p.tabW = pl->tabW;
   const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap[p.ft / 4 - 1]);
-  mdct4_fwd_kernel<R, EPI><<<grid, 8 * p.ft, fwd_smem_bytes<R>(p.ft), st>>>(p);
+  mdct4_fwd_kernel<R, EPI, OutT, EXACT><<<grid, 8 * p.ft, fwd_smem_bytes<R>(p.ft), st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return 0;
 }
 
-template <typename R, typename S, typename OutT, int PRO>
+template <typename R, typename S, typename OutT, int PRO, bool EXACT>
 int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaStream_t st) {
   if (p.B == 0 || p.F < 2 || p.out_len == 0) return 0;
   const int64_t nout = (p.out_len + kHop - 1) / kHop;   // output blocks actually needed (out_length crop)
@@ -149,9 +149,9 @@ int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaSt
   p.tiles_per_clip = (nout + p.ft - 2) / (p.ft - 1);
   p.ntiles = p.B * p.tiles_per_clip;
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
-  p.window = std::is_same<R, float>::value ? pl->window_syn : pl->window;
+  p.window = EXACT ? pl->window : pl->window_syn;   // only the bit-faithful flavour keeps the reference's synthesis window
   const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap[p.ft / 4 - 1]);
-  imdct4_inv_kernel<R, S, OutT, PRO><<<grid, 8 * p.ft, inv_smem_bytes<R, S>(p.ft), st>>>(p);
+  imdct4_inv_kernel<R, S, OutT, PRO, EXACT><<<grid, 8 * p.ft, inv_smem_bytes<R, S>(p.ft), st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return 0;
@@ -160,7 +160,8 @@ int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaSt
 int check_common(const mdctgan_plan* plan, int64_t B, int64_t F, int precision) {
   if (!plan) return fail(-1, "plan is NULL");
   if (B < 0 || F < 0) return fail(-1, "negative size (B=%lld, F=%lld)", (long long)B, (long long)F);
-  if (precision != MDCTGAN_F32 && precision != MDCTGAN_F64) return fail(-1, "precision must be MDCTGAN_F32 or MDCTGAN_F64");
+  if (precision != MDCTGAN_F32 && precision != MDCTGAN_F64 && precision != MDCTGAN_MIXED)
+    return fail(-1, "precision must be MDCTGAN_F32, MDCTGAN_F64 or MDCTGAN_MIXED");
   return 0;
 }
 
@@ -209,14 +210,18 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   auto is32 = [](int ft) { return inv_smem_bytes<float, float>(ft); };
   auto is64 = [](int ft) { return inv_smem_bytes<double, double>(ft); };
   auto is64f = [](int ft) { return inv_smem_bytes<double, float>(ft); };
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0>, fs32, pl->num_sms, pl->grid_fwd[0]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1>, fs32, pl->num_sms, pl->grid_fwd[1]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0>, fs64, pl->num_sms, pl->grid_fwd[2]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1>, fs64, pl->num_sms, pl->grid_fwd[3]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0>, is32, pl->num_sms, pl->grid_inv[0]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0>, is64, pl->num_sms, pl->grid_inv[1]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1>, is32, pl->num_sms, pl->grid_inv[2]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1>, is64f, pl->num_sms, pl->grid_inv[3]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0, float, false>, fs32, pl->num_sms, pl->grid_fwd[0]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1, float, false>, fs32, pl->num_sms, pl->grid_fwd[1]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, double, true>, fs64, pl->num_sms, pl->grid_fwd[2]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, true>, fs64, pl->num_sms, pl->grid_fwd[3]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, float, false>, fs64, pl->num_sms, pl->grid_fwd[4]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, false>, fs64, pl->num_sms, pl->grid_fwd[5]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0, false>, is32, pl->num_sms, pl->grid_inv[0]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4]))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5]))) return rc;
   *out = pl;
   return 0;
 }
@@ -245,8 +250,9 @@ int mdctgan_mdct4_forward(const mdctgan_plan* plan, const float* audio, int64_t 
   p.audio = audio; p.audio_stride = audio_stride; p.T = T; p.B = B; p.F = F;
   p.out = spec; p.out_clip_stride = spec_clip_stride; p.out_chan_stride = 0; p.channels = 1;
   p.np = NormParams{0, 1.f, 1.f, 0.f, 0.f};
-  if (precision == MDCTGAN_F32) return launch_fwd<float, 0>(plan, p, plan->grid_fwd[0], (cudaStream_t)stream);
-  return launch_fwd<double, 0>(plan, p, plan->grid_fwd[2], (cudaStream_t)stream);
+  if (precision == MDCTGAN_F32) return launch_fwd<float, 0, float, false>(plan, p, plan->grid_fwd[0], (cudaStream_t)stream);
+  if (precision == MDCTGAN_MIXED) return launch_fwd<double, 0, float, false>(plan, p, plan->grid_fwd[4], (cudaStream_t)stream);
+  return launch_fwd<double, 0, double, true>(plan, p, plan->grid_fwd[2], (cudaStream_t)stream);
 }
 
 int mdctgan_audio2mdct_forward(const mdctgan_plan* plan, const float* audio, int64_t B, int64_t T, int64_t audio_stride,
@@ -265,8 +271,9 @@ int mdctgan_audio2mdct_forward(const mdctgan_plan* plan, const float* audio, int
   p.audio = audio; p.audio_stride = audio_stride; p.T = T; p.B = B; p.F = F;
   p.out = out; p.out_clip_stride = out_clip_stride; p.out_chan_stride = out_chan_stride; p.channels = channels;
   p.np = make_norm(norm, nullptr, nullptr);
-  if (precision == MDCTGAN_F32) return launch_fwd<float, 1>(plan, p, plan->grid_fwd[1], (cudaStream_t)stream);
-  return launch_fwd<double, 1>(plan, p, plan->grid_fwd[3], (cudaStream_t)stream);
+  if (precision == MDCTGAN_F32) return launch_fwd<float, 1, float, false>(plan, p, plan->grid_fwd[1], (cudaStream_t)stream);
+  if (precision == MDCTGAN_MIXED) return launch_fwd<double, 1, float, false>(plan, p, plan->grid_fwd[5], (cudaStream_t)stream);
+  return launch_fwd<double, 1, float, true>(plan, p, plan->grid_fwd[3], (cudaStream_t)stream);
 }
 
 int mdctgan_imdct4_inverse(const mdctgan_plan* plan, const void* spec, int64_t B, int64_t F, int64_t spec_clip_stride,
@@ -280,8 +287,9 @@ int mdctgan_imdct4_inverse(const mdctgan_plan* plan, const void* spec, int64_t B
   p.spec = spec; p.spec_clip_stride = spec_clip_stride; p.B = B; p.F = F;
   p.out = audio; p.out_clip_stride = audio_stride; p.out_len = out_len;
   p.np = NormParams{0, 1.f, 1.f, 0.f, 0.f}; p.inv_a = 1.f; p.inv_b = 0.f;
-  if (precision == MDCTGAN_F32) return launch_inv<float, float, float, 0>(plan, p, plan->grid_inv[0], (cudaStream_t)stream);
-  return launch_inv<double, double, double, 0>(plan, p, plan->grid_inv[1], (cudaStream_t)stream);
+  if (precision == MDCTGAN_F32) return launch_inv<float, float, float, 0, false>(plan, p, plan->grid_inv[0], (cudaStream_t)stream);
+  if (precision == MDCTGAN_MIXED) return launch_inv<double, float, float, 0, false>(plan, p, plan->grid_inv[4], (cudaStream_t)stream);
+  return launch_inv<double, double, double, 0, true>(plan, p, plan->grid_inv[1], (cudaStream_t)stream);
 }
 
 int mdctgan_mdct2audio_inverse(const mdctgan_plan* plan, const float* spectro, int64_t B, int64_t F, int64_t spec_clip_stride,
@@ -297,8 +305,9 @@ int mdctgan_mdct2audio_inverse(const mdctgan_plan* plan, const float* spectro, i
   p.spec = spectro; p.spec_clip_stride = spec_clip_stride; p.B = B; p.F = F;
   p.out = audio; p.out_clip_stride = audio_stride; p.out_len = out_len;
   p.np = make_norm(norm, &p.inv_a, &p.inv_b);
-  if (precision == MDCTGAN_F32) return launch_inv<float, float, float, 1>(plan, p, plan->grid_inv[2], (cudaStream_t)stream);
-  return launch_inv<double, float, double, 1>(plan, p, plan->grid_inv[3], (cudaStream_t)stream);
+  if (precision == MDCTGAN_F32) return launch_inv<float, float, float, 1, false>(plan, p, plan->grid_inv[2], (cudaStream_t)stream);
+  if (precision == MDCTGAN_MIXED) return launch_inv<double, float, float, 1, false>(plan, p, plan->grid_inv[5], (cudaStream_t)stream);
+  return launch_inv<double, float, double, 1, true>(plan, p, plan->grid_inv[3], (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -359,7 +368,7 @@ extern "C" {
 
 int mdctgan_mdct4_forward_host(mdctgan_plan* plan, const float* audio, int64_t B, int64_t T, int64_t F, void* spec, int precision) {
   if (int rc = check_common(plan, B, F, precision)) return rc;
-  const size_t esz = precision == MDCTGAN_F32 ? 4 : 8;
+  const size_t esz = precision == MDCTGAN_F64 ? 8 : 4;
   return stream_clips(plan, audio, (size_t)T * 4, spec, (size_t)F * kBins * esz, B,
                       [&](void* din, void* dout, int64_t n, cudaStream_t st) {
                         return mdctgan_mdct4_forward(plan, (const float*)din, n, T, T, F, dout, F * kBins, precision, st);
@@ -379,7 +388,7 @@ int mdctgan_audio2mdct_forward_host(mdctgan_plan* plan, const float* audio, int6
 
 int mdctgan_imdct4_inverse_host(mdctgan_plan* plan, const void* spec, int64_t B, int64_t F, void* audio, int64_t out_len, int precision) {
   if (int rc = check_common(plan, B, F, precision)) return rc;
-  const size_t esz = precision == MDCTGAN_F32 ? 4 : 8;
+  const size_t esz = precision == MDCTGAN_F64 ? 8 : 4;
   return stream_clips(plan, spec, (size_t)F * kBins * esz, audio, (size_t)out_len * esz, B,
                       [&](void* din, void* dout, int64_t n, cudaStream_t st) {
                         return mdctgan_imdct4_inverse(plan, din, n, F, F * kBins, dout, out_len, out_len, precision, st);
@@ -389,7 +398,7 @@ int mdctgan_imdct4_inverse_host(mdctgan_plan* plan, const void* spec, int64_t B,
 int mdctgan_mdct2audio_inverse_host(mdctgan_plan* plan, const float* spectro, int64_t B, int64_t F, const mdctgan_norm* norm,
                                     void* audio, int64_t out_len, int precision) {
   if (int rc = check_common(plan, B, F, precision)) return rc;
-  const size_t esz = precision == MDCTGAN_F32 ? 4 : 8;
+  const size_t esz = precision == MDCTGAN_F64 ? 8 : 4;
   return stream_clips(plan, spectro, (size_t)F * kBins * 4, audio, (size_t)out_len * esz, B,
                       [&](void* din, void* dout, int64_t n, cudaStream_t st) {
                         return mdctgan_mdct2audio_inverse(plan, (const float*)din, n, F, F * kBins, norm, dout, out_len, out_len,

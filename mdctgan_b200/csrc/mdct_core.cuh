@@ -100,9 +100,23 @@ MDCT_HD constexpr int dft8_k(int p) { return (p >> 2) + 2 * (p & 3); }
 // wE/wO  = window at the even / odd sample positions the thread's 16 points read (forward only)
 template <typename R> struct ThreadTab {
   cx<R> T[16];
+  MDCT_HD cx<R> operator()(int k1) const { return T[k1]; }
 };
 struct WinTab {
   float wE[16], wO[16];
+  MDCT_HD float e(int r) const { return wE[r]; }
+  MDCT_HD float o(int r) const { return wO[r]; }
+};
+// The same tables read on the fly from shared memory (kernels; keeps 64 / 32 registers free per thread):
+// sT[k1*8 + j] (complex, pre-scaled) and sW[r*8 + j] = (wE, wO) -- the 8 lanes of a frame read consecutive slots.
+template <typename R> struct SmemT {
+  const cx<R>* base;   // + j
+  MDCT_HD cx<R> operator()(int k1) const { return base[k1 * 8]; }
+};
+struct SmemW {
+  const float* base;   // + 2*j
+  MDCT_HD float e(int r) const { return base[r * 16]; }
+  MDCT_HD float o(int r) const { return base[r * 16 + 1]; }
 };
 
 // Plan table layout in global memory (built once on the host in fp64, see capi.cu):
@@ -126,10 +140,11 @@ MDCT_HD void load_W(const float* __restrict__ tabW, int j, WinTab& w) {
 // row0 / row1: the 256 raw samples of block t / block t+1 (frame t covers padded samples
 // [256 t, 256 t + 512) = block t-1 .. t in clip coordinates; the caller passes the two rows).
 // Even sample E[e] = row[2e], odd sample O[o] = row[2o+1].
-// FUSE = true lets the compiler contract w*x into FMAs (fp32 flavour); FUSE = false keeps the
-// reference's fp32-rounded products (mdct.py:410), which the fp64 flavour needs for 1e-13 parity.
-template <typename R, bool FUSE>
-MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WinTab& w, cx<R>* v) {
+// NATIVE = true: products formed in R (fp32 flavour: contractable into FMAs; fp64 core on fp32 data: exact, since
+// 24 + 24 mantissa bits fit a double).  NATIVE = false keeps the reference's fp32-rounded products
+// (mdct.py:410), which the bit-faithful fp64 flavour needs for 1e-13 parity.
+template <typename R, bool NATIVE, typename WT>
+MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WT& w, cx<R>* v) {
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     // n = j + 8r; e = 2*((n+64) mod 128), o = 2*((63-n) mod 128)+1, written wrap-free so that every
@@ -137,21 +152,23 @@ MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WinTa
     const int e = (r < 8) ? 2 * j + 16 * r + 128 : 2 * j + 16 * r - 128;
     const int o = (r < 8) ? 127 - 2 * j - 16 * r : 383 - 2 * j - 16 * r;
     R ue, uo;
-    if (FUSE) {
+    const float we = w.e(r), wo = w.o(r);
+    if (NATIVE) {
+      const R wE = (R)we, wO = (R)wo;
       if (r < 8) {   // n < 64
-        ue = -(R)(w.wE[r] * row1[o]) - (R)(w.wO[r] * row1[e]);
-        uo = (R)(w.wO[r] * row0[o]) - (R)(w.wE[r] * row0[e]);
+        ue = -(wE * (R)row1[o]) - (wO * (R)row1[e]);
+        uo = (wO * (R)row0[o]) - (wE * (R)row0[e]);
       } else {
-        ue = (R)(w.wE[r] * row0[e]) - (R)(w.wO[r] * row0[o]);
-        uo = -(R)(w.wO[r] * row1[e]) - (R)(w.wE[r] * row1[o]);
+        ue = (wE * (R)row0[e]) - (wO * (R)row0[o]);
+        uo = -(wO * (R)row1[e]) - (wE * (R)row1[o]);
       }
     } else {
       if (r < 8) {
-        ue = -(R)fmul32(w.wE[r], row1[o]) - (R)fmul32(w.wO[r], row1[e]);
-        uo = (R)fmul32(w.wO[r], row0[o]) - (R)fmul32(w.wE[r], row0[e]);
+        ue = -(R)fmul32(we, row1[o]) - (R)fmul32(wo, row1[e]);
+        uo = (R)fmul32(wo, row0[o]) - (R)fmul32(we, row0[e]);
       } else {
-        ue = (R)fmul32(w.wE[r], row0[e]) - (R)fmul32(w.wO[r], row0[o]);
-        uo = -(R)fmul32(w.wO[r], row1[e]) - (R)fmul32(w.wE[r], row1[o]);
+        ue = (R)fmul32(we, row0[e]) - (R)fmul32(wo, row0[o]);
+        uo = -(R)fmul32(wo, row1[e]) - (R)fmul32(we, row1[o]);
       }
     }
     v[r] = (r == 0) ? cx<R>{ue, uo} : cmulc(cx<R>{ue, uo}, rho_re<R>(r), rho_im<R>(r));
@@ -175,12 +192,12 @@ MDCT_HD void inv_gather(const S* row, int j, cx<R>* v) {
 // with the 290-word frame pitch makes the 64-bit pass-2 loads bank-conflict free across a half warp.
 MDCT_HD int xch_slot(int k1, int j) { return k1 * 9 + j; }
 
-template <typename R> MDCT_HD void pass1(cx<R>* v, const ThreadTab<R>& t, int j, cx<R>* xch) {
+template <typename R, typename TT> MDCT_HD void pass1(cx<R>* v, const TT& t, int j, cx<R>* xch) {
   dft16(v);
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const int k1 = dft16_k(p);
-    xch[xch_slot(k1, j)] = cmul(v[p], t.T[k1]);
+    xch[xch_slot(k1, j)] = cmul(v[p], t(k1));
   }
 }
 

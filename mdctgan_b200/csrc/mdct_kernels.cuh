@@ -162,21 +162,49 @@ __device__ __forceinline__ void fwd_produce(const FwdParams& p, int64_t tile, fl
   }
 }
 
+constexpr int kTabTElems = 8 * 16;       // thread twiddles, [k1][j]
+constexpr int kTabWFloats = 8 * 16 * 2;  // window pairs, [r][j][2]
 template <typename R> __host__ __device__ constexpr size_t fwd_smem_bytes(int ft) {
-  return align16((size_t)kStages * (ft + 1) * kRawPitch * sizeof(float)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) + 64;
+  return align16((size_t)kStages * (ft + 1) * kRawPitch * sizeof(float)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
+         kTabTElems * sizeof(cx<R>) + kTabWFloats * sizeof(float) + 64;
+}
+#ifndef MDCT_MINBLOCKS_F32
+#define MDCT_MINBLOCKS_F32 5
+#endif
+#ifndef MDCT_MINBLOCKS_F64
+#define MDCT_MINBLOCKS_F64 3
+#endif
+// Stage the plan tables in shared memory: sT[k1*8 + j] = T[j][k1] * scale, sW[(r*8 + j)*2 + {0,1}] = (wE, wO)[j][r]
+template <typename R>
+__device__ __forceinline__ void stage_tables(const R* __restrict__ tabT, const float* __restrict__ tabW, R scale, cx<R>* sT, float* sW) {
+  for (int i = threadIdx.x; i < kTabTElems; i += blockDim.x) {
+    const int k1 = i >> 3, j = i & 7;
+    sT[i] = cx<R>{tabT[(j * 16 + k1) * 2 + 0] * scale, tabT[(j * 16 + k1) * 2 + 1] * scale};
+  }
+  if (sW) {
+    for (int i = threadIdx.x; i < kTabTElems; i += blockDim.x) {
+      const int r = i >> 3, j = i & 7;
+      sW[2 * i] = tabW[(j * 16 + r) * 2 + 0];
+      sW[2 * i + 1] = tabW[(j * 16 + r) * 2 + 1];
+    }
+  }
 }
 
-// EPI: 0 = raw coefficients (OutT = R), 1 = fused compress + abs-norm (OutT = float, 1 or 2 channels)
-template <typename R, int EPI>
-__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd_kernel(const FwdParams p) {
+// EPI: 0 = raw coefficients (OutT = R or float), 1 = fused compress + abs-norm (OutT = float, 1 or 2 channels).
+// EXACT (fp64 core only): the reference's fp32-rounded window products and library asinh (bit-faithful flavour);
+// otherwise products are formed in R and the compress epilogue is the fast fp32 one.
+template <typename R, int EPI, typename OutT, bool EXACT>
+__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? MDCT_MINBLOCKS_F32 : MDCT_MINBLOCKS_F64) mdct4_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int stage_floats = (p.ft + 1) * kRawPitch;
   float* raw = reinterpret_cast<float*>(smem_raw);
   cx<R>* xch_all = reinterpret_cast<cx<R>*>(smem_raw + align16((size_t)kStages * stage_floats * sizeof(float)));
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xch_all) + align16((size_t)p.ft * kXchStride * sizeof(cx<R>)));
+  cx<R>* sT = reinterpret_cast<cx<R>*>(reinterpret_cast<unsigned char*>(xch_all) + align16((size_t)p.ft * kXchStride * sizeof(cx<R>)));
+  float* sW = reinterpret_cast<float*>(sT + kTabTElems);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sW + kTabWFloats);
   uint64_t* empty = full + kStages;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(empty + kStages);
-  using OutT = typename std::conditional<EPI == 0, R, float>::type;
+  static_assert(EPI == 0 || std::is_same<OutT, float>::value, "the fused epilogue writes fp32");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -188,6 +216,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); cnt[s] = 0; }
     mbar_fence_init();
   }
+  stage_tables<R>(reinterpret_cast<const R*>(p.tabT), p.tabW, (EPI == 1 && p.np.mode == 1) ? (R)p.np.gain : (R)1, sT, sW);
   __syncthreads();
 
   int64_t tile = blockIdx.x;
@@ -199,13 +228,8 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
     }
   }
 
-  ThreadTab<R> tt;
-  WinTab wt;
-  {
-    const R scale = (EPI == 1 && p.np.mode == 1) ? (R)p.np.gain : (R)1;
-    load_T<R>(reinterpret_cast<const R*>(p.tabT), j, scale, tt);
-    load_W(p.tabW, j, wt);
-  }
+  const SmemT<R> tt{sT + j};
+  const SmemW wt{sW + 2 * j};
   const float c1 = (float)(0.6931471805599453 / kLn10F32) * p.np.aff_a;   // log2 -> ln -> /ln10_f32 -> affine
   cx<R>* const xch = xch_all + f * kXchStride;
 
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
     mbar_wait(&full[s], parity);
     if (active) {
       const float* row0 = raw + s * stage_floats + f * kRawPitch;
-      fwd_gather<R, sizeof(R) == 4>(row0, row0 + kRawPitch, j, wt, v);
+      fwd_gather<R, !EXACT>(row0, row0 + kRawPitch, j, wt, v);
     }
     __syncwarp();
     {   // this warp is done with stage s; the LAST warp to get here refills it with the tile kStages ahead
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) mdct4_fwd
             *reinterpret_cast<typename Vec2<OutT>::type*>(row + col) = o;
           } else {
             float s0, s1;
-            if (sizeof(R) == 8) {   // "exact" flavour: fp64 core and library asinh, rounded once to fp32
+            if (EXACT) {   // "exact" flavour: fp64 core and library asinh, rounded once to fp32
               if (p.np.mode == 1) {
                 s0 = (float)(asinh((double)d0) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
                 s1 = (float)(asinh((double)d1) / kLn10F32 * (double)p.np.aff_a + (double)p.np.aff_b);
@@ -314,7 +338,7 @@ __device__ __forceinline__ void inv_produce(const InvParams& p, int64_t tile, S*
 
 template <typename R, typename S> __host__ __device__ constexpr size_t inv_smem_bytes(int ft) {
   return align16((size_t)kStages * ft * kRawPitch * sizeof(S)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
-         align16((size_t)ft * kURow * sizeof(R)) + 512 * sizeof(float) + 64;
+         align16((size_t)ft * kURow * sizeof(R)) + 512 * sizeof(float) + kTabTElems * sizeof(cx<R>) + 64;
 }
 
 template <typename R> __device__ __forceinline__ void load4(const R* p, R* o);
@@ -385,8 +409,8 @@ __device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t til
 //   wait udone(i-1) -> overlap-add + store tile i-1 -> arrive odone(i-1)
 //   pass 1 / pass 2 of tile i (private exchange slice) -> wait odone(i-1) -> write U rows(i) -> arrive udone(i)
 // so both cross-warp dependencies (U rows complete / U rows free) are split-phase with real work in between.
-template <typename R, typename S, typename OutT, int PRO>
-__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_inv_kernel(const InvParams p) {
+template <typename R, typename S, typename OutT, int PRO, bool EXACT>
+__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? MDCT_MINBLOCKS_F32 : MDCT_MINBLOCKS_F64) imdct4_inv_kernel(const InvParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int stage_elems = p.ft * kRawPitch;
   unsigned char* sp_ = smem_raw;
@@ -394,6 +418,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
   cx<R>* xch_all = reinterpret_cast<cx<R>*>(sp_);     sp_ += align16((size_t)p.ft * kXchStride * sizeof(cx<R>));
   R* Ubuf = reinterpret_cast<R*>(sp_);                sp_ += align16((size_t)p.ft * kURow * sizeof(R));
   float* wsm = reinterpret_cast<float*>(sp_);         sp_ += 512 * sizeof(float);
+  cx<R>* sT = reinterpret_cast<cx<R>*>(sp_);          sp_ += kTabTElems * sizeof(cx<R>);
   uint64_t* full = reinterpret_cast<uint64_t*>(sp_);
   uint64_t* empty = full + kStages;
   uint64_t* udone = empty + kStages;
@@ -414,6 +439,10 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) wsm[i] = __ldg(p.window + i) * (float)(4.0 / 512.0);   // exact (power of 2)
+  // fp32 fused prologue: sinh(x ln10)/gain = (2^u - 2^-u) * (0.5/gain), u = (s*inv_a + inv_b) * ln10_f32 * log2(e);
+  // the constant factor rides on the thread twiddles
+  const bool fast_sinh_path = (PRO == 1 && !EXACT && p.np.mode == 1);
+  stage_tables<R>(reinterpret_cast<const R*>(p.tabT), nullptr, fast_sinh_path ? (R)(0.5f / p.np.gain) : (R)1, sT, nullptr);
   __syncthreads();
 
   int64_t tile = blockIdx.x;
@@ -425,13 +454,9 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
     }
   }
 
-  // fp32 fused prologue: sinh(x ln10)/gain = (2^u - 2^-u) * (0.5/gain), u = (s*inv_a + inv_b) * ln10_f32 * log2(e);
-  // the constant factor rides on the thread twiddles
-  const bool fast_sinh_path = (PRO == 1 && sizeof(R) == 4 && p.np.mode == 1);
   const float kexp = (float)(kLn10F32 * 1.4426950408889634);
   const float ka = fast_sinh_path ? p.inv_a * kexp : p.inv_a, kb = fast_sinh_path ? p.inv_b * kexp : p.inv_b;
-  ThreadTab<R> tt;
-  load_T<R>(reinterpret_cast<const R*>(p.tabT), j, fast_sinh_path ? (R)(0.5f / p.np.gain) : (R)1, tt);
+  const SmemT<R> tt{sT + j};
   const R inv_gain = (R)1 / (R)p.np.gain;
   cx<R>* const xch = xch_all + f * kXchStride;
   R* const Urow = Ubuf + f * kURow;
@@ -452,7 +477,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? 4 : 1) imdct4_in
       for (int r = 0; r < 16; ++r) {
         R a = (R)row[2 * j + 16 * r], bb = (R)row[255 - 2 * j - 16 * r];   // X[2n], X[255-2n], n = j + 8r
         if (PRO == 1) {
-          if (sizeof(R) == 8) {
+          if (EXACT) {
             a = (R)((double)a * (double)p.inv_a + (double)p.inv_b);
             bb = (R)((double)bb * (double)p.inv_a + (double)p.inv_b);
             if (p.np.mode == 1) { a = (R)(sinh((double)a * kLn10F32)) * inv_gain; bb = (R)(sinh((double)bb * kLn10F32)) * inv_gain; }

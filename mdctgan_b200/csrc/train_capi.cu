@@ -304,19 +304,25 @@ int mdctgan_segment_gather(const float* audio_dev, int64_t L, float* out_dev, in
   return 0;
 }
 
-int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream) {
+int mdctgan_segment_ola_part(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int crop_begin, int crop_end, int precision,
+                             void* stream) {
   if (!seg_dev || !out_dev) return mdctgan_set_error(-1, "segment_ola: NULL buffer");
   if (seg <= 0 || ov < 0 || 2 * ov > seg || n_seg <= 0) return mdctgan_set_error(-1, "segment_ola: bad shape (0 <= 2*overlap <= segment)");
+  if (crop_begin < 0 || crop_end < 0 || crop_begin > ov || crop_end > ov) return mdctgan_set_error(-1, "segment_ola: crop must lie in [0, overlap]");
   const int step = seg - ov;
-  const int64_t out_len = (n_seg - 1) * step + seg - 2 * (int64_t)ov;
+  const int64_t out_len = (n_seg - 1) * step + seg - (int64_t)crop_begin - (int64_t)crop_end;
   if (out_len <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == MDCTGAN_F64) segment_ola_kernel<double><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const double*)seg_dev, (double*)out_dev, out_len, n_seg, seg, step, ov);
-  else if (precision == MDCTGAN_F32) segment_ola_kernel<float><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const float*)seg_dev, (float*)out_dev, out_len, n_seg, seg, step, ov);
+  if (precision == MDCTGAN_F64) segment_ola_kernel<double><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const double*)seg_dev, (double*)out_dev, out_len, n_seg, seg, step, ov, crop_begin);
+  else if (precision == MDCTGAN_F32) segment_ola_kernel<float><<<grid_for((size_t)out_len, 256), 256, 0, st>>>((const float*)seg_dev, (float*)out_dev, out_len, n_seg, seg, step, ov, crop_begin);
   else return mdctgan_set_error(-1, "segment_ola: precision %d", precision);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;
+}
+
+int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int precision, void* stream) {
+  return mdctgan_segment_ola_part(seg_dev, out_dev, n_seg, seg, ov, ov, ov, precision, stream);
 }
 
 int mdctgan_metrics_rows(const float* hr, const float* lr, const float* sr, int64_t rows, int64_t T, double* rows_out, void* stream) {

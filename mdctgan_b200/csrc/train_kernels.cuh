@@ -848,9 +848,10 @@ __global__ void segment_gather_kernel(const float* __restrict__ audio, long long
 }
 
 template <typename T>
-__global__ void segment_ola_kernel(const T* __restrict__ x, T* __restrict__ out, long long out_len, long long n_seg, int seg, int step, int ov) {
+__global__ void segment_ola_kernel(const T* __restrict__ x, T* __restrict__ out, long long out_len, long long n_seg, int seg, int step, int ov,
+                                   int crop_begin) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < out_len; t += (long long)gridDim.x * blockDim.x) {
-    const long long q = t + ov;                     // position in the folded signal
+    const long long q = t + crop_begin;             // position in the folded signal (crop_begin = ov for a whole clip)
     long long s_hi = q / step;
     if (s_hi >= n_seg) s_hi = n_seg - 1;
     T acc = (T)0;

@@ -7,7 +7,8 @@ import torch
 from .. import _lib
 
 _PREC = {"fp64": _lib.F64, "float64": _lib.F64, torch.float64: _lib.F64,
-         "fp32": _lib.F32, "float32": _lib.F32, torch.float32: _lib.F32}
+         "fp32": _lib.F32, "float32": _lib.F32, torch.float32: _lib.F32,
+         "mixed": _lib.MIXED}
 
 
 def _stream_ptr(device) -> int:
@@ -42,7 +43,7 @@ class _TransformBase(torch.nn.Module):
         self._window_host = window.detach().to("cpu", torch.float32).contiguous()
         self.register_buffer("window", self._window_host.clone(), persistent=False)
         if precision not in _PREC:
-            raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}")
+            raise ValueError(f"precision must be 'fp64', 'mixed' or 'fp32', got {precision!r}")
         self.precision = _PREC[precision]
         self._plans = {}
 
@@ -64,7 +65,8 @@ class MDCT4(_TransformBase):
     """signal [T] or [..., T] fp32 -> (coefficients [..., F, n_fft/2], frames).
 
     ``precision='fp64'`` (default) returns float64 like the reference (mdct.py:387-390,421-423);
-    ``'fp32'`` is the HBM-roofline flavour.  ``frames`` (windowed frames, mdct.py:410-412) is only
+    ``'mixed'`` runs the same fp64 butterflies on fp32 tensors (round trip 0.3 eps*peak, inside the 2-ulp bar);
+    ``'fp32'`` is the all-fp32 fast flavour (round trip 2-2.8 eps*peak).  ``frames`` (windowed frames, mdct.py:410-412) is only
     materialised when ``return_frames=True``; otherwise an ``empty(1)`` placeholder like the reference.
     """
 

@@ -40,12 +40,12 @@ class Audio2MDCT(torch.nn.Module):
 
     Differences, all recorded in DESIGN.md: `pha` and the unused `mean/std/frames` entries are not
     materialised in arcsinh / raw mode (nothing downstream reads them); the
-    reference's throw-away `randn` draw (:49-54) is skipped.  `precision='fp32'` (default) runs the
-    HBM-roofline flavour; `'fp64'` runs fp64 butterflies + library asinh/sinh and returns fp64 audio
-    like the reference.
+    reference's throw-away `randn` draw (:49-54) is skipped.  `precision='mixed'` (default) runs fp64
+    butterflies on fp32 tensors with the fast fp32 compress / expand; `'fp32'` is the all-fp32 flavour;
+    `'fp64'` runs fp64 butterflies + library asinh/sinh and returns fp64 audio like the reference.
     """
 
-    def __init__(self, opt, device=None, precision: str = "fp32") -> None:
+    def __init__(self, opt, device=None, precision: str = "mixed") -> None:
         super().__init__()
         for k, v in vars(opt).items():
             setattr(self, k, v)
@@ -58,12 +58,15 @@ class Audio2MDCT(torch.nn.Module):
         self.min_value = opt.min_value
         self.window = kbdwin(self.win_length)
         prec64 = precision in ("fp64", "float64", torch.float64)
-        self.precision = _lib.F64 if prec64 else _lib.F32
-        # raw-coefficient transforms keep the reference dtypes (fp64 in / out)
+        if not prec64 and precision not in ("mixed", "fp32", "float32", torch.float32):
+            raise ValueError(f"Audio2MDCT: precision must be 'mixed', 'fp32' or 'fp64', got {precision!r}")
+        sub = "fp64" if prec64 else ("mixed" if precision == "mixed" else "fp32")
+        self.precision = {"fp64": _lib.F64, "mixed": _lib.MIXED, "fp32": _lib.F32}[sub]
+        # raw-coefficient transforms keep the reference dtypes (fp64 in / out) in the fp64 flavour
         self._mdct = MDCT4(n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
-                           device=self.device, precision="fp64" if prec64 else "fp32")
+                           device=self.device, precision=sub)
         self._imdct = IMDCT4(n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
-                             device=self.device, precision="fp64" if prec64 else "fp32")
+                             device=self.device, precision=sub)
         if self.explicit_encoding or not (self.arcsinh_transform or self.raw_mdct):
             raise NotImplementedError("Audio2MDCT: only the arcsinh (--arcsinh_transform) and --raw_mdct encodings are "
                                       "implemented in-kernel; the dB / explicit_encoding branches are listed as 'next' in DESIGN.md")
@@ -289,7 +292,7 @@ class Pix2PixHDModel(BaseModel):
             setattr(self, k, v)
         self.isTrain = opt.isTrain
         input_nc = opt.label_nc if getattr(opt, "label_nc", 0) != 0 else opt.input_nc
-        self.preprocess = Audio2MDCT(opt, device=self.device, precision=getattr(opt, "mdct_precision", "fp32"))
+        self.preprocess = Audio2MDCT(opt, device=self.device, precision=getattr(opt, "mdct_precision", "mixed"))
         self.freeze = opt.freeze_g_d or opt.freeze_g_u or opt.freeze_l_d or opt.freeze_l_u
         self.netG = networks.define_G(input_nc, opt.output_nc, opt.ngf, opt.netG, opt.n_downsample_global, opt.n_blocks_global,
                                       opt.n_local_enhancers, opt.n_blocks_local, opt.norm, gpu_ids=self.gpu_ids,
@@ -337,7 +340,7 @@ class Pix2PixHDModel(BaseModel):
 
             # all kernel-side weight images (forward + input-gradient, direct + tcgen05) in one buffer, refreshed by one launch
             self.packer = WeightPacker(self.netG, self.netD)
-            self._packed_at = (0, 0)
+            self._packed_at = None
 
     # ---- generator graph ---------------------------------------------------------------------------------
     def _lr_input(self, lr_audio):
@@ -349,6 +352,8 @@ class Pix2PixHDModel(BaseModel):
 
     def forward(self, lr_audio, hr_audio):
         """Generator half of the training graph (pix2pixHD_model.py:394-414), no autograd in this round."""
+        if getattr(self, "packer", None) is not None:
+            self._refresh_weight_images()
         lr_spectro, lr_input, lr_pha, lr_norm_param = self._lr_input(lr_audio)
         hr_spectro, hr_pha, hr_norm_param = self.preprocess.hr_forward(hr_audio)
         sr_spectro = self.netG.forward(lr_input)
@@ -356,9 +361,15 @@ class Pix2PixHDModel(BaseModel):
             sr_spectro = _ops.residual_scale_add(sr_spectro, lr_spectro, 0, 1.0)
         return sr_spectro, None, hr_spectro, hr_pha, hr_norm_param, lr_spectro, lr_pha, lr_norm_param
 
+    def _pack_key(self):
+        """What the kernel-side weight images were derived from: the optimisers (identity and step counts) and the version counter of
+        EVERY parameter (load_state_dict and in-place edits bump them; FusedAdam.step writes through raw pointers, hence the step counts)."""
+        return (id(self.optimizer_G), id(self.optimizer_D), self.optimizer_G.step_count, self.optimizer_D.step_count,
+                sum(p._version for p in self.bucket_G.params), sum(p._version for p in self.bucket_D.params))
+
     def _refresh_weight_images(self):
-        """Re-pack after optimiser steps / load_state_dict (keyed on the optimisers' step counts and the parameter versions)."""
-        key = (self.optimizer_G.step_count, self.optimizer_D.step_count, self.bucket_G.params[0]._version, self.bucket_D.params[0]._version)
+        """Re-pack after optimiser steps / load_state_dict / in-place parameter edits."""
+        key = self._pack_key()
         if key != self._packed_at:
             self.packer.refresh()
             self._packed_at = key
@@ -377,7 +388,12 @@ class Pix2PixHDModel(BaseModel):
         with _ops.stats_pass(self.device):
             graph.forward(lr_audio, hr_audio)
         self._graph = graph
-        g_gan, g_feat, d_real, d_fake = T.loss_tensors(graph, self.bucket_G.params[0], self.bucket_D.params[0])
+        # autograd anchors: any parameter that requires grad (the first one may be frozen: --freeze_g_d, niter_fix_global)
+        anchor_g = next((p for p in self.bucket_G.params if p.requires_grad), None)
+        anchor_d = next((p for p in self.bucket_D.params if p.requires_grad), None)
+        if anchor_g is None or anchor_d is None:
+            raise RuntimeError("_forward: every parameter of netG (or netD) is frozen; nothing to differentiate")
+        g_gan, g_feat, d_real, d_fake = T.loss_tensors(graph, anchor_g, anchor_d)
         losses = [g_gan] + ([] if self.no_ganFeat_loss else [g_feat]) + [d_real, d_fake]
         return [losses, None if not infer else graph.sr_spectro]
 
@@ -435,8 +451,7 @@ class Pix2PixHDModel(BaseModel):
             self.optimizer_G.step()
             self.optimizer_D.step()
             self.packer.refresh()                          # the next forward (and a CUDA-graph replay) sees the updated weights
-            self._packed_at = (self.optimizer_G.step_count, self.optimizer_D.step_count, self.bucket_G.params[0]._version,
-                               self.bucket_D.params[0]._version)
+            self._packed_at = self._pack_key()
         graph.release()
         return losses
 

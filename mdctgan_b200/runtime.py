@@ -63,26 +63,62 @@ class GraphedTrainStep:
         self._warmup = warmup
         self.graph = None
 
+    # ---- warm-up and capture must not train: everything a step mutates is snapshotted before and put back after
+    def _state(self):
+        m = self.model
+        opts = (m.optimizer_G, m.optimizer_D)
+        return {"flat": [m.bucket_G.flat.clone(), m.bucket_D.flat.clone()],
+                "adam": [(o.exp_avg.clone(), o.exp_avg_sq.clone(), None if o.step_dev is None else o.step_dev.clone(), o.step_count) for o in opts],
+                "buffers": [b.clone() for net in (m.netG, m.netD) for b in net.buffers()]}
+
+    def _restore(self, st):
+        m = self.model
+        with torch.no_grad():
+            m.bucket_G.flat.copy_(st["flat"][0])
+            m.bucket_D.flat.copy_(st["flat"][1])
+            for o, (ea, eas, sd, sc) in zip((m.optimizer_G, m.optimizer_D), st["adam"]):
+                o.exp_avg.copy_(ea)
+                o.exp_avg_sq.copy_(eas)
+                if sd is not None:
+                    o.step_dev.copy_(sd)
+                o.step_count = sc
+            bufs = [b for net in (m.netG, m.netD) for b in net.buffers()]
+            for b, v in zip(bufs, st["buffers"]):
+                b.copy_(v)
+        m.packer.refresh()          # kernel-side weight images of the restored weights (the captured step re-packs at its end)
+        m._packed_at = m._pack_key()
+
     def recapture(self):
         dev = self.lr_in.device
+        if any(o.step_dev is None for o in (self.model.optimizer_G, self.model.optimizer_D)):
+            raise RuntimeError("GraphedTrainStep needs the device-side Adam step counter (opt.graph_safe_adam)")
+        state = self._state()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(self._warmup, 2)):     # plans, attributes, weight packs, Adam state, NCCL warm
+            for _ in range(max(self._warmup, 2)):     # plans, attributes, weight packs, allocator pools, NCCL warm
                 self.model.train_step(self.lr_in, self.hr_in, self.world_size, self.all_reduce)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = self.model.train_step(self.lr_in, self.hr_in, self.world_size, self.all_reduce)
-        self._lr = self.model.optimizer_G.param_groups[0]["lr"]
+        self._restore(state)        # also undoes the host-side step_count bump of the (not executed) captured step
+        torch.cuda.synchronize(dev)
+        self._key = self._capture_key()
+
+    def _capture_key(self):
+        m = self.model
+        return (id(m.optimizer_G), id(m.optimizer_D), m.optimizer_G.param_groups[0]["lr"], m.optimizer_D.param_groups[0]["lr"])
 
     def replay(self):
-        if self.graph is None or self.model.optimizer_G.param_groups[0]["lr"] != self._lr:
+        """Re-captures when the learning rate changed (update_learning_rate) or an optimiser was replaced (update_fixed_params)."""
+        if self.graph is None or self._capture_key() != self._key:
             self.recapture()
         self.graph.replay()
         for o in (self.model.optimizer_G, self.model.optimizer_D):
             o.step_count += 1
+        self.model._packed_at = self.model._pack_key()
         return self.losses
 
     def __call__(self, lr_audio: torch.Tensor, hr_audio: torch.Tensor):

@@ -28,14 +28,14 @@ def kbdwin(n: int, beta: float = 12.0) -> torch.Tensor:   # util/util.py:179-186
 
 
 class MDCT4Port:
-    def __init__(self, n_fft=512, hop=256, window=None):
+    def __init__(self, n_fft=512, hop=256, window=None, device="cpu"):
         self.n, self.hop = n_fft, hop
-        self.w = kbdwin(n_fft) if window is None else window
+        self.w = (kbdwin(n_fft) if window is None else window).to(device)
         self.win = len(self.w)
         m = torch.arange(0, n_fft, dtype=torch.float64)
-        self.pre = torch.exp(-1j * torch.pi / n_fft * m)
+        self.pre = torch.exp(-1j * torch.pi / n_fft * m).to(device)
         k = torch.arange(1, n_fft, 2, dtype=torch.float64)
-        self.post = torch.exp(-1j * (torch.pi / (2 * n_fft) + torch.pi / 4) * k)
+        self.post = torch.exp(-1j * (torch.pi / (2 * n_fft) + torch.pi / 4) * k).to(device)
 
     def __call__(self, x: torch.Tensor, return_frames: bool = False):
         start = self.hop
@@ -50,14 +50,14 @@ class MDCT4Port:
 
 
 class IMDCT4Port:
-    def __init__(self, n_fft=512, hop=256, window=None, out_length=None):
+    def __init__(self, n_fft=512, hop=256, window=None, out_length=None, device="cpu"):
         self.n, self.hop, self.out_length = n_fft, hop, out_length
-        self.w = kbdwin(n_fft) if window is None else window
+        self.w = (kbdwin(n_fft) if window is None else window).to(device)
         self.win = len(self.w)
         k = torch.arange(1, n_fft, 2, dtype=torch.float64)
-        self.pre = torch.exp(-1j * (torch.pi / (2 * n_fft) + torch.pi / 4) * k)
+        self.pre = torch.exp(-1j * (torch.pi / (2 * n_fft) + torch.pi / 4) * k).to(device)
         m = torch.arange(0, 2 * n_fft, 2, dtype=torch.float64)
-        self.post = torch.exp(-1j * torch.pi / (2 * n_fft) * m)
+        self.post = torch.exp(-1j * torch.pi / (2 * n_fft) * m).to(device)
 
     def __call__(self, spec: torch.Tensor):
         assert spec.dim() == 3 and spec.shape[-1] == self.n // 2
@@ -71,12 +71,13 @@ class IMDCT4Port:
 class Audio2MDCTPort:
     """arcsinh + abs_norm branch (the configs' branch)."""
 
-    def __init__(self, gain=1000.0, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0), n_fft=512, hop=256):
-        self.gain, self.src, self.rng = gain, src_range, norm_range
+    def __init__(self, gain=1000.0, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0), n_fft=512, hop=256, device="cpu"):
+        """`device="cuda"`: the same torch ops on the GPU (cuFFT) -- the torch-eager "kernel to beat" leg of bench.py."""
+        self.gain, self.src, self.rng, self.device = gain, src_range, norm_range, device
         self.w = kbdwin(n_fft)
-        self.fwd = MDCT4Port(n_fft, hop, self.w)
-        self.inv = IMDCT4Port(n_fft, hop, self.w)
-        self.ln10 = torch.log(torch.tensor(10.0))   # fp32 constant, pix2pixHD_model.py:100,133
+        self.fwd = MDCT4Port(n_fft, hop, self.w, device=device)
+        self.inv = IMDCT4Port(n_fft, hop, self.w, device=device)
+        self.ln10 = torch.log(torch.tensor(10.0)).to(device)   # fp32 constant, pix2pixHD_model.py:100,133
 
     def to_spectro(self, audio: torch.Tensor):
         spec, frames = self.fwd(audio, True)         # the reference always asks for the frames clone (:34)
@@ -84,11 +85,11 @@ class Audio2MDCTPort:
         pha = torch.sign(spec)
         s = torch.arcsinh(self.gain * spec) / self.ln10
         mean, std = s.mean().float(), s.var().sqrt().float()      # computed and never consumed (:108-109)
-        noise = torch.randn(pha.size())                           # the throw-away draw of :49-54
+        noise = torch.randn(pha.size(), device=spec.device)       # the throw-away draw of :49-54
         noise = (noise - noise.min()) / (noise.max() - noise.min())
         pha = pha * noise
-        lo = torch.tensor([self.src[0]])[None, None, None, :]
-        hi = torch.tensor([self.src[1]])[None, None, None, :]
+        lo = torch.tensor([self.src[0]], device=spec.device)[None, None, None, :]
+        hi = torch.tensor([self.src[1]], device=spec.device)[None, None, None, :]
         s = (s - lo) / (hi - lo)
         s = s * (self.rng[1] - self.rng[0]) + self.rng[0]
         return s.float(), pha, {"max": hi, "min": lo, "mean": mean, "std": std, "frames": frames}

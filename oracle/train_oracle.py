@@ -40,7 +40,7 @@ def losses(pG, pD, lr_spectro, hr_spectro, *, netG="local", n_down=3, n_blocks_g
     d_fake = sum(F.mse_loss(p[-1], torch.zeros_like(p[-1])) for p in pred_fake_pool)
     d_real = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_real)
     g_gan = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_fake)
-    g_feat = torch.zeros(())
+    g_feat = torch.zeros((), device=lr_spectro.device)
     if use_feat:
         fw, dw = 4.0 / (n_layers_D + 1), 1.0 / num_D
         for i in range(num_D):
@@ -80,20 +80,24 @@ def train_step(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, steps=1, **c
     return out
 
 
-def make_stepper(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, **cfg):
-    """A closure running one full iteration of train.py:160-202 per call (spectrograms included), for the timed CPU
-    baseline of bench.py; returns the four loss values of the iteration."""
+def make_stepper(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, device="cpu", cuda_graph=False, **cfg):
+    """A closure running one full iteration of train.py:160-202 per call (spectrograms included), for the timed baselines of
+    bench.py; returns the four loss values of the iteration.  `device="cuda"` runs the very same torch ops on the GPU (cuDNN /
+    cuFFT, torch autograd, torch.optim.Adam): the torch-eager "kernel to beat" (SURVEY.md 8d); `cuda_graph=True` additionally
+    captures the whole iteration in one torch.cuda.CUDAGraph (capturable Adam) and the closure replays it (returns None)."""
+    dev = torch.device(device)
     floatsG = {k for k, v in sdG.items() if v.dtype.is_floating_point and "running_" not in k}
-    pG = {k: (v.clone().requires_grad_(True) if k in floatsG else v.clone()) for k, v in sdG.items()}
-    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
-    optG = torch.optim.Adam([pG[k] for k in pG if k in floatsG], lr=lr, betas=(beta1, 0.999))
-    optD = torch.optim.Adam(list(pD.values()), lr=lr, betas=(beta1, 0.999))
+    pG = {k: (v.detach().to(dev).clone().requires_grad_(True) if k in floatsG else v.detach().to(dev).clone()) for k, v in sdG.items()}
+    pD = {k: v.detach().to(dev).clone().requires_grad_(True) for k, v in sdD.items()}
+    kw = dict(capturable=True) if cuda_graph else {}
+    optG = torch.optim.Adam([pG[k] for k in pG if k in floatsG], lr=lr, betas=(beta1, 0.999), **kw)
+    optD = torch.optim.Adam(list(pD.values()), lr=lr, betas=(beta1, 0.999), **kw)
     from . import torch_port as P
 
-    a2m = P.Audio2MDCTPort(1000.0, (-5.0, 5.0), (-1.0, 1.0), 512, 256)
-    lr_t, hr_t = torch.as_tensor(lr_audio), torch.as_tensor(hr_audio)
+    a2m = P.Audio2MDCTPort(1000.0, (-5.0, 5.0), (-1.0, 1.0), 512, 256, device=dev)
+    lr_t, hr_t = torch.as_tensor(lr_audio).to(dev), torch.as_tensor(hr_audio).to(dev)
 
-    def step():
+    def iteration():
         with torch.no_grad():
             ls, hs = a2m.to_spectro(lr_t)[0], a2m.to_spectro(hr_t)[0]      # the reference's complex128 512-pt FFT formulation
         (g_gan, g_feat, d_real, d_fake), _ = losses(pG, pD, ls, hs, **cfg)
@@ -105,6 +109,29 @@ def make_stepper(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, **cfg):
         optD.zero_grad()
         loss_D.backward()
         optD.step()
-        return [float(g_gan.detach()), float(g_feat.detach()), float(d_real.detach()), float(d_fake.detach())]
+        return g_gan, g_feat, d_real, d_fake
 
-    return step
+    if not cuda_graph:
+        def step():
+            return [float(v.detach()) for v in iteration()]
+
+        return step
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            iteration()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    optG.zero_grad(set_to_none=True)
+    optD.zero_grad(set_to_none=True)
+    with torch.cuda.graph(graph):
+        static_losses = torch.stack([v.detach() for v in iteration()])
+
+    def replay():
+        graph.replay()
+        return static_losses
+
+    return replay

@@ -39,7 +39,8 @@ static void frame_core(const PlanTablesHost& tabs, R scale, Gather gather, R* D)
   }
 }
 
-template <typename R>
+// NATIVE / ROUND32: see mdct_core.cuh fwd_gather; ROUND32 = the kernel's fp32 store of the coefficients
+template <typename R, bool NATIVE, bool ROUND32>
 static void fwd_impl(const float* x, int64_t T, int64_t F, const float* window, double* out) {
   PlanTablesHost tabs;
   build_plan_tables(window, tabs);
@@ -55,19 +56,19 @@ static void fwd_impl(const float* x, int64_t T, int64_t F, const float* window, 
     const float *row0 = &rows[t * kRawPitch], *row1 = &rows[(t + 1) * kRawPitch];
     frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) {
       WinTab w; load_W(tabs.W.data(), j, w);
-      fwd_gather<R, sizeof(R) == 4>(row0, row1, j, w, v);
+      fwd_gather<R, NATIVE>(row0, row1, j, w, v);
     }, D.data());
-    for (int k = 0; k < 256; ++k) out[t * 256 + k] = (double)D[k];
+    for (int k = 0; k < 256; ++k) out[t * 256 + k] = ROUND32 ? (double)(float)D[k] : (double)D[k];
   }
 }
 
-template <typename R>
+template <typename R, bool SYN, bool ROUND32>
 static void inv_impl(const double* spec, int64_t F, const float* window_in, double* audio /*(F-1)*256*/) {
   PlanTablesHost tabs;
   build_plan_tables(window_in, tabs);
   std::vector<float> wsyn;
   build_synthesis_window(window_in, 512, wsyn);
-  const float* window = sizeof(R) == 4 ? wsyn.data() : window_in;   // same choice as capi.cu launch_inv
+  const float* window = SYN ? wsyn.data() : window_in;   // same choice as capi.cu launch_inv
   std::vector<R> U(F * kURow);
   for (int64_t t = 0; t < F; ++t) {
     frame_core<R>(tabs, (R)1, [&](int j, cx<R>* v) { inv_gather<R, double>(&spec[t * 256], j, v); }, &U[t * kURow]);
@@ -77,16 +78,21 @@ static void inv_impl(const double* spec, int64_t F, const float* window_in, doub
     for (int i = 0; i < 256; ++i) {
       R a = unfold_first<R>(&U[(q + 1) * kURow], i) * (R)window[i];
       R b = unfold_second<R>(&U[q * kURow], i) * (R)window[256 + i];
-      audio[q * 256 + i] = (double)((a + b) * sc);
+      audio[q * 256 + i] = ROUND32 ? (double)(float)((a + b) * sc) : (double)((a + b) * sc);
     }
 }
 
 extern "C" {
 int emu_window_symmetric(const float* w) { return window_is_symmetric(w, 512) ? 1 : 0; }
-void emu_mdct_fwd(const float* x, int64_t T, int64_t F, const float* window, double* out, int use_double) {
-  if (use_double) fwd_impl<double>(x, T, F, window, out); else fwd_impl<float>(x, T, F, window, out);
+// flavour: 0 = fp32 core, 1 = fp64 core / fp64 I/O (bit-faithful), 2 = "mixed": fp64 core on fp32 I/O
+void emu_mdct_fwd(const float* x, int64_t T, int64_t F, const float* window, double* out, int flavour) {
+  if (flavour == 1) fwd_impl<double, false, false>(x, T, F, window, out);
+  else if (flavour == 2) fwd_impl<double, true, true>(x, T, F, window, out);
+  else fwd_impl<float, true, false>(x, T, F, window, out);
 }
-void emu_imdct(const double* spec, int64_t F, const float* window, double* audio, int use_double) {
-  if (use_double) inv_impl<double>(spec, F, window, audio); else inv_impl<float>(spec, F, window, audio);
+void emu_imdct(const double* spec, int64_t F, const float* window, double* audio, int flavour) {
+  if (flavour == 1) inv_impl<double, false, false>(spec, F, window, audio);
+  else if (flavour == 2) inv_impl<double, true, true>(spec, F, window, audio);
+  else inv_impl<float, true, false>(spec, F, window, audio);
 }
 }

@@ -70,13 +70,14 @@ def test_round_trip_within_2ulp_of_peak(emu, seed):
     x = (0.1 * rng.standard_normal(8192)).astype(np.float32)
     w = O.kbdwin(512)
     peak = np.abs(x).max()
-    for dbl in (True, False):
-        y = emu_inv(emu, emu_fwd(emu, x, 33, w, dbl), w, dbl)
-        if not dbl:
+    # flavour 1: fp64 = the reference's own floor (<= 2); 0: fp32, inherent fp32-FFT noise (<= 4, measured 2.8);
+    # 2: mixed = fp64 butterflies on fp32 tensors + TDAC-exact synthesis window (measured 0.33; the default and benchmarked one)
+    for flavour, gate in ((1, 2.0), (0, 4.0), (2, 0.5)):
+        y = emu_inv(emu, emu_fwd(emu, x, 33, w, flavour), w, flavour)
+        if flavour == 0:
             y = y.astype(np.float32).astype(np.float64)
-        # fp64 flavour = the reference's own floor (<= 2); fp32 flavour: inherent fp32-FFT noise (<= 4, measured 2.8)
-        assert np.abs(y - x).max() <= (2 if dbl else 4) * EPS * peak, (dbl, np.abs(y - x).max() / (EPS * peak))
-        assert rel_l2(y, x) <= 2 * EPS
+        assert np.abs(y - x).max() <= gate * EPS * peak, (flavour, np.abs(y - x).max() / (EPS * peak))
+        assert rel_l2(y, x) <= min(gate, 2.0) * EPS
 
 
 def test_window_symmetry_check(emu):

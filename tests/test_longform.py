@@ -89,3 +89,51 @@ def test_longform_generator_matches_per_segment_inference():
         want = LO.overlap_add(torch.cat(outs, dim=0), 3840, ov)
         assert got.shape == want.shape
         assert torch.allclose(got.cpu(), want.to(got.dtype), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [(100000, 7936, 256), (2880000, 32512, 256), (9000, 3840, 128), (63488, 7936, 0)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_layout_covers_the_clip(case, world):
+    """Host logic of the segment-sharded generation: contiguous runs, every segment owned once, the shard outputs
+    tile the assembled clip with exactly `overlap` shared samples at interior edges."""
+    from mdctgan_b200 import longform as LF
+
+    L, seg, ov = case
+    n = LO.seg_pad_audio(longform_clip(L, seg, ov), seg, ov).shape[0]
+    runs = [LF.shard_segments(n, r, world) for r in range(world)]
+    assert runs[0][0] == 0 and runs[-1][1] == n and all(runs[i][1] == runs[i + 1][0] for i in range(world - 1))
+    step = seg - ov
+    total = (n - 1) * step + seg - 2 * ov
+    pos = 0
+    for lo, hi in runs:
+        if hi <= lo:
+            continue
+        length = (hi - lo - 1) * step + seg - (ov if lo == 0 else 0) - (ov if hi == n else 0)
+        off = LF.shard_offset(lo, seg, ov)
+        assert off == (pos - ov if lo > 0 else 0)
+        pos = off + length
+    assert pos == total
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(100000, 7936, 256), (9000, 3840, 128), (63488, 7936, 0), (2880000, 32512, 256)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_overlap_add_bit_exact(case, world):
+    """Every rank folds its own contiguous run of segments; summing the `overlap` shared samples at the shard edges reproduces
+    the single-device fold bit for bit (the same two-term sums)."""
+    from mdctgan_b200 import longform as LF
+
+    L, seg, ov = case
+    dev = torch.device("cuda:0")
+    segs = LF.seg_pad_audio(longform_clip(L, seg, ov).to(dev), seg, ov)
+    n = segs.shape[0]
+    for dt in (torch.float32, torch.float64):
+        y = (segs * 1.25 + 0.01).to(dt)          # stands for the generated segments
+        whole = LF.overlap_add(y, ov)
+        parts = []
+        for r in range(world):
+            lo, hi = LF.shard_segments(n, r, world)
+            if hi > lo:
+                parts.append((LF.overlap_add(y[lo:hi], ov, (ov if lo == 0 else 0, ov if hi == n else 0)), lo))
+        got = LF.stitch_shards(parts, seg, ov)
+        assert got.shape == whole.shape and torch.equal(got, whole)
