@@ -567,7 +567,7 @@ class LaunchProfiler:
                     flops = 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)
                 elif _n == "mdctgan_conv2d_wgrad":
                     B, Cin, Ho, Wo, Cout, kh, stride, transposed = a[1], a[4], a[6], a[7], a[8], a[9], a[11], a[14]
-                    tag = f"wgrad[fp32] k{kh} s{stride}{'T' if transposed else ''} {Cin}->{Cout} B{B} @{Ho}x{Wo}"
+                    tag = f"wgrad[{'tcgen05' if a[-2] else 'fp32'}] k{kh} s{stride}{'T' if transposed else ''} {Cin}->{Cout} B{B} @{Ho}x{Wo}"
                     flops = 2.0 * B * Ho * Wo * Cout * kh * kh * Cin / (stride * stride if transposed else 1)
                 elif _n == "mdctgan_adam_flat":
                     nbytes = 28.0 * a[4]          # p, g, m, v read (16 B) + p, m, v written (12 B) per parameter

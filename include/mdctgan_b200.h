@@ -162,13 +162,16 @@ int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* s
  * dgrad has no entry of its own: the input gradient of nn.Conv2d is mdctgan_conv2d_nhwc / _umma with transposed = 1
  * on the output gradient with the weights packed [kh*kw*Cout][Cin]; of nn.ConvTranspose2d the plain convolution.
  */
-/* dW (+= , float atomics) and dbias (+=) of nn.Conv2d / nn.ConvTranspose2d: x = the layer's raw input with its deferred
+/* dW (+= , float reductions) and dbias (+=) of nn.Conv2d / nn.ConvTranspose2d: x = the layer's raw input with its deferred
  * normalisation / activation (as in mdctgan_conv2d_nhwc), dy = gradient of the raw convolution output [B,Ho,Wo,Cout];
- * dW[co][ci][tap] lives at dw[co*s_co + ci*s_ci + tap*s_tap] (the parameter's own layout, e.g. a slice of the flat bucket). */
+ * dW[co][ci][tap] lives at dw[co*s_co + ci*s_ci + tap*s_tap] (the parameter's own layout, e.g. a slice of the flat bucket).
+ * engine: 0 = fp32 FFMA kernel (any shape); 1 = tcgen05 MN-major implicit GEMM, 3xTF32 (fp32-class); 2 = tcgen05, single TF32
+ * pass.  Engines 1 / 2 need mdctgan_conv2d_wgrad_umma_supported(Cin, Cout) and explicit in_scale / in_shift (no in_stats). */
+int mdctgan_conv2d_wgrad_umma_supported(int Cin, int Cout);
 int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const float* dy, int Ho, int Wo, int Cout, int kh, int kw, int stride,
                          int pad, int pad_mode, int transposed, const float* in_scale, const float* in_shift, int in_per_sample, int in_act,
                          const double* in_stats, double in_count, float in_eps, float* dw, int64_t s_co, int64_t s_ci, int64_t s_tap,
-                         float* dbias, void* stream);
+                         float* dbias, int engine, void* stream);
 /* Backward of v = act(norm(x)): mode 0 InstanceNorm2d(affine=False) (networks.py:26), 1 train-mode BatchNorm2d (BottleStack).
  * stats = the forward (sum, sumsq) [B][C][2]; red = zeroed [B][C][2] scratch; dgamma / dbeta accumulated (mode 1, nullable). */
 int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
@@ -206,13 +209,13 @@ int mdctgan_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, f
 int mdctgan_counter_inc(int64_t* counter_dev, void* stream);
 /* Kernel-side weight images of every convolution of a model in ONE launch (run after each optimiser step; replaces the
  * per-layer host-side re-layouts).  Element (k, n) of descriptor d: tap = k / Kch, kc = k % Kch, value =
- * src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)]; written to dst_kn[k*N + n] (nullable) and / or as TF32 hi|lo into the
+ * src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)*s_tap]; written to dst_kn[k*N + n] (nullable) and / or as TF32 hi|lo into the
  * tcgen05 image dst_umma (nullable; layout of mdctgan_conv2d_umma_pack_weight, kchunks*2*N*32 floats, rows k >= K zero).
  * work_begin = prefix sum of kchunks*32*N.  `descs_dev`: device array of n_desc descriptors. */
 typedef struct mdctgan_pack_desc {
   const float* src; float* dst_kn; float* dst_umma;
   int32_t K, N, Kch, taps, flip, kchunks;
-  int64_t s_kch, s_n;
+  int64_t s_kch, s_n, s_tap;
   int64_t work_begin;
 } mdctgan_pack_desc;
 int mdctgan_pack_weights_multi(const void* descs_dev, int n_desc, int64_t total_work, void* stream);

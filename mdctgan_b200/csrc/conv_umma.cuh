@@ -41,6 +41,7 @@ constexpr int kRows = kBM * 8 / kProducerThreads;   // rows of the A tile per pr
 static_assert(kRows == 2, "validity queue packs 2 bits per chunk");
 constexpr int kThreads = (kProducerWarps + 2) * 32;   // + MMA warp + weight-loader warp
 constexpr int kMaxCin = 1024;
+constexpr int kNormTab = 4096;        // floats per deferred-normalisation table (scale, shift): samples in a tile x Cin
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;           // sign + 8 exponent + 10 mantissa bits
 
 struct ConvUmmaParams {
@@ -54,7 +55,8 @@ struct ConvUmmaParams {
   double* stats;        // [B][Cout][2] or null
   int K, kchunks, splits;
   int classes;          // 1, or stride^2 output parity classes of a ConvTranspose2d (see TileGeom)
-  int m_tiles;          // 128-pixel tiles per (sample, class)
+  int m_tiles;          // 128-pixel tiles per (sample, class); span: per class, over the pixels of ALL samples back to back
+  int span;             // 1: tiles run over the flattened (sample, pixel) index -- planes smaller than a tile share one
   long long* trace;     // debug: per-CTA phase timestamps [CTA][16] (clock64; slot 0 = globaltimer), or null
 };
 
@@ -81,7 +83,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C ABI), never as a hung GPU.
-__device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
   long long t0 = 0;
@@ -188,13 +190,16 @@ struct Cfg {
   static constexpr int kStagingBytes = ((kBM * kPitch * 4 + 1023) / 1024) * 1024;
   static constexpr int kRedBytes = 2 * kProducerThreads * 4 * 8;          // [2][RP][BN] doubles, RP*BN = 4 * producer threads
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kMaxCin * 4 + 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kNormTab * 4 + 256;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
   static_assert(kStagingBytes + kRedBytes <= kStages * kStageBytes, "staging must fit in the pipeline buffers");
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
 };
 
-// Which output pixels a CTA tile covers: up to 128 pixels of ONE sample (so the per-sample InstanceNorm affine of the
-// input and the per-sample statistics of the output are CTA-uniform).  Ordinary convolutions: consecutive pixels of
+// Which output pixels a CTA tile covers: 128 consecutive rows of the flattened (sample, pixel) index of one class.  Planes of
+// 128 pixels and more are tiled per sample; smaller planes (the 2x16 bottleneck of the reference's generator: 32 pixels)
+// share a tile across samples (`span`), with the per-sample InstanceNorm affine of the input looked up per row and the
+// per-sample statistics of the output reduced sample by sample in the epilogue.  Ordinary convolutions: consecutive pixels of
 // the sample.  ConvTranspose2d with stride s: the s*s output parity classes ((oy + pad) % s, (ox + pad) % s) each
 // see only the taps ky = py + s*i, kx = px + s*j (for k3 s2 p1: 1, 2, 2 or 4 of the 9 taps), so tiles are formed per
 // class and the K loop walks the live taps only -- 4x fewer chunks than zero-filling the dead ones.
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t smem_a = smem_u32(smem);
   float* s_scale = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
-  float* s_shift = s_scale + kMaxCin;
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_shift + kMaxCin);
+  float* s_shift = s_scale + kNormTab;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_shift + kNormTab);
   uint64_t* empty = full + C::kStages;
   uint64_t* tmem_full = empty + C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -266,11 +271,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   trace_mark(p, 1, tid == 0);
   int bx = blockIdx.x;
   const int mt = bx % p.m_tiles; bx /= p.m_tiles;
-  const int b = bx % p.B; bx /= p.B;
+  int b_tile = 0;
+  if (!p.span) { b_tile = bx % p.B; bx /= p.B; }
   const int cls = bx % p.classes, nt = bx / p.classes;
   const TileGeom tg = make_geom(p, cls);
   const int split = blockIdx.y;                       // == rank of this CTA in its cluster (cluster = (1, splits, 1))
-  const int m0 = mt * kBM, n0 = nt * BN;              // first class-local pixel of the tile within sample b
+  // rows of the tile = flattened (sample, class-local pixel) indices [m0, m0 + 128) below row_limit
+  const int m0 = (p.span ? 0 : b_tile * tg.hw) + mt * kBM, n0 = nt * BN;
+  const int row_limit = p.span ? p.B * tg.hw : (b_tile + 1) * tg.hw;
+  const int b_first = m0 / tg.hw;
+  const int b_last = min((min(m0 + kBM, row_limit) - 1) / tg.hw, p.B - 1);      // samples the tile touches (b_last < b_first: empty tile)
   const int kc_begin = (int)((long long)tg.kchunks * split / p.splits);
   const int kc_end = (int)((long long)tg.kchunks * (split + 1) / p.splits);
   const int nk = kc_end - kc_begin;
@@ -288,12 +298,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   // The deferred normalisation of the producing layer, CTA-uniform: scale / shift of sample b into shared memory --
   // ready-made, derived here from the producer's raw (sum, sumsq) statistics (InstanceNorm2d: no separate finalize
   // launch), or the identity.
+  // table rows: one per sample the tile touches (per-sample normalisation), else one
+  const bool has_norm = p.in.stats != nullptr || p.in.scale != nullptr;
+  const int tab_rows = (has_norm && p.in.per_sample) ? (b_last - b_first + 1) : 1;
   {
-    const size_t off = p.in.per_sample ? (size_t)b * p.Cin : 0;
+    const int n_tab = tab_rows * p.Cin;
+    const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
     if (p.in.stats) {
       const double inv_n = 1.0 / (double)p.in.count;
 #pragma unroll 1
-      for (int c = tid; c < p.Cin; c += kThreads) {
+      for (int c = tid; c < n_tab; c += kThreads) {
         const double mean = p.in.stats[2 * (off + c)] * inv_n;
         double var = p.in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
         var = var < 0.0 ? 0.0 : var;
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       }
     } else if (p.in.scale) {
 #pragma unroll 1
-      for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
+      for (int c = tid; c < n_tab; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
     } else {
 #pragma unroll 1
       for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = 1.f; s_shift[c] = 0.f; }
@@ -328,13 +342,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     const int rb = tid >> 3;      // rows rb, rb + 64
     const uint32_t row_off = (uint32_t)(rb >> 3) * 1024u + (uint32_t)(rb & 7) * 128u + (uint32_t)((j ^ (rb & 7)) << 4);
     const float slope = p.in.act == nnk::kActRelu ? 0.f : (p.in.act == nnk::kActLeaky ? 0.2f : 1.f);
-    const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
-    int oyb[kRows], oxb[kRows];
+    const float* xb = p.x;
+    int oyb[kRows], oxb[kRows], xoff[kRows], toff[kRows];      // toff: offset of the row's sample in the normalisation table
     bool rvalid[kRows];
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-      const int pix = m0 + rb + kRowStep * i;
-      rvalid[i] = pix < tg.hw;
+      const int row = m0 + rb + kRowStep * i;
+      rvalid[i] = row < row_limit;
+      const int bs = rvalid[i] ? row / tg.hw : b_first;
+      const int pix = row - bs * tg.hw;
+      xoff[i] = bs * p.H * p.W * p.Cin;
+      toff[i] = tab_rows > 1 ? (bs - b_first) * p.Cin : 0;
       const int oyc = pix / tg.woc;
       oyb[i] = oyc * tg.mul + tg.addy;
       oxb[i] = (pix - oyc * tg.woc) * tg.mul + tg.addx;
@@ -358,12 +376,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         const uint32_t ok2 = (okq >> (2 * newer)) & 3u;
         const int s = q % C::kStages;
         const uint32_t a_hi = smem_a + s * C::kStageBytes + row_off;
-        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c2);
-        const float4 sh = *reinterpret_cast<const float4*>(s_shift + c2);
 #pragma unroll
         for (int i = 0; i < kRows; ++i) {
           float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok2 & (1u << i)) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + toff[i] + c2);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + toff[i] + c2);
             e = lds128(a_hi + i * (kRowStep * 128));
             e.x = fmaf(e.x, sc.x, sh.x); e.y = fmaf(e.y, sc.y, sh.y); e.z = fmaf(e.z, sc.z, sh.z); e.w = fmaf(e.w, sc.w, sh.w);
             e.x = fmaxf(e.x, slope * e.x); e.y = fmaxf(e.y, slope * e.y); e.z = fmaxf(e.z, slope * e.z); e.w = fmaxf(e.w, slope * e.w);
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
             } else {
               ok = ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
             }
-            rowoff[i] = ok ? (iy * p.W + ix) * p.Cin : -1;
+            rowoff[i] = ok ? xoff[i] + (iy * p.W + ix) * p.Cin : -1;
           }
         }
         const uint32_t dst = smem_a + s * C::kStageBytes + row_off;
@@ -504,59 +522,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   constexpr int kRedHalf = kProducerThreads * 4;
   const int r_begin = kBM * split / p.splits, r_end = kBM * (split + 1) / p.splits;
   const int cq = tid % CQ, rg = tid / CQ;
-  if (tid < kProducerThreads) {
-    double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
-    const int n = n0 + cq * 4;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  const int n = n0 + cq * 4;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias && tid < kProducerThreads) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  // one pass per sample the tile touches: rows of that sample are reduced / stored, then its (sum, sumsq) go out
 #pragma unroll 1
-    for (int r = r_begin + rg; r < r_end; r += RP) {
-      const int pix = m0 + r;
-      if (pix >= tg.hw) break;
-      float4 acc = bias;
+  for (int sb = b_first; sb <= b_last; ++sb) {
+    const int lo = max(r_begin, sb * tg.hw - m0), hi = min(r_end, min((sb + 1) * tg.hw, row_limit) - m0);
+    if (tid < kProducerThreads) {
+      double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+      for (int r = lo + rg; r < hi; r += RP) {
+        const int pix = m0 + r - sb * tg.hw;
+        float4 acc = bias;
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {             // rank order: deterministic
-        if (s < p.splits) {
-          const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
-          const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        for (int s = 0; s < 8; ++s) {             // rank order: deterministic
+          if (s < p.splits) {
+            const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
+            const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
         }
+        if (p.stats) {
+          const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
+          ssum[0] += a0; ssq[0] = fma(a0, a0, ssq[0]); ssum[1] += a1; ssq[1] = fma(a1, a1, ssq[1]);
+          ssum[2] += a2; ssq[2] = fma(a2, a2, ssq[2]); ssum[3] += a3; ssq[3] = fma(a3, a3, ssq[3]);
+        }
+        acc.x = nnk::apply_act(acc.x, p.act); acc.y = nnk::apply_act(acc.y, p.act);
+        acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
+        const int oyc = pix / tg.woc;
+        const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
+        *reinterpret_cast<float4*>(p.y + (((size_t)sb * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
       }
       if (p.stats) {
-        const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
-        ssum[0] += a0; ssq[0] = fma(a0, a0, ssq[0]); ssum[1] += a1; ssq[1] = fma(a1, a1, ssq[1]);
-        ssum[2] += a2; ssq[2] = fma(a2, a2, ssq[2]); ssum[3] += a3; ssq[3] = fma(a3, a3, ssq[3]);
-      }
-      acc.x = nnk::apply_act(acc.x, p.act); acc.y = nnk::apply_act(acc.y, p.act);
-      acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
-      const int oyc = pix / tg.woc;
-      const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
-      *reinterpret_cast<float4*>(p.y + (((size_t)b * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
-    }
-    if (p.stats) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { red[rg * BN + cq * 4 + u] = ssum[u]; red[kRedHalf + rg * BN + cq * 4 + u] = ssq[u]; }
+        for (int u = 0; u < 4; ++u) { red[rg * BN + cq * 4 + u] = ssum[u]; red[kRedHalf + rg * BN + cq * 4 + u] = ssq[u]; }
+      }
+    }
+    if (p.stats) {        // block-uniform branch
+      __syncthreads();
+      if (tid < BN && hi > lo) {
+        double s = 0.0, q = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
+        double* st = p.stats + ((size_t)sb * p.Cout + n0 + tid) * 2;
+        red_add_f64(st, s);
+        red_add_f64(st + 1, q);
+      }
+      if (sb < b_last) __syncthreads();   // `red` is rewritten by the next sample's pass
     }
   }
   trace_mark(p, 8, tid == 0);
-  if (p.stats) {        // block-uniform branch
-    __syncthreads();
-    if (tid < BN) {
-      double s = 0.0, q = 0.0;
-#pragma unroll 4
-      for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
-      double* st = p.stats + ((size_t)b * p.Cout + n0 + tid) * 2;
-      red_add_f64(st, s);
-      red_add_f64(st + 1, q);
-    }
-  }
   trace_mark(p, 9, tid == 0);
   if (p.splits > 1) cluster.sync();   // no CTA may exit while a peer still reads its shared memory
   trace_mark(p, 10, tid == 0);
 }
 
 // [K][Cout] fp32 (nn_ops.pack_conv_weight layout) -> the kernel's shared-memory image, TF32 hi / lo parts
-__global__ void pack_weight_umma_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int Cout, int kchunks) {
+static __global__ void pack_weight_umma_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int Cout, int kchunks) {
   const size_t total = (size_t)kchunks * kKC * Cout;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(i % Cout);

@@ -36,7 +36,8 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
     return mdctgan_set_error(-1, "conv2d: in_stats is the InstanceNorm2d form (per sample, count > 0, no in_scale)");
   if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
     return mdctgan_set_error(-1, "conv2d: bad shape");
-  if (Cin > 1024) return mdctgan_set_error(-2, "conv2d: Cin %d > 1024 unsupported", Cin);
+  if (Cin > 1024 && (in_scale || in_stats))      // the per-channel scale / shift tables live in shared memory
+    return mdctgan_set_error(-2, "conv2d: Cin %d > 1024 with a deferred normalisation is unsupported", Cin);
   if (pad_mode == kPadReflect && (pad >= H || pad >= W)) return mdctgan_set_error(-1, "conv2d: reflection pad %d >= input size %dx%d", pad, H, W);
   if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d: in_scale / in_shift must come together");
   if (B == 0) return 0;
@@ -224,7 +225,7 @@ int launch_umma(umma::ConvUmmaParams& p, int n_tiles, int min_kchunks, cudaStrea
     CKN(cudaFuncSetAttribute(umma::conv2d_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.B * p.classes * n_tiles;
+  const int tiles = p.m_tiles * (p.span ? 1 : p.B) * p.classes * n_tiles;
   // split K over a cluster while the whole grid still fits the device in one wave
   int splits = 1;
   for (int s = 8; s >= 2; --s) {
@@ -292,30 +293,45 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   int min_kchunks = p.kchunks;
   // ConvTranspose2d: tiles per output parity class, K loop over the live taps only (conv_umma.cuh TileGeom)
   p.classes = 1;
-  int hw_class = Ho * Wo;
+  int hw_class = Ho * Wo, hw_min = Ho * Wo;
   if (transposed && stride > 1 && Cin % umma::kKC == 0 && kh >= stride && kw >= stride && Ho >= stride && Wo >= stride) {
     p.classes = stride * stride;
     min_kchunks = (kh / stride) * (kw / stride) * (Cin / umma::kKC);
     hw_class = ((Ho + stride - 1) / stride) * ((Wo + stride - 1) / stride);   // the largest class (classes are ragged for odd sizes)
+    hw_min = (Ho / stride) * (Wo / stride);                                   // the smallest one
   }
   else if (transposed && stride > 1)
     return mdctgan_set_error(-2, "conv2d_umma: ConvTranspose2d stride %d needs Cin %% 32 == 0, k >= stride, Ho, Wo >= stride", stride);
   if (transposed && pad_mode == kPadReflect) return mdctgan_set_error(-1, "conv2d_umma: reflection padding on a transposed convolution");
-  p.m_tiles = (hw_class + umma::kBM - 1) / umma::kBM;     // tiles never span samples
   if (in_stats) {
     if (in_scale) return mdctgan_set_error(-1, "conv2d_umma: pass either in_scale/in_shift or in_stats");
     if (!in_per_sample || in_count <= 0) return mdctgan_set_error(-1, "conv2d_umma: in_stats is the InstanceNorm2d form (per sample, count > 0)");
     p.in.stats = in_stats; p.in.count = (float)in_count; p.in.eps = in_eps;
   }
+  // Planes smaller than a 128-row tile share tiles across samples (conv_umma.cuh `span`) when the per-sample normalisation
+  // tables of every sample a tile can touch fit in shared memory.
+  p.span = 0;
+  p.m_tiles = (hw_class + umma::kBM - 1) / umma::kBM;
+  if (hw_class < umma::kBM && B > 1) {
+    const int per_tile = (umma::kBM + hw_min - 2) / hw_min + 1;                // samples a 128-row window can straddle
+    const bool per_sample_norm = (in_scale || in_stats) && in_per_sample;
+    if (!per_sample_norm || (long long)(per_tile < B ? per_tile : B) * Cin <= umma::kNormTab) {
+      p.span = 1;
+      p.m_tiles = (B * hw_class + umma::kBM - 1) / umma::kBM;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  // BN = 128 halves the shared-memory traffic per output (the K loop of this kernel is shared-memory-bandwidth bound: the A tile
-  // is re-read by every MMA) -- taken when the 128-wide tiles, split over K, still give about a wave of CTAs
-  const long long tiles128 = (long long)p.m_tiles * B * p.classes * (Cout / 128);
+  // Tile width: BN = 128 halves the shared-memory traffic per output (the A tile is re-read by every MMA), but at the reference's
+  // shapes the grid is the constraint: take the widest tile that still gives about a wave of CTAs once K is split over a cluster.
+  const long long m_ctas = (long long)p.m_tiles * (p.span ? 1 : B) * p.classes;
   const int max_split = min_kchunks < 8 ? min_kchunks : 8;
-  if (Cout % 128 == 0 && (tiles128 >= 74 || tiles128 * max_split >= 96))
-    rc = precision == 0 ? launch_umma<128, true>(p, Cout / 128, min_kchunks, st) : launch_umma<128, false>(p, Cout / 128, min_kchunks, st);
-  else if (Cout % 64 == 0) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
+  int bn = 32;
+  if (Cout % 128 == 0 && (m_ctas * (Cout / 128) >= 74 || m_ctas * (Cout / 128) * max_split >= 96)) bn = 128;
+  else if (Cout % 64 == 0 && (m_ctas * (Cout / 64) >= 74 || m_ctas * (Cout / 64) * max_split >= 96 || Cout % 32 != 0)) bn = 64;
+  else if (Cout % 64 == 0 && m_ctas * (Cout / 32) * max_split < 96) bn = 64;     // nothing fills the device: fewer, wider tiles
+  if (bn == 128) rc = precision == 0 ? launch_umma<128, true>(p, Cout / 128, min_kchunks, st) : launch_umma<128, false>(p, Cout / 128, min_kchunks, st);
+  else if (bn == 64) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
   else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, min_kchunks, st) : launch_umma<32, false>(p, Cout / 32, min_kchunks, st);
   if (rc) return rc;
   mdctgan_count_launch();

@@ -4,6 +4,7 @@
 
 #include "../../include/mdctgan_b200.h"
 #include "train_kernels.cuh"
+#include "wgrad_umma.cuh"
 
 using namespace trk;
 
@@ -26,10 +27,67 @@ int grid_for(size_t total, int block) {
 
 extern "C" {
 
+}  // extern "C"
+
+namespace {
+template <int BN, bool SPLIT3>
+int launch_wgrad_umma(umma::WgradUmmaParams& p, cudaStream_t st) {
+  using C = umma::WgCfg<BN, SPLIT3>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CKT(cudaFuncSetAttribute(umma::conv_wgrad_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  p.n_tiles = p.Cout / BN;
+  const int m_tiles = (p.K + umma::kBM - 1) / umma::kBM;
+  const int tiles = m_tiles * p.n_tiles;
+  // split the reduction over pixels until about one wave of CTAs exists; every split costs one more set of output reductions
+  int psplit = tiles >= 148 ? 1 : (148 + tiles - 1) / tiles;
+  if (psplit > p.chunks) psplit = p.chunks;
+  if (psplit > 65535) psplit = 65535;
+  umma::conv_wgrad_umma_kernel<BN, SPLIT3><<<dim3(tiles, psplit), umma::kWgThreads, C::kSmemBytes, st>>>(p);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mdctgan_conv2d_wgrad_umma_supported(int Cin, int Cout) { return (Cin % 32 == 0 && Cout % 32 == 0) ? 1 : 0; }
+
+/* engine: 0 = fp32 FFMA kernel, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32 */
 int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const float* dy, int Ho, int Wo, int Cout, int kh, int kw, int stride,
                          int pad, int pad_mode, int transposed, const float* in_scale, const float* in_shift, int in_per_sample, int in_act,
                          const double* in_stats, double in_count, float in_eps, float* dw, int64_t s_co, int64_t s_ci, int64_t s_tap,
-                         float* dbias, void* stream) {
+                         float* dbias, int engine, void* stream) {
+  if (engine != 0) {
+    if (!x || !dy || !dw) return mdctgan_set_error(-1, "conv2d_wgrad: NULL buffer");
+    if (engine != 1 && engine != 2) return mdctgan_set_error(-1, "conv2d_wgrad: engine %d (0 fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32)", engine);
+    if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+      return mdctgan_set_error(-1, "conv2d_wgrad: bad shape");
+    if (!mdctgan_conv2d_wgrad_umma_supported(Cin, Cout))
+      return mdctgan_set_error(-2, "conv2d_wgrad: the tcgen05 kernel needs Cin %% 32 == 0 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
+    if (in_stats) return mdctgan_set_error(-1, "conv2d_wgrad: the tcgen05 kernel takes explicit in_scale / in_shift (resolve the statistics first)");
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_wgrad: in_scale / in_shift must come together");
+    if ((long long)B * Ho * Wo > 0x7fffffffLL - 64 || (long long)B * H * W * Cin > 0x7fffffffLL)
+      return mdctgan_set_error(-2, "conv2d_wgrad: tensor too large for 32-bit offsets");
+    if (B == 0) return 0;
+    umma::WgradUmmaParams p{};
+    p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.dy = dy; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+    p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
+    p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
+    p.dw = dw; p.s_co = s_co; p.s_ci = s_ci; p.s_tap = s_tap; p.dbias = dbias;
+    p.K = kh * kw * Cin; p.P = B * Ho * Wo; p.chunks = (p.P + umma::kWgPix - 1) / umma::kWgPix;
+    { const char* dbg = getenv("MDCTGAN_WGRAD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (Cout % 128 == 0) rc = engine == 1 ? launch_wgrad_umma<128, true>(p, st) : launch_wgrad_umma<128, false>(p, st);
+    else if (Cout % 64 == 0) rc = engine == 1 ? launch_wgrad_umma<64, true>(p, st) : launch_wgrad_umma<64, false>(p, st);
+    else rc = engine == 1 ? launch_wgrad_umma<32, true>(p, st) : launch_wgrad_umma<32, false>(p, st);
+    if (rc) return rc;
+    mdctgan_count_launch();
+    CKT(cudaGetLastError());
+    return 0;
+  }
   if (!x || !dy || !dw) return mdctgan_set_error(-1, "conv2d_wgrad: NULL buffer");
   if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
     return mdctgan_set_error(-1, "conv2d_wgrad: bad shape");

@@ -770,12 +770,13 @@ __global__ void disc_input_bwd_kernel(const float* __restrict__ g, const float* 
 // Kernel-side weight images of EVERY convolution of a model in ONE launch (after each optimiser step): from the
 // parameter's own layout to  [K][N] (direct kernels)  and / or the tcgen05 kernel's pre-swizzled TF32 hi|lo image
 // (conv_umma.cuh), for the forward GEMM and for the input-gradient GEMM (transposed geometry / flipped taps).
-//   element (k, n):  tap = k / Kch, kc = k % Kch;  src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)]
+//   element (k, n):  tap = k / Kch, kc = k % Kch;  src[kc*s_kch + n*s_n + (flip ? taps-1-tap : tap)*s_tap]
+// (s_tap = 1 for the reference's parameter layout; Cin*Cout for the [kh][kw][Cin][Cout] storage order of optim.FlatBucket)
 // ------------------------------------------------------------------------------------------------
 struct PackDesc {
   const float* src; float* dst_kn; float* dst_umma;
   int K, N, Kch, taps, flip, kchunks;
-  long long s_kch, s_n;
+  long long s_kch, s_n, s_tap;
   long long work_begin;          // prefix sum of kchunks*32*N over the descriptors
 };
 constexpr unsigned kTf32MaskPack = 0xFFFFE000u;
@@ -813,7 +814,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc*
       float v = 0.f;
       if (k < d.K) {
         const int tap = k / d.Kch, kc = k - tap * d.Kch;
-        v = __ldg(d.src + kc * d.s_kch + n * d.s_n + (d.flip ? d.taps - 1 - tap : tap));
+        v = __ldg(d.src + kc * d.s_kch + n * d.s_n + (long long)(d.flip ? d.taps - 1 - tap : tap) * d.s_tap);
         if (d.dst_kn) d.dst_kn[(size_t)k * d.N + n] = v;
       }
       if (d.dst_umma) {
@@ -964,13 +965,22 @@ __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackDesc*
   const int taps = d.taps;
   const int total = 32 * 32 * taps;
   const bool n_outer = d.s_n > d.s_kch;         // which of (n, kc) has the larger stride in the parameter layout
-  for (int idx = threadIdx.x; idx < total; idx += 256) {
-    const int tap = idx % taps;
-    const int ab = idx / taps;
-    const int inner = ab & 31, outer = ab >> 5;
-    const int n = n_outer ? outer : inner, kc = n_outer ? inner : outer;
-    const float v = __ldg(d.src + (long long)(kc0 + kc) * d.s_kch + (long long)(n0 + n) * d.s_n + tap);
-    sm_pack[tap * kPackTapStride + kc * 33 + n] = v;
+  if (d.s_tap == 1) {                           // reference parameter layout: the taps of one (n, kc) are contiguous
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+      const int tap = idx % taps;
+      const int ab = idx / taps;
+      const int inner = ab & 31, outer = ab >> 5;
+      const int n = n_outer ? outer : inner, kc = n_outer ? inner : outer;
+      const float v = __ldg(d.src + (long long)(kc0 + kc) * d.s_kch + (long long)(n0 + n) * d.s_n + tap);
+      sm_pack[tap * kPackTapStride + kc * 33 + n] = v;
+    }
+  } else {                                      // [tap][ci][co] storage: 32 consecutive values of the unit-stride index per warp
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+      const int inner = idx & 31, outer = (idx >> 5) & 31, tap = idx >> 10;
+      const int n = n_outer ? outer : inner, kc = n_outer ? inner : outer;
+      const float v = __ldg(d.src + (long long)(kc0 + kc) * d.s_kch + (long long)(n0 + n) * d.s_n + (long long)tap * d.s_tap);
+      sm_pack[tap * kPackTapStride + kc * 33 + n] = v;
+    }
   }
   __syncthreads();
   // rows of the image: (tap_dst, n) -> 32 consecutive k = tap_dst*Kch + kc0 .. +31; a warp writes one row (lane = kc)

@@ -126,11 +126,15 @@ class Audio2MDCT(torch.nn.Module):
             if mask_size == -1:
                 mask_size = int(nb * (1 - 1 / self.up_ratio))
             if mask_size > 0:   # reference: mask_size == 0 would make an empty slice -> no-op
+                # the reference masks the 1-channel lr_spectro (pix2pixHD_model.py:57-80) and only then derives the second network
+                # channel |s|*2+lo from it (:400-402): the masked band of channel 2 is |noise|*2+lo (lo under --fit_residual)
                 if self.fit_residual:
-                    out[:, :, :, nb - mask_size:] = 0
+                    out[:, 0, :, nb - mask_size:] = 0
                 else:
-                    noise = torch.randn(B, channels, F, mask_size, device=x.device)
-                    out[:, :, :, nb - mask_size:] = noise / (noise.max() - noise.min())
+                    noise = torch.randn(B, 1, F, mask_size, device=x.device)
+                    out[:, 0:1, :, nb - mask_size:] = noise / (noise.max() - noise.min())
+                if channels == 2:
+                    out[:, 1, :, nb - mask_size:] = out[:, 0, :, nb - mask_size:].abs() * 2 + float(self.norm_range[0])
         lo, hi = self._src_minmax(x.device)
         return out, None, {"max": hi, "min": lo, "mean": None, "std": None, "frames": None}
 
@@ -242,7 +246,7 @@ class BaseModel(torch.nn.Module):
         """`<checkpoints_dir>/<name>/<epoch>_net_<label>.pth` = plain state_dict (base_model.py:43-46)."""
         os.makedirs(self.save_dir, exist_ok=True)
         # parameters are views into one flat buffer (optim.FlatBucket): clone so the file holds plain per-tensor storages
-        torch.save({k: v.detach().clone() for k, v in network.state_dict().items()},
+        torch.save({k: v.detach().contiguous().clone() for k, v in network.state_dict().items()},
                    os.path.join(self.save_dir, "%s_net_%s.pth" % (epoch_label, network_label)))
 
     def load_network(self, network, network_label, epoch_label, save_dir=""):

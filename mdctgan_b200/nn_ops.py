@@ -61,7 +61,8 @@ def _L():
         # train step
         L.mdctgan_conv2d_wgrad.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                            c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_double, c_float, c_void_p, c_int64,
-                                           c_int64, c_int64, c_void_p, c_void_p]
+                                           c_int64, c_int64, c_void_p, c_int, c_void_p]
+        L.mdctgan_conv2d_wgrad_umma_supported.argtypes = [c_int, c_int]
         L.mdctgan_norm_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_int, c_void_p, c_void_p, c_int,
                                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
         L.mdctgan_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
@@ -220,6 +221,18 @@ def pack_conv_weight(w: torch.Tensor, transposed: bool = False) -> torch.Tensor:
 
 def umma_supported(cin: int, cout: int) -> bool:
     return CONV_ENGINE != "direct" and bool(_L().mdctgan_conv2d_umma_supported(int(cin), int(cout)))
+
+
+WGRAD_ENGINE = os.environ.get("MDCTGAN_WGRAD_ENGINE", "")      # "" = follow CONV_ENGINE; "direct" forces the fp32 FFMA weight gradient
+
+
+def wgrad_engine(cin: int, cout: int) -> int:
+    """Engine code of mdctgan_conv2d_wgrad for a layer: 1 / 2 = tcgen05 MN-major implicit GEMM (3xTF32 / single-pass TF32) where the
+    channel counts are tensor-core shaped (Cin % 32 == 0, Cout % 32 == 0), else 0 = the fp32 FFMA kernel."""
+    eng = WGRAD_ENGINE or CONV_ENGINE
+    if eng == "direct" or not _L().mdctgan_conv2d_wgrad_umma_supported(int(cin), int(cout)):
+        return 0
+    return 2 if eng == "tf32" else 1
 
 
 def pack_conv_weight_umma(w_kn: torch.Tensor) -> torch.Tensor:
@@ -694,16 +707,22 @@ class _ConvOp:
         if wgrad and own.weight.requires_grad:
             dw = grad_of(own.weight)
             db = grad_of(own.bias) if (own.bias is not None and own.bias.requires_grad) else None
-            taps = self.kh * self.kw
-            s_co, s_ci = (taps, Cout * taps) if self.transposed else (Cin * taps, taps)
+            # element strides of dW[co][ci][tap] in the gradient tensor's own layout (the parameter's: contiguous reference layout, or
+            # the [kh][kw][Cin][Cout] storage order of optim.FlatBucket, where co is contiguous)
+            st_ = dw.stride()
+            s_ci, s_co = (st_[0], st_[1]) if self.transposed else (st_[1], st_[0])
+            s_tap = st_[3]
+            if self.kh > 1 and st_[2] != self.kw * s_tap:
+                raise RuntimeError(f"conv2d wgrad: unsupported weight-gradient strides {st_}")
             # nothing reads a weight gradient before the optimiser step: the wgrad kernels run on a side stream, concurrently with
             # the dgrad / norm-backward chain of the main stream (most kernels of this step fill a fraction of the 148 SMs)
             side = _side_stream(dy)
+            engine = wgrad_engine(Cin, Cout)
             with torch.cuda.device(dy.device), (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 _lib.check(L.mdctgan_conv2d_wgrad(f.x.data_ptr(), B, H, W, Cin, dy.data_ptr(), Ho, Wo, Cout, self.kh, self.kw, self.stride,
                                                   self.pad, self.pad_mode, 1 if self.transposed else 0, _ptr(f.scale), _ptr(f.shift),
                                                   1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
-                                                  dw.data_ptr(), s_co, s_ci, 1, _ptr(db), _stream(dy)))
+                                                  dw.data_ptr(), s_co, s_ci, s_tap, _ptr(db), engine, _stream(dy)))
             hook = _wgrad_hooks.get(id(own))
             if hook is not None:      # e.g. "every gradient of this all-reduce bucket has been enqueued" (bucketed exchange)
                 hook(side if side is not None else torch.cuda.current_stream(dy.device))

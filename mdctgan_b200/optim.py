@@ -12,13 +12,35 @@ from typing import List
 
 import torch
 
+import os
+
 from . import _lib
 from . import nn_ops as ops
+
+KN_LAYOUT = os.environ.get("MDCTGAN_KN_LAYOUT", "1") != "0"      # convolution weights stored [kh][kw][Cin][Cout] in the flat buckets
+
+
+def _kn_views(module: torch.nn.Module):
+    """id(weight) -> permutation that maps the kernel-side storage order [kh][kw][Cin][Cout] back to the parameter's logical shape,
+    for every convolution weight of `module`.  In that order the master copy IS the [kh*kw*Cin][Cout] image the direct kernels
+    read, the tcgen05 weight gradient writes whole 128-byte rows (co contiguous) instead of scattered 4-byte reductions, and
+    both GEMM geometries (forward: MN-major, input gradient: K-major) see 128-byte runs.  The logical tensors (state_dict,
+    load_state_dict, checkpoints: reference layout [Cout][Cin][kh][kw] / [Cin][Cout][kh][kw]) are unchanged -- only strides."""
+    from .models.networks import Conv2d, ConvTranspose2d
+
+    out = {}
+    for m in module.modules():
+        if isinstance(m, ConvTranspose2d):
+            out[id(m.weight)] = ((2, 3, 0, 1), (2, 3, 0, 1))      # logical [ci][co][kh][kw] -> storage (kh, kw, ci, co); and back
+        elif isinstance(m, Conv2d):
+            out[id(m.weight)] = ((2, 3, 1, 0), (3, 2, 0, 1))      # logical [co][ci][kh][kw] -> storage (kh, kw, ci, co); and back
+    return out
 
 
 class FlatBucket:
     """All parameters of `module` re-pointed into one flat buffer (16-byte aligned segments), with a matching flat
-    gradient buffer whose views are installed as `p.grad`."""
+    gradient buffer whose views are installed as `p.grad`.  Convolution weights are stored in the kernel-side order
+    [kh][kw][Cin][Cout] (`_kn_views`); their `.data` / `.grad` are permuted views with the reference's logical shape."""
 
     @staticmethod
     def padded_numel(module: torch.nn.Module) -> int:
@@ -46,11 +68,21 @@ class FlatBucket:
             grad_storage = torch.zeros(off, dtype=torch.float32, device=dev)
         assert grad_storage.numel() == off and grad_storage.dtype == torch.float32 and grad_storage.is_contiguous()
         self.grad = grad_storage
+        self._kn = _kn_views(module) if KN_LAYOUT else {}
         with torch.no_grad():
             for p, o in zip(params, self.offsets):
-                self.flat[o:o + p.numel()].view_as(p).copy_(p)
-                p.data = self.flat[o:o + p.numel()].view_as(p)
-                p.grad = self.grad[o:o + p.numel()].view_as(p)
+                self._view(self.flat, p, o).copy_(p)
+                p.data = self._view(self.flat, p, o)
+                p.grad = self._view(self.grad, p, o)
+
+    def _view(self, flat: torch.Tensor, p: torch.Tensor, o: int) -> torch.Tensor:
+        """The logical-shape view of parameter `p`'s segment of a flat buffer (permuted for convolution weights)."""
+        seg = flat[o:o + p.numel()]
+        perm = self._kn.get(id(p))
+        if perm is None:
+            return seg.view_as(p)
+        to_storage, to_logical = perm
+        return seg.view([p.shape[i] for i in to_storage]).permute(*to_logical)
 
     def trainable_runs(self, subset=None):
         """Maximal contiguous [begin, end) runs of the flat buffer whose parameters require grad (and are in `subset`, a set of
@@ -70,7 +102,7 @@ class FlatBucket:
     def reattach_grads(self):
         """Re-install the gradient views (after something set p.grad = None)."""
         for p, o in zip(self.params, self.offsets):
-            p.grad = self.grad[o:o + p.numel()].view_as(p)
+            p.grad = self._view(self.grad, p, o)
 
 
 class FusedAdam(torch.optim.Optimizer):

@@ -19,7 +19,8 @@ from . import nn_ops as ops
 
 class _Desc(ctypes.Structure):
     _fields_ = [("src", c_void_p), ("dst_kn", c_void_p), ("dst_umma", c_void_p), ("K", c_int32), ("N", c_int32), ("Kch", c_int32),
-                ("taps", c_int32), ("flip", c_int32), ("kchunks", c_int32), ("s_kch", c_int64), ("s_n", c_int64), ("work_begin", c_int64)]
+                ("taps", c_int32), ("flip", c_int32), ("kchunks", c_int32), ("s_kch", c_int64), ("s_n", c_int64), ("s_tap", c_int64),
+                ("work_begin", c_int64)]
 
 
 class WeightPacker:
@@ -36,7 +37,7 @@ class WeightPacker:
         dev = layers[0].weight.device
         plans, total_floats = [], 0
 
-        def plan(layer, role, K, N, Kch, taps, flip, s_kch, s_n, strided_transposed=False):
+        def plan(layer, role, K, N, Kch, taps, flip, s_kch, s_n, s_tap, strided_transposed=False):
             nonlocal total_floats
             kchunks = (K + 31) // 32
             use_umma = bool(L.mdctgan_conv2d_umma_supported(Kch, N))
@@ -44,8 +45,10 @@ class WeightPacker:
                 use_umma = False                    # the tensor-core kernel runs strided transposed geometry per parity class only
             # the [K][N] image is only read by the direct fp32 kernels: skip it where the tcgen05 kernel runs the layer
             want_kn = (not use_umma) or ops.CONV_ENGINE == "direct"
+            # [kh][kw][Cin][Cout] storage (optim.FlatBucket): the master copy already IS the forward [K][N] image
+            alias_kn = want_kn and not flip and s_n == 1 and s_kch == N and s_tap == Kch * N
             off_kn = None
-            if want_kn:
+            if want_kn and not alias_kn:
                 off_kn = total_floats
                 total_floats += (K * N + 3) // 4 * 4
             off_um = None
@@ -53,21 +56,32 @@ class WeightPacker:
                 total_floats = (total_floats + 31) // 32 * 32          # 128-byte aligned: the image is fetched by TMA bulk copies
                 off_um = total_floats
                 total_floats += kchunks * 2 * N * 32
-            plans.append(dict(layer=layer, role=role, K=K, N=N, Kch=Kch, taps=taps, flip=flip, s_kch=s_kch, s_n=s_n, kchunks=kchunks,
-                              off_kn=off_kn, off_um=off_um))
+            if alias_kn and off_um is None:          # nothing to derive: the layer reads its weights in place
+                st = layer.__dict__.setdefault("_static_pack", {})
+                st[role] = (layer.weight.detach().permute(2, 3, 0, 1).reshape(K, N) if isinstance(layer, ConvTranspose2d)
+                            else layer.weight.detach().permute(2, 3, 1, 0).reshape(K, N), None, bool(flip))
+                assert st[role][0].data_ptr() == layer.weight.data_ptr() and st[role][0].is_contiguous()
+                return
+            plans.append(dict(layer=layer, role=role, K=K, N=N, Kch=Kch, taps=taps, flip=flip, s_kch=s_kch, s_n=s_n, s_tap=s_tap, kchunks=kchunks,
+                              off_kn=off_kn, off_um=off_um, alias_kn=alias_kn))
 
         for m in layers:
             kh, kw = m.kernel_size
             taps = kh * kw
             ci, co = m.in_channels, m.out_channels
+            st = m.weight.stride()                  # the parameter's actual element strides (reference layout or FlatBucket's storage order)
+            if kh > 1 and st[2] != kw * st[3]:
+                raise RuntimeError(f"WeightPacker: unsupported weight strides {st}")
             if isinstance(m, ConvTranspose2d):      # weight [Cin][Cout][kh][kw]
-                plan(m, "fwd", taps * ci, co, ci, taps, 0, co * taps, taps, strided_transposed=m.stride[0] > 1)
+                s_ci, s_co, s_tap = st[0], st[1], st[3]
+                plan(m, "fwd", taps * ci, co, ci, taps, 0, s_ci, s_co, s_tap, strided_transposed=m.stride[0] > 1)
                 if dgrad:
-                    plan(m, "dgrad", taps * co, ci, co, taps, 0, taps, co * taps)
+                    plan(m, "dgrad", taps * co, ci, co, taps, 0, s_co, s_ci, s_tap)
             else:                                   # weight [Cout][Cin][kh][kw]
-                plan(m, "fwd", taps * ci, co, ci, taps, 0, taps, ci * taps)
+                s_co, s_ci, s_tap = st[0], st[1], st[3]
+                plan(m, "fwd", taps * ci, co, ci, taps, 0, s_ci, s_co, s_tap)
                 if dgrad:
-                    plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, ci * taps, taps, strided_transposed=m.stride[0] > 1)
+                    plan(m, "dgrad", taps * co, ci, co, taps, 1 if m.stride[0] == 1 else 0, s_co, s_ci, s_tap, strided_transposed=m.stride[0] > 1)
         self.buf = torch.zeros(total_floats + 32, dtype=torch.float32, device=dev)
         base_off = (-(self.buf.data_ptr() // 4)) % 32                     # align the buffer itself to 128 bytes
         # descriptors that qualify for the tiled (coalesced) kernel: tensor-core image only, 32-aligned channel counts
@@ -82,6 +96,10 @@ class WeightPacker:
             if p["off_kn"] is not None:
                 kn = self.buf[base_off + p["off_kn"]: base_off + p["off_kn"] + p["K"] * p["N"]].view(p["K"], p["N"])
                 kn_ptr = kn.data_ptr()
+            elif p["alias_kn"]:                     # the master copy in [kh][kw][Cin][Cout] order is the image
+                kn = (m.weight.detach().permute(2, 3, 0, 1) if isinstance(m, ConvTranspose2d) else m.weight.detach().permute(2, 3, 1, 0)).reshape(p["K"], p["N"])
+                assert kn.data_ptr() == m.weight.data_ptr() and kn.is_contiguous()
+                kn_ptr = None
             else:                                   # shape-only placeholder (stride 0): never dereferenced, _conv_launch checks
                 kn = self.buf[:1].as_strided((p["K"], p["N"]), (0, 0))
                 kn_ptr = None
@@ -91,7 +109,7 @@ class WeightPacker:
                 um = self.buf[base_off + p["off_um"]: base_off + p["off_um"] + n_um]
                 assert um.data_ptr() % 128 == 0
             descs[i] = _Desc(m.weight.data_ptr(), kn_ptr, um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],
-                             p["taps"], p["flip"], p["kchunks"], p["s_kch"], p["s_n"], work)
+                             p["taps"], p["flip"], p["kchunks"], p["s_kch"], p["s_n"], p["s_tap"], work)
             work += p["kchunks"] * 32 * p["N"]
             if i == n_generic - 1:
                 self.total_work = work                                    # the generic kernel stops here

@@ -78,6 +78,8 @@ class Audio2MDCTPort:
         self.fwd = MDCT4Port(n_fft, hop, self.w, device=device)
         self.inv = IMDCT4Port(n_fft, hop, self.w, device=device)
         self.ln10 = torch.log(torch.tensor(10.0)).to(device)   # fp32 constant, pix2pixHD_model.py:100,133
+        self.lo = torch.tensor([src_range[0]])[None, None, None, :].to(device)
+        self.hi = torch.tensor([src_range[1]])[None, None, None, :].to(device)
 
     def to_spectro(self, audio: torch.Tensor):
         spec, frames = self.fwd(audio, True)         # the reference always asks for the frames clone (:34)
@@ -88,8 +90,7 @@ class Audio2MDCTPort:
         noise = torch.randn(pha.size(), device=spec.device)       # the throw-away draw of :49-54
         noise = (noise - noise.min()) / (noise.max() - noise.min())
         pha = pha * noise
-        lo = torch.tensor([self.src[0]], device=spec.device)[None, None, None, :]
-        hi = torch.tensor([self.src[1]], device=spec.device)[None, None, None, :]
+        lo, hi = self.lo, self.hi
         s = (s - lo) / (hi - lo)
         s = s * (self.rng[1] - self.rng[0]) + self.rng[0]
         return s.float(), pha, {"max": hi, "min": lo, "mean": mean, "std": std, "frames": frames}

@@ -49,15 +49,22 @@ def losses(pG, pD, lr_spectro, hr_spectro, *, netG="local", n_down=3, n_blocks_g
     return [g_gan, g_feat, d_real, d_fake], sr
 
 
-def train_step(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, steps=1, **cfg):
+def train_step(sdG, sdD, lr_audio, hr_audio, *, lr=2e-4, beta1=0.5, steps=1, dtype=None, **cfg):
     """`steps` iterations of train.py:160-202 on the same batch.  Returns per-step losses, the gradients of the
-    first step and the parameters after the last one."""
+    first step and the parameters after the last one.  `dtype=torch.float64` runs the same graph in double precision on the
+    same fp32 inputs and weights: the ground truth the fp32 implementations (this oracle in fp32, the CUDA path) are measured
+    against in the conditioning-aware gradient test (tests/test_train_gpu.py)."""
+    if dtype is not None:
+        sdG = {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in sdG.items()}
+        sdD = {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in sdD.items()}
     floatsG = {k for k, v in sdG.items() if v.dtype.is_floating_point and "running_" not in k}
     pG = {k: (v.clone().requires_grad_(True) if k in floatsG else v.clone()) for k, v in sdG.items()}
     pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
     optG = torch.optim.Adam([pG[k] for k in pG if k in floatsG], lr=lr, betas=(beta1, 0.999))
     optD = torch.optim.Adam(list(pD.values()), lr=lr, betas=(beta1, 0.999))
     ls, hs = spectro(lr_audio), spectro(hr_audio)
+    if dtype is not None:
+        ls, hs = ls.to(dtype), hs.to(dtype)
     out = {"losses": []}
     for it in range(steps):
         (g_gan, g_feat, d_real, d_fake), sr = losses(pG, pD, ls, hs, **cfg)

@@ -88,11 +88,12 @@ int emu_window_symmetric(const float* w) { return window_is_symmetric(w, 512) ? 
 void emu_mdct_fwd(const float* x, int64_t T, int64_t F, const float* window, double* out, int flavour) {
   if (flavour == 1) fwd_impl<double, false, false>(x, T, F, window, out);
   else if (flavour == 2) fwd_impl<double, true, true>(x, T, F, window, out);
+  else if (flavour == 3) fwd_impl<double, false, true>(x, T, F, window, out);
   else fwd_impl<float, true, false>(x, T, F, window, out);
 }
 void emu_imdct(const double* spec, int64_t F, const float* window, double* audio, int flavour) {
   if (flavour == 1) inv_impl<double, false, false>(spec, F, window, audio);
-  else if (flavour == 2) inv_impl<double, true, true>(spec, F, window, audio);
+  else if (flavour == 2 || flavour == 3) inv_impl<double, true, true>(spec, F, window, audio);
   else inv_impl<float, true, false>(spec, F, window, audio);
 }
 }

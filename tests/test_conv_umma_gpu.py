@@ -51,6 +51,12 @@ UMMA_CASES = [
     (4, 512, 2, 16, 512, 3, 1, 1, True, False),    # cfg4 bottleneck: BN = 128 tiles, 3-stage ring, cluster of 8
     (2, 128, 16, 64, 128, 3, 1, 1, True, False),   # BN = 128, 8 M-tiles per sample
     (2, 256, 5, 33, 512, 4, 1, 2, False, False),   # PatchGAN 4x4 s1 -> 512 channels (BN = 128), ragged last tile
+    # planes smaller than a tile: tiles span samples (conv_umma.cuh `span`)
+    (5, 64, 3, 10, 64, 3, 1, 1, True, False),      # 30-pixel planes: a tile straddles 5 samples, none aligned
+    (6, 32, 2, 6, 96, 3, 1, 1, False, False),      # 12-pixel planes, 72 rows in all: one partial tile
+    (4, 64, 2, 8, 32, 3, 2, 1, False, True),       # ConvTranspose2d, 16-pixel parity classes spanning the 4 samples
+    (3, 64, 3, 5, 32, 4, 2, 2, False, True),       # ragged parity classes (5x9 output), spanning
+    (7, 128, 3, 11, 128, 3, 2, 1, False, False),   # stride 2 -> 2x6 planes, 84 rows
 ]
 
 

@@ -56,7 +56,11 @@ LAYER_CASES = [
     (2, 8, 16, 32, 1, 7, 1, 3, True, False, "in", 1),       # generator head 7x7 reflect (Cout = 1)
     (2, 2, 16, 32, 8, 7, 1, 3, True, False, None, 0),       # generator stem (Cin = 2)
     (2, 64, 2, 16, 128, 1, 1, 0, False, False, None, 0),    # 1x1 (BottleStack)
-    (4, 256, 4, 32, 256, 3, 1, 1, True, False, "in", 1),    # cfg2 residual conv (tcgen05 path for forward / dgrad)
+    (4, 256, 4, 32, 256, 3, 1, 1, True, False, "in", 1),    # cfg2 residual conv (tcgen05 path for forward / dgrad / wgrad)
+    (4, 512, 2, 16, 512, 3, 1, 1, True, False, "in", 1),    # cfg3/cfg4 trunk conv: the dominant shape of the train step
+    (2, 64, 9, 17, 128, 4, 2, 2, False, False, "in", 2),    # PatchGAN stride-2 layer, ragged planes
+    (2, 32, 6, 10, 96, 3, 1, 1, False, False, None, 0),     # Cout % 64 != 0 -> 32-wide tcgen05 tiles
+    (1, 32, 32, 64, 32, 3, 1, 1, True, False, "in", 1),     # many pixels, few tiles: the reduction is split over CTAs
 ]
 
 
@@ -207,6 +211,47 @@ def test_fused_adam_matches_torch(dev):
         np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().numpy(), rtol=0, atol=2e-7)
 
 
+@pytest.mark.parametrize("layout", ["param", "kn"])
+@pytest.mark.parametrize("shape", [(4, 512, 2, 16, 512, 3, 1, 1, 1, 0), (2, 64, 9, 17, 128, 4, 2, 2, 0, 0), (3, 32, 5, 7, 32, 3, 1, 1, 0, 0),
+                                   (2, 64, 4, 8, 32, 3, 2, 1, 0, 1), (1, 96, 16, 32, 64, 5, 1, 2, 0, 0), (8, 128, 3, 5, 256, 1, 1, 0, 0, 0)])
+def test_wgrad_tcgen05_matches_fp32_kernel(dev, shape, layout):
+    """The MN-major tcgen05 weight-gradient kernel (csrc/wgrad_umma.cuh) against the fp32 FFMA kernel through the same C-ABI entry:
+    3xTF32 engine <= 2e-6 rel-L2 (fp32-class), single-pass TF32 <= 2e-3; both output layouts (the parameter's own
+    [Cout][Cin][kh][kw] strides and the co-contiguous [tap][ci][co] one that takes the 16-byte vector reductions)."""
+    from mdctgan_b200 import _lib
+    from mdctgan_b200 import nn_ops as ops
+
+    B, Cin, H, W, Cout, k, stride, pad, reflect, transposed = shape
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout + k)
+    if transposed:
+        Ho, Wo = (H - 1) * stride - 2 * pad + k + 1, (W - 1) * stride - 2 * pad + k + 1
+    else:
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    dy = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    scale = (0.5 + torch.rand(B * Cin, generator=g)).to(dev)
+    shift = (0.2 * torch.randn(B * Cin, generator=g)).to(dev)
+    taps = k * k
+    s_co, s_ci, s_tap = ((taps, Cout * taps, 1) if transposed else (Cin * taps, taps, 1)) if layout == "param" else (1, Cout, Cin * Cout)
+    L = ops._L()
+    out = {}
+    for eng in (0, 1, 2):
+        dw = torch.zeros(Cout * Cin * taps, device=dev)
+        db = torch.zeros(Cout, device=dev)
+        _lib.check(L.mdctgan_conv2d_wgrad(x.data_ptr(), B, H, W, Cin, dy.data_ptr(), Ho, Wo, Cout, k, k, stride, pad, 1 if reflect else 0,
+                                          transposed, scale.data_ptr(), shift.data_ptr(), 1, 1, None, 0.0, 1e-5, dw.data_ptr(), s_co, s_ci, s_tap,
+                                          db.data_ptr(), eng, torch.cuda.current_stream(dev).cuda_stream))
+        torch.cuda.synchronize()
+        out[eng] = (dw.cpu().double(), db.cpu().double())
+    ref_w, ref_b = out[0]
+    assert float(ref_w.norm()) > 0
+    for eng, tol in ((1, 2e-6), (2, 2e-3)):
+        e_w = float((out[eng][0] - ref_w).norm() / ref_w.norm())
+        e_b = float((out[eng][1] - ref_b).norm() / ref_b.norm())
+        print(f"wgrad {shape} {layout} engine {eng}: dW {e_w:.2e} db {e_b:.2e}")
+        assert e_w < tol and e_b < 2e-6, (eng, e_w, e_b)
+
+
 def _build_model(flags, seed, dev):
     from mdctgan_b200.models.models import create_model
     from mdctgan_b200.options.train_options import TrainOptions
@@ -288,7 +333,7 @@ def test_train_step_matches_oracle_and_reference(dev, name, api):
             continue
         e = rel_l2(gG[k].numpy(), v.numpy())
         worst = max(worst, e)
-        assert e < (0.25 if name == "tr_cfg4" else 2e-2), (k, e)
+        assert e < (0.12 if name == "tr_cfg4" else 2e-2), (k, e)      # cfg4: conditioning-limited, see the three-way test below
     gmaxD = max(float(v.abs().max()) for v in ref["gradD"].values())
     for k, v in ref["gradD"].items():
         if float(v.abs().max()) < 1e-4 * gmaxD:
@@ -299,17 +344,85 @@ def test_train_step_matches_oracle_and_reference(dev, name, api):
     # parameters after TRAIN_STEPS Adam steps: each element moves by ~lr per step in the direction of sign(gradient), so an element
     # whose (tiny) gradient differs in sign between the two implementations ends 2*lr apart: with a fraction f of such elements the
     # distance is ~2*sqrt(f) of the distance moved (random signs would give 1.41); 0.25 <=> f < 1.6 % of the elements
+    worst_moved = 0.0
     for k, v in ref["paramsG"].items():
         if v.dim() >= 2:
             got = model.netG.state_dict()[k].detach().cpu()
             moved = (v - sdG[k]).norm().item()
+            worst_moved = max(worst_moved, (got - v).norm().item() / max(moved, 1e-30))
             assert (got - v).norm().item() < (1.0 if name in ("tr_cfg4", "tr_small_rc") else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
     for k, v in ref["paramsD"].items():
         if v.dim() >= 2:
             got = model.netD.state_dict()[k].detach().cpu()
             moved = (v - sdD[k]).norm().item()
             assert (got - v).norm().item() < (1.0 if name in ("tr_cfg4", "tr_small_rc") else 0.25) * moved + 1e-12, (k, (got - v).norm().item(), moved)
-    print(f"{name}/{api}: losses {losses[0]}, worst G-gradient rel-L2 {worst:.2e}")
+    print(f"{name}/{api}: losses {losses[0]}, worst G-gradient rel-L2 {worst:.2e}, post-Adam distance / distance moved: worst {worst_moved:.3f}")
+
+
+def test_cfg4_gradients_three_way_against_fp64_truth(dev):
+    """Conditioning-aware gate for the whole-network gradients of BASELINE configs[3].  The cfg4 graph holds
+    ~1e5 ReLU / LeakyReLU masks and L1 signs behind 32-pixel InstanceNorm planes, so two correct fp32 implementations differ by
+    percent-level amounts per tensor (single mask flips).  Ground truth = the oracle run in fp64 on the same fp32 weights and
+    inputs; yardstick = the fp32 oracle's own distance from it (what the reference's arithmetic achieves).  Every gradient tensor
+    of the CUDA path must be within K x that distance of the truth (+ a floor of 1e-5 of the tensor's norm), the median tensor
+    within KMED x, and every tensor within 10 % of the truth in absolute terms."""
+    from make_golden_nets import TRAIN_FLAGS
+    from oracle import train_oracle as TO
+    from test_oracle_train import build_nets, flags_to_cfg
+
+    # measured on B200 (profiles/r02_gradient_conditioning.txt): fp32 FFMA engine median 2.0 / max 7.4; 3xTF32 tcgen05 engine (default)
+    # median 4.4 / max 11.4 -- tensor-core accumulation is not IEEE fp32 summation; single-pass TF32 (what torch's default
+    # cudnn.allow_tf32 does): median 39 (46 % off the truth: decorrelated).  The gate is for the default engine.
+    K, KMED = 14.0, 6.0
+    gold = dict(np.load(os.path.join(GOLDEN, "train_golden.npz")))
+    name = "tr_cfg4"
+    flags, batch, T, seed = TRAIN_FLAGS[name]
+    cfg = flags_to_cfg(flags)
+    model = _build_model(flags, seed, dev)
+    G0, D0 = build_nets(cfg, seed)
+    model.netG.load_state_dict(G0.state_dict())
+    model.netD.load_state_dict(D0.state_dict())
+    sdG = {k: v.detach().cpu().clone() for k, v in model.netG.state_dict().items()}
+    sdD = {k: v.detach().cpu().clone() for k, v in model.netD.state_dict().items()}
+    kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D",
+                              "fit_residual", "down", "up")}
+    lr_a, hr_a = gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"]
+    r32 = TO.train_step(sdG, sdD, lr_a, hr_a, steps=1, **kw)
+    r64 = TO.train_step(sdG, sdD, lr_a, hr_a, steps=1, dtype=torch.float64, **kw)
+    # the same fp32 spectrograms on all three sides (the transform has its own parity tests; its 3e-6 differences from the oracle's
+    # numpy transform would otherwise be an INPUT perturbation 50x above fp32 rounding, amplified by the same chaotic factor)
+    spec = {lr_a.tobytes(): TO.spectro(lr_a).to(dev), hr_a.tobytes(): TO.spectro(hr_a).to(dev)}
+    lo_hi = model.preprocess._src_minmax(dev)
+
+    def oracle_spectro(audio, mask=False, mask_size=-1, channels=1, out=None):
+        s1 = spec[audio.detach().cpu().numpy().tobytes()]
+        s = s1 if channels == 1 else torch.cat((s1, s1.abs() * 2 + float(model.norm_range[0])), dim=1).contiguous()
+        return s, None, {"max": lo_hi[1], "min": lo_hi[0], "mean": None, "std": None, "frames": None}
+
+    model.preprocess.to_spectro = oracle_spectro
+    model.train_step(torch.from_numpy(lr_a).to(dev), torch.from_numpy(hr_a).to(dev))
+    ours = {"gradG": {k: p.grad.detach().cpu().double() for k, p in model.netG.named_parameters()},
+            "gradD": {k: p.grad.detach().cpu().double() for k, p in model.netD.named_parameters()}}
+    for which in ("gradG", "gradD"):
+        gmax = max(float(v.norm()) for v in r64[which].values())
+        ratios = []
+        for k, truth in r64[which].items():
+            n = float(truth.norm())
+            if n < 1e-6 * gmax:                      # zero-gradient tensors (biases in front of a norm): rounding noise on every side
+                assert float(ours[which][k].norm()) < 1e-3 * gmax, k
+                continue
+            e_ref = float((r32[which][k].double() - truth).norm()) / n
+            e_our = float((ours[which][k] - truth).norm()) / n
+            ratios.append((e_our / max(e_ref, 1e-5), k, e_our, e_ref))
+        rs = np.array([r[0] for r in ratios])
+        worst = max(ratios)
+        print(f"{which}: {len(ratios)} tensors, |ours - fp64| / |oracle_fp32 - fp64|: median {np.median(rs):.2f}, 90% {np.quantile(rs, 0.9):.2f}, "
+              f"max {worst[0]:.2f} ({worst[1]}: ours {worst[2]:.2e}, oracle {worst[3]:.2e}); ours vs truth: median "
+              f"{np.median([r[2] for r in ratios]):.2e}, max {max(r[2] for r in ratios):.2e}")
+        for ratio, k, e_our, e_ref in ratios:
+            assert e_our <= K * e_ref + 1e-5, (which, k, e_our, e_ref)
+            assert e_our <= 0.10, (which, k, e_our)
+        assert float(np.median(rs)) <= KMED, (which, float(np.median(rs)))
 
 
 def test_weight_packer_matches_per_layer_packing(dev):
