@@ -77,9 +77,9 @@ struct mdctgan_plan {
 namespace {
 
 // Persistent grid = resident CTAs per SM x SM count, for each tile height ft in {4, 8, 12, 16}.
-template <typename K, typename SmemFn> int setup_kernel(K kernel, SmemFn smem_of, int num_sms, int* grid_out) {
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(kMaxFramesPerTile)));
-  for (int i = 0; i < 4; ++i) {
+template <typename K, typename SmemFn> int setup_kernel(K kernel, SmemFn smem_of, int num_sms, int* grid_out, int max_ft) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(max_ft)));
+  for (int i = 0; i < max_ft / 4; ++i) {
     const int ft = 4 * (i + 1);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * (i + 1), smem_of(ft)));
@@ -90,10 +90,10 @@ template <typename K, typename SmemFn> int setup_kernel(K kernel, SmemFn smem_of
 }
 
 // Frames per tile: minimise (tiles per clip) x (rows staged per tile); `halo` = frames recomputed per tile.
-int pick_ft(int64_t units, int halo) {
-  int best = kMaxFramesPerTile;
+int pick_ft(int64_t units, int halo, int max_ft) {
+  int best = max_ft;
   int64_t best_cost = INT64_MAX;
-  for (int ft = kMaxFramesPerTile; ft >= 4; ft -= 4) {
+  for (int ft = max_ft; ft >= 4; ft -= 4) {
     const int64_t per = ft - halo;
     const int64_t cost = ((units + per - 1) / per) * (ft + 1);
     if (cost < best_cost) { best_cost = cost; best = ft; }
@@ -128,7 +128,7 @@ int check_norm(const mdctgan_norm* n) {
 
 template <typename R, int EPI, typename OutT, bool EXACT>
 int launch_fwd(const mdctgan_plan* pl, FwdParams& p, const int* grid_cap, cudaStream_t st) {
-  p.ft = pick_ft(p.F, 0);
+  p.ft = pick_ft(p.F, 0, KCfg<R>::kMaxFt);
   p.tiles_per_clip = (p.F + p.ft - 1) / p.ft;
   p.ntiles = p.B * p.tiles_per_clip;
   if (p.ntiles == 0) return 0;
@@ -145,7 +145,7 @@ template <typename R, typename S, typename OutT, int PRO, bool EXACT>
 int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaStream_t st) {
   if (p.B == 0 || p.F < 2 || p.out_len == 0) return 0;
   const int64_t nout = (p.out_len + kHop - 1) / kHop;   // output blocks actually needed (out_length crop)
-  p.ft = pick_ft(nout, 1);
+  p.ft = pick_ft(nout, 1, KCfg<R>::kMaxFt);
   p.tiles_per_clip = (nout + p.ft - 2) / (p.ft - 1);
   p.ntiles = p.B * p.tiles_per_clip;
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
@@ -210,18 +210,18 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   auto is32 = [](int ft) { return inv_smem_bytes<float, float>(ft); };
   auto is64 = [](int ft) { return inv_smem_bytes<double, double>(ft); };
   auto is64f = [](int ft) { return inv_smem_bytes<double, float>(ft); };
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0, float, false>, fs32, pl->num_sms, pl->grid_fwd[0]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1, float, false>, fs32, pl->num_sms, pl->grid_fwd[1]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, double, true>, fs64, pl->num_sms, pl->grid_fwd[2]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, true>, fs64, pl->num_sms, pl->grid_fwd[3]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, float, false>, fs64, pl->num_sms, pl->grid_fwd[4]))) return rc;
-  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, false>, fs64, pl->num_sms, pl->grid_fwd[5]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0, false>, is32, pl->num_sms, pl->grid_inv[0]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4]))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5]))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0, float, false>, fs32, pl->num_sms, pl->grid_fwd[0], KCfg<float>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1, float, false>, fs32, pl->num_sms, pl->grid_fwd[1], KCfg<float>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, double, true>, fs64, pl->num_sms, pl->grid_fwd[2], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, true>, fs64, pl->num_sms, pl->grid_fwd[3], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, float, false>, fs64, pl->num_sms, pl->grid_fwd[4], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, false>, fs64, pl->num_sms, pl->grid_fwd[5], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0, false>, is32, pl->num_sms, pl->grid_inv[0], KCfg<float>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2], KCfg<float>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5], KCfg<double>::kMaxFt))) return rc;
   *out = pl;
   return 0;
 }

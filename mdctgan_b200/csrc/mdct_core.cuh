@@ -113,10 +113,10 @@ template <typename R> struct SmemT {
   const cx<R>* base;   // + j
   MDCT_HD cx<R> operator()(int k1) const { return base[k1 * 8]; }
 };
-struct SmemW {
-  const float* base;   // + 2*j
-  MDCT_HD float e(int r) const { return base[r * 16]; }
-  MDCT_HD float o(int r) const { return base[r * 16 + 1]; }
+template <typename R> struct SmemW {
+  const R* base;       // + 2*j; already converted to the core type
+  MDCT_HD R e(int r) const { return base[r * 16]; }
+  MDCT_HD R o(int r) const { return base[r * 16 + 1]; }
 };
 
 // Plan table layout in global memory (built once on the host in fp64, see capi.cu):
@@ -152,7 +152,7 @@ MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WT& w
     const int e = (r < 8) ? 2 * j + 16 * r + 128 : 2 * j + 16 * r - 128;
     const int o = (r < 8) ? 127 - 2 * j - 16 * r : 383 - 2 * j - 16 * r;
     R ue, uo;
-    const float we = w.e(r), wo = w.o(r);
+    const auto we = w.e(r), wo = w.o(r);
     if (NATIVE) {
       const R wE = (R)we, wO = (R)wo;
       if (r < 8) {   // n < 64
@@ -164,11 +164,11 @@ MDCT_HD void fwd_gather(const float* row0, const float* row1, int j, const WT& w
       }
     } else {
       if (r < 8) {
-        ue = -(R)fmul32(we, row1[o]) - (R)fmul32(wo, row1[e]);
-        uo = (R)fmul32(wo, row0[o]) - (R)fmul32(we, row0[e]);
+        ue = -(R)fmul32((float)we, row1[o]) - (R)fmul32((float)wo, row1[e]);
+        uo = (R)fmul32((float)wo, row0[o]) - (R)fmul32((float)we, row0[e]);
       } else {
-        ue = (R)fmul32(we, row0[e]) - (R)fmul32(wo, row0[o]);
-        uo = -(R)fmul32(wo, row1[e]) - (R)fmul32(we, row1[o]);
+        ue = (R)fmul32((float)we, row0[e]) - (R)fmul32((float)wo, row0[o]);
+        uo = -(R)fmul32((float)wo, row1[e]) - (R)fmul32((float)we, row1[o]);
       }
     }
     v[r] = (r == 0) ? cx<R>{ue, uo} : cmulc(cx<R>{ue, uo}, rho_re<R>(r), rho_im<R>(r));

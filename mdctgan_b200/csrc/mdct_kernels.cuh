@@ -29,8 +29,13 @@
 
 namespace mdctk {
 
-constexpr int kStages = 2;
-constexpr int kMaxThreads = 128;
+// Per-core-type launch shape.  fp32 core: 2-stage input ring, tiles of up to 16 frames (128 threads).  fp64 core (168 registers,
+// 16-byte exchange slots): ONE input stage and tiles of at most 12 frames (96 threads), so that 4 (forward) / 3 (inverse) CTAs
+// share an SM -- the fp64 kernels are latency bound (ncu r02c: 2.25 warps per scheduler, 5.5 cycles per issued instruction),
+// co-resident CTAs hide the tile load instead of a second stage.
+template <typename R> struct KCfg;
+template <> struct KCfg<float> { static constexpr int kStages = 2, kMaxFt = 16, kMinBlocksFwd = 5, kMinBlocksInv = 4; };
+template <> struct KCfg<double> { static constexpr int kStages = 1, kMaxFt = 12, kMinBlocksFwd = 4, kMinBlocksInv = 3; };
 
 struct FwdParams {
   const float* audio; int64_t audio_stride; int64_t T;
@@ -165,18 +170,12 @@ __device__ __forceinline__ void fwd_produce(const FwdParams& p, int64_t tile, fl
 constexpr int kTabTElems = 8 * 16;       // thread twiddles, [k1][j]
 constexpr int kTabWFloats = 8 * 16 * 2;  // window pairs, [r][j][2]
 template <typename R> __host__ __device__ constexpr size_t fwd_smem_bytes(int ft) {
-  return align16((size_t)kStages * (ft + 1) * kRawPitch * sizeof(float)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
-         kTabTElems * sizeof(cx<R>) + kTabWFloats * sizeof(float) + 64;
+  return align16((size_t)KCfg<R>::kStages * (ft + 1) * kRawPitch * sizeof(float)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
+         kTabTElems * sizeof(cx<R>) + kTabWFloats * sizeof(R) + 64;
 }
-#ifndef MDCT_MINBLOCKS_F32
-#define MDCT_MINBLOCKS_F32 5
-#endif
-#ifndef MDCT_MINBLOCKS_F64
-#define MDCT_MINBLOCKS_F64 3
-#endif
 // Stage the plan tables in shared memory: sT[k1*8 + j] = T[j][k1] * scale, sW[(r*8 + j)*2 + {0,1}] = (wE, wO)[j][r]
 template <typename R>
-__device__ __forceinline__ void stage_tables(const R* __restrict__ tabT, const float* __restrict__ tabW, R scale, cx<R>* sT, float* sW) {
+__device__ __forceinline__ void stage_tables(const R* __restrict__ tabT, const float* __restrict__ tabW, R scale, cx<R>* sT, R* sW) {
   for (int i = threadIdx.x; i < kTabTElems; i += blockDim.x) {
     const int k1 = i >> 3, j = i & 7;
     sT[i] = cx<R>{tabT[(j * 16 + k1) * 2 + 0] * scale, tabT[(j * 16 + k1) * 2 + 1] * scale};
@@ -184,8 +183,8 @@ __device__ __forceinline__ void stage_tables(const R* __restrict__ tabT, const f
   if (sW) {
     for (int i = threadIdx.x; i < kTabTElems; i += blockDim.x) {
       const int r = i >> 3, j = i & 7;
-      sW[2 * i] = tabW[(j * 16 + r) * 2 + 0];
-      sW[2 * i + 1] = tabW[(j * 16 + r) * 2 + 1];
+      sW[2 * i] = (R)tabW[(j * 16 + r) * 2 + 0];         // converted once per CTA (the fp64 core would convert per use)
+      sW[2 * i + 1] = (R)tabW[(j * 16 + r) * 2 + 1];
     }
   }
 }
@@ -194,13 +193,14 @@ __device__ __forceinline__ void stage_tables(const R* __restrict__ tabT, const f
 // EXACT (fp64 core only): the reference's fp32-rounded window products and library asinh (bit-faithful flavour);
 // otherwise products are formed in R and the compress epilogue is the fast fp32 one.
 template <typename R, int EPI, typename OutT, bool EXACT>
-__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? MDCT_MINBLOCKS_F32 : MDCT_MINBLOCKS_F64) mdct4_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(8 * KCfg<R>::kMaxFt, KCfg<R>::kMinBlocksFwd) mdct4_fwd_kernel(const FwdParams p) {
+  constexpr int kStages = KCfg<R>::kStages;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int stage_floats = (p.ft + 1) * kRawPitch;
   float* raw = reinterpret_cast<float*>(smem_raw);
   cx<R>* xch_all = reinterpret_cast<cx<R>*>(smem_raw + align16((size_t)kStages * stage_floats * sizeof(float)));
   cx<R>* sT = reinterpret_cast<cx<R>*>(reinterpret_cast<unsigned char*>(xch_all) + align16((size_t)p.ft * kXchStride * sizeof(cx<R>)));
-  float* sW = reinterpret_cast<float*>(sT + kTabTElems);
+  R* sW = reinterpret_cast<R*>(sT + kTabTElems);
   uint64_t* full = reinterpret_cast<uint64_t*>(sW + kTabWFloats);
   uint64_t* empty = full + kStages;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(empty + kStages);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? MDCT_MINBLOCKS_F
   }
 
   const SmemT<R> tt{sT + j};
-  const SmemW wt{sW + 2 * j};
+  const SmemW<R> wt{sW + 2 * j};
   const float c1 = (float)(0.6931471805599453 / kLn10F32) * p.np.aff_a;   // log2 -> ln -> /ln10_f32 -> affine
   cx<R>* const xch = xch_all + f * kXchStride;
 
@@ -337,7 +337,7 @@ __device__ __forceinline__ void inv_produce(const InvParams& p, int64_t tile, S*
 }
 
 template <typename R, typename S> __host__ __device__ constexpr size_t inv_smem_bytes(int ft) {
-  return align16((size_t)kStages * ft * kRawPitch * sizeof(S)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
+  return align16((size_t)KCfg<R>::kStages * ft * kRawPitch * sizeof(S)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
          align16((size_t)ft * kURow * sizeof(R)) + 512 * sizeof(float) + kTabTElems * sizeof(cx<R>) + 64;
 }
 
@@ -410,7 +410,8 @@ __device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t til
 //   pass 1 / pass 2 of tile i (private exchange slice) -> wait odone(i-1) -> write U rows(i) -> arrive udone(i)
 // so both cross-warp dependencies (U rows complete / U rows free) are split-phase with real work in between.
 template <typename R, typename S, typename OutT, int PRO, bool EXACT>
-__global__ void __launch_bounds__(kMaxThreads, sizeof(R) == 4 ? MDCT_MINBLOCKS_F32 : MDCT_MINBLOCKS_F64) imdct4_inv_kernel(const InvParams p) {
+__global__ void __launch_bounds__(8 * KCfg<R>::kMaxFt, KCfg<R>::kMinBlocksInv) imdct4_inv_kernel(const InvParams p) {
+  constexpr int kStages = KCfg<R>::kStages;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int stage_elems = p.ft * kRawPitch;
   unsigned char* sp_ = smem_raw;
