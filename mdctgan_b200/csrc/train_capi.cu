@@ -41,8 +41,9 @@ int launch_wgrad_umma(umma::WgradUmmaParams& p, cudaStream_t st) {
   p.n_tiles = p.Cout / BN;
   const int m_tiles = (p.K + umma::kBM - 1) / umma::kBM;
   const int tiles = m_tiles * p.n_tiles;
-  // split the reduction over pixels until about one wave of CTAs exists; every split costs one more set of output reductions
-  int psplit = tiles >= 148 ? 1 : (148 + tiles - 1) / tiles;
+  // split the reduction over pixels while the CTAs still fit ONE wave (1 CTA per SM: the ring takes most of the shared memory);
+  // every split costs one more set of output reductions
+  int psplit = tiles >= 148 ? 1 : 148 / tiles;
   if (psplit > p.chunks) psplit = p.chunks;
   if (psplit > 65535) psplit = 65535;
   umma::conv_wgrad_umma_kernel<BN, SPLIT3><<<dim3(tiles, psplit), umma::kWgThreads, C::kSmemBytes, st>>>(p);

@@ -199,6 +199,8 @@ def run_layers(layers: Sequence[nn.Module], f: Feat) -> Feat:
     while i < n:
         L = layers[i]
         nxt = layers[i + 1] if i + 1 < n else None
+        if ops._marks:
+            ops.mark(L)
         if isinstance(L, ReflectionPad2d):
             pad_reflect = L.padding
             i += 1

@@ -227,6 +227,9 @@ from .. import nn_ops as _ops  # noqa: E402
 
 # opt-in: split the gradient exchange into an early bucket (overlapped with the generator sweep) + the rest (3 collectives per step)
 BUCKETED_ALLREDUCE = os.environ.get("MDCTGAN_BUCKETED_ALLREDUCE", "0") == "1"
+# Pipelined update (default): per-bucket [all-reduce ->] Adam -> weight images on an update stream as soon as the bucket's gradients
+# are complete, overlapping the rest of the backward sweep.  "0": one all-reduce + whole-network Adam + packing after the sweeps.
+PIPELINED_UPDATE = os.environ.get("MDCTGAN_PIPELINED_UPDATE", "1") != "0"
 
 
 class BaseModel(torch.nn.Module):
@@ -340,10 +343,9 @@ class Pix2PixHDModel(BaseModel):
             self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe, params=params_G)
             self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
             self._graph = None
-            from ..packing import WeightPacker
-
-            # all kernel-side weight images (forward + input-gradient, direct + tcgen05) in one buffer, refreshed by one launch
-            self.packer = WeightPacker(self.netG, self.netD)
+            # update buckets: contiguous flat ranges of parameters whose Adam step and kernel-side weight images are issued as soon as
+            # their gradients are complete (while the rest of the backward sweep still runs); one weight packer per bucket
+            self._plan_update_buckets()
             self._packed_at = None
 
     # ---- generator graph ---------------------------------------------------------------------------------
@@ -410,8 +412,19 @@ class Pix2PixHDModel(BaseModel):
 
         graph = T.GanGraph(self)
         self._refresh_weight_images()
+        pipelined = PIPELINED_UPDATE and not BUCKETED_ALLREDUCE and _ops.SIDE_STREAM_WGRAD
         with _ops.stats_pass(self.device):
             self.grad_all.zero_()                          # one memset for both buckets
+            self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size
+            self.optimizer_G.begin_step()                  # step counters first: the bucket updates below run on their own stream
+            self.optimizer_D.begin_step()
+            if pipelined:
+                upd = _ops.aux_stream(self.device, "update")
+                upd.wait_stream(torch.cuda.current_stream(self.device))
+                for bk in self._buckets:
+                    bk.done = False
+                    if bk.mark is not None and bk.net == "G":
+                        _ops._marks[id(bk.mark)] = (lambda _bk=bk: self._flush_bucket(_bk, all_reduce, None))
             losses = graph.forward(lr_audio, hr_audio)
             # the two sweeps only read the tapes and write disjoint gradients: the discriminator sweep runs on its own stream,
             # concurrently with the generator sweep; weight-gradient kernels of both go to the side stream
@@ -438,26 +451,114 @@ class Pix2PixHDModel(BaseModel):
                 sD.wait_stream(main)
                 with torch.cuda.stream(sD):
                     graph.backward_D(half, half, join=False)
-                graph.backward_G(join=False)
+                    ev_sD = torch.cuda.Event()
+                    ev_sD.record(sD)
+                after_D = None
+                if pipelined:
+                    # the discriminator's update overlaps the generator sweep -- but only once that sweep has passed through the
+                    # discriminator itself (it back-propagates the generator loss through the OLD discriminator weights)
+                    def after_D():
+                        evs = [ev_sD]
+                        sw = _ops._side.get(self.device.index)
+                        for st_ in ([main] + ([sw.stream] if (sw is not None and sw.active) else [])):
+                            e_ = torch.cuda.Event()
+                            e_.record(st_)
+                            evs.append(e_)
+                        for bk in self._buckets:
+                            if bk.net == "D":
+                                self._flush_bucket(bk, all_reduce, evs)
+                graph.backward_G(join=False, after_D=after_D)
                 main.wait_stream(sD)
             else:
                 graph.backward_G(join=False)
                 graph.backward_D(half, half, join=False)
             _ops.join_side_work(self.device)              # the exchange / optimiser read the gradients from here on
-            if eb is not None:
+            if pipelined:
+                _ops._marks.clear()
+                for bk in self._buckets:                   # whatever no tape mark flushed (frozen trunks, unmarked leftovers)
+                    if not bk.done:
+                        self._flush_bucket(bk, all_reduce, None)
+                main.wait_stream(upd)
+            elif eb is not None:
                 _ops._wgrad_hooks.pop(id(trig), None)
                 main.wait_stream(comm)
                 all_reduce(self.grad_all[:lo_b])
                 all_reduce(self.grad_all[hi_b:])
             elif all_reduce is not None:
                 all_reduce(self.grad_all)                  # ONE collective per step
-            self.optimizer_G.grad_scale = self.optimizer_D.grad_scale = 1.0 / world_size
-            self.optimizer_G.step()
-            self.optimizer_D.step()
-            self.packer.refresh()                          # the next forward (and a CUDA-graph replay) sees the updated weights
+            if not pipelined:
+                for o in (self.optimizer_G, self.optimizer_D):
+                    o.step_range(0, o.bucket.numel)
+                self.packer.refresh()                      # the next forward (and a CUDA-graph replay) sees the updated weights
+            self.optimizer_G.end_step()
+            self.optimizer_D.end_step()
             self._packed_at = self._pack_key()
         graph.release()
         return losses
+
+    def _plan_update_buckets(self):
+        """Update buckets of the pipelined train step.  Generator: the top-level children of its sequential trunks (`model`, and
+        `model1_1` / `model1_2` of a LocalEnhancer), grouped in backward order into contiguous flat ranges of >= 1/8 of the
+        parameters; a tape mark in front of a bucket's first child fires when the backward sweep has passed all of it
+        (nn_ops._MarkOp).  Discriminator: one bucket, flushed when its sweep has been issued.  Each bucket owns the weight packer
+        of its layers."""
+        from types import SimpleNamespace
+
+        from ..packing import WeightPacker
+
+        nG = self.bucket_G.numel
+        offs = {id(p): (o, o + (p.numel() + 3) // 4 * 4) for p, o in zip(self.bucket_G.params, self.bucket_G.offsets)}
+        buckets, covered = [], 0
+        target = max(nG // 8, 1 << 20)
+        trunks = [m for m in (getattr(self.netG, n, None) for n in ("model", "model1_1", "model1_2")) if isinstance(m, torch.nn.Sequential)]
+        for trunk in trunks:
+            kids = [c for c in trunk if next(c.parameters(), None) is not None]
+            group, size = [], 0
+            for c in reversed(kids):
+                group.insert(0, c)
+                size += sum(p.numel() for p in c.parameters())
+                if size >= target or c is kids[0]:
+                    ps = [p for m in group for p in m.parameters()]
+                    lo, hi = min(offs[id(p)][0] for p in ps), max(offs[id(p)][1] for p in ps)
+                    if hi - lo == sum(offs[id(p)][1] - offs[id(p)][0] for p in ps):      # contiguous in the flat buffer
+                        buckets.append(SimpleNamespace(net="G", lo=lo, hi=hi, glo=lo, ghi=hi, mark=group[0], modules=list(group), done=False))
+                        covered += hi - lo
+                    group, size = [], 0
+        if covered != nG or not buckets:          # unknown generator structure: one bucket, flushed after the sweeps
+            buckets = [SimpleNamespace(net="G", lo=0, hi=nG, glo=0, ghi=nG, mark=None, modules=[self.netG], done=False)]
+        nD = self.bucket_D.numel
+        buckets.append(SimpleNamespace(net="D", lo=0, hi=nD, glo=nG, ghi=nG + nD, mark=None, modules=[self.netD], done=False))
+        for bk in buckets:
+            has_conv = any(isinstance(m, (networks.Conv2d, networks.ConvTranspose2d)) for mod in bk.modules for m in mod.modules())
+            bk.packer = WeightPacker(*bk.modules) if has_conv else None
+        self._buckets = buckets
+        self.packer = SimpleNamespace(refresh=lambda: [bk.packer.refresh() for bk in self._buckets if bk.packer is not None],
+                                      parts=[bk.packer for bk in buckets if bk.packer is not None])
+
+    def _flush_bucket(self, bk, all_reduce, events):
+        """[all-reduce ->] Adam -> weight images of one update bucket on the update stream, after everything enqueued so far on the
+        current stream and on the weight-gradient side stream (`events` = None), or after `events`."""
+        if bk.done:
+            return
+        bk.done = True
+        upd = _ops.aux_stream(self.device, "update")
+        cur = torch.cuda.current_stream(self.device)
+        if events is None:
+            events = []
+            sw = _ops._side.get(self.device.index)
+            for st in ([cur] + ([sw.stream] if (sw is not None and sw.active) else [])):
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events.append(ev)
+        for ev in events:
+            upd.wait_event(ev)
+        opt_ = self.optimizer_G if bk.net == "G" else self.optimizer_D
+        with torch.cuda.stream(upd):
+            if all_reduce is not None:
+                all_reduce(self.grad_all[bk.glo:bk.ghi])
+            opt_.step_range(bk.lo, bk.hi)
+            if bk.packer is not None:
+                bk.packer.refresh()
 
     def _early_bucket(self):
         """(lo, hi, trigger module) of the flat gradient range that is complete long before the end of the generator sweep: the

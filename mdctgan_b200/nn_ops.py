@@ -223,6 +223,8 @@ def umma_supported(cin: int, cout: int) -> bool:
     return CONV_ENGINE != "direct" and bool(_L().mdctgan_conv2d_umma_supported(int(cin), int(cout)))
 
 
+# development switches: run the forward / input-gradient convolutions of the tensor-core layers on the fp32 kernels ("direct")
+_ROLE_ENGINE = {"fwd": os.environ.get("MDCTGAN_FWD_ENGINE", ""), "dgrad": os.environ.get("MDCTGAN_DGRAD_ENGINE", "")}
 WGRAD_ENGINE = os.environ.get("MDCTGAN_WGRAD_ENGINE", "")      # "" = follow CONV_ENGINE; "direct" forces the fp32 FFMA weight gradient
 
 
@@ -248,7 +250,7 @@ def pack_conv_weight_umma(w_kn: torch.Tensor) -> torch.Tensor:
 
 def _conv_launch(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, kh: int, kw: int, stride: int = 1, pad: int = 0,
                  pad_mode: int = PAD_ZERO, transposed: bool = False, output_padding: int = 0, act: int = ACT_NONE,
-                 want_stats: bool = False, w_umma: Optional[torch.Tensor] = None, out_hw=None) -> Feat:
+                 want_stats: bool = False, w_umma: Optional[torch.Tensor] = None, out_hw=None, role: str = "fwd") -> Feat:
     """One convolution launch (no tape).  `out_hw` forces the output size of a transposed convolution (dgrad)."""
     x = f.x
     _req(x, "conv2d input")
@@ -268,7 +270,7 @@ def _conv_launch(f: Feat, w_packed: torch.Tensor, bias: Optional[torch.Tensor], 
         raise RuntimeError("conv2d: input still carries un-finalised statistics (missing norm layer?)")
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     stats = _new_stats(B, Cout, x.device) if want_stats else None
-    use_umma = w_umma is not None and CONV_ENGINE != "direct"
+    use_umma = w_umma is not None and CONV_ENGINE != "direct" and _ROLE_ENGINE.get(role, "") != "direct"
     if use_umma and transposed and stride > 1 and (Ho < stride or Wo < stride or Cin % 32 or kh < stride or kw < stride):
         use_umma = False        # the tensor-core kernel runs strided transposed convolutions per output parity class only
     if not use_umma and w_packed.stride(0) == 0:
@@ -585,6 +587,27 @@ class _ParallelOp:
                 main.wait_stream(_branch_stream(self.device, i, main))
 
 
+class _MarkOp:
+    """A position on the tape: when the backward sweep (with weight gradients) reaches it, every op recorded after it has been
+    back-propagated -- e.g. "all gradients of this update bucket have been enqueued" (the pipelined optimiser step)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def backward(self, G, wgrad, nb):
+        if wgrad:
+            self.fn()
+
+
+_marks = {}             # id(module) -> callable, consulted by models.networks.run_layers before it runs the module
+
+
+def mark(module) -> None:
+    fn = _marks.get(id(module))
+    if fn is not None and _tape is not None:
+        _tape.ops.append(_MarkOp(fn))
+
+
 class Tape:
     def __init__(self):
         self.ops = []
@@ -732,16 +755,16 @@ class _ConvOp:
         wd, wd_umma, flipped = own.packed_dgrad()
         g = Feat(dy)
         if self.transposed:          # ConvTranspose2d: a plain strided convolution of dy
-            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=self.stride, pad=self.pad, w_umma=wd_umma).x
+            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=self.stride, pad=self.pad, w_umma=wd_umma, role="dgrad").x
             assert dv.shape[1:3] == (H, W)
         elif flipped:                # stride 1: plain convolution with the taps flipped, pad' = k - 1 - pad
             p_eff = 0 if self.pad_mode == PAD_REFLECT else self.pad
-            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=1, pad=self.kh - 1 - p_eff, w_umma=wd_umma).x
+            dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=1, pad=self.kh - 1 - p_eff, w_umma=wd_umma, role="dgrad").x
         else:                        # strided nn.Conv2d: transposed convolution of dy, output size forced to the input's
             p_eff = 0 if self.pad_mode == PAD_REFLECT else self.pad
             hw = (H + 2 * self.pad, W + 2 * self.pad) if self.pad_mode == PAD_REFLECT else (H, W)
             dv = _conv_launch(g, wd, None, kh=self.kh, kw=self.kw, stride=self.stride, pad=p_eff, transposed=True, w_umma=wd_umma,
-                              out_hw=hw).x
+                              out_hw=hw, role="dgrad").x
         if self.pad_mode == PAD_REFLECT:
             assert dv.shape[1:3] == (H + 2 * self.pad, W + 2 * self.pad), (dv.shape, H, W, self.pad)
             dx = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dv.device)

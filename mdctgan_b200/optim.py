@@ -133,24 +133,43 @@ class FusedAdam(torch.optim.Optimizer):
                 break
 
     @torch.no_grad()
-    def step(self, closure=None):
-        if closure is not None:
-            raise NotImplementedError("FusedAdam.step(closure)")
+    def begin_step(self):
+        """Advance the step counters (host and device) once per optimiser step, before the first `step_range`."""
+        self.step_count += 1
+        if self.step_dev is not None:
+            b = self.bucket
+            with torch.cuda.device(b.flat.device):
+                _lib.check(ops._L().mdctgan_counter_inc(self.step_dev.data_ptr(), torch.cuda.current_stream(b.flat.device).cuda_stream))
+
+    @torch.no_grad()
+    def step_range(self, lo: int, hi: int):
+        """Adam on the trainable parameters inside the flat range [lo, hi) -- one launch per contiguous run, on the current stream.
+        The pipelined train step updates a range as soon as its gradients are complete (models/pix2pixHD_model.py)."""
         g = self.param_groups[0]
         b = self.bucket
-        self.step_count += 1
         L = ops._L()
         with torch.cuda.device(b.flat.device):
             st = torch.cuda.current_stream(b.flat.device).cuda_stream
-            if self.step_dev is not None:
-                _lib.check(L.mdctgan_counter_inc(self.step_dev.data_ptr(), st))
-            for lo, hi in b.trainable_runs(self._subset):
-                _lib.check(L.mdctgan_adam_flat(b.flat[lo:hi].data_ptr(), b.grad[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
-                                               self.exp_avg_sq[lo:hi].data_ptr(), hi - lo, float(g["lr"]), float(g["betas"][0]),
+            for rlo, rhi in b.trainable_runs(self._subset):
+                rlo, rhi = max(rlo, lo), min(rhi, hi)
+                if rhi <= rlo:
+                    continue
+                _lib.check(L.mdctgan_adam_flat(b.flat[rlo:rhi].data_ptr(), b.grad[rlo:rhi].data_ptr(), self.exp_avg[rlo:rhi].data_ptr(),
+                                               self.exp_avg_sq[rlo:rhi].data_ptr(), rhi - rlo, float(g["lr"]), float(g["betas"][0]),
                                                float(g["betas"][1]), float(g["eps"]), float(self.grad_scale), self.step_count,
                                                self.step_dev.data_ptr() if self.step_dev is not None else None, st))
-        for p in b.params:          # kernel-side weight images (packed / tcgen05) are keyed on the version counter
+
+    def end_step(self):
+        for p in self.bucket.params:          # kernel-side weight images (packed / tcgen05) are keyed on the version counter
             p._version_bump = getattr(p, "_version_bump", 0) + 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedAdam.step(closure)")
+        self.begin_step()
+        self.step_range(0, self.bucket.numel)
+        self.end_step()
         return None
 
     def state_dict(self):

@@ -44,7 +44,7 @@ class WeightPacker:
             if strided_transposed and (Kch % 32 or min(layer.kernel_size) < layer.stride[0]):
                 use_umma = False                    # the tensor-core kernel runs strided transposed geometry per parity class only
             # the [K][N] image is only read by the direct fp32 kernels: skip it where the tcgen05 kernel runs the layer
-            want_kn = (not use_umma) or ops.CONV_ENGINE == "direct"
+            want_kn = (not use_umma) or ops.CONV_ENGINE == "direct" or ops._ROLE_ENGINE.get("dgrad" if role == "dgrad" else "fwd", "") == "direct"
             # [kh][kw][Cin][Cout] storage (optim.FlatBucket): the master copy already IS the forward [K][N] image
             alias_kn = want_kn and not flip and s_n == 1 and s_kch == N and s_tap == Kch * N
             off_kn = None

@@ -95,7 +95,8 @@ class GanGraph:
 
     # ------------------------------------------------------------------ backward sweeps
     @torch.no_grad()
-    def backward_G(self, g_gan: Optional[torch.Tensor] = None, g_feat: Optional[torch.Tensor] = None, use_gan=True, use_feat=True, join=True):
+    def backward_G(self, g_gan: Optional[torch.Tensor] = None, g_feat: Optional[torch.Tensor] = None, use_gan=True, use_feat=True, join=True,
+                   after_D=None):
         """d(g_gan * G_GAN + g_feat * G_GAN_Feat) / d(G parameters) accumulated into their .grad (the flat bucket).
         g_*: 0-dim CUDA tensors (upstream gradients of the loss tensors) or None = 1."""
         m, B = self.m, self.B
@@ -117,6 +118,8 @@ class GanGraph:
                                                          g.data_ptr(), 0, _st(g)))
                         G.add(f, g)
             self.tapeD.backward(G, wgrad=False, nb=B, join=False)
+            if after_D is not None:                                       # from here on nothing reads the discriminator's weights
+                after_D()
             gin = G.pop(self.din)                                         # [B,F,N,3]
             dsr = torch.empty((B, self.Fr, self.N, 1), dtype=torch.float32, device=m.device)
             _lib.check(L.mdctgan_disc_input_bwd(gin.data_ptr(), self.sr_spectro.data_ptr(), dsr.data_ptr(), dsr.numel(), _st(dsr)))
