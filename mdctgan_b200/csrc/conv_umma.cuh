@@ -167,10 +167,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
 }
 
 // 3xTF32 split x = hi + lo.  hi keeps the top 10 mantissa bits (low 13 bits cleared: exact in the tensor core whatever
-// rounding the hardware applies to fp32 containers); lo = x - hi is exact in fp32 (<= 13 significant bits) and is rounded to
-// the NEAREST TF32 here (tf32_rn) -- left to the tensor core it would be truncated toward zero, and since lo always has the sign
-// of x that truncation is a systematic bias that accumulates linearly over K (measured: generator output 6.3e-5 from the fp64
-// truth with truncation vs 3.5e-5 for the fp32 FFMA kernels).  Residual per product ~2^-22 |x|, unbiased.
+// rounding the hardware applies to fp32 containers); lo = x - hi is exact in fp32 (<= 13 significant bits) and is
+// consumed as TF32 by the tensor core (its truncation of lo leaves a residual <= 2^-21 |x|).  Rounding lo to the nearest TF32
+// in the gather was measured (r02): generator output 6.0e-5 instead of 6.3e-5 from the fp64 truth (fp32 FFMA kernels: 3.5e-5) for
+// +35 % time in the issue-bound gather loop -- the residual is dominated by the tensor core's fp32 accumulation, not by lo.
 __host__ __device__ __forceinline__ float tf32_hi(float v) {
 #ifdef __CUDA_ARCH__
   return __uint_as_float(__float_as_uint(v) & kTf32Mask);
@@ -297,39 +297,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     __syncwarp();
     tmem_alloc(tmem_slot, C::kTmemCols);
   }
-  // The deferred normalisation of the producing layer, CTA-uniform: scale / shift of sample b into shared memory --
-  // ready-made, derived here from the producer's raw (sum, sumsq) statistics (InstanceNorm2d: no separate finalize
-  // launch), or the identity.
-  // table rows: one per sample the tile touches (per-sample normalisation), else one
-  const bool has_norm = p.in.stats != nullptr || p.in.scale != nullptr;
-  const int tab_rows = (has_norm && p.in.per_sample) ? (b_last - b_first + 1) : 1;
-  {
-    const int n_tab = tab_rows * p.Cin;
-    const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
-    if (p.in.stats) {
-      const double inv_n = 1.0 / (double)p.in.count;
-#pragma unroll 1
-      for (int c = tid; c < n_tab; c += kThreads) {
-        const double mean = p.in.stats[2 * (off + c)] * inv_n;
-        double var = p.in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
-        s_scale[c] = (float)rstd;
-        s_shift[c] = (float)(-mean * rstd);
-      }
-    } else if (p.in.scale) {
-#pragma unroll 1
-      for (int c = tid; c < n_tab; c += kThreads) { s_scale[c] = __ldg(p.in.scale + off + c); s_shift[c] = __ldg(p.in.shift + off + c); }
-    } else {
-#pragma unroll 1
-      for (int c = tid; c < p.Cin; c += kThreads) { s_scale[c] = 1.f; s_shift[c] = 0.f; }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   trace_mark(p, 2, tid == 0);
+  const bool has_norm = p.in.stats != nullptr || p.in.scale != nullptr;
+  const int tab_rows = (has_norm && p.in.per_sample) ? (b_last - b_first + 1) : 1;   // rows of the normalisation tables
 
   if (warp < kProducerWarps) {
     // ================= A producers: implicit im2col gather -> normalise -> TF32 hi/lo -> swizzled smem =========
@@ -368,9 +342,75 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     bool tap_dirty = true;
     int rowoff[kRows];
     uint32_t okq = 0;             // validity bits of the chunks in flight, 2 per chunk, newest in the low bits
+    // issue side of the pipeline: the cp.async gathers of chunk `it` (called kAhead chunks ahead of the transform)
+    auto issue_chunk = [&](int it) {
+        // ---- issue chunk it
+      const int s = it % C::kStages;
+      mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
+      if (tap_dirty) {
+        tap_dirty = false;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          int iy = oyb[i] + tg.sgn * ky, ix = oxb[i] + tg.sgn * kx;
+          bool ok = rvalid[i] && tap < tg.ntaps;
+          if (p.pad_mode == nnk::kPadReflect) {
+            iy = iy < 0 ? -iy : iy; iy = iy >= p.H ? 2 * p.H - 2 - iy : iy;
+            ix = ix < 0 ? -ix : ix; ix = ix >= p.W ? 2 * p.W - 2 - ix : ix;
+          } else {
+            ok = ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          }
+          rowoff[i] = ok ? xoff[i] + (iy * p.W + ix) * p.Cin : -1;
+        }
+      }
+      const uint32_t dst = smem_a + s * C::kStageBytes + row_off;
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) {
+        const bool ok = rowoff[i] >= 0;
+        bits |= ok ? (1u << i) : 0u;
+        cp_async16_zfill(dst + i * (kRowStep * 128), ok ? xb + rowoff[i] + c : xb, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      okq = (okq << 2) | bits;
+      c += kKC;
+      while (c >= p.Cin) {
+        c -= p.Cin; ++tap; tap_dirty = true;
+        if (++kx == tg.nkx) { kx = 0; ++ky; }
+      }
+    };
 #pragma unroll 1
-    for (int it = 0; it < nk + kAhead; ++it) {
-      if (it >= kAhead) {
+    for (int it = 0; it < kAhead; ++it)
+      if (it < nk) issue_chunk(it);
+    {
+      // The deferred normalisation of the producing layer -> scale / shift tables in shared memory (one row per sample the tile
+      // touches for a per-sample norm, else one): ready-made, derived here from the producer's raw (sum, sumsq) statistics
+      // (InstanceNorm2d: no separate finalize launch), or the identity.  Filled by the producer warps AFTER their first
+      // gathers (and the first weight copies) are in flight -- only the transform below needs it.
+      const int n_tab = tab_rows * p.Cin;
+      const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
+      if (p.in.stats) {
+        const double inv_n = 1.0 / (double)p.in.count;
+#pragma unroll 1
+        for (int cc = tid; cc < n_tab; cc += kProducerThreads) {
+          const double mean = p.in.stats[2 * (off + cc)] * inv_n;
+          double var = p.in.stats[2 * (off + cc) + 1] * inv_n - mean * mean;
+          var = var < 0.0 ? 0.0 : var;
+          const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
+          s_scale[cc] = (float)rstd;
+          s_shift[cc] = (float)(-mean * rstd);
+        }
+      } else if (p.in.scale) {
+#pragma unroll 1
+        for (int cc = tid; cc < n_tab; cc += kProducerThreads) { s_scale[cc] = __ldg(p.in.scale + off + cc); s_shift[cc] = __ldg(p.in.shift + off + cc); }
+      } else {
+#pragma unroll 1
+        for (int cc = tid; cc < p.Cin; cc += kProducerThreads) { s_scale[cc] = 1.f; s_shift[cc] = 0.f; }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");      // producer warps only
+    }
+#pragma unroll 1
+    for (int it = kAhead; it < nk + kAhead; ++it) {
+      {
         // ---- process chunk q = it - kAhead
         const int q = it - kAhead;
         if (it < nk) cp_async_wait<kAhead - 1>(); else cp_async_wait<0>();
@@ -391,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
           if (SPLIT3) {
             const float4 hi = make_float4(tf32_hi(e.x), tf32_hi(e.y), tf32_hi(e.z), tf32_hi(e.w));
             sts128(a_hi + i * (kRowStep * 128), hi);
-            sts128(a_hi + C::kABytes + i * (kRowStep * 128), make_float4(tf32_rn(e.x - hi.x), tf32_rn(e.y - hi.y), tf32_rn(e.z - hi.z), tf32_rn(e.w - hi.w)));
+            sts128(a_hi + C::kABytes + i * (kRowStep * 128), make_float4(e.x - hi.x, e.y - hi.y, e.z - hi.z, e.w - hi.w));
           } else {
             sts128(a_hi + i * (kRowStep * 128), make_float4(tf32_rn(e.x), tf32_rn(e.y), tf32_rn(e.z), tf32_rn(e.w)));
           }
@@ -403,41 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         if (lane == 0) mbar_arrive(&full[s]);
         if (q == 0) trace_mark(p, 3, tid == 0);
       }
-      if (it < nk) {
-        // ---- issue chunk it
-        const int s = it % C::kStages;
-        mbar_wait(&empty[s], ((uint32_t)(it / C::kStages) & 1u) ^ 1u);
-        if (tap_dirty) {
-          tap_dirty = false;
-#pragma unroll
-          for (int i = 0; i < kRows; ++i) {
-            int iy = oyb[i] + tg.sgn * ky, ix = oxb[i] + tg.sgn * kx;
-            bool ok = rvalid[i] && tap < tg.ntaps;
-            if (p.pad_mode == nnk::kPadReflect) {
-              iy = iy < 0 ? -iy : iy; iy = iy >= p.H ? 2 * p.H - 2 - iy : iy;
-              ix = ix < 0 ? -ix : ix; ix = ix >= p.W ? 2 * p.W - 2 - ix : ix;
-            } else {
-              ok = ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-            }
-            rowoff[i] = ok ? xoff[i] + (iy * p.W + ix) * p.Cin : -1;
-          }
-        }
-        const uint32_t dst = smem_a + s * C::kStageBytes + row_off;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int i = 0; i < kRows; ++i) {
-          const bool ok = rowoff[i] >= 0;
-          bits |= ok ? (1u << i) : 0u;
-          cp_async16_zfill(dst + i * (kRowStep * 128), ok ? xb + rowoff[i] + c : xb, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        okq = (okq << 2) | bits;
-        c += kKC;
-        while (c >= p.Cin) {
-          c -= p.Cin; ++tap; tap_dirty = true;
-          if (++kx == tg.nkx) { kx = 0; ++ky; }
-        }
-      }
+      if (it < nk) issue_chunk(it);
     }
     trace_mark(p, 4, tid == 0);
     // ================= epilogue part 1: accumulator TMEM -> registers -> staging tile in shared memory =========
@@ -527,16 +533,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   const int n = n0 + cq * 4;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias && tid < kProducerThreads) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-  // one pass per sample the tile touches: rows of that sample are reduced / stored, then its (sum, sumsq) go out
-#pragma unroll 1
-  for (int sb = b_first; sb <= b_last; ++sb) {
-    const int lo = max(r_begin, sb * tg.hw - m0), hi = min(r_end, min((sb + 1) * tg.hw, row_limit) - m0);
-    if (tid < kProducerThreads) {
-      double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-      for (int r = lo + rg; r < hi; r += RP) {
-        const int pix = m0 + r - sb * tg.hw;
-        float4 acc = bias;
+  // split-K reduction first, for every row this thread owns (rows r_begin + rg + i*RP), all remote loads in flight together
+  constexpr int kMaxRows = kBM / RP;
+  constexpr bool kHoist = kMaxRows <= 4;      // BN = 128: 8 rows per thread would spill; it keeps the loads in the sample loop
+  float4 accv[kHoist ? kMaxRows : 1];
+  if (kHoist && tid < kProducerThreads) {
+#pragma unroll
+    for (int i = 0; i < (kHoist ? kMaxRows : 1); ++i) {
+      const int r = r_begin + rg + i * RP;
+      float4 acc = bias;
+      if (r < r_end && m0 + r < row_limit) {
 #pragma unroll
         for (int s = 0; s < 8; ++s) {             // rank order: deterministic
           if (s < p.splits) {
@@ -545,6 +551,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
             acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
           }
         }
+      }
+      accv[i] = acc;
+    }
+  }
+  // then one pass per sample the tile touches: its rows are stored, its (sum, sumsq) go out
+#pragma unroll 1
+  for (int sb = b_first; sb <= b_last; ++sb) {
+    const int lo = max(r_begin, sb * tg.hw - m0), hi = min(r_end, min((sb + 1) * tg.hw, row_limit) - m0);
+    if (tid < kProducerThreads) {
+      double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
+      auto finish_row = [&](int r, float4 acc) {      // statistics, activation, store of one reduced row of sample sb
+        const int pix = m0 + r - sb * tg.hw;
         if (p.stats) {
           const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
           ssum[0] += a0; ssq[0] = fma(a0, a0, ssq[0]); ssum[1] += a1; ssq[1] = fma(a1, a1, ssq[1]);
@@ -555,18 +573,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         const int oyc = pix / tg.woc;
         const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
         *reinterpret_cast<float4*>(p.y + (((size_t)sb * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
+      };
+      if (kHoist) {
+#pragma unroll
+        for (int i = 0; i < (kHoist ? kMaxRows : 1); ++i) {
+          const int r = r_begin + rg + i * RP;
+          if (r >= lo && r < hi) finish_row(r, accv[i]);
+        }
+      } else {
+#pragma unroll 1
+        for (int r = lo + ((rg - (lo - r_begin)) % RP + RP) % RP; r < hi; r += RP) {      // my rows (r = r_begin + rg mod RP) inside [lo, hi)
+          float4 acc = bias;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {             // rank order: deterministic
+            if (s < p.splits) {
+              const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
+              const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
+              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+          }
+          finish_row(r, acc);
+        }
       }
       if (p.stats) {
+        // lanes with the same column quad (lane % CQ) hold different row groups: fold them inside the warp first, so that the
+        // block-level step below adds one partial per WARP (16) instead of one per row group (up to 64)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { red[rg * BN + cq * 4 + u] = ssum[u]; red[kRedHalf + rg * BN + cq * 4 + u] = ssq[u]; }
+        for (int off = CQ; off < 32; off <<= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ssum[u] += __shfl_xor_sync(0xffffffffu, ssum[u], off);
+            ssq[u] += __shfl_xor_sync(0xffffffffu, ssq[u], off);
+          }
+        }
+        if (lane < CQ) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { red[warp * BN + cq * 4 + u] = ssum[u]; red[kRedHalf + warp * BN + cq * 4 + u] = ssq[u]; }
+        }
       }
     }
     if (p.stats) {        // block-uniform branch
       __syncthreads();
       if (tid < BN && hi > lo) {
         double s = 0.0, q = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < RP; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
+#pragma unroll
+        for (int r = 0; r < kProducerWarps; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
         double* st = p.stats + ((size_t)sb * p.Cout + n0 + tid) * 2;
         red_add_f64(st, s);
         red_add_f64(st + 1, q);

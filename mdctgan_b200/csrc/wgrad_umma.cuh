@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
           if (SPLIT3) {
             const float4 hi = make_float4(tf32_hi(e.x), tf32_hi(e.y), tf32_hi(e.z), tf32_hi(e.w));
             sts128(st_a + off, hi);
-            sts128(st_a + C::kABytes + off, make_float4(tf32_rn(e.x - hi.x), tf32_rn(e.y - hi.y), tf32_rn(e.z - hi.z), tf32_rn(e.w - hi.w)));
+            sts128(st_a + C::kABytes + off, make_float4(e.x - hi.x, e.y - hi.y, e.z - hi.z, e.w - hi.w));
           } else {
             sts128(st_a + off, make_float4(tf32_rn(e.x), tf32_rn(e.y), tf32_rn(e.z), tf32_rn(e.w)));
           }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
             if (SPLIT3) {
               const float4 hi = make_float4(tf32_hi(e.x), tf32_hi(e.y), tf32_hi(e.z), tf32_hi(e.w));
               sts128(st_b + off, hi);
-              sts128(st_b + C::kBBytes + off, make_float4(tf32_rn(e.x - hi.x), tf32_rn(e.y - hi.y), tf32_rn(e.z - hi.z), tf32_rn(e.w - hi.w)));
+              sts128(st_b + C::kBBytes + off, make_float4(e.x - hi.x, e.y - hi.y, e.z - hi.z, e.w - hi.w));
             } else {
               sts128(st_b + off, make_float4(tf32_rn(e.x), tf32_rn(e.y), tf32_rn(e.z), tf32_rn(e.w)));
             }

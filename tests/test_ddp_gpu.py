@@ -1,5 +1,6 @@
-"""2 GPUs, NCCL: the batch-sharded train step (one all-reduce of the flat [grad_G | grad_D] bucket, 1/world folded into Adam)
-computes the gradient of the global batch.  A configuration without BatchNorm is used (InstanceNorm only: per-sample
+"""2 GPUs, NCCL: the batch-sharded train step (all-reduce of the flat [grad_G | grad_D] bucket -- per update bucket as the gradients
+complete by default, one collective with MDCTGAN_PIPELINED_UPDATE=0 --, 1/world folded into Adam) computes the gradient of the
+global batch.  A configuration without BatchNorm is used (InstanceNorm only: per-sample
 statistics, so sharding the batch changes no forward value and the comparison is tight); with BottleStack attention the
 BatchNorm statistics are per rank by design (the reference has no multi-GPU semantics to match).
 Skipped on boxes with fewer than 2 GPUs."""
@@ -58,7 +59,9 @@ def _worker(rank, world, port, out):
     grads_dp = model.grad_all.clone() / world
     model.train_step(lr_all[mine.start:mine.stop].to(dev), hr_all[mine.start:mine.stop].to(dev), world, ex)
     in_sync = check_replicas_in_sync(model.bucket_G.flat) and check_replicas_in_sync(model.bucket_D.flat)
-    res = dict(in_sync=in_sync, calls=ex.calls)
+    from mdctgan_b200.models import pix2pixHD_model as PM
+
+    res = dict(in_sync=in_sync, calls=ex.calls, buckets=len(model._buckets) if PM.PIPELINED_UPDATE and not PM.BUCKETED_ALLREDUCE else 0)
     if rank == 0:                                          # the same two steps by ONE process on the global batch
         single = build()
         single.bucket_G.flat.copy_(w0[0])
@@ -86,6 +89,9 @@ def test_sharded_step_equals_global_batch_step():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out[0]["in_sync"] and out[1]["in_sync"]
     bucketed = os.environ.get("MDCTGAN_BUCKETED_ALLREDUCE", "0") == "1"
-    assert out[0]["calls"] == (6 if bucketed else 2)     # ONE collective per step (three with the opt-in bucketed exchange)
+    # default (pipelined update): one all-reduce per update bucket, issued as soon as the bucket's gradients are complete;
+    # MDCTGAN_PIPELINED_UPDATE=0: ONE collective per step (three with the older opt-in bucketed exchange)
+    expect = 2 * out[0]["buckets"] if out[0]["buckets"] else (6 if bucketed else 2)
+    assert out[0]["calls"] == expect, (out[0]["calls"], expect)
     assert out[0]["grad_rel"] < 1e-4, out[0]
     assert out[0]["param_rel_to_move"] < 0.05, out[0]
