@@ -240,6 +240,12 @@ int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int s
 int mdctgan_segment_ola_part(const void* seg_dev, void* out_dev, int64_t n_seg, int seg, int ov, int crop_begin, int crop_end,
                              int precision, void* stream);
 
+/* AudioDataset.__getitem__ noise injection (data/audio_dataset.py:72-78): out = lr + sqrt(sum(lr^2)/segment_length/10^(snr/10)) /
+ * std(noise) * (noise - mean(noise)), `noise` = the caller's N(0,1) draw (torch.randn in the reference), std unbiased.
+ * scratch3_dev: 3 doubles of device scratch.  Two launches. */
+int mdctgan_add_noise(const float* lr_dev, const float* noise_dev, float* out_dev, int64_t n, double segment_length, double snr_db,
+                      double* scratch3_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Evaluation metrics (util/util.py:132-177 compute_matrics; callers train.py:116-117, generate_audio.py:59-60).
  */

@@ -384,6 +384,20 @@ int mdctgan_segment_ola(const void* seg_dev, void* out_dev, int64_t n_seg, int s
   return mdctgan_segment_ola_part(seg_dev, out_dev, n_seg, seg, ov, ov, ov, precision, stream);
 }
 
+int mdctgan_add_noise(const float* lr_dev, const float* noise_dev, float* out_dev, int64_t n, double segment_length, double snr_db,
+                      double* scratch3_dev, void* stream) {
+  if (!lr_dev || !noise_dev || !out_dev || !scratch3_dev) return mdctgan_set_error(-1, "add_noise: NULL buffer");
+  if (n < 2 || segment_length <= 0) return mdctgan_set_error(-1, "add_noise: need n >= 2 samples and segment_length > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  CKT(cudaMemsetAsync(scratch3_dev, 0, 3 * sizeof(double), st));
+  add_noise_sums_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(lr_dev, noise_dev, (long long)n, scratch3_dev);
+  add_noise_apply_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(lr_dev, noise_dev, out_dev, (long long)n, scratch3_dev, segment_length, snr_db);
+  mdctgan_count_launch();
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_metrics_rows(const float* hr, const float* lr, const float* sr, int64_t rows, int64_t T, double* rows_out, void* stream) {
   if (!hr || !lr || !sr || !rows_out) return mdctgan_set_error(-1, "metrics_rows: NULL buffer");
   if (rows <= 0 || T <= 0) return 0;

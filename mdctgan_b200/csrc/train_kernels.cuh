@@ -1059,6 +1059,37 @@ __global__ void __launch_bounds__(256) resample_fir_kernel(const float* __restri
 }
 
 // torch.optim.Adam (no weight decay, no amsgrad), fp32, one flat buffer.  g is pre-scaled by grad_scale (1/world).
+// ------------------------------------------------------------------------------------------------
+// AudioDataset.__getitem__ noise injection (data/audio_dataset.py:72-78):
+//   noise -= mean(noise); noise *= sqrt(sum(lr^2) / segment_length / 10^(snr/10)) / std(noise) (unbiased); lr += noise
+// add_noise_sums_kernel: (sum n, sum n^2, sum lr^2) in fp64 -> acc[3]; add_noise_apply_kernel: the affine on every sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_noise_sums_kernel(const float* __restrict__ lr, const float* __restrict__ noise, long long n, double* acc) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = noise[i], x = lr[i];
+    s0 += v; s1 = fma(v, v, s1); s2 = fma(x, x, s2);
+  }
+  __shared__ double sh[3][256];
+  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) { sh[0][threadIdx.x] += sh[0][threadIdx.x + k]; sh[1][threadIdx.x] += sh[1][threadIdx.x + k]; sh[2][threadIdx.x] += sh[2][threadIdx.x + k]; }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) atomicAdd(acc + threadIdx.x, sh[threadIdx.x][0]);
+}
+__global__ void add_noise_apply_kernel(const float* __restrict__ lr, const float* __restrict__ noise, float* __restrict__ out, long long n,
+                                       const double* __restrict__ acc, double segment_length, double snr_db) {
+  const double mean = acc[0] / (double)n;
+  const double var = (acc[1] - (double)n * mean * mean) / (double)(n - 1);                // torch.std: unbiased
+  const double noise_var = acc[2] / segment_length / pow(10.0, snr_db / 10.0);
+  // the reference works in fp32: noise - mean, sqrt(noise_var) / std * noise, lr + noise (data/audio_dataset.py:73-78)
+  const float meanf = (float)mean, scale = sqrtf((float)noise_var) / (float)sqrt(var);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = lr[i] + scale * (noise[i] - meanf);
+}
+
 struct AdamParams {
   float* p; const float* g; float* m; float* v; size_t n;
   float lr, beta1, beta2, eps, grad_scale, bias_c1, bias_c2_sqrt;

@@ -152,6 +152,35 @@ def gen_resample():
     np.savez_compressed(os.path.join(HERE, "resample_golden.npz"), **out)
 
 
+AUGMENT_CASES = [  # (L, orig_sr, lr_sr, hr_sr, segment_length, add_noise, snr, seed)
+    (40000, 48000, 12000, 48000, 32512, True, 55.0, 801), (20000, 48000, 16000, 48000, 32512, True, 30.0, 802),
+    (30000, 44100, 8000, 48000, 7936, False, 55.0, 803), (9000, 48000, 12000, 48000, 7936, True, 10.0, 804)]
+
+
+def gen_augment():
+    """AudioDataset.__getitem__ of the reference itself (data/audio_dataset.py:54-82) with `readaudio` stubbed to return a seeded
+    waveform: the three resamples, the noise injection (torch.randn under a known seed) and seg_pad_audio."""
+    import torchaudio
+
+    if not hasattr(torchaudio, "set_audio_backend"):
+        torchaudio.set_audio_backend = lambda *a, **k: None
+    from data.audio_dataset import AudioDataset
+
+    out = {}
+    for (L, osr, lsr, hsr, seg, noise_on, snr, seed) in AUGMENT_CASES:
+        ds = object.__new__(AudioDataset)
+        ds.hr_sampling_rate, ds.lr_sampling_rate, ds.segment_length, ds.add_noise, ds.snr = hsr, lsr, seg, noise_on, snr
+        g = torch.Generator().manual_seed(seed)
+        wave = 0.1 * torch.randn(1, L, generator=g)
+        ds.readaudio = lambda idx, _w=wave, _sr=osr: (_w.clone(), _sr)
+        torch.manual_seed(seed + 1)                     # the draw __getitem__ makes: torch.randn(lr_waveform.size())
+        item = ds[0]
+        key = f"{L}_{osr}_{lsr}_{seg}_{int(noise_on)}"
+        out[f"hr_{key}"], out[f"lr_{key}"] = item["HR_audio"].numpy(), item["LR_audio"].numpy()
+        print(key, item["HR_audio"].shape, item["LR_audio"].shape)
+    np.savez_compressed(os.path.join(HERE, "augment_golden.npz"), **out)
+
+
 OPTION_ARGV = [[], ["--netG", "local", "--ngf", "56", "--fp16", "--batchSize", "20", "--lr", "1.5e-4", "--upsample_type", "interpolate",
                      "--downsample_type", "resconv", "--n_blocks_attn_g", "3", "--heads_g", "6", "--niter", "60", "--niter_decay", "60",
                      "--num_D", "3", "--fit_residual", "--param_key_map", "model.1:2,model.4:5", "--gen_overlap", "256", "--phase", "test"]]
@@ -299,6 +328,8 @@ if __name__ == "__main__":
         gen_normalize()
     if "resample" in what:
         gen_resample()
+    if "augment" in what:
+        gen_augment()
     if "options" in what:
         gen_options()
     if "nets" in what or "train" in what or "infer" in what:

@@ -177,3 +177,97 @@ def test_train_py_fp16_sequence_with_gradscaler(tmp_path):
     assert m_amp.optimizer_G.step_count == 1 and m_amp.optimizer_D.step_count == 1
     moved = float((m_ref.bucket_G.flat - m_amp.bucket_G.flat).norm()) / float(2e-4 * m_ref.bucket_G.flat.numel() ** 0.5)
     assert moved < 0.2, moved
+
+
+def test_load_network_fallbacks(tmp_path):
+    """The reference's three-level load (models/base_model.py:49-111): strict -> "pretrained has excessive layers" (keep the keys
+    the model has) -> "--param_key_map" remap of the second key component for renumbered layers."""
+    from mdctgan_b200.models.models import create_model
+
+    opt = our_opt("inf_small", gpu="0")
+    opt.checkpoints_dir, opt.name = str(tmp_path), "fb"
+    torch.manual_seed(5)
+    src = create_model(opt)
+    sd = {k: v.detach().cpu().clone() for k, v in src.netG.state_dict().items()}
+    d = os.path.join(str(tmp_path), "fb")
+    os.makedirs(d, exist_ok=True)
+    # (2) excessive layers: extra keys in the file are dropped
+    extra = dict(sd)
+    extra["model.99.weight"] = torch.zeros(3, 3)
+    extra["not_a_layer.bias"] = torch.ones(7)
+    torch.save(extra, os.path.join(d, "a_net_G.pth"))
+    torch.manual_seed(6)
+    dst = create_model(opt)
+    assert not torch.equal(dst.netG.state_dict()["model.1.weight"].cpu(), sd["model.1.weight"])
+    dst.load_network(dst.netG, "G", "a")
+    for k, v in sd.items():
+        assert torch.equal(dst.netG.state_dict()[k].cpu(), v), k
+    # (3) renumbered layers: the file calls the model's `model.4` layer `model.3` -> --param_key_map model.3:4
+    #     (and lacks model.4 itself, so neither the strict nor the filtered load can succeed)
+    ren = {}
+    for k, v in sd.items():
+        parts = k.split(".")
+        if parts[0] == "model" and parts[1] == "4":
+            parts[1] = "3"
+        ren[".".join(parts)] = v
+    assert "model.3.weight" in ren and "model.4.weight" not in ren
+    torch.save(ren, os.path.join(d, "b_net_G.pth"))
+    torch.manual_seed(7)
+    dst2 = create_model(opt)
+    dst2.opt.param_key_map = {"model.3": "4"}
+    dst2.load_network(dst2.netG, "G", "b")
+    for k, v in sd.items():
+        assert torch.equal(dst2.netG.state_dict()[k].cpu(), v), k
+    # the loaded weights are what the kernels then use (weight images are re-derived)
+    dst2.eval()
+    src.eval()
+    x = 0.05 * torch.randn(2, 3840).cuda()
+    assert torch.equal(dst2.inference(x)[1], src.inference(x)[1])
+    # a missing generator file is an error, a missing discriminator file is not (base_model.py:54-57)
+    with pytest.raises(FileNotFoundError):
+        dst2.load_network(dst2.netG, "G", "nope")
+    dst2.load_network(dst2.netD, "D", "nope")
+
+
+def test_graphed_train_step_equals_eager_steps(tmp_path):
+    """runtime.GraphedTrainStep: capture / warm-up must not train: N replays == N eager train_step calls from the same
+    state (float atomics in the weight-gradient reductions make the comparison a tolerance, not bit equality), the host step counter
+    follows the device one, and a new optimiser (update_fixed_params) or learning rate triggers a re-capture."""
+    from mdctgan_b200.models.models import create_model
+    from mdctgan_b200.runtime import GraphedTrainStep
+
+    opt = our_opt("inf_small", gpu="0")
+    opt.checkpoints_dir, opt.name = str(tmp_path), "g"
+    x, y = 0.05 * torch.randn(2, 3840).cuda(), 0.1 * torch.randn(2, 3840).cuda()
+    torch.manual_seed(8)
+    a = create_model(opt)
+    a.train()
+    torch.manual_seed(8)
+    b = create_model(opt)
+    b.train()
+    b.netG.load_state_dict(a.netG.state_dict())
+    b.netD.load_state_dict(a.netD.state_dict())
+    w0 = a.bucket_G.flat.clone()
+    gts = GraphedTrainStep(a, 2, 3840)
+    gts.lr_in.copy_(x)
+    gts.hr_in.copy_(y)
+    gts.recapture()
+    assert torch.equal(a.bucket_G.flat, w0) and a.optimizer_G.step_count == 0 and int(a.optimizer_G.step_dev) == 0      # no training yet
+    la, lb = [], []
+    for _ in range(3):
+        la.append(gts(x, y).clone())
+        lb.append(b.train_step(x, y).clone())
+    assert a.optimizer_G.step_count == 3 == int(a.optimizer_G.step_dev) and a.optimizer_D.step_count == 3
+    for u, v in zip(la, lb):
+        assert torch.allclose(u, v, rtol=2e-3, atol=0), (u, v)
+    assert torch.allclose(la[0], lb[0], rtol=1e-5, atol=0)                # first step: identical weights
+    moved = float((b.bucket_G.flat - w0).norm())
+    assert float((a.bucket_G.flat - b.bucket_G.flat).norm()) < 0.05 * moved
+    # learning-rate change -> re-capture, still no extra training
+    a.update_learning_rate()
+    w1, sc = a.bucket_G.flat.clone(), a.optimizer_G.step_count
+    gts.lr_in.copy_(x)
+    gts.recapture()
+    assert torch.equal(a.bucket_G.flat, w1) and a.optimizer_G.step_count == sc
+    gts(x, y)
+    assert a.optimizer_G.step_count == sc + 1 and not torch.equal(a.bucket_G.flat, w1)
