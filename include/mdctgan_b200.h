@@ -86,6 +86,22 @@ int mdctgan_mdct2audio_inverse(const mdctgan_plan* plan, const float* spectro_de
 int mdctgan_spectro_normalize(const void* x, void* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream);
 int mdctgan_spectro_denormalize(const void* s, double* y, int64_t n, const mdctgan_norm* norm, int precision, void* stream);
 
+/* Secondary encodings of Audio2MDCT (pix2pixHD_model.py:83-163), element-wise fp64 around the raw MDCT4 / IMDCT4 launches.
+ * mode: MDCTGAN_MODE_RAW / _ARCSINH / _DB (default options, :104-106) / _EXPLICIT (--explicit_encoding, :84-95: 2 channels).
+ * encode: raw coefficients [B][plane] (fp32 or fp64 per `precision`) -> enc fp64 [B][C][plane]; sign (nullable) = torch.sign(spectro)
+ *         as fp32 (:36); minmax (nullable) = fp32 [B][C][2] (min, max) of every plane (the no --abs_norm branch, :111-114).
+ * affine: (enc - min) / (max - min) * (norm_hi - norm_lo) + norm_lo -> fp32 (:116-123); minmax NULL = the abs-norm src_range.
+ * decode: denormalize (:127-137) + channel recombination / phase product of to_audio (:142-157) -> raw coefficients fp64 [B][plane];
+ *         pha (nullable, dB mode) = fp32 [B][plane] multiplier. */
+#define MDCTGAN_MODE_DB 2
+#define MDCTGAN_MODE_EXPLICIT 3
+int mdctgan_spectro_encode(const void* spec, int precision, int64_t B, int64_t plane, int mode, double gain, double alpha, double min_value,
+                           double* enc, float* sign, float* minmax, void* stream);
+int mdctgan_spectro_affine(const double* enc, int64_t planes, int64_t plane, const float* minmax, double src_lo, double src_hi,
+                           double norm_lo, double norm_hi, float* out, void* stream);
+int mdctgan_spectro_decode(const float* s, int64_t B, int64_t plane, int mode, double gain, double alpha, double min_value, const float* minmax,
+                           double src_lo, double src_hi, double norm_lo, double norm_hi, const float* pha, double* out, void* stream);
+
 /* Host-buffer forms of the four calls above (the end-to-end path a non-torch caller uses): inputs and
  * outputs are HOST arrays, densely packed; clips are streamed host->device->host in chunks over three
  * CUDA streams so copies overlap the kernels.  They synchronise before returning.  Scratch device
@@ -194,6 +210,10 @@ int mdctgan_attention_abs_pos_bwd(const float* qkv, const float* emb_h, const fl
 /* GANLoss, LSGAN branch (networks.py:127-137): *slot += coef * sum((x - target)^2); g (+)= 2*coef*(*gscale)*(x - target) */
 int mdctgan_mse_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream);
 int mdctgan_mse_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream);
+/* The same pair for nn.BCELoss on sigmoid outputs (GANLoss with --no_lsgan, networks.py:107-108; torch's -100 log clamp and 1e-12
+ * denominator clamp). */
+int mdctgan_bce_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream);
+int mdctgan_bce_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream);
 /* feature matching (pix2pixHD_model.py:447-451): *slot += coef * sum|a - b|; g (+)= coef*(*gscale)*sign(a - b) */
 int mdctgan_l1_pair_fwd(const float* a, const float* b, int64_t n, double coef, double* slot, void* stream);
 int mdctgan_l1_pair_bwd(const float* a, const float* b, int64_t n, float coef, const float* gscale, float* g, int accumulate, void* stream);

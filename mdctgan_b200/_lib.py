@@ -11,7 +11,7 @@ _LIB_NAME = "libmdctgan_b200.so"
 _lib = None
 
 F32, F64, MIXED = 0, 1, 2     # MIXED: fp64 butterflies on fp32 tensors
-MODE_RAW, MODE_ARCSINH = 0, 1
+MODE_RAW, MODE_ARCSINH, MODE_DB, MODE_EXPLICIT = 0, 1, 2, 3   # DB / EXPLICIT: element-wise codec kernels only (csrc/spectro_codec.cuh)
 
 
 class _Norm(ctypes.Structure):

@@ -1,7 +1,8 @@
 // conv_umma.cuh -- tcgen05 implicit-GEMM convolution for sm_100a (the generator / discriminator hot loop).
 //
 // Reference layers covered: every nn.Conv2d / nn.ConvTranspose2d of models/networks.py whose channel counts
-// are tensor-core shaped (Cin % 4 == 0, Cout % 32 == 0): the ResnetBlock 3x3 convolutions (:440-457, > 80 % of
+// are tensor-core shaped (Cin % 4 == 0, Cout % 4 == 0; the packed weight image pads Cout to a multiple of 32 with zero rows, the
+// epilogue masks them -- the reference's train.sh recipe has 56 / 112 channels): the ResnetBlock 3x3 convolutions (:440-457, > 80 % of
 // the generator FLOPs), the stride-2 down / transposed up layers (:327-330, :347-350) and the PatchGAN 4x4
 // layers (:649-670).  The Cin = 2 stem and the Cout = 1 heads stay on the direct kernels of nn_kernels.cuh.
 //
@@ -46,9 +47,10 @@ constexpr uint32_t kTf32Mask = 0xFFFFE000u;           // sign + 8 exponent + 10 
 
 struct ConvUmmaParams {
   const float* x; int B, H, W, Cin;
-  const float* wp;      // packed weights: [kchunks][2 (hi, lo)][Cout][32], 16-byte pieces swizzled by (n & 7)
+  const float* wp;      // packed weights: [kchunks][2 (hi, lo)][CoutP][32], 16-byte pieces swizzled by (n & 7); CoutP = Cout rounded up to 32
   const float* bias;    // [Cout] or null
   float* y; int Ho, Wo, Cout;
+  int CoutP;            // rows per (chunk, part) of the packed weight image: Cout rounded up to a multiple of 32
   int kh, kw, stride, pad, pad_mode, transposed;
   nnk::InputNorm in;
   int act;
@@ -504,9 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
           const int t = wkc / tg.cpt, ty = t / tg.nkx;
           wkc = ((tg.py + tg.cs * ty) * p.kw + tg.px + tg.cs * (t - ty * tg.nkx)) * tg.cpt + (wkc - t * tg.cpt);
         }
-        const float* src = p.wp + (((size_t)wkc * 2) * p.Cout + n0) * kKC;
+        const float* src = p.wp + (((size_t)wkc * 2) * p.CoutP + n0) * kKC;
         bulk_g2s(b_hi, src, C::kBBytes, &full[s]);
-        if (SPLIT3) bulk_g2s(b_hi + C::kBBytes, src + (size_t)p.Cout * kKC, C::kBBytes, &full[s]);
+        if (SPLIT3) bulk_g2s(b_hi + C::kBBytes, src + (size_t)p.CoutP * kKC, C::kBBytes, &full[s]);
       }
     }
     __syncwarp();
@@ -532,7 +534,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
   const int cq = tid % CQ, rg = tid / CQ;
   const int n = n0 + cq * 4;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias && tid < kProducerThreads) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  const bool col_ok = n < p.Cout;             // Cout % 4 == 0: a column quad is all-valid or all-padding
+  if (p.bias && tid < kProducerThreads && col_ok) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
   // split-K reduction first, for every row this thread owns (rows r_begin + rg + i*RP), all remote loads in flight together
   constexpr int kMaxRows = kBM / RP;
   constexpr bool kHoist = kMaxRows <= 4;      // BN = 128: 8 rows per thread would spill; it keeps the loads in the sample loop
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         acc.z = nnk::apply_act(acc.z, p.act); acc.w = nnk::apply_act(acc.w, p.act);
         const int oyc = pix / tg.woc;
         const int oyo = oyc * tg.cs + tg.offy, oxo = (pix - oyc * tg.woc) * tg.cs + tg.offx;
-        *reinterpret_cast<float4*>(p.y + (((size_t)sb * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
+        if (col_ok) *reinterpret_cast<float4*>(p.y + (((size_t)sb * p.Ho + oyo) * p.Wo + oxo) * p.Cout + n) = acc;
       };
       if (kHoist) {
 #pragma unroll
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     }
     if (p.stats) {        // block-uniform branch
       __syncthreads();
-      if (tid < BN && hi > lo) {
+      if (tid < BN && hi > lo && n0 + tid < p.Cout) {
         double s = 0.0, q = 0.0;
 #pragma unroll
         for (int r = 0; r < kProducerWarps; ++r) { s += red[r * BN + tid]; q += red[kRedHalf + r * BN + tid]; }
@@ -632,8 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
 }
 
 // [K][Cout] fp32 (nn_ops.pack_conv_weight layout) -> the kernel's shared-memory image, TF32 hi / lo parts
-static __global__ void pack_weight_umma_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int Cout, int kchunks) {
-  const size_t total = (size_t)kchunks * kKC * Cout;
+static __global__ void pack_weight_umma_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int Cout, int CoutP, int kchunks) {
+  const size_t total = (size_t)kchunks * kKC * Cout;      // rows Cout .. CoutP-1 of the image stay zero (the caller clears it)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(i % Cout);
     const int k = (int)(i / Cout);
@@ -642,9 +645,9 @@ static __global__ void pack_weight_umma_kernel(const float* __restrict__ w, floa
     const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & kTf32Mask);   // nearest TF32 of the remainder
     const int kc = k >> 5, kk = k & 31;
     const int piece = (kk >> 2) ^ (n & 7);
-    const size_t dst = (((size_t)kc * 2) * Cout + n) * kKC + piece * 4 + (kk & 3);
+    const size_t dst = (((size_t)kc * 2) * CoutP + n) * kKC + piece * 4 + (kk & 3);
     out[dst] = hi;
-    out[dst + (size_t)Cout * kKC] = lo;
+    out[dst + (size_t)CoutP * kKC] = lo;
   }
 }
 

@@ -254,16 +254,22 @@ extern "C" {
 /* debug: per-CTA phase timestamps of the following mdctgan_conv2d_umma launches ([grid.y][grid.x][16] int64), NULL = off */
 int mdctgan_conv2d_umma_set_trace(long long* dev_buf) { g_umma_trace = dev_buf; return 0; }
 
-int mdctgan_conv2d_umma_supported(int Cin, int Cout) { return (Cin % 4 == 0 && Cin <= umma::kMaxCin && Cout % 32 == 0) ? 1 : 0; }
+int mdctgan_conv2d_umma_supported(int Cin, int Cout) { return (Cin % 4 == 0 && Cin <= umma::kMaxCin && Cout % 4 == 0 && Cout >= 16) ? 1 : 0; }
 
-int64_t mdctgan_conv2d_umma_packed_floats(int K, int Cout) { return (int64_t)((K + umma::kKC - 1) / umma::kKC) * 2 * Cout * umma::kKC; }
+static int cout_padded(int Cout) { return (Cout + 31) / 32 * 32; }
+
+int64_t mdctgan_conv2d_umma_packed_floats(int K, int Cout) {
+  return (int64_t)((K + umma::kKC - 1) / umma::kKC) * 2 * cout_padded(Cout) * umma::kKC;
+}
 
 int mdctgan_conv2d_umma_pack_weight(const float* w_kn, int K, int Cout, float* out, void* stream) {
   if (!w_kn || !out) return mdctgan_set_error(-1, "umma pack: NULL buffer");
-  if (K <= 0 || Cout <= 0 || Cout % 8) return mdctgan_set_error(-1, "umma pack: bad shape K=%d Cout=%d", K, Cout);
+  if (K <= 0 || Cout <= 0 || Cout % 4) return mdctgan_set_error(-1, "umma pack: bad shape K=%d Cout=%d", K, Cout);
   const int kchunks = (K + umma::kKC - 1) / umma::kKC;
   const size_t total = (size_t)kchunks * umma::kKC * Cout;
-  umma::pack_weight_umma_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_kn, out, K, Cout, kchunks);
+  if (cout_padded(Cout) != Cout)       // the padding rows of the image are zero
+    CKN(cudaMemsetAsync(out, 0, (size_t)mdctgan_conv2d_umma_packed_floats(K, Cout) * sizeof(float), (cudaStream_t)stream));
+  umma::pack_weight_umma_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_kn, out, K, Cout, cout_padded(Cout), kchunks);
   mdctgan_count_launch();
   CKN(cudaGetLastError());
   return 0;
@@ -277,7 +283,7 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
     return mdctgan_set_error(-1, "conv2d_umma: bad shape");
   if (!mdctgan_conv2d_umma_supported(Cin, Cout))
-    return mdctgan_set_error(-2, "conv2d_umma: Cin %d (need %%4, <= %d) / Cout %d (need %%32) unsupported", Cin, umma::kMaxCin, Cout);
+    return mdctgan_set_error(-2, "conv2d_umma: Cin %d (need %%4, <= %d) / Cout %d (need %%4, >= 16) unsupported", Cin, umma::kMaxCin, Cout);
   if (pad_mode == kPadReflect && (pad >= H || pad >= W)) return mdctgan_set_error(-1, "conv2d_umma: reflection pad %d >= input size %dx%d", pad, H, W);
   if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_umma: in_scale / in_shift must come together");
   if (precision != 0 && precision != 1) return mdctgan_set_error(-1, "conv2d_umma: precision %d (0 = 3xTF32 fp32-class, 1 = TF32)", precision);
@@ -289,6 +295,8 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode; p.transposed = transposed;
   p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
   p.act = act; p.stats = stats; p.trace = g_umma_trace;
+  p.CoutP = cout_padded(Cout);
+  const int CoutP = p.CoutP;
   p.K = kh * kw * Cin; p.kchunks = (p.K + umma::kKC - 1) / umma::kKC;
   int min_kchunks = p.kchunks;
   // ConvTranspose2d: tiles per output parity class, K loop over the live taps only (conv_umma.cuh TileGeom)
@@ -327,12 +335,12 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   const long long m_ctas = (long long)p.m_tiles * (p.span ? 1 : B) * p.classes;
   const int max_split = min_kchunks < 8 ? min_kchunks : 8;
   int bn = 32;
-  if (Cout % 128 == 0 && (m_ctas * (Cout / 128) >= 74 || m_ctas * (Cout / 128) * max_split >= 96)) bn = 128;
-  else if (Cout % 64 == 0 && (m_ctas * (Cout / 64) >= 74 || m_ctas * (Cout / 64) * max_split >= 96 || Cout % 32 != 0)) bn = 64;
-  else if (Cout % 64 == 0 && m_ctas * (Cout / 32) * max_split < 96) bn = 64;     // nothing fills the device: fewer, wider tiles
-  if (bn == 128) rc = precision == 0 ? launch_umma<128, true>(p, Cout / 128, min_kchunks, st) : launch_umma<128, false>(p, Cout / 128, min_kchunks, st);
-  else if (bn == 64) rc = precision == 0 ? launch_umma<64, true>(p, Cout / 64, min_kchunks, st) : launch_umma<64, false>(p, Cout / 64, min_kchunks, st);
-  else rc = precision == 0 ? launch_umma<32, true>(p, Cout / 32, min_kchunks, st) : launch_umma<32, false>(p, Cout / 32, min_kchunks, st);
+  if (CoutP % 128 == 0 && (m_ctas * (CoutP / 128) >= 74 || m_ctas * (CoutP / 128) * max_split >= 96)) bn = 128;
+  else if (CoutP % 64 == 0 && (m_ctas * (CoutP / 64) >= 74 || m_ctas * (CoutP / 64) * max_split >= 96)) bn = 64;
+  else if (CoutP % 64 == 0 && m_ctas * (CoutP / 32) * max_split < 96) bn = 64;     // nothing fills the device: fewer, wider tiles
+  if (bn == 128) rc = precision == 0 ? launch_umma<128, true>(p, CoutP / 128, min_kchunks, st) : launch_umma<128, false>(p, CoutP / 128, min_kchunks, st);
+  else if (bn == 64) rc = precision == 0 ? launch_umma<64, true>(p, CoutP / 64, min_kchunks, st) : launch_umma<64, false>(p, CoutP / 64, min_kchunks, st);
+  else rc = precision == 0 ? launch_umma<32, true>(p, CoutP / 32, min_kchunks, st) : launch_umma<32, false>(p, CoutP / 32, min_kchunks, st);
   if (rc) return rc;
   mdctgan_count_launch();
   CKN(cudaGetLastError());

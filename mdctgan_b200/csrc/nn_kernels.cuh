@@ -18,7 +18,7 @@
 
 namespace nnk {
 
-enum Act : int { kActNone = 0, kActRelu = 1, kActLeaky = 2, kActTanh = 3 };
+enum Act : int { kActNone = 0, kActRelu = 1, kActLeaky = 2, kActTanh = 3, kActSigmoid = 4 };   // sigmoid: the --no_lsgan PatchGAN head (networks.py:672)
 enum PadMode : int { kPadZero = 0, kPadReflect = 1 };
 
 // How a consumer sees a producer's raw output: v = act(x * scale[b][c] + shift[b][c]).
@@ -68,6 +68,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == kActRelu) return fmaxf(v, 0.f);
   if (act == kActLeaky) return v > 0.f ? v : 0.2f * v;
   if (act == kActTanh) return tanhf(v);
+  if (act == kActSigmoid) return 1.f / (1.f + expf(-v));
   return v;
 }
 

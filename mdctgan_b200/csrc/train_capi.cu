@@ -4,6 +4,7 @@
 
 #include "../../include/mdctgan_b200.h"
 #include "train_kernels.cuh"
+#include "spectro_codec.cuh"
 #include "wgrad_umma.cuh"
 
 using namespace trk;
@@ -30,15 +31,15 @@ extern "C" {
 }  // extern "C"
 
 namespace {
-template <int BN, bool SPLIT3>
+template <int NBLK, bool SPLIT3>
 int launch_wgrad_umma(umma::WgradUmmaParams& p, cudaStream_t st) {
-  using C = umma::WgCfg<BN, SPLIT3>;
+  using C = umma::WgCfg<NBLK, SPLIT3>;
   static bool attr_set = false;
   if (!attr_set) {
-    CKT(cudaFuncSetAttribute(umma::conv_wgrad_umma_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    CKT(cudaFuncSetAttribute(umma::conv_wgrad_umma_kernel<NBLK, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  p.n_tiles = p.Cout / BN;
+  p.n_tiles = (p.Cout + C::BN - 1) / C::BN;
   const int m_tiles = (p.K + umma::kBM - 1) / umma::kBM;
   const int tiles = m_tiles * p.n_tiles;
   // split the reduction over pixels while the CTAs still fit ONE wave (1 CTA per SM: the ring takes most of the shared memory);
@@ -46,14 +47,41 @@ int launch_wgrad_umma(umma::WgradUmmaParams& p, cudaStream_t st) {
   int psplit = tiles >= 148 ? 1 : 148 / tiles;
   if (psplit > p.chunks) psplit = p.chunks;
   if (psplit > 65535) psplit = 65535;
-  umma::conv_wgrad_umma_kernel<BN, SPLIT3><<<dim3(tiles, psplit), umma::kWgThreads, C::kSmemBytes, st>>>(p);
+  umma::conv_wgrad_umma_kernel<NBLK, SPLIT3><<<dim3(tiles, psplit), umma::kWgThreads, C::kSmemBytes, st>>>(p);
   return 0;
+}
+
+// N tile = nblk blocks of 32 output channels.  Wide tiles amortise the im2col gather (it is repeated per N tile); narrow ones give the
+// grid its CTAs when the pixel reduction is too short to be split: the widest tile that still yields ~a wave of CTAs.
+int pick_wgrad_nblk(int K, int Cout, int chunks) {
+  const int m_tiles = (K + umma::kBM - 1) / umma::kBM;
+  const int blocks = (Cout + 31) / 32;
+  const int max_split = chunks / 4 > 0 ? chunks / 4 : 1;
+  for (int nblk = blocks < 8 ? blocks : 8; nblk >= 1; --nblk) {
+    const long long ctas = (long long)m_tiles * ((blocks + nblk - 1) / nblk) * max_split;
+    if (ctas >= 120) return nblk;
+  }
+  return 1;
+}
+
+template <bool SPLIT3>
+int launch_wgrad_umma_n(int nblk, umma::WgradUmmaParams& p, cudaStream_t st) {
+  switch (nblk) {
+    case 1: return launch_wgrad_umma<1, SPLIT3>(p, st);
+    case 2: return launch_wgrad_umma<2, SPLIT3>(p, st);
+    case 3: return launch_wgrad_umma<3, SPLIT3>(p, st);
+    case 4: return launch_wgrad_umma<4, SPLIT3>(p, st);
+    case 5: return launch_wgrad_umma<5, SPLIT3>(p, st);
+    case 6: return launch_wgrad_umma<6, SPLIT3>(p, st);
+    case 7: return launch_wgrad_umma<7, SPLIT3>(p, st);
+    default: return launch_wgrad_umma<8, SPLIT3>(p, st);
+  }
 }
 }  // namespace
 
 extern "C" {
 
-int mdctgan_conv2d_wgrad_umma_supported(int Cin, int Cout) { return (Cin % 32 == 0 && Cout % 32 == 0) ? 1 : 0; }
+int mdctgan_conv2d_wgrad_umma_supported(int Cin, int Cout) { return (Cin % 4 == 0 && Cout % 4 == 0 && Cin >= 16 && Cout >= 16) ? 1 : 0; }
 
 /* engine: 0 = fp32 FFMA kernel, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32 */
 int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const float* dy, int Ho, int Wo, int Cout, int kh, int kw, int stride,
@@ -66,7 +94,7 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
       return mdctgan_set_error(-1, "conv2d_wgrad: bad shape");
     if (!mdctgan_conv2d_wgrad_umma_supported(Cin, Cout))
-      return mdctgan_set_error(-2, "conv2d_wgrad: the tcgen05 kernel needs Cin %% 32 == 0 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
+      return mdctgan_set_error(-2, "conv2d_wgrad: the tcgen05 kernel needs Cin %% 4 == 0, Cout %% 4 == 0, both >= 16 (got %d, %d)", Cin, Cout);
     if (in_stats) return mdctgan_set_error(-1, "conv2d_wgrad: the tcgen05 kernel takes explicit in_scale / in_shift (resolve the statistics first)");
     if ((in_scale == nullptr) != (in_shift == nullptr)) return mdctgan_set_error(-1, "conv2d_wgrad: in_scale / in_shift must come together");
     if ((long long)B * Ho * Wo > 0x7fffffffLL - 64 || (long long)B * H * W * Cin > 0x7fffffffLL)
@@ -78,12 +106,9 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
     p.in.scale = in_scale; p.in.shift = in_shift; p.in.per_sample = in_per_sample; p.in.act = in_act;
     p.dw = dw; p.s_co = s_co; p.s_ci = s_ci; p.s_tap = s_tap; p.dbias = dbias;
     p.K = kh * kw * Cin; p.P = B * Ho * Wo; p.chunks = (p.P + umma::kWgPix - 1) / umma::kWgPix;
-    { const char* dbg = getenv("MDCTGAN_WGRAD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (Cout % 128 == 0) rc = engine == 1 ? launch_wgrad_umma<128, true>(p, st) : launch_wgrad_umma<128, false>(p, st);
-    else if (Cout % 64 == 0) rc = engine == 1 ? launch_wgrad_umma<64, true>(p, st) : launch_wgrad_umma<64, false>(p, st);
-    else rc = engine == 1 ? launch_wgrad_umma<32, true>(p, st) : launch_wgrad_umma<32, false>(p, st);
+    const int nblk = pick_wgrad_nblk(p.K, Cout, p.chunks);
+    const int rc = engine == 1 ? launch_wgrad_umma_n<true>(nblk, p, st) : launch_wgrad_umma_n<false>(nblk, p, st);
     if (rc) return rc;
     mdctgan_count_launch();
     CKT(cudaGetLastError());
@@ -264,6 +289,24 @@ int mdctgan_mse_const_bwd(const float* x, int64_t n, float target, float coef, c
   if (!x || !g) return mdctgan_set_error(-1, "mse_const_bwd: NULL buffer");
   if (n <= 0) return 0;
   mse_const_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, target, coef, gscale, g, accumulate);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_bce_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream) {
+  if (!x || !slot) return mdctgan_set_error(-1, "bce_const_fwd: NULL buffer");
+  if (n <= 0) return 0;
+  bce_const_fwd_kernel<<<grid_for((size_t)n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, target, coef, slot);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_bce_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream) {
+  if (!x || !g) return mdctgan_set_error(-1, "bce_const_bwd: NULL buffer");
+  if (n <= 0) return 0;
+  bce_const_bwd_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, target, coef, gscale, g, accumulate);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;
@@ -507,6 +550,63 @@ int mdctgan_spectro_denormalize(const void* s, double* y, int64_t n, const mdctg
   if (precision == MDCTGAN_F64) spectro_denormalize_kernel<double><<<grid_for((size_t)n, 256), 256, 0, st>>>((const double*)s, y, (size_t)n, p);
   else if (precision == MDCTGAN_F32) spectro_denormalize_kernel<float><<<grid_for((size_t)n, 256), 256, 0, st>>>((const float*)s, y, (size_t)n, p);
   else return mdctgan_set_error(-1, "spectro_denormalize: precision %d", precision);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+/* ---- secondary encodings of Audio2MDCT (pix2pixHD_model.py:83-163): dB / explicit_encoding / per-sample min-max ---- */
+static int codec_mode_ok(int mode) { return mode >= codec::kModeRaw && mode <= codec::kModeExplicit; }
+
+int mdctgan_spectro_encode(const void* spec, int precision, int64_t B, int64_t plane, int mode, double gain, double alpha, double min_value,
+                           double* enc, float* sign, float* minmax, void* stream) {
+  if (!spec || !enc) return mdctgan_set_error(-1, "spectro_encode: NULL buffer");
+  if (precision != MDCTGAN_F32 && precision != MDCTGAN_F64) return mdctgan_set_error(-1, "spectro_encode: precision %d", precision);
+  if (!codec_mode_ok(mode)) return mdctgan_set_error(-2, "spectro_encode: mode %d", mode);
+  if (B <= 0 || plane <= 0) return 0;
+  if (B > 65535) return mdctgan_set_error(-1, "spectro_encode: batch %lld > 65535", (long long)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = mode == codec::kModeExplicit ? 2 : 1;
+  const int nmm = (int)(B * C * 2);
+  if (minmax) codec::minmax_keys_init_kernel<<<(nmm + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned*>(minmax), nmm);
+  codec::EncodeParams p{spec, precision == MDCTGAN_F64, (long long)B, (long long)plane, mode, gain, alpha, min_value, enc, sign,
+                        reinterpret_cast<unsigned*>(minmax)};
+  long long chunks = (plane + 256 * 8 - 1) / (256 * 8);
+  if (chunks > 1024) chunks = 1024;
+  codec::spectro_encode_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, st>>>(p);
+  if (minmax) codec::minmax_keys_to_float_kernel<<<(nmm + 255) / 256, 256, 0, st>>>(reinterpret_cast<unsigned*>(minmax), nmm);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_spectro_affine(const double* enc, int64_t planes, int64_t plane, const float* minmax, double src_lo, double src_hi,
+                           double norm_lo, double norm_hi, float* out, void* stream) {
+  if (!enc || !out) return mdctgan_set_error(-1, "spectro_affine: NULL buffer");
+  if (planes <= 0 || plane <= 0) return 0;
+  if (planes > 65535) return mdctgan_set_error(-1, "spectro_affine: %lld planes > 65535", (long long)planes);
+  if (!minmax && !(src_hi > src_lo)) return mdctgan_set_error(-1, "spectro_affine: empty src_range");
+  if (!(norm_hi > norm_lo)) return mdctgan_set_error(-1, "spectro_affine: empty norm_range");
+  long long chunks = (plane + 256 * 8 - 1) / (256 * 8);
+  if (chunks > 1024) chunks = 1024;
+  codec::AffineParams p{(long long)planes, (long long)plane, minmax, src_lo, src_hi, norm_lo, norm_hi};
+  codec::spectro_affine_kernel<<<dim3((unsigned)chunks, (unsigned)planes), 256, 0, (cudaStream_t)stream>>>(enc, out, p);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_spectro_decode(const float* s, int64_t B, int64_t plane, int mode, double gain, double alpha, double min_value, const float* minmax,
+                           double src_lo, double src_hi, double norm_lo, double norm_hi, const float* pha, double* out, void* stream) {
+  if (!s || !out) return mdctgan_set_error(-1, "spectro_decode: NULL buffer");
+  if (!codec_mode_ok(mode)) return mdctgan_set_error(-2, "spectro_decode: mode %d", mode);
+  if (B <= 0 || plane <= 0) return 0;
+  if (B > 65535) return mdctgan_set_error(-1, "spectro_decode: batch %lld > 65535", (long long)B);
+  if (!(norm_hi > norm_lo)) return mdctgan_set_error(-1, "spectro_decode: empty norm_range");
+  long long chunks = (plane + 256 * 8 - 1) / (256 * 8);
+  if (chunks > 1024) chunks = 1024;
+  codec::DecodeParams p{s, (long long)B, (long long)plane, mode, gain, alpha, min_value, minmax, src_lo, src_hi, norm_lo, norm_hi, pha, out};
+  codec::spectro_decode_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(p);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;

@@ -40,6 +40,7 @@ __device__ __forceinline__ float act_grad_from_pre(float pre, int act) {   // d 
 }
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {     // same, from the activated value
   if (act == kActTanh) return 1.f - y * y;
+  if (act == nnk::kActSigmoid) return y * (1.f - y);
   return act_grad_from_pre(y, act);   // ReLU / LeakyReLU keep the sign
 }
 
@@ -725,6 +726,26 @@ __global__ void mse_const_bwd_kernel(const float* __restrict__ x, size_t n, floa
     g[i] = accumulate ? g[i] + v : v;
   }
 }
+// nn.BCELoss against a constant target (GANLoss with --no_lsgan, networks.py:107-108): mean of -(t log p + (1 - t) log(1 - p)), the logs
+// clamped at -100 and the gradient (p - t) / max(p (1 - p), 1e-12) exactly like torch (binary_cross_entropy / _backward)
+__global__ void __launch_bounds__(256) bce_const_fwd_kernel(const float* __restrict__ x, size_t n, float target, double coef, double* slot) {
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float p = x[i];
+    s -= target * fmaxf(logf(p), -100.f) + (1.f - target) * fmaxf(log1pf(-p), -100.f);
+  }
+  const double t = block_sum_256((double)s);
+  if (threadIdx.x == 0) atomicAdd(slot, coef * t);
+}
+__global__ void bce_const_bwd_kernel(const float* __restrict__ x, size_t n, float target, float coef, const float* __restrict__ gscale,
+                                     float* __restrict__ g, int accumulate) {
+  const float k = coef * (gscale ? __ldg(gscale) : 1.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = x[i];
+    const float v = k * (p - target) / fmaxf((1.f - p) * p, 1e-12f);
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
 __global__ void __launch_bounds__(256) l1_pair_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double coef, double* slot) {
   float s = 0.f;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s += fabsf(a[i] - b[i]);
@@ -822,9 +843,10 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc*
         const float lo_v = __uint_as_float((__float_as_uint(v - hi_v) + 0x1000u) & kTf32MaskPack);   // nearest TF32 of the remainder
         const int kcn = k >> 5, kk = k & 31;
         const int piece = (kk >> 2) ^ (n & 7);
-        const size_t dst = (((size_t)kcn * 2) * d.N + n) * 32 + piece * 4 + (kk & 3);
+        const int np = (d.N + 31) / 32 * 32;     // image rows per (chunk, part): N padded to 32 (padding rows stay zero)
+        const size_t dst = (((size_t)kcn * 2) * np + n) * 32 + piece * 4 + (kk & 3);
         d.dst_umma[dst] = hi_v;
-        d.dst_umma[dst + (size_t)d.N * 32] = lo_v;
+        d.dst_umma[dst + (size_t)np * 32] = lo_v;
       }
     }
   }

@@ -35,26 +35,26 @@ struct WgradUmmaParams {
   float* dw; long long s_co, s_ci, s_tap;
   float* dbias;
   int K;                    // kh*kw*Cin
-  int n_tiles;              // Cout / BN
+  int n_tiles;              // ceil(Cout / BN)
   int P;                    // B*Ho*Wo: reduction length
   int chunks;               // ceil(P / 32)
-  int debug;                // MDCTGAN_WGRAD_DEBUG (development probes; 0 in production)
 };
 
 constexpr int kWgPix = 32;                       // pixels per pipeline stage = 4 MMA k-steps
 constexpr int kWgThreads = (kProducerWarps + 1) * 32;
 
-template <int BN, bool SPLIT3>
+template <int NBLK, bool SPLIT3>
 struct WgCfg {
-  static constexpr int kNBlk = BN / 32;
+  static constexpr int BN = 32 * NBLK;
+  static constexpr int kNBlk = NBLK;
   static constexpr int kParts = SPLIT3 ? 2 : 1;
   static constexpr int kABytes = kWgPix * 4 * 128;                 // [8 pixel quads][4 MN blocks][4 rows][128 B]
   static constexpr int kBBytes = kWgPix * kNBlk * 128;
   static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
   static constexpr int kStages = (200 * 1024 / kStageBytes) >= 4 ? 4 : (200 * 1024 / kStageBytes);
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));      // power of two >= BN
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + BN * 4 + 256;
-  static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
+  static_assert(NBLK >= 1 && NBLK <= 8, "N tile = 1..8 blocks of 32 output channels (UMMA N <= 256)");
   static_assert(kStages >= 2, "stages");
 };
 
@@ -84,9 +84,10 @@ __device__ __forceinline__ void red_add_f32(float* gptr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(gptr)), "f"(a) : "memory");
 }
 
-template <int BN, bool SPLIT3>
+template <int NBLK, bool SPLIT3>
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const WgradUmmaParams p) {
-  using C = WgCfg<BN, SPLIT3>;
+  using C = WgCfg<NBLK, SPLIT3>;
+  constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_a = smem_u32(smem);
@@ -127,14 +128,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
   if (warp < kProducerWarps) {
     // ================= producers: gather A (im2col rows) and B (dY rows) -> transform -> TF32 hi / lo, swizzled =================
     constexpr int kAhead = C::kStages - 1;
-    constexpr int kBPer = (8 * BN + kProducerThreads - 1) / kProducerThreads;      // B pieces per thread per stage (BN/64, >= 1)
+    constexpr int kBPer = (8 * BN + kProducerThreads - 1) / kProducerThreads;      // B pieces per thread per stage: ceil(BN / 64)
     const int c16 = tid & 7;
-    // A: piece (p_local = (tid >> 5) + 16 i, MN block j = (tid >> 3) & 3): the block's tap and first channel are thread constants
+    // A: piece (p_local = (tid >> 5) + 16 i, MN block j = (tid >> 3) & 3, 16-byte piece c16): its 4 consecutive k = tap*Cin + ci never
+    // straddle a tap (Cin % 4 == 0); tap and first channel are thread constants
     const int ja = (tid >> 3) & 3;
-    const int kblk = m0 + 32 * ja;
-    const bool a_live = kblk < p.K;
-    const int tap = a_live ? kblk / p.Cin : 0;
-    const int ci0 = (a_live ? kblk - tap * p.Cin : 0) + 4 * c16;
+    const int kpiece = m0 + 32 * ja + 4 * c16;
+    const bool a_live = kpiece < p.K;
+    const int tap = a_live ? kpiece / p.Cin : 0;
+    const int ci0 = a_live ? kpiece - tap * p.Cin : 0;
     const int ky = tap / p.kw, kx = tap - ky * p.kw;
     const int HWo = p.Ho * p.Wo;
     const bool has_norm = p.in.scale != nullptr;
@@ -145,7 +147,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
       sh = __ldg(reinterpret_cast<const float4*>(p.in.shift + ci0));
     }
     // B: piece id = tid + 512 i: c16 = id & 7, block jb = (id >> 3) % kNBlk, p_local = id / (8 kNBlk)
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float bsum[kBPer][4];          // column sums of dY, per B piece of this thread (pieces of one thread sit in different N blocks)
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
     uint32_t okq = 0;             // validity bits of the A pieces of the chunks in flight, 2 per chunk, newest in the low bits
 
 #pragma unroll 1
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
             const int jb = (id >> 3) % C::kNBlk, pl = id / (8 * C::kNBlk);
             const uint32_t off = mn_piece_off(pl, jb, c16, (uint32_t)(C::kNBlk * 512));
             const float4 e = lds128(st_b + off);          // zero-filled beyond P
-            if (want_bias) { bsum[0] += e.x; bsum[1] += e.y; bsum[2] += e.z; bsum[3] += e.w; }
+            if (want_bias) { bsum[i][0] += e.x; bsum[i][1] += e.y; bsum[i][2] += e.z; bsum[i][3] += e.w; }
             if (SPLIT3) {
               const float4 hi = make_float4(tf32_hi(e.x), tf32_hi(e.y), tf32_hi(e.z), tf32_hi(e.w));
               sts128(st_b + off, hi);
@@ -239,8 +243,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
             const int jb = (id >> 3) % C::kNBlk, pl = id / (8 * C::kNBlk);
             const int pp = pbase + pl;
             const uint32_t dst = st_b + mn_piece_off(pl, jb, c16, (uint32_t)(C::kNBlk * 512));
-            const bool ok = pp < p.P;
-            cp_async16_zfill(dst, ok ? p.dy + (size_t)pp * p.Cout + n0 + 32 * jb + 4 * c16 : p.dy, ok ? 16u : 0u);
+            const int co = n0 + 32 * jb + 4 * c16;
+            const bool ok = pp < p.P && co < p.Cout;          // Cout % 4 == 0: a piece is all-valid or all-padding
+            cp_async16_zfill(dst, ok ? p.dy + (size_t)pp * p.Cout + co : p.dy, ok ? 16u : 0u);
           }
         }
         cp_async_commit();
@@ -252,11 +257,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
 #pragma unroll
       for (int i = 0; i < kBPer; ++i) {
         const int id = tid + kProducerThreads * i;
-        // every piece of this thread has the same (jb, c16) only when kBPer == 1 or the id stride keeps them: 512 % (8 kNBlk) == 0
-        if (id < 8 * BN && i == 0) {
+        if (id < 8 * BN) {
           const int jb = (id >> 3) % C::kNBlk;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) atomicAdd(&s_bias[jb * 32 + c16 * 4 + u], bsum[u]);
+          for (int u = 0; u < 4; ++u) atomicAdd(&s_bias[jb * 32 + c16 * 4 + u], bsum[i][u]);
         }
       }
     }
@@ -273,17 +277,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
     for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += (kProducerWarps / 4) * 16) {
       float a[16];
       tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, a);      // whole warp (sync.aligned)
-      if (p.debug & 1) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) a[u] += 1000.f;
-      }
       if (row_ok) {
         if (p.s_co == 1) {
 #pragma unroll
-          for (int u = 0; u < 16; u += 4) red_add_v4(rowp + c0 + u, a[u], a[u + 1], a[u + 2], a[u + 3]);
+          for (int u = 0; u < 16; u += 4)
+            if (n0 + c0 + u < p.Cout) red_add_v4(rowp + c0 + u, a[u], a[u + 1], a[u + 2], a[u + 3]);
         } else {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) red_add_f32(rowp + (long long)(c0 + u) * p.s_co, a[u]);
+          for (int u = 0; u < 16; ++u)
+            if (n0 + c0 + u < p.Cout) red_add_f32(rowp + (long long)(c0 + u) * p.s_co, a[u]);
         }
       }
     }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
   } else {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      const uint32_t idesc = (p.debug & 2) ? make_idesc_tf32(BN) : ((p.debug & 4) ? (make_idesc_tf32(BN) | (1u << 15)) : ((p.debug & 8) ? (make_idesc_tf32(BN) | (1u << 16)) : make_idesc_tf32_mn(BN)));
+      constexpr uint32_t idesc = make_idesc_tf32_mn(BN);
       constexpr uint32_t kSboB = C::kNBlk * 512;        // bytes between the 4-pixel atoms of B; a k-step (8 pixels) is two of them
 #pragma unroll 1
       for (int it = 0; it < nk; ++it) {
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_umma_kernel(const Wg
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
-  if (want_bias && tid < BN) red_add_f32(p.dbias + n0 + tid, s_bias[tid]);
+  if (want_bias && tid < BN && n0 + tid < p.Cout) red_add_f32(p.dbias + n0 + tid, s_bias[tid]);
 }
 
 }  // namespace umma

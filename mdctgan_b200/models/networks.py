@@ -180,11 +180,15 @@ class Tanh(nn.Module):
     pass
 
 
+class Sigmoid(nn.Module):
+    """The --no_lsgan PatchGAN head (networks.py:671-672)."""
+
+
 class AvgPool3s2(nn.Module):
     """nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False) (networks.py:249-250, :525-526)."""
 
 
-_ACT_CODE = {ReLU: ops.ACT_RELU, LeakyReLU: ops.ACT_LEAKY, Tanh: ops.ACT_TANH}
+_ACT_CODE = {ReLU: ops.ACT_RELU, LeakyReLU: ops.ACT_LEAKY, Tanh: ops.ACT_TANH, Sigmoid: ops.ACT_SIGMOID}
 
 
 def _act_of(layer) -> Optional[int]:
@@ -483,8 +487,6 @@ class NLayerDiscriminator(nn.Module):
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, getIntermFeat=False):
         super().__init__()
         norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
-        if use_sigmoid:
-            raise NotImplementedError("use_sigmoid (--no_lsgan) is listed as next in DESIGN.md")
         self.getIntermFeat, self.n_layers = getIntermFeat, n_layers
         kw, padw = 4, 2
         sequence = [[Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), LeakyReLU(0.2, True)]]
@@ -495,6 +497,10 @@ class NLayerDiscriminator(nn.Module):
         nf_prev, nf = nf, min(nf * 2, 512)
         sequence += [[Conv2d(nf_prev, nf, kernel_size=kw, stride=1, padding=padw), norm_layer(nf), LeakyReLU(0.2, True)]]
         sequence += [[Conv2d(nf, 1, kernel_size=kw, stride=1, padding=padw)]]
+        if use_sigmoid:
+            # like the reference (networks.py:671-672): with getIntermFeat the forward walks models 0 .. n_layers + 1 only (:686), so the
+            # sigmoid stage is constructed but never applied -- BCELoss then needs --no_ganFeat_loss (getIntermFeat False) to see probabilities
+            sequence += [[Sigmoid()]]
         if getIntermFeat:
             for n in range(len(sequence)):
                 setattr(self, "model" + str(n), nn.Sequential(*sequence[n]))

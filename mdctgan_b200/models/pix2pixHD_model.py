@@ -67,13 +67,19 @@ class Audio2MDCT(torch.nn.Module):
                            device=self.device, precision=sub)
         self._imdct = IMDCT4(n_fft=self.n_fft, hop_length=self.hop_length, win_length=self.win_length, window=self.window,
                              device=self.device, precision=sub)
-        if self.explicit_encoding or not (self.arcsinh_transform or self.raw_mdct):
-            raise NotImplementedError("Audio2MDCT: only the arcsinh (--arcsinh_transform) and --raw_mdct encodings are "
-                                      "implemented in-kernel; the dB / explicit_encoding branches are listed as 'next' in DESIGN.md")
-        if not self.abs_norm:
-            raise NotImplementedError("Audio2MDCT: per-sample min/max normalisation (no --abs_norm) is listed as 'next' in DESIGN.md")
-        mode = _lib.MODE_ARCSINH if self.arcsinh_transform else _lib.MODE_RAW
-        self._norm = _lib.NormSpec(mode, float(self.arcsinh_gain), tuple(float(v) for v in self.src_range),
+        # Which encoding (pix2pixHD_model.py:83-106, in the reference's order of precedence) and which path: the arcsinh / raw encodings
+        # with --abs_norm (every shipped script) are fused into the transform kernels; dB, --explicit_encoding and the per-sample
+        # min / max normalisation run as element-wise kernels around the raw transform (csrc/spectro_codec.cuh).
+        if self.explicit_encoding:
+            self._mode = _lib.MODE_EXPLICIT
+        elif self.arcsinh_transform:
+            self._mode = _lib.MODE_ARCSINH
+        elif self.raw_mdct:
+            self._mode = _lib.MODE_RAW
+        else:
+            self._mode = _lib.MODE_DB
+        self._fused = self._mode in (_lib.MODE_ARCSINH, _lib.MODE_RAW) and bool(self.abs_norm)
+        self._norm = _lib.NormSpec(self._mode if self._fused else _lib.MODE_RAW, float(self.arcsinh_gain), tuple(float(v) for v in self.src_range),
                                    tuple(float(v) for v in self.norm_range))
         self._cnorm = self._norm.c()
         self._minmax: Dict[int, tuple] = {}
@@ -90,7 +96,7 @@ class Audio2MDCT(torch.nn.Module):
     def _check_norm_param(self, norm_param) -> None:
         lo, hi = norm_param["min"], norm_param["max"]
         if torch.is_tensor(lo) and lo.numel() != 1:
-            raise NotImplementedError("to_audio: per-sample min/max normalisation is not implemented (abs_norm only)")
+            raise ValueError("to_audio: per-sample min / max parameters on an --abs_norm model")
 
     # ------------------------------------------------------------------ forward transform
     @torch.no_grad()
@@ -103,6 +109,7 @@ class Audio2MDCT(torch.nn.Module):
         """
         _require_cuda(audio, "Audio2MDCT.to_spectro")
         dim0 = audio.shape[0]   # len(signal): samples for 1-D input, batch size otherwise (mdct.py:394)
+        orig = audio
         if audio.dim() == 1:
             audio = audio[None]
         x = audio.to(torch.float32)
@@ -113,6 +120,8 @@ class Audio2MDCT(torch.nn.Module):
         B, T = x.shape
         nb = self.n_fft // 2
         F = _lib.frame_count(T, dim0, self.hop_length, self.win_length, True)
+        if not self._fused:
+            return self._to_spectro_generic(orig, B, F, nb, mask, mask_size, channels, out)
         if out is None:
             out = torch.empty((B, channels, F, nb), dtype=torch.float32, device=x.device)
         else:
@@ -123,18 +132,7 @@ class Audio2MDCT(torch.nn.Module):
                     self._mdct._plan(x.device).handle, x.data_ptr(), B, T, x.stride(0) if B > 1 else T, F, self._cnorm,
                     out.data_ptr(), channels, channels * F * nb, F * nb, self.precision, _stream_ptr(x.device)))
         if mask:
-            if mask_size == -1:
-                mask_size = int(nb * (1 - 1 / self.up_ratio))
-            if mask_size > 0:   # reference: mask_size == 0 would make an empty slice -> no-op
-                # the reference masks the 1-channel lr_spectro (pix2pixHD_model.py:57-80) and only then derives the second network
-                # channel |s|*2+lo from it (:400-402): the masked band of channel 2 is |noise|*2+lo (lo under --fit_residual)
-                if self.fit_residual:
-                    out[:, 0, :, nb - mask_size:] = 0
-                else:
-                    noise = torch.randn(B, 1, F, mask_size, device=x.device)
-                    out[:, 0:1, :, nb - mask_size:] = noise / (noise.max() - noise.min())
-                if channels == 2:
-                    out[:, 1, :, nb - mask_size:] = out[:, 0, :, nb - mask_size:].abs() * 2 + float(self.norm_range[0])
+            self._apply_mask(out, B, F, nb, mask_size, channels)
         lo, hi = self._src_minmax(x.device)
         return out, None, {"max": hi, "min": lo, "mean": None, "std": None, "frames": None}
 
@@ -150,6 +148,8 @@ class Audio2MDCT(torch.nn.Module):
     def to_audio(self, log_spectro: torch.Tensor, norm_param=None, pha=None, out_length: Optional[int] = None):
         """normalised spectrogram [B, 1, F, N] (or [B, F, N]) fp32 -> audio [B, 1, 1, (F-1)*hop]."""
         _require_cuda(log_spectro, "Audio2MDCT.to_audio")
+        if not self._fused:
+            return self._to_audio_generic(log_spectro, norm_param, pha, out_length)
         if norm_param is not None:
             self._check_norm_param(norm_param)
         s = log_spectro
@@ -171,6 +171,111 @@ class Audio2MDCT(torch.nn.Module):
                     self._mdct._plan(s.device).handle, s.data_ptr(), B, F, s.stride(0) if B > 1 else F * nb, self._cnorm,
                     audio.data_ptr(), out_len, out_len, self.precision, _stream_ptr(s.device)))
         return audio
+
+    # ------------------------------------------------------------------ secondary encodings (dB / explicit / per-sample min-max)
+    def _apply_mask(self, out, B, F, nb, mask_size, channels):
+        """pix2pixHD_model.py:57-80 on the 1-channel lr_spectro, then the second network channel |s|*2+lo from it (:400-402)."""
+        if mask_size == -1:
+            mask_size = int(nb * (1 - 1 / self.up_ratio))
+        if mask_size <= 0:      # reference: mask_size == 0 would make an empty slice (SURVEY appendix C) -> no-op
+            return
+        if self.fit_residual:
+            out[:, 0, :, nb - mask_size:] = 0
+        else:
+            noise = torch.randn(B, 1, F, mask_size, device=out.device)
+            out[:, 0:1, :, nb - mask_size:] = noise / (noise.max() - noise.min())
+        if channels == 2:
+            out[:, 1, :, nb - mask_size:] = out[:, 0, :, nb - mask_size:].abs() * 2 + float(self.norm_range[0])
+
+    def _to_spectro_generic(self, audio, B, F, nb, mask, mask_size, channels, out):
+        """dB / --explicit_encoding / no --abs_norm (pix2pixHD_model.py:32-125): raw MDCT4 launch -> spectro_encode (+ per-plane min /
+        max) -> spectro_affine.  Returns (log_spectro fp32 [B, C, F, N], pha = sign(spectro) [* noise], norm_param) like the reference."""
+        from ctypes import c_double, c_int, c_int64, c_void_p
+
+        spec, _ = self._mdct(audio)                             # raw coefficients [B, F, N] (fp32; fp64 in the fp64 flavour)
+        spec = spec.reshape(B, F, nb).contiguous()
+        dev = spec.device
+        C = 2 if self._mode == _lib.MODE_EXPLICIT else 1
+        want2 = channels == 2 and C == 1
+        enc = torch.empty((B, C, F, nb), dtype=torch.float64, device=dev)
+        sign = torch.empty((B, 1, F, nb), dtype=torch.float32, device=dev)
+        minmax = None if self.abs_norm else torch.empty((B, C, 2), dtype=torch.float32, device=dev)
+        res = torch.empty((B, C, F, nb), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        L.mdctgan_spectro_encode.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.mdctgan_spectro_affine.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_double, c_double, c_double, c_double, c_void_p, c_void_p]
+        if B and F:
+            with torch.cuda.device(dev):
+                st = _stream_ptr(dev)
+                _lib.check(L.mdctgan_spectro_encode(spec.data_ptr(), _lib.F64 if spec.dtype == torch.float64 else _lib.F32, B, F * nb, self._mode,
+                                                    float(self.arcsinh_gain), float(self.alpha), float(self.min_value), enc.data_ptr(),
+                                                    sign.data_ptr(), minmax.data_ptr() if minmax is not None else None, st))
+                _lib.check(L.mdctgan_spectro_affine(enc.data_ptr(), B * C, F * nb, minmax.data_ptr() if minmax is not None else None,
+                                                    float(self.src_range[0]), float(self.src_range[1]), float(self.norm_range[0]),
+                                                    float(self.norm_range[1]), res.data_ptr(), st))
+        if want2:                                               # the generator's second input channel |s|*2+lo (:400-402)
+            two = torch.empty((B, 2, F, nb), dtype=torch.float32, device=dev) if out is None else out
+            two[:, 0:1] = res
+            two[:, 1:2] = res.abs() * 2 + float(self.norm_range[0])
+            res = two
+        elif out is not None:
+            out.copy_(res)
+            res = out
+        pha = sign
+        if not self.explicit_encoding:                          # :49-54: sign * min-max-scaled noise
+            noise = torch.randn(sign.shape, device=dev)
+            pha = sign * ((noise - noise.min()) / (noise.max() - noise.min()))
+        if mask:
+            self._apply_mask(res, B, F, nb, mask_size, 2 if want2 else 1)
+        if minmax is not None:
+            lo, hi = minmax[:, :, 0, None, None].contiguous(), minmax[:, :, 1, None, None].contiguous()
+        else:
+            lo, hi = self._src_minmax(dev)
+        return res, pha, {"max": hi, "min": lo, "mean": None, "std": None, "frames": None}
+
+    def _to_audio_generic(self, log_spectro, norm_param, pha, out_length):
+        """pix2pixHD_model.py:127-163 for the secondary encodings: spectro_decode (denormalise, dB -> amplitude, channel recombination /
+        phase product with the random pseudo phase of the frames beyond F / up_ratio) -> raw IMDCT4 launch."""
+        from ctypes import c_double, c_int, c_int64, c_void_p
+
+        s = log_spectro.to(torch.float32)
+        C = 2 if self._mode == _lib.MODE_EXPLICIT else 1
+        if s.dim() == 3:
+            s = s[:, None]
+        assert s.dim() == 4 and s.shape[1] == C and s.shape[-1] == self.n_fft // 2, f"to_audio expects [B, {C}, F, {self.n_fft // 2}]"
+        s = s.contiguous()
+        B, _, F, nb = s.shape
+        dev = s.device
+        minmax = None
+        lo_v, hi_v = float(self.src_range[0]), float(self.src_range[1])
+        if norm_param is not None:
+            lo, hi = torch.as_tensor(norm_param["min"]), torch.as_tensor(norm_param["max"])
+            if lo.numel() == 1:
+                lo_v, hi_v = float(lo.reshape(-1)[0]), float(hi.reshape(-1)[0])
+            else:
+                minmax = torch.stack((lo.to(dev, torch.float32).reshape(B, C), hi.to(dev, torch.float32).reshape(B, C)), dim=-1).contiguous()
+        mult = None
+        if self._mode == _lib.MODE_DB and self.up_ratio > 1:    # :150-157 (the reference concatenates along the FRAME axis)
+            if pha is None:
+                raise ValueError("to_audio: the dB encoding needs the `pha` returned by to_spectro")
+            ph = pha.to(dev, torch.float32).reshape(B, F, nb)
+            keep = int(F * (1 / self.up_ratio))
+            pseudo = (2 * torch.randint(low=0, high=2, size=(B, F - keep, nb), device=dev) - 1).to(torch.float32)
+            mult = torch.cat((ph[:, :keep], pseudo), dim=1).contiguous()
+        raw = torch.empty((B, F, nb), dtype=torch.float64, device=dev)
+        L = _lib.lib()
+        L.mdctgan_spectro_decode.argtypes = [c_void_p, c_int64, c_int64, c_int, c_double, c_double, c_double, c_void_p, c_double, c_double,
+                                             c_double, c_double, c_void_p, c_void_p, c_void_p]
+        if B and F:
+            with torch.cuda.device(dev):
+                _lib.check(L.mdctgan_spectro_decode(s.data_ptr(), B, F * nb, self._mode, float(self.arcsinh_gain), float(self.alpha),
+                                                    float(self.min_value), minmax.data_ptr() if minmax is not None else None, lo_v, hi_v,
+                                                    float(self.norm_range[0]), float(self.norm_range[1]),
+                                                    mult.data_ptr() if mult is not None else None, raw.data_ptr(), _stream_ptr(dev)))
+        if self.precision != _lib.F64:
+            raw = raw.to(torch.float32)
+        audio, _ = self._imdct(raw)
+        return audio if out_length is None else audio[..., :int(out_length)]
 
     # ------------------------------------------------------------------ un-fused pieces (API parity)
     @torch.no_grad()

@@ -22,7 +22,7 @@ from . import _lib
 
 import os
 
-ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
 
 # Which convolution kernel runs the tensor-core-shaped layers (Cin % 4 == 0, Cout % 32 == 0):
@@ -73,6 +73,8 @@ def _L():
                                                     c_int, c_int, c_float, c_void_p]
         L.mdctgan_mse_const_fwd.argtypes = [c_void_p, c_int64, c_float, c_double, c_void_p, c_void_p]
         L.mdctgan_mse_const_bwd.argtypes = [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]
+        L.mdctgan_bce_const_fwd.argtypes = [c_void_p, c_int64, c_float, c_double, c_void_p, c_void_p]
+        L.mdctgan_bce_const_bwd.argtypes = [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]
         L.mdctgan_l1_pair_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]
         L.mdctgan_l1_pair_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]
         L.mdctgan_f64_to_f32.argtypes = [c_void_p, c_void_p, c_int, c_void_p]

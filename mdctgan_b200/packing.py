@@ -55,7 +55,7 @@ class WeightPacker:
             if use_umma:
                 total_floats = (total_floats + 31) // 32 * 32          # 128-byte aligned: the image is fetched by TMA bulk copies
                 off_um = total_floats
-                total_floats += kchunks * 2 * N * 32
+                total_floats += kchunks * 2 * ((N + 31) // 32 * 32) * 32       # N padded to 32 rows: the padding stays zero (buffer is zeroed)
             if alias_kn and off_um is None:          # nothing to derive: the layer reads its weights in place
                 st = layer.__dict__.setdefault("_static_pack", {})
                 st[role] = (layer.weight.detach().permute(2, 3, 0, 1).reshape(K, N) if isinstance(layer, ConvTranspose2d)
@@ -105,7 +105,7 @@ class WeightPacker:
                 kn_ptr = None
             um = None
             if p["off_um"] is not None:
-                n_um = p["kchunks"] * 2 * p["N"] * 32
+                n_um = p["kchunks"] * 2 * ((p["N"] + 31) // 32 * 32) * 32
                 um = self.buf[base_off + p["off_um"]: base_off + p["off_um"] + n_um]
                 assert um.data_ptr() % 128 == 0
             descs[i] = _Desc(m.weight.data_ptr(), kn_ptr, um.data_ptr() if um is not None else None, p["K"], p["N"], p["Kch"],

@@ -47,9 +47,12 @@ class GanGraph:
         m = self.m
         if not m._two_channel:
             raise NotImplementedError("train step: only the --abs_spectro --arcsinh_transform input encoding (every shipped script) is built")
-        if m.no_lsgan:
-            raise NotImplementedError("train step: --no_lsgan (BCE) is listed as next in DESIGN.md")
         L = ops._L()
+        if m.no_lsgan and not m.no_ganFeat_loss:
+            # reference: with the feature-matching outputs on (getIntermFeat) the sigmoid stage is never applied (networks.py:686), and
+            # nn.BCELoss rejects the raw logits -- fail like it does instead of training on something else
+            raise RuntimeError("--no_lsgan needs --no_ganFeat_loss: with intermediate features the reference's discriminator returns logits "
+                               "(networks.py:671-686) and nn.BCELoss raises on values outside [0, 1]")
         dev = m.device
         lr_spectro, lr_input, _, _ = m._lr_input(lr_audio)              # [B,1,F,N] view of [B,2,F,N]
         hr_spectro, _, _ = m.preprocess.hr_forward(hr_audio)             # [B,1,F,N]
@@ -82,9 +85,10 @@ class GanGraph:
                 pred = scale[-1].x                                        # [2B,h,w,1]
                 n = pred[:B].numel()
                 fake_p, real_p = pred.data_ptr(), pred[B:].data_ptr()
-                _lib.check(L.mdctgan_mse_const_fwd(fake_p, n, 1.0, 1.0 / n, a + 0 * 8, st))      # G_GAN
-                _lib.check(L.mdctgan_mse_const_fwd(real_p, n, 1.0, 1.0 / n, a + 2 * 8, st))      # D_real
-                _lib.check(L.mdctgan_mse_const_fwd(fake_p, n, 0.0, 1.0 / n, a + 3 * 8, st))      # D_fake
+                gan_fwd = L.mdctgan_bce_const_fwd if m.no_lsgan else L.mdctgan_mse_const_fwd     # GANLoss: nn.BCELoss / nn.MSELoss (networks.py:105-108)
+                _lib.check(gan_fwd(fake_p, n, 1.0, 1.0 / n, a + 0 * 8, st))      # G_GAN
+                _lib.check(gan_fwd(real_p, n, 1.0, 1.0 / n, a + 2 * 8, st))      # D_real
+                _lib.check(gan_fwd(fake_p, n, 0.0, 1.0 / n, a + 3 * 8, st))      # D_fake
                 if not m.no_ganFeat_loss:
                     for f in scale[:-1]:
                         nf = f.x[:B].numel()
@@ -108,7 +112,8 @@ class GanGraph:
                 if use_gan:
                     g = torch.empty_like(pred.x[:B])
                     n = g.numel()
-                    _lib.check(L.mdctgan_mse_const_bwd(pred.x.data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_gan), g.data_ptr(), 0, _st(g)))
+                    gan_bwd = L.mdctgan_bce_const_bwd if m.no_lsgan else L.mdctgan_mse_const_bwd
+                    _lib.check(gan_bwd(pred.x.data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_gan), g.data_ptr(), 0, _st(g)))
                     G.add(pred, g)
                 if use_feat and not m.no_ganFeat_loss:
                     for f in scale[:-1]:
@@ -142,8 +147,9 @@ class GanGraph:
                     pred = scale[-1]
                     g = torch.empty_like(pred.x)
                     n = pred.x[:B].numel()
-                    _lib.check(L.mdctgan_mse_const_bwd(pred.x.data_ptr(), n, 0.0, 1.0 / n, ops._ptr(g_fake), g.data_ptr(), 0, _st(g)))
-                    _lib.check(L.mdctgan_mse_const_bwd(pred.x[B:].data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_real), g[B:].data_ptr(), 0, _st(g)))
+                    gan_bwd = L.mdctgan_bce_const_bwd if m.no_lsgan else L.mdctgan_mse_const_bwd
+                    _lib.check(gan_bwd(pred.x.data_ptr(), n, 0.0, 1.0 / n, ops._ptr(g_fake), g.data_ptr(), 0, _st(g)))
+                    _lib.check(gan_bwd(pred.x[B:].data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_real), g[B:].data_ptr(), 0, _st(g)))
                     G.add(pred, g)
                 self.tapeD.backward(G, wgrad=True, nb=None, join=False)
                 if join:

@@ -147,20 +147,29 @@ def _overlap_add(y, n_fft, hop, win, center, out_length):
 
 
 # --------------------------------------------------------------------------- compress / normalise
-def compress(spec, *, arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False, min_value=1e-7,
+def _amp_to_db(x, amin):
+    """torchaudio.functional.amplitude_to_DB(x, multiplier=20.0, amin, db_multiplier=1.0) as the reference calls it."""
+    return 20.0 * np.log10(np.clip(x, amin, None)) - 20.0
+
+
+def compress(spec, *, arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False, explicit_encoding=False, alpha=0.6, min_value=1e-7,
              abs_norm=True, src_range=(-5.0, 5.0), norm_range=(0.0, 1.0)):
-    """Audio2MDCT.normalize (pix2pixHD_model.py:83-125), single-channel branches.
+    """Audio2MDCT.normalize (pix2pixHD_model.py:83-125): explicit_encoding (2 channels) / arcsinh / raw / dB, abs-norm or per-plane min-max.
 
     Returns (log_spectro fp64, max, min, mean fp32, std fp32).  With abs_norm the
     max/min are the fp32 constants the reference builds (shape [1,1,1,1]).
     """
     x = np.asarray(spec, dtype=np.float64)
-    if arcsinh_transform:
+    if explicit_encoding:      # :84-95
+        neg = 0.5 * (np.abs(x) - x)
+        pos = x + neg
+        s = np.concatenate((_amp_to_db(alpha * pos + (1 - alpha) * neg, min_value), _amp_to_db((1 - alpha) * pos + alpha * neg, min_value)), axis=1)
+    elif arcsinh_transform:
         s = np.arcsinh(arcsinh_gain * x) / LN10_F32
     elif raw_mdct:
         s = x
-    else:  # amplitude_to_DB(|x|+min_value, 20, min_value, 1)
-        s = 20.0 * np.log10(np.clip(np.abs(x) + min_value, min_value, None))
+    else:  # :104-106
+        s = _amp_to_db(np.abs(x) + min_value, min_value)
     mean = np.float32(s.mean())
     std = np.float32(np.sqrt(s.var(ddof=1))) if s.size > 1 else np.float32(np.nan)
     if abs_norm:
@@ -175,16 +184,16 @@ def compress(spec, *, arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False
     return s, hi_src, lo_src, mean, std
 
 
-def expand(log_spectro, lo_src, hi_src, *, arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False,
+def expand(log_spectro, lo_src, hi_src, *, arcsinh_transform=True, arcsinh_gain=500.0, raw_mdct=False, explicit_encoding=False, alpha=0.6,
            min_value=1e-7, norm_range=(0.0, 1.0)):
-    """Audio2MDCT.denormalize (pix2pixHD_model.py:127-137)."""
+    """Audio2MDCT.denormalize (pix2pixHD_model.py:127-137); the explicit_encoding flag is only accepted (it acts in to_audio)."""
     s = (np.asarray(log_spectro).astype(np.float64) - norm_range[0]) / (norm_range[1] - norm_range[0])
     s = s * (np.asarray(hi_src) - np.asarray(lo_src)) + np.asarray(lo_src)
     if arcsinh_transform:
         return np.sinh(s * LN10_F32) / arcsinh_gain
     if raw_mdct:
         return s
-    return np.power(10.0, 0.1 * s) ** 0.5 - min_value  # DB_to_amplitude(x, 10, 0.5)
+    return 10.0 * np.power(np.power(10.0, 0.1 * s), 0.5) - min_value  # aF.DB_to_amplitude(x, 10.0, 0.5) - min_value
 
 
 def to_spectro(audio, window, *, n_fft=512, hop=256, **kw):
@@ -200,9 +209,14 @@ def to_spectro(audio, window, *, n_fft=512, hop=256, **kw):
     return s.astype(np.float32), np.sign(spec), hi_src, lo_src
 
 
-def to_audio(log_spectro, lo_src, hi_src, window, *, n_fft=512, hop=256, **kw):
-    """Audio2MDCT.to_audio, arcsinh / raw branches (pix2pixHD_model.py:139-163)."""
+def to_audio(log_spectro, lo_src, hi_src, window, *, n_fft=512, hop=256, pha=None, **kw):
+    """Audio2MDCT.to_audio (pix2pixHD_model.py:139-163).  dB mode: `pha` is the phase multiplier actually applied (the reference
+    builds it from the sign, noise and a random pseudo phase for the upper frames, :150-157 -- the caller passes the result)."""
     kw.pop("abs_norm", None)
     kw.pop("src_range", None)
     x = expand(log_spectro, lo_src, hi_src, **kw)
+    if kw.get("explicit_encoding", False):
+        x = ((x[:, 0] - x[:, 1]) / (2 * kw.get("alpha", 0.6) - 1))[:, None]
+    elif not kw.get("arcsinh_transform", True) and not kw.get("raw_mdct", False) and pha is not None:
+        x = x * np.asarray(pha, dtype=np.float64)
     return imdct4(x[:, 0], window, n_fft, hop)

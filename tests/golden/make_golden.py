@@ -202,6 +202,49 @@ def gen_options():
     print("options:", len(out[0]), "fields")
 
 
+ENCODING_CASES = [("db_abs", dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=False, abs_norm=True, src_range=[-180.0, 20.0])),
+                  ("db_minmax", dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=False, abs_norm=False)),
+                  ("explicit_minmax", dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=True, abs_norm=False)),
+                  ("explicit_abs", dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=True, abs_norm=True, src_range=[-180.0, 20.0])),
+                  ("arcsinh_minmax", dict(arcsinh_transform=True, raw_mdct=False, explicit_encoding=False, abs_norm=False)),
+                  ("raw_minmax", dict(arcsinh_transform=False, raw_mdct=True, explicit_encoding=False, abs_norm=False))]
+
+
+def gen_encodings():
+    """Audio2MDCT.to_spectro / to_audio of the reference itself (pix2pixHD_model.py:32-163) on the secondary encodings: dB magnitude
+    (default options), --explicit_encoding, and the per-sample min / max normalisation (no --abs_norm) of every encoding.  The random
+    factors are kept out of the golden: `pha` is passed as the plain sign (the reference multiplies it by noise, :49-54), and
+    up_ratio is set just above 1 so that only the LAST frame receives the random pseudo phase of :150-157 (tests compare the samples
+    no later frame touches: [: (F - 2) * hop])."""
+    from models.pix2pixHD_model import Audio2MDCT
+
+    out = {}
+    g = torch.Generator().manual_seed(33)
+    audio = 0.1 * torch.randn(2, 7936, generator=g)
+    audio[1] *= 0.01
+    logs = (torch.rand(2, 2, 32, 256, generator=g) * 2 - 1).float()
+    out["audio"], out["log_spectro"] = audio.numpy(), logs.numpy()
+    for tag, over in ENCODING_CASES:
+        opt = ref_opt(["--segment_length", "7936", "--bins", "32"])
+        for k, v in over.items():
+            setattr(opt, k, v)
+        a2m = Audio2MDCT(opt)
+        torch.manual_seed(5)
+        s, pha, npar = a2m.to_spectro(audio.clone())
+        out[f"{tag}_spectro"] = s.numpy()
+        out[f"{tag}_max"], out[f"{tag}_min"] = np.asarray(npar["max"].numpy(), dtype=np.float32), np.asarray(npar["min"].numpy(), dtype=np.float32)
+        raw, _ = a2m._mdct(audio.clone(), True)
+        sign = torch.sign(raw.unsqueeze(1))
+        out["sign"] = sign.numpy().astype(np.float32)
+        a2m.up_ratio = 1.0001
+        rt = a2m.to_audio(s.clone(), npar, sign.clone())
+        C = s.shape[1]
+        out[f"{tag}_decode"] = a2m.to_audio(logs[:, :C].clone(), npar, sign.clone()).numpy()
+        keep = 30 * 256
+        print(tag, tuple(s.shape), s.dtype, tuple(rt.shape), rt.dtype, "round trip max err", float((rt.reshape(2, -1)[:, :keep].float() - audio[:, :keep]).abs().max()))
+    np.savez_compressed(os.path.join(HERE, "encodings_golden.npz"), **out)
+
+
 def gen_normalize():
     """Audio2MDCT.normalize / denormalize of the reference itself (pix2pixHD_model.py:83-137), arcsinh and raw branches, abs_norm."""
     from models.pix2pixHD_model import Audio2MDCT
@@ -326,13 +369,15 @@ if __name__ == "__main__":
         gen_metrics()
     if "normalize" in what:
         gen_normalize()
+    if "encodings" in what:
+        gen_encodings()
     if "resample" in what:
         gen_resample()
     if "augment" in what:
         gen_augment()
     if "options" in what:
         gen_options()
-    if "nets" in what or "train" in what or "infer" in what:
+    if "nets" in what or "train" in what or "infer" in what:   # ("train_bce" has its own entry below)
         from make_golden_nets import gen_nets, gen_train  # noqa: E402
 
         if "nets" in what:
@@ -343,3 +388,7 @@ if __name__ == "__main__":
             gen_infer()
         if "train" in what:
             gen_train()
+    if "train_bce" in what:
+        from make_golden_nets import gen_train_bce  # noqa: E402
+
+        gen_train_bce()

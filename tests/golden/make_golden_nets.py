@@ -205,3 +205,54 @@ def gen_train():
         print(name, "done", losses_all)
     np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
     print("wrote train_golden.npz")
+
+
+# --no_lsgan (nn.BCELoss on a sigmoid PatchGAN head, networks.py:105-108,671-672).  The reference's discriminator applies the sigmoid only
+# without intermediate features (networks.py:686 walks models 0 .. n_layers + 1), so the flag works with --no_ganFeat_loss only.
+TRAIN_BCE_FLAGS = {"tr_small_bce": (TRAIN_FLAGS["tr_small"][0] + ["--no_lsgan", "--no_ganFeat_loss"], 3, 3840, 5154)}
+
+
+def gen_train_bce():
+    """The reference's own train iteration (train.py:160-202) under --no_lsgan --no_ganFeat_loss: losses of TRAIN_STEPS iterations, every
+    gradient tensor of the first one, parameter checksums after the last -> tests/golden/train_bce_golden.npz."""
+    from make_golden import ref_opt
+    from models.models import create_model
+
+    out = {}
+    for name, (flags, batch, T, seed) in TRAIN_BCE_FLAGS.items():
+        opt = ref_opt(flags)
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = create_model(opt)
+        model.train()
+        lr, hr = make_lr_audio(batch, T, seed), make_hr_audio(batch, T, seed)
+        out[f"{name}_lr_audio"], out[f"{name}_hr_audio"] = lr.numpy(), hr.numpy()
+        out[f"{name}_G_cksum0"] = state_checksum(model.netG.state_dict())
+        out[f"{name}_D_cksum0"] = state_checksum(model.netD.state_dict())
+        out[f"{name}_D_keys"] = np.array(list(model.netD.state_dict().keys()))
+        out[f"{name}_loss_names"] = np.array(list(model.loss_names))
+        losses_all = []
+        for it in range(TRAIN_STEPS):
+            losses, _ = model._forward(lr, hr)
+            d = dict(zip(model.loss_names, losses))
+            losses_all.append([float(d[k]) for k in ("G_GAN", "D_real", "D_fake")])
+            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+            loss_G = d["G_GAN"] + d.get("G_GAN_Feat", 0)
+            model.optimizer_G.zero_grad()
+            loss_G.backward()
+            if it == 0:
+                for k, p in model.netG.named_parameters():
+                    out[f"{name}_gradG::{k}"] = p.grad.numpy().copy()
+            model.optimizer_G.step()
+            model.optimizer_D.zero_grad()
+            loss_D.backward()
+            if it == 0:
+                for k, p in model.netD.named_parameters():
+                    out[f"{name}_gradD::{k}"] = p.grad.numpy().copy()
+            model.optimizer_D.step()
+        out[f"{name}_losses"] = np.array(losses_all)
+        out[f"{name}_G_cksum_after"] = state_checksum(model.netG.state_dict())
+        out[f"{name}_D_cksum_after"] = state_checksum(model.netD.state_dict())
+        print(name, "done", list(model.loss_names), losses_all)
+    np.savez_compressed(os.path.join(HERE, "train_bce_golden.npz"), **out)
+    print("wrote train_bce_golden.npz")

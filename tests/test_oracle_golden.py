@@ -127,3 +127,38 @@ def test_torch_port_matches_reference(mdct_golden):
     ls, pha, prm = a2m.to_spectro(torch.from_numpy(g["b4_x"]))
     assert np.array_equal(ls.numpy(), g["a2m_log_spectro"])
     assert rel_l2(a2m.to_audio(ls, prm, pha).numpy(), g["a2m_audio"]) < 1e-14
+
+
+ENCODING_CASES = {
+    "db_abs": dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=False, abs_norm=True, src_range=(-180.0, 20.0)),
+    "db_minmax": dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=False, abs_norm=False),
+    "explicit_minmax": dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=True, abs_norm=False),
+    "explicit_abs": dict(arcsinh_transform=False, raw_mdct=False, explicit_encoding=True, abs_norm=True, src_range=(-180.0, 20.0)),
+    "arcsinh_minmax": dict(arcsinh_transform=True, raw_mdct=False, explicit_encoding=False, abs_norm=False),
+    "raw_minmax": dict(arcsinh_transform=False, raw_mdct=True, explicit_encoding=False, abs_norm=False),
+}
+ENC_COMMON = dict(arcsinh_gain=1000.0, alpha=0.6, min_value=1e-7, norm_range=(-1.0, 1.0))
+
+
+def test_secondary_encodings_match_reference(mdct_golden):
+    """dB / explicit_encoding / per-plane min-max branches of Audio2MDCT (pix2pixHD_model.py:83-163) against the reference's own
+    to_spectro / to_audio outputs (tests/golden/encodings_golden.npz, make_golden.py gen_encodings)."""
+    import os
+
+    from conftest import GOLDEN
+
+    g = dict(np.load(os.path.join(GOLDEN, "encodings_golden.npz")))
+    w = mdct_golden["kbdwin512"]
+    keep = 30 * 256       # samples the last frame (random pseudo phase in the reference, :150-157) does not touch
+    for tag, kw in ENCODING_CASES.items():
+        kw = dict(ENC_COMMON, **kw)
+        ls, sign, hi, lo = O.to_spectro(g["audio"], w, **kw)
+        assert ls.shape == g[f"{tag}_spectro"].shape, tag
+        assert np.array_equal(hi.reshape(-1), g[f"{tag}_max"].reshape(-1)) and np.array_equal(lo.reshape(-1), g[f"{tag}_min"].reshape(-1)), tag
+        assert np.abs(ls - g[f"{tag}_spectro"]).max() <= 2e-7 * max(1.0, np.abs(g[f"{tag}_spectro"]).max()), tag
+        assert np.array_equal(sign.astype(np.float32), g["sign"]), tag
+        C = ls.shape[1]
+        dkw = {k: v for k, v in kw.items() if k not in ("abs_norm", "src_range")}
+        a = O.to_audio(g["log_spectro"][:, :C], lo, hi, w, pha=g["sign"], **dkw)
+        ref = g[f"{tag}_decode"].reshape(2, -1)
+        assert rel_l2(a.reshape(2, -1)[:, :keep], ref[:, :keep]) < 1e-12, tag

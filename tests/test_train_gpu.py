@@ -214,7 +214,10 @@ def test_fused_adam_matches_torch(dev):
 @pytest.mark.parametrize("layout", ["param", "kn"])
 @pytest.mark.parametrize("shape", [(4, 512, 2, 16, 512, 3, 1, 1, 1, 0), (2, 64, 9, 17, 128, 4, 2, 2, 0, 0), (3, 32, 5, 7, 32, 3, 1, 1, 0, 0),
                                    (2, 64, 4, 8, 32, 3, 2, 1, 0, 1), (1, 96, 16, 32, 64, 5, 1, 2, 0, 0), (8, 128, 3, 5, 256, 1, 1, 0, 0, 0),
-                                   (8, 256, 6, 34, 512, 4, 1, 2, 0, 0), (8, 64, 17, 129, 128, 4, 2, 2, 0, 0), (4, 256, 4, 18, 512, 4, 1, 2, 0, 0)])
+                                   (8, 256, 6, 34, 512, 4, 1, 2, 0, 0), (8, 64, 17, 129, 128, 4, 2, 2, 0, 0), (4, 256, 4, 18, 512, 4, 1, 2, 0, 0),
+                                   # train.sh recipe (ngf 56): channel counts that are multiples of 4 but not of 32; N tiles of 2 .. 7 blocks
+                                   (2, 56, 8, 16, 112, 3, 1, 1, 1, 0), (2, 112, 9, 14, 56, 5, 1, 2, 0, 0), (1, 224, 6, 10, 224, 3, 1, 1, 0, 0),
+                                   (3, 56, 6, 6, 56, 3, 2, 1, 0, 0), (2, 448, 4, 6, 224, 5, 1, 2, 0, 0), (1, 20, 40, 64, 168, 3, 1, 1, 0, 0)])
 def test_wgrad_tcgen05_matches_fp32_kernel(dev, shape, layout):
     """The MN-major tcgen05 weight-gradient kernel (csrc/wgrad_umma.cuh) against the fp32 FFMA kernel through the same C-ABI entry:
     3xTF32 engine <= 3e-5 rel-L2 (fp32-class: 3e-7 on short reductions, 1.1e-5 at 2000 pixels -- the fp32 FFMA kernel it is compared
@@ -482,3 +485,68 @@ def test_weight_packer_matches_per_layer_packing(dev):
     m = layers[0]
     packer.detach()
     assert torch.equal(m.packed_umma(), ops.pack_conv_weight_umma(ops.pack_conv_weight(m.weight, False)))
+
+
+@pytest.mark.parametrize("api", ["autograd", "train_step"])
+def test_no_lsgan_train_step_matches_reference(dev, api):
+    """--no_lsgan --no_ganFeat_loss (sigmoid PatchGAN head + nn.BCELoss, networks.py:105-108,671-672): two iterations of
+    train.py:160-202 against the reference's own outputs (tests/golden/train_bce_golden.npz, make_golden_nets.gen_train_bce):
+    the three losses, every gradient tensor of the first iteration."""
+    from make_golden_nets import TRAIN_BCE_FLAGS, TRAIN_STEPS, state_checksum
+    from mdctgan_b200.models import networks
+    from test_oracle_train import flags_to_cfg
+
+    name = "tr_small_bce"
+    gold = dict(np.load(os.path.join(GOLDEN, "train_bce_golden.npz")))
+    flags, batch, T, seed = TRAIN_BCE_FLAGS[name]
+    cfg = flags_to_cfg(flags)
+    model = _build_model(flags, seed, dev)
+    assert model.loss_names == list(gold[f"{name}_loss_names"])
+    # the reference golden was made on CPU: the same seeded CPU initialisation, G first, then D (sigmoid head, no intermediate features)
+    torch.manual_seed(seed)
+    G0 = networks.define_G(2, 1, cfg["ngf"], cfg["netG"], cfg["n_down"], cfg["n_blocks_global"], 1, cfg["n_blocks_local"], "instance",
+                           input_size=(cfg["bins"], 256), n_attn_g=cfg["n_attn"], heads_g=cfg["heads"], dim_head_g=cfg["dim_head"])
+    D0 = networks.define_D(3, cfg["ndf"], cfg["n_layers_D"], "instance", True, cfg["num_D"], False)
+    assert list(D0.state_dict().keys()) == list(gold[f"{name}_D_keys"])
+    np.testing.assert_allclose(state_checksum(G0.state_dict()), gold[f"{name}_G_cksum0"], rtol=1e-12)
+    np.testing.assert_allclose(state_checksum(D0.state_dict()), gold[f"{name}_D_cksum0"], rtol=1e-12)
+    model.netG.load_state_dict(G0.state_dict())
+    model.netD.load_state_dict(D0.state_dict())
+    lr_d, hr_d = torch.from_numpy(gold[f"{name}_lr_audio"]).to(dev), torch.from_numpy(gold[f"{name}_hr_audio"]).to(dev)
+    losses = []
+    for it in range(TRAIN_STEPS):
+        if api == "autograd":
+            ls, _ = model._forward(lr_d, hr_d)
+            d = dict(zip(model.loss_names, ls))
+            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+            loss_G = d["G_GAN"]
+            model.optimizer_G.zero_grad()
+            loss_G.backward()
+            if it == 0:
+                gG = {k: p.grad.detach().cpu().clone() for k, p in model.netG.named_parameters()}
+            model.optimizer_G.step()
+            model.optimizer_D.zero_grad()
+            loss_D.backward()
+            if it == 0:
+                gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
+            model.optimizer_D.step()
+            losses.append([float(d[k]) for k in ("G_GAN", "D_real", "D_fake")])
+        else:
+            lv = model.train_step(lr_d, hr_d).cpu().tolist()      # [G_GAN, G_GAN_Feat (= 0: disabled), D_real, D_fake]
+            assert lv[1] == 0.0
+            losses.append([lv[0], lv[2], lv[3]])
+            if it == 0:
+                gG = {k: p.grad.detach().cpu().clone() for k, p in model.netG.named_parameters()}
+                gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
+    np.testing.assert_allclose(np.array(losses)[0], gold[f"{name}_losses"][0], rtol=5e-4)
+    np.testing.assert_allclose(np.array(losses)[1:], gold[f"{name}_losses"][1:], rtol=1e-2)
+    for tag, got in (("gradG", gG), ("gradD", gD)):
+        ref = {k[len(name) + len(tag) + 3:]: v for k, v in gold.items() if k.startswith(f"{name}_{tag}::")}
+        assert set(ref) == set(got)
+        gmax = max(float(np.abs(v).max()) for v in ref.values())
+        for k, v in ref.items():
+            if float(np.abs(v).max()) < 1e-4 * gmax:
+                assert float(got[k].abs().max()) < 1e-3 * gmax, (tag, k)
+                continue
+            e = rel_l2(got[k].numpy(), v)
+            assert e < 2e-2, (tag, k, e)
