@@ -32,7 +32,8 @@ class NormSpec:
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # MDCTGAN_LIB: another build of the same library (tuning sweeps, tools/build_variants.sh); never a different implementation
+    return os.environ.get("MDCTGAN_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 def lib():

@@ -145,7 +145,7 @@ template <typename R, typename S, typename OutT, int PRO, bool EXACT>
 int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaStream_t st) {
   if (p.B == 0 || p.F < 2 || p.out_len == 0) return 0;
   const int64_t nout = (p.out_len + kHop - 1) / kHop;   // output blocks actually needed (out_length crop)
-  p.ft = pick_ft(nout, 1, KCfg<R>::kMaxFt);
+  p.ft = pick_ft(nout, 1, KCfg<R>::kMaxFtInv);
   p.tiles_per_clip = (nout + p.ft - 2) / (p.ft - 1);
   p.ntiles = p.B * p.tiles_per_clip;
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
@@ -216,12 +216,12 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, true>, fs64, pl->num_sms, pl->grid_fwd[3], KCfg<double>::kMaxFt))) return rc;
   if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, float, false>, fs64, pl->num_sms, pl->grid_fwd[4], KCfg<double>::kMaxFt))) return rc;
   if ((rc = setup_kernel(mdct4_fwd_kernel<double, 1, float, false>, fs64, pl->num_sms, pl->grid_fwd[5], KCfg<double>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0, false>, is32, pl->num_sms, pl->grid_inv[0], KCfg<float>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1], KCfg<double>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2], KCfg<float>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3], KCfg<double>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4], KCfg<double>::kMaxFt))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5], KCfg<double>::kMaxFt))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 0, false>, is32, pl->num_sms, pl->grid_inv[0], KCfg<float>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1], KCfg<double>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2], KCfg<float>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3], KCfg<double>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4], KCfg<double>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5], KCfg<double>::kMaxFtInv))) return rc;
   *out = pl;
   return 0;
 }

@@ -42,6 +42,7 @@ constexpr int kRows = kBM * 8 / kProducerThreads;   // rows of the A tile per pr
 static_assert(kRows == 2, "validity queue packs 2 bits per chunk");
 constexpr int kThreads = (kProducerWarps + 2) * 32;   // + MMA warp + weight-loader warp
 constexpr int kMaxCin = 1024;
+constexpr int kMaxSplits = 16;       // split-K ranks = CTAs of one cluster (8 portable; 16 with cudaFuncAttributeNonPortableClusterSizeAllowed)
 constexpr int kNormTab = 4096;        // floats per deferred-normalisation table (scale, shift): samples in a tile x Cin
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;           // sign + 8 exponent + 10 mantissa bits
 
@@ -391,15 +392,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       const int n_tab = tab_rows * p.Cin;
       const size_t off = p.in.per_sample ? (size_t)b_first * p.Cin : 0;
       if (p.in.stats) {
+        // four entries per thread and pass: the eight statistics loads are issued together (an L2 round trip each: rolled one by one
+        // they were 4 us of this kernel's prologue on a 4 x 512-channel table)
         const double inv_n = 1.0 / (double)p.in.count;
+        const double2* st2 = reinterpret_cast<const double2*>(p.in.stats) + off;
 #pragma unroll 1
-        for (int cc = tid; cc < n_tab; cc += kProducerThreads) {
-          const double mean = p.in.stats[2 * (off + cc)] * inv_n;
-          double var = p.in.stats[2 * (off + cc) + 1] * inv_n - mean * mean;
-          var = var < 0.0 ? 0.0 : var;
-          const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
-          s_scale[cc] = (float)rstd;
-          s_shift[cc] = (float)(-mean * rstd);
+        for (int c0 = tid; c0 < n_tab; c0 += 4 * kProducerThreads) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = c0 + u * kProducerThreads;
+            v[u] = cc < n_tab ? __ldg(st2 + cc) : make_double2(0.0, 1.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = c0 + u * kProducerThreads;
+            if (cc < n_tab) {      // (warp-uniform: the fp64 divide / square root of padding entries would cost a microsecond on small tables)
+              const double mean = v[u].x * inv_n;
+              double var = v[u].y * inv_n - mean * mean;
+              var = var < 0.0 ? 0.0 : var;
+              const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
+              s_scale[cc] = (float)rstd; s_shift[cc] = (float)(-mean * rstd);
+            }
+          }
         }
       } else if (p.in.scale) {
 #pragma unroll 1
@@ -547,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       float4 acc = bias;
       if (r < r_end && m0 + r < row_limit) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {             // rank order: deterministic
+        for (int s = 0; s < kMaxSplits; ++s) {    // rank order: deterministic
           if (s < p.splits) {
             const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
             const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
@@ -559,8 +574,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
     }
   }
   // then one pass per sample the tile touches: its rows are stored, its (sum, sumsq) go out
+  // (only the samples that own rows of THIS rank's share [r_begin, r_end): on a spanning tile that is usually one of several)
+  const int r_last = min(r_end, row_limit - m0) - 1;
+  const int sb_first = r_last >= r_begin ? max(b_first, (m0 + r_begin) / tg.hw) : 1, sb_last = r_last >= r_begin ? min(b_last, (m0 + r_last) / tg.hw) : 0;
 #pragma unroll 1
-  for (int sb = b_first; sb <= b_last; ++sb) {
+  for (int sb = sb_first; sb <= sb_last; ++sb) {
     const int lo = max(r_begin, sb * tg.hw - m0), hi = min(r_end, min((sb + 1) * tg.hw, row_limit) - m0);
     if (tid < kProducerThreads) {
       double ssum[4] = {0.0, 0.0, 0.0, 0.0}, ssq[4] = {0.0, 0.0, 0.0, 0.0};
@@ -588,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         for (int r = lo + ((rg - (lo - r_begin)) % RP + RP) % RP; r < hi; r += RP) {      // my rows (r = r_begin + rg mod RP) inside [lo, hi)
           float4 acc = bias;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {             // rank order: deterministic
+          for (int s = 0; s < kMaxSplits; ++s) {    // rank order: deterministic
             if (s < p.splits) {
               const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
               const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
         red_add_f64(st, s);
         red_add_f64(st + 1, q);
       }
-      if (sb < b_last) __syncthreads();   // `red` is rewritten by the next sample's pass
+      if (sb < sb_last) __syncthreads();   // `red` is rewritten by the next sample's pass
     }
   }
   trace_mark(p, 8, tid == 0);

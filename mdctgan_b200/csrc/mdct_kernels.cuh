@@ -34,8 +34,21 @@ namespace mdctk {
 // share an SM -- the fp64 kernels are latency bound (ncu r02c: 2.25 warps per scheduler, 5.5 cycles per issued instruction),
 // co-resident CTAs hide the tile load instead of a second stage.
 template <typename R> struct KCfg;
-template <> struct KCfg<float> { static constexpr int kStages = 2, kMaxFt = 16, kMinBlocksFwd = 5, kMinBlocksInv = 4; };
-template <> struct KCfg<double> { static constexpr int kStages = 1, kMaxFt = 12, kMinBlocksFwd = 4, kMinBlocksInv = 3; };
+template <> struct KCfg<float> { static constexpr int kStages = 2, kMaxFt = 16, kMaxFtInv = 16, kMinBlocksFwd = 5, kMinBlocksInv = 4; };
+// r02j sweep on B200 (8192 x 8192, tools/build_variants.sh): the fp64 kernels run at a fixed rate PER WARP (throughput follows the number of
+// resident warps: 12 / SM at 168 registers), a second input stage costs warps and loses; the inverse, whose warps meet at two mbarriers
+// per tile, gains 20 % from 8-frame tiles (64-thread CTAs, 4 per SM): 0.353 -> 0.285 ms.
+#ifndef MDCT_F64_STAGES      // tuning knobs of the fp64 core (tools/build_variants.sh sweeps them)
+#define MDCT_F64_STAGES 1
+#define MDCT_F64_MAXFT 12
+#define MDCT_F64_MAXFT_INV 8
+#define MDCT_F64_MINB_FWD 4
+#define MDCT_F64_MINB_INV 4
+#endif
+template <> struct KCfg<double> {
+  static constexpr int kStages = MDCT_F64_STAGES, kMaxFt = MDCT_F64_MAXFT, kMaxFtInv = MDCT_F64_MAXFT_INV, kMinBlocksFwd = MDCT_F64_MINB_FWD,
+                       kMinBlocksInv = MDCT_F64_MINB_INV;
+};
 
 struct FwdParams {
   const float* audio; int64_t audio_stride; int64_t T;
@@ -410,7 +423,7 @@ __device__ __forceinline__ void inv_output_phase(const InvParams& p, int64_t til
 //   pass 1 / pass 2 of tile i (private exchange slice) -> wait odone(i-1) -> write U rows(i) -> arrive udone(i)
 // so both cross-warp dependencies (U rows complete / U rows free) are split-phase with real work in between.
 template <typename R, typename S, typename OutT, int PRO, bool EXACT>
-__global__ void __launch_bounds__(8 * KCfg<R>::kMaxFt, KCfg<R>::kMinBlocksInv) imdct4_inv_kernel(const InvParams p) {
+__global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv) imdct4_inv_kernel(const InvParams p) {
   constexpr int kStages = KCfg<R>::kStages;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int stage_elems = p.ft * kRawPitch;

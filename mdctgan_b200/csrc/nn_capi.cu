@@ -1,5 +1,6 @@
 // nn_capi.cu -- C ABI of the network kernels (see include/mdctgan_b200.h, "network layers").
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/mdctgan_b200.h"
@@ -49,7 +50,14 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
   p.act = act; p.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   const int HWo = Ho * Wo;
-  if (Cout <= 4 && !stats) {
+  if (Cout == 1 && !stats && Cin % 4 == 0 && Cin <= 512 && (in_act == kActNone || in_act == kActRelu || in_act == kActLeaky)) {
+    // one output channel: LANES lanes per pixel with the thread's normalisation in registers (conv2d_cout1_kernel)
+    if (Cin <= 32) conv2d_cout1_kernel<8, 1><<<B * ((HWo + 31) / 32), 256, 0, st>>>(p);
+    else if (Cin <= 64) conv2d_cout1_kernel<8, 2><<<B * ((HWo + 31) / 32), 256, 0, st>>>(p);
+    else if (Cin <= 128) conv2d_cout1_kernel<32, 1><<<B * ((HWo + 7) / 8), 256, 0, st>>>(p);
+    else if (Cin <= 256) conv2d_cout1_kernel<32, 2><<<B * ((HWo + 7) / 8), 256, 0, st>>>(p);
+    else conv2d_cout1_kernel<32, 4><<<B * ((HWo + 7) / 8), 256, 0, st>>>(p);
+  } else if (Cout <= 4 && !stats) {
     const int bps = (HWo + 31) / 32;
     const size_t smem = ((size_t)kh * kw * Cin * Cout + 2 * (size_t)Cin) * sizeof(float);
     if (smem > 200 * 1024) return mdctgan_set_error(-2, "conv2d: Cout<=4 kernel needs %zu bytes of shared memory", smem);
@@ -196,10 +204,26 @@ int mdctgan_nhwc_to_nchw(const float* x, float* y, int B, int C, int HW, void* s
 
 // ---- tcgen05 implicit-GEMM convolution (conv_umma.cuh) --------------------------------------------------
 namespace {
+// Largest split-K cluster: 16 CTAs (non-portable size) by default; MDCTGAN_UMMA_MAX_SPLIT = 8 keeps the portable limit (A/B switch)
+int umma_split_cap() {
+  static int cap = 0;
+  if (!cap) {
+    const char* e = getenv("MDCTGAN_UMMA_MAX_SPLIT");
+    cap = e ? atoi(e) : umma::kMaxSplits;
+    if (cap < 1) cap = 1;
+    if (cap > umma::kMaxSplits) cap = umma::kMaxSplits;
+  }
+  return cap;
+}
+
 template <int BN, bool SPLIT3>
 int umma_max_clusters(int splits) {   // how many clusters of `splits` CTAs fit on the device at once (cached)
-  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static int cache[umma::kMaxSplits + 1] = {};
   if (cache[splits]) return cache[splits];
+  if (splits > 8) {      // beyond the portable cluster size
+    static bool np_set = false;
+    if (!np_set) { cudaFuncSetAttribute(umma::conv2d_umma_kernel<BN, SPLIT3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); cudaGetLastError(); np_set = true; }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(1, splits, 1);
   cfg.blockDim = dim3(umma::kThreads);
@@ -211,7 +235,7 @@ int umma_max_clusters(int splits) {   // how many clusters of `splits` CTAs fit 
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, umma::conv2d_umma_kernel<BN, SPLIT3>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
-    n = 148 / splits;   // conservative guess
+    n = splits > 8 ? -1 : 148 / splits;   // conservative guess; non-portable sizes the device refuses are never chosen
   }
   cache[splits] = n;
   return n;
@@ -228,7 +252,7 @@ int launch_umma(umma::ConvUmmaParams& p, int n_tiles, int min_kchunks, cudaStrea
   const int tiles = p.m_tiles * (p.span ? 1 : p.B) * p.classes * n_tiles;
   // split K over a cluster while the whole grid still fits the device in one wave
   int splits = 1;
-  for (int s = 8; s >= 2; --s) {
+  for (int s = umma_split_cap(); s >= 2; --s) {
     if (s > min_kchunks) continue;
     if (tiles <= umma_max_clusters<BN, SPLIT3>(s)) { splits = s; break; }
   }
@@ -333,7 +357,7 @@ int mdctgan_conv2d_umma(const float* x, int B, int H, int W, int Cin, const floa
   // Tile width: BN = 128 halves the shared-memory traffic per output (the A tile is re-read by every MMA), but at the reference's
   // shapes the grid is the constraint: take the widest tile that still gives about a wave of CTAs once K is split over a cluster.
   const long long m_ctas = (long long)p.m_tiles * (p.span ? 1 : B) * p.classes;
-  const int max_split = min_kchunks < 8 ? min_kchunks : 8;
+  const int max_split = min_kchunks < umma_split_cap() ? min_kchunks : umma_split_cap();
   int bn = 32;
   if (CoutP % 128 == 0 && (m_ctas * (CoutP / 128) >= 74 || m_ctas * (CoutP / 128) * max_split >= 96)) bn = 128;
   else if (CoutP % 64 == 0 && (m_ctas * (CoutP / 64) >= 74 || m_ctas * (CoutP / 64) * max_split >= 96)) bn = 64;

@@ -326,6 +326,66 @@ __global__ void __launch_bounds__(256) conv2d_cout_small_kernel(const ConvParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cout == 1, Cin % 4 == 0 (generator head 7x7 -> 1 + tanh: LANES = 8; PatchGAN heads 4x4 512 -> 1: LANES = 32): LANES lanes per
+// output pixel, lane l owns the channel quads c = 4 l + 4 LANES i (i < NI <= 4).  The r01 / r02 profiles had the Cout <= 4 kernel above
+// at 70 - 85 us on these layers: 12 shared-memory loads per tap (weights + scale / shift, scalar) next to one global load on the
+// 7x7 head (LSU-issue bound), and a 256-iteration serial load chain per thread on the 512-channel heads (latency bound).  Here the
+// deferred normalisation of the thread's channels lives in registers, weights come as float4 through L1 (__ldg: every pixel
+// group reads the same K floats), and the tap loop is unrolled so that several independent global loads are in flight.
+// ------------------------------------------------------------------------------------------------
+template <int LANES, int NI>
+__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const ConvParams p) {
+  __shared__ float s_scale[1024], s_shift[1024];
+  const int HWo = p.Ho * p.Wo;
+  constexpr int kPix = 256 / LANES;
+  const int blocks_per_sample = (HWo + kPix - 1) / kPix;
+  const int b = blockIdx.x / blocks_per_sample;
+  const int m = (blockIdx.x - b * blocks_per_sample) * kPix + threadIdx.x / LANES;
+  const int l = threadIdx.x % LANES;
+  const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+  if (has_norm) norm_to_smem(p.in, b, p.Cin, s_scale, s_shift, threadIdx.x, 256);
+  __syncthreads();
+  float4 sc[NI], sh[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = 4 * l + 4 * LANES * i;
+    sc[i] = make_float4(1.f, 1.f, 1.f, 1.f); sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_norm && c < p.Cin) { sc[i] = *reinterpret_cast<const float4*>(s_scale + c); sh[i] = *reinterpret_cast<const float4*>(s_shift + c); }
+  }
+  const float slope = !has_norm ? 1.f : (p.in.act == kActRelu ? 0.f : (p.in.act == kActLeaky ? 0.2f : 1.f));   // v = max(e, slope e)
+  float acc = 0.f;
+  if (m < HWo) {
+    const int oy = m / p.Wo, ox = m - oy * p.Wo;
+    const float* xb = p.x + (size_t)b * p.H * p.W * p.Cin;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = in_coord(oy, ky, p.H, p.stride, p.pad, p.pad_mode, p.transposed);
+      if (iy < 0) continue;
+#pragma unroll 4
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = in_coord(ox, kx, p.W, p.stride, p.pad, p.pad_mode, p.transposed);
+        if (ix < 0) continue;
+        const float* px = xb + ((size_t)iy * p.W + ix) * p.Cin;
+        const float* wt = p.w + (size_t)(ky * p.kw + kx) * p.Cin;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int c = 4 * l + 4 * LANES * i;
+          if (c < p.Cin) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(px + c));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wt + c));
+            float e0 = fmaf(q.x, sc[i].x, sh[i].x), e1 = fmaf(q.y, sc[i].y, sh[i].y), e2 = fmaf(q.z, sc[i].z, sh[i].z), e3 = fmaf(q.w, sc[i].w, sh[i].w);
+            e0 = fmaxf(e0, slope * e0); e1 = fmaxf(e1, slope * e1); e2 = fmaxf(e2, slope * e2); e3 = fmaxf(e3, slope * e3);
+            acc = fmaf(e0, w.x, acc); acc = fmaf(e1, w.y, acc); acc = fmaf(e2, w.z, acc); acc = fmaf(e3, w.w, acc);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = LANES / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (m < HWo && l == 0) p.y[(size_t)b * HWo + m] = apply_act(acc + (p.bias ? __ldg(p.bias) : 0.f), p.act);
+}
+
+// ------------------------------------------------------------------------------------------------
 // (sum, sumsq) -> (scale, shift).  InstanceNorm2d(affine=False, eps): per (b, c); BatchNorm2d: per c, with
 // optional affine and running-statistics update (momentum) in training mode, or running statistics in eval.
 // ------------------------------------------------------------------------------------------------

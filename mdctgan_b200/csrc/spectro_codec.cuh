@@ -104,9 +104,11 @@ struct AffineParams {
 // :116-123: (x - min) / (max - min) * (hi - lo) + lo, fp64, rounded to fp32 once (to_spectro returns .float())
 __global__ void __launch_bounds__(256) spectro_affine_kernel(const double* __restrict__ enc, float* __restrict__ out, const AffineParams p) {
   const long long pl = blockIdx.y;
-  const double lo = p.minmax ? (double)p.minmax[2 * pl] : p.src_lo, hi = p.minmax ? (double)p.minmax[2 * pl + 1] : p.src_hi;
+  // audio_min / audio_max are fp32 tensors in the reference: their difference is an fp32 subtraction, the rest promotes to fp64
+  const float lo_f = p.minmax ? p.minmax[2 * pl] : (float)p.src_lo, hi_f = p.minmax ? p.minmax[2 * pl + 1] : (float)p.src_hi;
+  const double lo = (double)lo_f, span = (double)__fsub_rn(hi_f, lo_f);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.plane; i += (long long)gridDim.x * 256) {
-    double s = (enc[pl * p.plane + i] - lo) / (hi - lo);
+    double s = (enc[pl * p.plane + i] - lo) / span;
     out[pl * p.plane + i] = (float)(s * (p.norm_hi - p.norm_lo) + p.norm_lo);
   }
 }
@@ -129,9 +131,9 @@ __global__ void __launch_bounds__(256) spectro_decode_kernel(const DecodeParams 
     double d[2] = {0.0, 0.0};
     for (int c = 0; c < C; ++c) {
       const long long pl = b * C + c;
-      const double lo = p.minmax ? (double)p.minmax[2 * pl] : p.src_lo, hi = p.minmax ? (double)p.minmax[2 * pl + 1] : p.src_hi;
+      const float lo_f = p.minmax ? p.minmax[2 * pl] : (float)p.src_lo, hi_f = p.minmax ? p.minmax[2 * pl + 1] : (float)p.src_hi;
       double x = ((double)p.s[pl * p.plane + i] - p.norm_lo) / (p.norm_hi - p.norm_lo);
-      x = x * (hi - lo) + lo;
+      x = x * (double)__fsub_rn(hi_f, lo_f) + (double)lo_f;      // (max - min): an fp32 subtraction in the reference (:130)
       if (p.mode == kModeArcsinh) x = sinh(x * 2.3025851249694824) / p.gain;
       else if (p.mode != kModeRaw) x = 10.0 * pow(pow(10.0, 0.1 * x), 0.5) - p.min_value;      // aF.DB_to_amplitude(x, 10.0, 0.5) - min_value
       d[c] = x;

@@ -724,9 +724,9 @@ class _ConvOp:
             return
         if self.act != ACT_NONE:
             dy = act_bwd(dy, _sl(self.out.x, nb), self.act)
-        f = _explicit_norm(_view_feat(self.f, nb), self.f if nb is None else None)
+        fv = _view_feat(self.f, nb)
         own = self.owner
-        B, H, W, Cin = f.x.shape
+        B, H, W, Cin = fv.x.shape
         _, Ho, Wo, Cout = dy.shape
         L = _L()
         if wgrad and own.weight.requires_grad:
@@ -744,6 +744,9 @@ class _ConvOp:
             side = _side_stream(dy)
             engine = wgrad_engine(Cin, Cout)
             with torch.cuda.device(dy.device), (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                # the explicit (scale, shift) of a deferred InstanceNorm is only read by this weight-gradient launch: its finalize
+                # launch goes to the side stream with it (44 launches per cfg4 step off the dgrad chain of the main stream)
+                f = _explicit_norm(fv, self.f if nb is None else None)
                 _lib.check(L.mdctgan_conv2d_wgrad(f.x.data_ptr(), B, H, W, Cin, dy.data_ptr(), Ho, Wo, Cout, self.kh, self.kw, self.stride,
                                                   self.pad, self.pad_mode, 1 if self.transposed else 0, _ptr(f.scale), _ptr(f.shift),
                                                   1 if f.per_sample else 0, f.act, _ptr(f.norm_stats), f.norm_count, f.norm_eps,
@@ -773,7 +776,7 @@ class _ConvOp:
             with torch.cuda.device(dv.device):
                 _lib.check(L.mdctgan_reflect_pad_bwd(dv.data_ptr(), dx.data_ptr(), B, H, W, Cin, self.pad, _stream(dv)))
             dv = dx
-        assert dv.shape == f.x.shape, (dv.shape, f.x.shape)
+        assert dv.shape == fv.x.shape, (dv.shape, fv.x.shape)
         G.add(self.f, dv)
 
 

@@ -59,7 +59,34 @@ def timed(fn, name, n=30):
     print(f"{e0.elapsed_time(e1) / n:8.3f} ms  {name}", flush=True)
 
 
+def g_only():
+    with ops.stats_pass(dev):
+        m = model
+        lr_spectro, lr_input, _, _ = m._lr_input(lr)
+        m.preprocess.hr_forward(hr)
+        tape = ops.Tape()
+        with ops.recording(tape):
+            m.netG.run(ops.to_nhwc(lr_input))
+
+
+def sweeps(which):
+    g = T.GanGraph(model)
+    with ops.stats_pass(dev):
+        model.grad_all.zero_()
+        g.forward(lr, hr)
+        half = model._half_scalar()
+        if which == "D":
+            g.backward_D(half, half, join=False)
+        else:
+            g.backward_G(join=False)
+        ops.join_side_work(dev)
+    g.release()
+
+
+timed(g_only, "2 MDCT + generator forward only")
 timed(lambda: prefix(1), "forward (2 MDCT, G, D on [fake; real], losses)")
+timed(lambda: sweeps("G"), "forward + generator sweep only (D dgrad on the fake half, G dgrad + wgrad)")
+timed(lambda: sweeps("D"), "forward + discriminator sweep only (dgrad + wgrad)")
 timed(lambda: prefix(2), "forward + both sweeps (dgrad, wgrad, norm backward), no update")
 PM.PIPELINED_UPDATE = True
 timed(lambda: model.train_step(lr, hr), "full step, pipelined per-bucket update")
