@@ -561,12 +561,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
       const int r = r_begin + rg + i * RP;
       float4 acc = bias;
       if (r < r_end && m0 + r < row_limit) {
+        if (p.splits == 1) {                      // (block-uniform) no reduction: the common case on large planes
+          const float4 t = *reinterpret_cast<const float4*>(stage_out + r * C::kPitch + cq * 4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        } else {
 #pragma unroll
-        for (int s = 0; s < kMaxSplits; ++s) {    // rank order: deterministic
-          if (s < p.splits) {
-            const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
-            const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          for (int s = 0; s < kMaxSplits; ++s) {  // rank order: deterministic
+            if (s < p.splits) {
+              const float4 t = *reinterpret_cast<const float4*>(cluster.map_shared_rank(stage_out, s) + r * C::kPitch + cq * 4);
+              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
           }
         }
       }
@@ -605,12 +609,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
 #pragma unroll 1
         for (int r = lo + ((rg - (lo - r_begin)) % RP + RP) % RP; r < hi; r += RP) {      // my rows (r = r_begin + rg mod RP) inside [lo, hi)
           float4 acc = bias;
+          if (p.splits == 1) {
+            const float4 t = *reinterpret_cast<const float4*>(stage_out + r * C::kPitch + cq * 4);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          } else {
 #pragma unroll
-          for (int s = 0; s < kMaxSplits; ++s) {    // rank order: deterministic
-            if (s < p.splits) {
-              const float* src = p.splits > 1 ? cluster.map_shared_rank(stage_out, s) : stage_out;
-              const float4 t = *reinterpret_cast<const float4*>(src + r * C::kPitch + cq * 4);
-              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            for (int s = 0; s < kMaxSplits; ++s) {  // rank order: deterministic
+              if (s < p.splits) {
+                const float4 t = *reinterpret_cast<const float4*>(cluster.map_shared_rank(stage_out, s) + r * C::kPitch + cq * 4);
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+              }
             }
           }
           finish_row(r, acc);

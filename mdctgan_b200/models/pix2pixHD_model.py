@@ -509,6 +509,17 @@ class Pix2PixHDModel(BaseModel):
         return [losses, None if not infer else graph.sr_spectro]
 
     def train_step(self, lr_audio, hr_audio, world_size: int = 1, all_reduce=None):
+        if not _ops.STREAM_PRIORITY:
+            return self._train_step(lr_audio, hr_audio, world_size, all_reduce)
+        cur = torch.cuda.current_stream(self.device)      # the dependent chain on a high-priority stream (nn_ops.STREAM_PRIORITY)
+        hi = _ops.aux_stream(self.device, "main_hi")
+        hi.wait_stream(cur)
+        with torch.cuda.stream(hi):
+            out = self._train_step(lr_audio, hr_audio, world_size, all_reduce)
+        cur.wait_stream(hi)
+        return out
+
+    def _train_step(self, lr_audio, hr_audio, world_size: int = 1, all_reduce=None):
         """One whole iteration of train.py:160-202 without autograd in the loop: forward, generator sweep,
         discriminator sweep, [ONE all-reduce over the two flat gradient buckets], both Adam steps.  Mathematically the
         reference order (G step before D backward) because loss_D never depends on the updated G.
@@ -564,8 +575,7 @@ class Pix2PixHDModel(BaseModel):
                     # discriminator itself (it back-propagates the generator loss through the OLD discriminator weights)
                     def after_D():
                         evs = [ev_sD]
-                        sw = _ops._side.get(self.device.index)
-                        for st_ in ([main] + ([sw.stream] if (sw is not None and sw.active) else [])):
+                        for st_ in [main] + _ops.side_streams(self.device):
                             e_ = torch.cuda.Event()
                             e_.record(st_)
                             evs.append(e_)
@@ -650,8 +660,7 @@ class Pix2PixHDModel(BaseModel):
         cur = torch.cuda.current_stream(self.device)
         if events is None:
             events = []
-            sw = _ops._side.get(self.device.index)
-            for st in ([cur] + ([sw.stream] if (sw is not None and sw.active) else [])):
+            for st in [cur] + _ops.side_streams(self.device):
                 ev = torch.cuda.Event()
                 ev.record(st)
                 events.append(ev)

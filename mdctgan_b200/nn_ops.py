@@ -478,22 +478,33 @@ _tape = None
 
 
 class _SideWork:
-    """A second CUDA stream for work whose results are only needed at the end of the step (weight gradients)."""
+    """Side CUDA streams for work whose results are only needed at the end of the step (weight gradients and the norm_finalize they
+    read).  Several streams, used round-robin: the weight-gradient kernels of a step are short and latency-bound, on ONE stream they
+    serialise into a chain about as long as the sweep itself (cfg4: 2.2 ms of kernels next to a 2.4 ms sweep) and the update tail
+    waits for its end."""
 
     def __init__(self, device):
         self.device = device
-        self.stream = torch.cuda.Stream(device)
-        self.keep = []          # tensors read on the side stream: kept alive until join() so the allocator cannot recycle them
+        self.streams = [torch.cuda.Stream(device) for _ in range(N_SIDE_STREAMS)]
+        self.next = 0
+        self.keep = []          # tensors read on the side streams: kept alive until join() so the allocator cannot recycle them
         self.active = False
+
+    @property
+    def stream(self):           # (single-stream view: the opt-in bucketed exchange runs with N_SIDE_STREAMS = 1)
+        return self.streams[0]
 
 
 _side = {}
 _wgrad_hooks = {}       # id(module) -> callable(stream the module's weight-gradient kernel was enqueued on)
 SIDE_STREAM_WGRAD = os.environ.get("MDCTGAN_SIDE_WGRAD", "1") != "0"
+# r02: 2 / 3 / 4 side streams measured 5.07 / 5.07 / 5.11 ms per cfg4 step against 4.91 with one -- the step is bound by SM contention, and one
+# stream throttles the weight gradients to what the dependent chain leaves free
+N_SIDE_STREAMS = 1 if os.environ.get("MDCTGAN_BUCKETED_ALLREDUCE", "0") == "1" else max(1, int(os.environ.get("MDCTGAN_SIDE_STREAMS", "1")))
 
 
 def _side_stream(dy: torch.Tensor):
-    """Fork: make the side stream wait for everything issued so far on the current stream; returns it (or None when disabled)."""
+    """Fork: make a side stream wait for everything issued so far on the current stream; returns it (or None when disabled)."""
     if not SIDE_STREAM_WGRAD:
         return None
     key = dy.device.index
@@ -501,27 +512,44 @@ def _side_stream(dy: torch.Tensor):
     if sw is None:
         sw = _side[key] = _SideWork(dy.device)
     main = torch.cuda.current_stream(dy.device)
-    if main == sw.stream:
+    if any(main == st for st in sw.streams):
         return None
+    st = sw.streams[sw.next % len(sw.streams)]
+    sw.next += 1
     ev = torch.cuda.Event()
     ev.record(main)
-    sw.stream.wait_event(ev)
+    st.wait_event(ev)
     sw.keep.append(dy)
     sw.active = True
-    return sw.stream
+    return st
+
+
+def side_streams(device):
+    """The side streams that carry work of the current step (for joins / events)."""
+    sw = _side.get(torch.device(device).index)
+    return list(sw.streams) if (sw is not None and sw.active) else []
 
 
 def join_side_work(device) -> None:
-    """Join: the current stream waits for the side stream (call before anything reads the weight gradients)."""
+    """Join: the current stream waits for the side streams (call before anything reads the weight gradients)."""
     sw = _side.get(torch.device(device).index)
     if sw is None or not sw.active:
         return
-    torch.cuda.current_stream(sw.device).wait_stream(sw.stream)
+    cur = torch.cuda.current_stream(sw.device)
+    for st in sw.streams:
+        cur.wait_stream(st)
     sw.keep.clear()
     sw.active = False
+    sw.next = 0
 
 
 _branch_streams = {}
+# MDCTGAN_STREAM_PRIORITY=1: the streams of the dependent chain (sweeps, branches) get a higher CUDA priority than the weight-gradient
+# side stream and the update stream, whose kernels only have to finish by the end of the step
+STREAM_PRIORITY = os.environ.get("MDCTGAN_STREAM_PRIORITY", "1") == "1"
+_HI = -1 if STREAM_PRIORITY else 0
+# r02 (cfg4 step): no priorities 4.91 ms; chain high / update low 4.71; discriminator sweep low as well 4.69 (it hides behind the generator's)
+_LOW_PRIORITY = set(os.environ.get("MDCTGAN_LOW_PRIORITY_STREAMS", "update,sweep_D").split(","))
 PARALLEL_BRANCHES = os.environ.get("MDCTGAN_PARALLEL_BRANCHES", "1") != "0"
 
 
@@ -531,7 +559,7 @@ def _branch_stream(device, i: int, parent=None):
     parent = parent if parent is not None else torch.cuda.current_stream(device)
     key = (torch.device(device).index, parent.cuda_stream, i)
     if key not in _branch_streams:
-        _branch_streams[key] = torch.cuda.Stream(device)
+        _branch_streams[key] = torch.cuda.Stream(device, priority=getattr(parent, "priority", 0) if STREAM_PRIORITY else 0)      # a branch inherits its parent's priority
     return _branch_streams[key]
 
 
@@ -539,7 +567,7 @@ def aux_stream(device, name: str):
     """A named long-lived stream (e.g. the discriminator sweep of the train step)."""
     key = (torch.device(device).index, name)
     if key not in _branch_streams:
-        _branch_streams[key] = torch.cuda.Stream(device)
+        _branch_streams[key] = torch.cuda.Stream(device, priority=0 if name in _LOW_PRIORITY else _HI)
     return _branch_streams[key]
 
 
@@ -707,9 +735,13 @@ def _explicit_norm(f: Feat, cache_on: Optional[Feat]) -> Feat:
         with torch.cuda.device(f.x.device):
             _lib.check(_L().mdctgan_norm_finalize(f.norm_stats.data_ptr(), B, C, f.norm_count, f.norm_eps, 0, None, None, None, None, 0.0,
                                                   scale.data_ptr(), shift.data_ptr(), _stream(f.x)))
-        cached = (scale, shift)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(f.x.device))
+        cached = (scale, shift, ev)
         if cache_on is not None:
             cache_on._explicit = cached
+    else:
+        torch.cuda.current_stream(f.x.device).wait_event(cached[2])      # computed on another (side) stream
     return Feat(f.x, cached[0], cached[1], True, f.act, None, None, 0.0, f.norm_eps, f.needs_grad)
 
 
