@@ -151,7 +151,7 @@ int launch_inv(const mdctgan_plan* pl, InvParams& p, const int* grid_cap, cudaSt
   p.tabT = std::is_same<R, float>::value ? (const void*)pl->tabT32 : (const void*)pl->tabT64;
   p.window = EXACT ? pl->window : pl->window_syn;   // only the bit-faithful flavour keeps the reference's synthesis window
   const int grid = (int)std::min<int64_t>(p.ntiles, grid_cap[p.ft / 4 - 1]);
-  imdct4_inv_kernel<R, S, OutT, PRO, EXACT><<<grid, 8 * p.ft, inv_smem_bytes<R, S>(p.ft), st>>>(p);
+  imdct4_inv_kernel<R, S, OutT, PRO, EXACT><<<grid, 8 * p.ft, inv_smem_bytes<R, S, typename UType<R, OutT, EXACT>::type>(p.ft), st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return 0;
@@ -210,6 +210,7 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   auto is32 = [](int ft) { return inv_smem_bytes<float, float>(ft); };
   auto is64 = [](int ft) { return inv_smem_bytes<double, double>(ft); };
   auto is64f = [](int ft) { return inv_smem_bytes<double, float>(ft); };
+  auto is64m = [](int ft) { return inv_smem_bytes<double, float, UType<double, float, false>::type>(ft); };      // mixed flavour
   if ((rc = setup_kernel(mdct4_fwd_kernel<float, 0, float, false>, fs32, pl->num_sms, pl->grid_fwd[0], KCfg<float>::kMaxFt))) return rc;
   if ((rc = setup_kernel(mdct4_fwd_kernel<float, 1, float, false>, fs32, pl->num_sms, pl->grid_fwd[1], KCfg<float>::kMaxFt))) return rc;
   if ((rc = setup_kernel(mdct4_fwd_kernel<double, 0, double, true>, fs64, pl->num_sms, pl->grid_fwd[2], KCfg<double>::kMaxFt))) return rc;
@@ -220,8 +221,8 @@ int mdctgan_plan_create(mdctgan_plan** out, int n_fft, int hop, int win, const f
   if ((rc = setup_kernel(imdct4_inv_kernel<double, double, double, 0, true>, is64, pl->num_sms, pl->grid_inv[1], KCfg<double>::kMaxFtInv))) return rc;
   if ((rc = setup_kernel(imdct4_inv_kernel<float, float, float, 1, false>, is32, pl->num_sms, pl->grid_inv[2], KCfg<float>::kMaxFtInv))) return rc;
   if ((rc = setup_kernel(imdct4_inv_kernel<double, float, double, 1, true>, is64f, pl->num_sms, pl->grid_inv[3], KCfg<double>::kMaxFtInv))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64f, pl->num_sms, pl->grid_inv[4], KCfg<double>::kMaxFtInv))) return rc;
-  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64f, pl->num_sms, pl->grid_inv[5], KCfg<double>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 0, false>, is64m, pl->num_sms, pl->grid_inv[4], KCfg<double>::kMaxFtInv))) return rc;
+  if ((rc = setup_kernel(imdct4_inv_kernel<double, float, float, 1, false>, is64m, pl->num_sms, pl->grid_inv[5], KCfg<double>::kMaxFtInv))) return rc;
   *out = pl;
   return 0;
 }

@@ -349,9 +349,18 @@ __device__ __forceinline__ void inv_produce(const InvParams& p, int64_t tile, S*
   }
 }
 
-template <typename R, typename S> __host__ __device__ constexpr size_t inv_smem_bytes(int ft) {
+#ifndef MDCT_U_F32
+#define MDCT_U_F32 0
+#endif
+// Element type of the inverse's U rows (DCT-IV results awaiting window + overlap-add).  MDCT_U_F32: the mixed flavour (fp64 core, fp32
+// tensors) parks them as fp32 -- 8.7 KB less shared memory per 8-frame tile (one more CTA per SM) and an fp32 output phase.
+template <typename R, typename OutT, bool EXACT> struct UType { using type = R; };
+#if MDCT_U_F32
+template <> struct UType<double, float, false> { using type = float; };
+#endif
+template <typename R, typename S, typename U = R> __host__ __device__ constexpr size_t inv_smem_bytes(int ft) {
   return align16((size_t)KCfg<R>::kStages * ft * kRawPitch * sizeof(S)) + align16((size_t)ft * kXchStride * sizeof(cx<R>)) +
-         align16((size_t)ft * kURow * sizeof(R)) + 512 * sizeof(float) + kTabTElems * sizeof(cx<R>) + 64;
+         align16((size_t)ft * kURow * sizeof(U)) + 512 * sizeof(float) + kTabTElems * sizeof(cx<R>) + 64;
 }
 
 template <typename R> __device__ __forceinline__ void load4(const R* p, R* o);
@@ -429,8 +438,9 @@ __global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv
   const int stage_elems = p.ft * kRawPitch;
   unsigned char* sp_ = smem_raw;
   S* raw = reinterpret_cast<S*>(sp_);                 sp_ += align16((size_t)kStages * stage_elems * sizeof(S));
+  using UT = typename UType<R, OutT, EXACT>::type;
   cx<R>* xch_all = reinterpret_cast<cx<R>*>(sp_);     sp_ += align16((size_t)p.ft * kXchStride * sizeof(cx<R>));
-  R* Ubuf = reinterpret_cast<R*>(sp_);                sp_ += align16((size_t)p.ft * kURow * sizeof(R));
+  UT* Ubuf = reinterpret_cast<UT*>(sp_);              sp_ += align16((size_t)p.ft * kURow * sizeof(UT));
   float* wsm = reinterpret_cast<float*>(sp_);         sp_ += 512 * sizeof(float);
   cx<R>* sT = reinterpret_cast<cx<R>*>(sp_);          sp_ += kTabTElems * sizeof(cx<R>);
   uint64_t* full = reinterpret_cast<uint64_t*>(sp_);
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv
   const SmemT<R> tt{sT + j};
   const R inv_gain = (R)1 / (R)p.np.gain;
   cx<R>* const xch = xch_all + f * kXchStride;
-  R* const Urow = Ubuf + f * kURow;
+  UT* const Urow = Ubuf + f * kURow;
 
   uint32_t it = 0;
 #pragma unroll 1
@@ -529,7 +539,7 @@ __global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv
     __syncwarp();
     if (it >= 1) {
       mbar_wait(udone, (it - 1) & 1);                               // U rows of tile it-1 complete in every warp
-      inv_output_phase<R, OutT>(p, tile - gridDim.x, Ubuf, wsm);
+      inv_output_phase<UT, OutT>(p, tile - gridDim.x, Ubuf, wsm);
       __syncwarp();
       if (lane == 0) mbar_arrive(odone);
     }
@@ -543,8 +553,8 @@ __global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv
         for (int k2 = 0; k2 < 8; ++k2) {
           int col; R d0, d1;
           out_pair<R>(y, j, h, k2, col, d0, d1);
-          typename Vec2<R>::type o; o.x = d0; o.y = d1;
-          *reinterpret_cast<typename Vec2<R>::type*>(Urow + col) = o;
+          typename Vec2<UT>::type o; o.x = (UT)d0; o.y = (UT)d1;
+          *reinterpret_cast<typename Vec2<UT>::type*>(Urow + col) = o;
         }
     }
     __syncwarp();
@@ -552,7 +562,7 @@ __global__ void __launch_bounds__(8 * KCfg<R>::kMaxFtInv, KCfg<R>::kMinBlocksInv
   }
   if (it >= 1) {   // drain: the last tile's overlap-add
     mbar_wait(udone, (it - 1) & 1);
-    inv_output_phase<R, OutT>(p, tile - gridDim.x, Ubuf, wsm);
+    inv_output_phase<UT, OutT>(p, tile - gridDim.x, Ubuf, wsm);
   }
 }
 

@@ -45,11 +45,13 @@ class BottleBlock(nn.Module):
         super().__init__()
         from .networks import BatchNorm2d, Conv2d, ReLU
 
-        if dim != dim_out or downsample:
-            raise NotImplementedError("BottleBlock with a projection shortcut / downsample: the reference always builds "
-                                      "dim == dim_out, downsample=False (networks.py:342-344)")
+        if downsample:
+            raise NotImplementedError("BottleBlock(downsample=True) is never built by the reference (networks.py:235,344)")
         activation = activation if activation is not None else ReLU()
-        self.shortcut = nn.Identity()
+        if dim != dim_out:       # projection shortcut (the local-branch stack of networks.py:232-235: dim ngf -> dim_out 2 ngf)
+            self.shortcut = nn.Sequential(Conv2d(dim, dim_out, 1, stride=1, padding=0, bias=False), BatchNorm2d(dim_out), activation)
+        else:
+            self.shortcut = nn.Identity()
         inner_in, inner_out = dim_out // proj_factor, heads * dim_head
         self.net = nn.Sequential(
             Conv2d(dim, inner_in, 1, bias=False), BatchNorm2d(inner_in), activation,
@@ -66,7 +68,8 @@ class BottleBlock(nn.Module):
         h = run_layers([n[0], n[1], n[2]], f)           # conv1x1 -> BN -> ReLU (pending)
         h = n[3].run(h)                                  # attention (plain) + statistics for the BN that follows
         h = run_layers([n[5], n[6], n[7], n[8]], h)      # BN -> ReLU -> conv1x1 -> BN (pending)
-        return ops.combine(h, f, act_out=ops.ACT_RELU)   # relu(net(x) + x)
+        sc = f if isinstance(self.shortcut, nn.Identity) else run_layers(list(self.shortcut), f)      # conv1x1 -> BN -> ReLU (pending)
+        return ops.combine(h, sc, act_out=ops.ACT_RELU)  # relu(net(x) + shortcut(x))
 
 
 class BottleStack(nn.Module):

@@ -407,8 +407,6 @@ class LocalEnhancer(nn.Module):
         super().__init__()
         norm_layer = norm_layer if norm_layer is not None else functools.partial(BatchNorm2d, affine=True)
         self.n_local_enhancers = n_local_enhancers
-        if n_attn_l > 0:
-            raise NotImplementedError("n_attn_l > 0 (local attention sandwich, networks.py:218-237) is listed as next in DESIGN.md")
         downsample_layer, upsample_layer = _sampling_layers(downsample_type, upsample_type)
         ngf_global = ngf * (2 ** n_local_enhancers)
         g = GlobalGenerator(input_nc, output_nc, ngf_global, n_downsample_global, n_blocks_global, norm_layer,
@@ -420,6 +418,23 @@ class LocalEnhancer(nn.Module):
                             downsample_layer(ngf_global, ngf_global * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global * 2), ReLU(True)]
         model_upsample: List[nn.Module] = [ResnetBlock(ngf_global * 2, padding_type=padding_type, norm_layer=norm_layer)
                                            for _ in range(n_blocks_local)]
+        if n_attn_l > 0:
+            # attention bottleneck in the local branch (networks.py:218-237): 8x down (the second / third step and the three up steps are
+            # the SAME layer objects applied repeatedly -- the reference builds them with `[...] * 2` / `[...] * 3`, so the weights are
+            # shared and their state_dict entries appear once per position), a BottleStack whose first block has a projection shortcut
+            # (dim ngf -> 2 ngf), 8x up.  Construction order = the reference's (the position embeddings are drawn at construction).
+            from .bottleneck import BottleStack
+
+            middle = n_blocks_local // 2
+            down = [downsample_layer(ngf_global * 2, ngf_global, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global), ReLU(True)]
+            down += [downsample_layer(ngf_global, ngf_global, kernel_size=3, stride=2, padding=1), norm_layer(ngf_global), ReLU(True)] * 2
+            model_upsample.insert(middle, nn.Sequential(*down))
+            attn_block = BottleStack(dim=ngf_global, fmap_size=tuple(s // 16 for s in input_size), dim_out=ngf_global * 2, num_layers=n_attn_l,
+                                     proj_factor=proj_factor_l, downsample=False, heads=heads_l, dim_head=dim_head_l, activation=ReLU(True),
+                                     rel_pos_emb=False)
+            model_upsample.insert(middle + 1, attn_block)
+            model_upsample += [upsample_layer(in_channels=ngf_global * 2, out_channels=ngf_global * 2, kernel_size=3, stride=2, padding=1,
+                                              output_padding=1), norm_layer(ngf_global), ReLU(True)] * 3
         model_upsample += [upsample_layer(in_channels=ngf_global * 2, out_channels=ngf_global, kernel_size=3, stride=2, padding=1,
                                           output_padding=1), norm_layer(ngf_global), ReLU(True)]
         model_upsample += [ReflectionPad2d(3), Conv2d(ngf, output_nc, kernel_size=7, padding=0), Tanh()]

@@ -388,7 +388,9 @@ if __name__ == "__main__":
             gen_infer()
         if "train" in what:
             gen_train()
-    if "train_bce" in what:
-        from make_golden_nets import gen_train_bce  # noqa: E402
+    if "train_bce" in what or "train_attnl" in what:
+        from make_golden_nets import gen_train_extra  # noqa: E402
 
-        gen_train_bce()
+        for w in what:
+            if w in ("train_bce", "train_attnl"):
+                gen_train_extra(w + "_golden.npz")

@@ -207,52 +207,66 @@ def gen_train():
     print("wrote train_golden.npz")
 
 
-# --no_lsgan (nn.BCELoss on a sigmoid PatchGAN head, networks.py:105-108,671-672).  The reference's discriminator applies the sigmoid only
-# without intermediate features (networks.py:686 walks models 0 .. n_layers + 1), so the flag works with --no_ganFeat_loss only.
+# Option branches outside the shipped recipes, each pinned by the reference's own train iteration (train.py:160-202):
+#   tr_small_bce    --no_lsgan (nn.BCELoss on a sigmoid PatchGAN head, networks.py:105-108,671-672).  The reference's discriminator applies
+#                   the sigmoid only without intermediate features (networks.py:686 walks models 0 .. n_layers + 1), so the flag works
+#                   with --no_ganFeat_loss only.
+#   tr_small_attnl  --n_blocks_attn_l 1 (attention sandwich of the local branch, networks.py:218-237: weight-shared down / up layers,
+#                   BottleStack with a projection shortcut).  bins 32: the 8x-down map must be at least 1 x 1 after // 16.
 TRAIN_BCE_FLAGS = {"tr_small_bce": (TRAIN_FLAGS["tr_small"][0] + ["--no_lsgan", "--no_ganFeat_loss"], 3, 3840, 5154)}
+_attnl = [a for a in TRAIN_FLAGS["tr_small"][0]]
+_attnl[_attnl.index("--bins") + 1] = "32"
+_attnl[_attnl.index("--segment_length") + 1] = "7936"
+_attnl[_attnl.index("--n_blocks_local") + 1] = "3"
+TRAIN_ATTNL_FLAGS = {"tr_small_attnl": (_attnl + ["--n_blocks_attn_l", "1", "--heads_l", "2", "--dim_head_l", "32"], 2, 7936, 5155)}
+TRAIN_EXTRA = {"train_bce_golden.npz": TRAIN_BCE_FLAGS, "train_attnl_golden.npz": TRAIN_ATTNL_FLAGS}
 
 
-def gen_train_bce():
-    """The reference's own train iteration (train.py:160-202) under --no_lsgan --no_ganFeat_loss: losses of TRAIN_STEPS iterations, every
-    gradient tensor of the first one, parameter checksums after the last -> tests/golden/train_bce_golden.npz."""
+def gen_train_extra(which=None):
+    """The reference's own train iteration (train.py:160-202) under the option branches above: losses of TRAIN_STEPS iterations, every
+    gradient tensor of the first one, parameter checksums after the last -> tests/golden/train_{bce,attnl}_golden.npz."""
     from make_golden import ref_opt
     from models.models import create_model
 
-    out = {}
-    for name, (flags, batch, T, seed) in TRAIN_BCE_FLAGS.items():
-        opt = ref_opt(flags)
-        torch.manual_seed(seed)
-        with contextlib.redirect_stdout(io.StringIO()):
-            model = create_model(opt)
-        model.train()
-        lr, hr = make_lr_audio(batch, T, seed), make_hr_audio(batch, T, seed)
-        out[f"{name}_lr_audio"], out[f"{name}_hr_audio"] = lr.numpy(), hr.numpy()
-        out[f"{name}_G_cksum0"] = state_checksum(model.netG.state_dict())
-        out[f"{name}_D_cksum0"] = state_checksum(model.netD.state_dict())
-        out[f"{name}_D_keys"] = np.array(list(model.netD.state_dict().keys()))
-        out[f"{name}_loss_names"] = np.array(list(model.loss_names))
-        losses_all = []
-        for it in range(TRAIN_STEPS):
-            losses, _ = model._forward(lr, hr)
-            d = dict(zip(model.loss_names, losses))
-            losses_all.append([float(d[k]) for k in ("G_GAN", "D_real", "D_fake")])
-            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
-            loss_G = d["G_GAN"] + d.get("G_GAN_Feat", 0)
-            model.optimizer_G.zero_grad()
-            loss_G.backward()
-            if it == 0:
-                for k, p in model.netG.named_parameters():
-                    out[f"{name}_gradG::{k}"] = p.grad.numpy().copy()
-            model.optimizer_G.step()
-            model.optimizer_D.zero_grad()
-            loss_D.backward()
-            if it == 0:
-                for k, p in model.netD.named_parameters():
-                    out[f"{name}_gradD::{k}"] = p.grad.numpy().copy()
-            model.optimizer_D.step()
-        out[f"{name}_losses"] = np.array(losses_all)
-        out[f"{name}_G_cksum_after"] = state_checksum(model.netG.state_dict())
-        out[f"{name}_D_cksum_after"] = state_checksum(model.netD.state_dict())
-        print(name, "done", list(model.loss_names), losses_all)
-    np.savez_compressed(os.path.join(HERE, "train_bce_golden.npz"), **out)
-    print("wrote train_bce_golden.npz")
+    for fname, table in TRAIN_EXTRA.items():
+        if which is not None and fname != which:
+            continue
+        out = {}
+        for name, (flags, batch, T, seed) in table.items():
+            opt = ref_opt(flags)
+            torch.manual_seed(seed)
+            with contextlib.redirect_stdout(io.StringIO()):
+                model = create_model(opt)
+            model.train()
+            lr, hr = make_lr_audio(batch, T, seed), make_hr_audio(batch, T, seed)
+            out[f"{name}_lr_audio"], out[f"{name}_hr_audio"] = lr.numpy(), hr.numpy()
+            out[f"{name}_G_cksum0"] = state_checksum(model.netG.state_dict())
+            out[f"{name}_D_cksum0"] = state_checksum(model.netD.state_dict())
+            out[f"{name}_G_keys"] = np.array(list(model.netG.state_dict().keys()))
+            out[f"{name}_D_keys"] = np.array(list(model.netD.state_dict().keys()))
+            out[f"{name}_loss_names"] = np.array(list(model.loss_names))
+            losses_all = []
+            for it in range(TRAIN_STEPS):
+                losses, _ = model._forward(lr, hr)
+                d = dict(zip(model.loss_names, losses))
+                losses_all.append([float(d[k].detach()) for k in model.loss_names])
+                loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+                loss_G = d["G_GAN"] + d.get("G_GAN_Feat", 0)
+                model.optimizer_G.zero_grad()
+                loss_G.backward()
+                if it == 0:
+                    for k, p in model.netG.named_parameters():
+                        out[f"{name}_gradG::{k}"] = p.grad.numpy().copy()
+                model.optimizer_G.step()
+                model.optimizer_D.zero_grad()
+                loss_D.backward()
+                if it == 0:
+                    for k, p in model.netD.named_parameters():
+                        out[f"{name}_gradD::{k}"] = p.grad.numpy().copy()
+                model.optimizer_D.step()
+            out[f"{name}_losses"] = np.array(losses_all)
+            out[f"{name}_G_cksum_after"] = state_checksum(model.netG.state_dict())
+            out[f"{name}_D_cksum_after"] = state_checksum(model.netD.state_dict())
+            print(name, "done", list(model.loss_names), losses_all)
+        np.savez_compressed(os.path.join(HERE, fname), **out)
+        print("wrote", fname)

