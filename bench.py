@@ -704,7 +704,7 @@ def run_ours(args):
         loss_D.backward()
         model.optimizer_D.step()
 
-    for _ in range(2):
+    for _ in range(7):            # runtime.GraphedAPI: 3 eager iterations, then the forward / sweep segments are captured and replayed
         api_step()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -713,6 +713,16 @@ def run_ours(args):
         api_step()
     torch.cuda.synchronize(dev)
     api_ms = 1e3 * (time.perf_counter() - t0) / n_api
+    model._graph_api, api_saved = None, model._graph_api      # the same sequence with every launch issued eagerly, for the record
+    for _ in range(2):
+        api_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        api_step()
+    torch.cuda.synchronize(dev)
+    api_eager_ms = 1e3 * (time.perf_counter() - t0) / 5
+    model._graph_api = api_saved
     clocks = sampler.stop()
 
     # ---- strong scaling (SURVEY.md 8d cfg4 "report both"): the FIXED global batch 32, 32 / N segments per GPU
@@ -851,9 +861,11 @@ def run_ours(args):
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SEG * 4, "d2h_bytes_per_step": 16,
                     "ms_per_step": e2e_ms, "api": "runtime.GraphedTrainStep(model)(pinned lr_audio, pinned hr_audio) -> 4 losses copied to "
                                                   "pinned host memory, stream-synchronised every step"},
-            "reference_api": {"value": audio_s / world / (api_ms * 1e-3), "ms_per_step": api_ms, "n_gpus": 1,
+            "reference_api": {"value": audio_s / world / (api_ms * 1e-3), "ms_per_step": api_ms, "n_gpus": 1, "ms_per_step_all_eager": api_eager_ms,
                               "api": "train.py:160-202 verbatim on rank 0: model._forward -> loss_G.backward() -> optimizer_G.step() -> "
-                                     "loss_D.backward() -> optimizer_D.step(), eager (host-launch bound), no all-reduce"},
+                                     "loss_D.backward() -> optimizer_D.step(); after 3 eager iterations the forward and the two sweeps replay "
+                                     "captured segments (runtime.GraphedAPI), zero_grad / Adam / weight images stay eager; no all-reduce; "
+                                     "ms_per_step_all_eager = the same with MDCTGAN_GRAPH_API=0 (host-launch bound)"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
             "losses_first_step_rel_err_vs_cpu_baseline": err, "losses_last_step": last_losses,
         }

@@ -448,6 +448,10 @@ class Pix2PixHDModel(BaseModel):
             self.optimizer_G = FusedAdam(self.bucket_G, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe, params=params_G)
             self.optimizer_D = FusedAdam(self.bucket_D, lr=opt.lr, betas=(opt.beta1, 0.999), graph_safe=graph_safe)
             self._graph = None
+            # the reference-shaped API (_forward / loss.backward()) replays captured segments after a short eager warm-up (runtime.GraphedAPI)
+            from ..runtime import GraphedAPI
+
+            self._graph_api = GraphedAPI(self) if os.environ.get("MDCTGAN_GRAPH_API", "1") != "0" else None
             # update buckets: contiguous flat ranges of parameters whose Adam step and kernel-side weight images are issued as soon as
             # their gradients are complete (while the rest of the backward sweep still runs); one weight packer per bucket
             self._plan_update_buckets()
@@ -494,10 +498,12 @@ class Pix2PixHDModel(BaseModel):
 
         if not self.isTrain:
             raise RuntimeError("_forward needs a training model (opt.isTrain)")
-        graph = T.GanGraph(self)
         self._refresh_weight_images()
-        with _ops.stats_pass(self.device):
-            graph.forward(lr_audio, hr_audio)
+        graph = self._graph_api.forward(lr_audio, hr_audio) if self._graph_api is not None else None
+        if graph is None:                                 # eager (warm-up iterations of a batch shape, or MDCTGAN_GRAPH_API=0)
+            graph = T.GanGraph(self)
+            with _ops.stats_pass(self.device):
+                graph.forward(lr_audio, hr_audio)
         self._graph = graph
         # autograd anchors: any parameter that requires grad (the first one may be frozen: --freeze_g_d, niter_fix_global)
         anchor_g = next((p for p in self.bucket_G.params if p.requires_grad), None)

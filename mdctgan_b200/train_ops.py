@@ -174,6 +174,12 @@ class _GLosses(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g0, g1):
         gr = ctx.graph
+        seg = getattr(gr, "_api_segments", None)
+        if seg is not None:          # captured sweep (runtime.GraphedAPI)
+            from .runtime import GraphedAPI
+
+            GraphedAPI.backward(seg, "G", (g0, g1))
+            return None, None
         gr.backward_G(g0.contiguous() if g0 is not None else None, g1.contiguous() if g1 is not None else None,
                       use_gan=g0 is not None, use_feat=g1 is not None)
         return None, None
@@ -188,6 +194,12 @@ class _DLosses(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_real, g_fake):
         gr = ctx.graph
+        seg = getattr(gr, "_api_segments", None)
+        if seg is not None:          # captured sweep (runtime.GraphedAPI)
+            from .runtime import GraphedAPI
+
+            GraphedAPI.backward(seg, "D", (g_real, g_fake))
+            return None, None
         z = None
         if g_real is None or g_fake is None:
             z = torch.zeros((), dtype=torch.float32, device=gr.losses.device)

@@ -568,3 +568,53 @@ def test_option_branches_train_step_matches_reference(dev, api, name):
     # cannot be tighter than the reference's own reproducibility.
     bar = 2e-2 if bce else 0.25
     assert worst["gradG"][0] < bar and worst["gradD"][0] < 2e-2, worst
+
+
+def test_reference_api_replays_captured_segments(dev):
+    """runtime.GraphedAPI: the verbatim train.py:160-202 sequence (model._forward -> loss_G.backward() -> optimizer_G.step() ->
+    loss_D.backward() -> optimizer_D.step()) switches from eager launches to three captured segments after its warm-up iterations;
+    7 iterations with the switch (3 eager + 4 replayed, fresh audio every iteration) must train like 7 eager ones."""
+    import mdctgan_b200
+    from make_golden_nets import TRAIN_FLAGS
+
+    flags, batch, T, seed = TRAIN_FLAGS["tr_small"]
+    g = torch.Generator().manual_seed(7)
+    audio = [(0.1 * torch.randn(batch, T, generator=g), 0.1 * torch.randn(batch, T, generator=g)) for _ in range(7)]
+
+    def run(graphed):
+        model = _build_model(flags, seed, dev)
+        if not graphed:
+            model._graph_api = None
+        assert (model._graph_api is not None) == graphed
+        losses, launches = [], []
+        for lr_a, hr_a in audio:
+            n0 = mdctgan_b200.launch_count()
+            ls, _ = model._forward(lr_a.to(dev), hr_a.to(dev))
+            d = dict(zip(model.loss_names, ls))
+            loss_D = (d["D_fake"] + d["D_real"]) * 0.5
+            loss_G = d["G_GAN"] + d["G_GAN_Feat"]
+            model.optimizer_G.zero_grad()
+            loss_G.backward()
+            model.optimizer_G.step()
+            model.optimizer_D.zero_grad()
+            loss_D.backward()
+            model.optimizer_D.step()
+            losses.append([float(d[k]) for k in model.loss_names])
+            launches.append(mdctgan_b200.launch_count() - n0)
+        sd = {k: v.detach().cpu().clone() for k, v in list(model.netG.state_dict().items()) + [("D." + k, v) for k, v in model.netD.state_dict().items()]}
+        return np.array(losses), launches, sd
+
+    l_e, n_e, sd_e = run(False)
+    l_g, n_g, sd_g = run(True)
+    # replayed iterations issue no C-ABI launches of their own except Adam / weight images / zero_grad (the captured ones are not counted)
+    assert n_g[0] == n_e[0] and n_g[2] == n_e[2]
+    assert max(n_g[4:]) < 0.15 * n_e[4], (n_g, n_e)
+    # two eager runs already differ at ~1e-5 from the second iteration on (float atomics order + Adam's first steps being sign updates)
+    np.testing.assert_allclose(l_g[:1], l_e[:1], rtol=1e-6)
+    np.testing.assert_allclose(l_g[:3], l_e[:3], rtol=1e-4)
+    np.testing.assert_allclose(l_g, l_e, rtol=5e-3)
+    print("losses eager", l_e[-1], "graphed", l_g[-1], "launches per iteration", n_e[-1], "->", n_g[-1])
+    moved = 0.0
+    for k, v in sd_e.items():
+        if v.dtype.is_floating_point and v.dim() >= 2:
+            assert (sd_g[k] - v).norm().item() <= 0.05 * v.norm().item() + 1e-6, k
