@@ -335,6 +335,7 @@ BUCKETED_ALLREDUCE = os.environ.get("MDCTGAN_BUCKETED_ALLREDUCE", "0") == "1"
 # Pipelined update (default): per-bucket [all-reduce ->] Adam -> weight images on an update stream as soon as the bucket's gradients
 # are complete, overlapping the rest of the backward sweep.  "0": one all-reduce + whole-network Adam + packing after the sweeps.
 PIPELINED_UPDATE = os.environ.get("MDCTGAN_PIPELINED_UPDATE", "1") != "0"
+COMM_STREAM = os.environ.get("MDCTGAN_COMM_STREAM", "1") != "0"      # per-bucket collectives on their own stream (A/B switch)
 
 
 class BaseModel(torch.nn.Module):
@@ -670,6 +671,17 @@ class Pix2PixHDModel(BaseModel):
                 ev = torch.cuda.Event()
                 ev.record(st)
                 events.append(ev)
+        if all_reduce is not None and COMM_STREAM:
+            # the exchange of bucket i+1 overlaps the Adam / weight-image launches of bucket i: collectives on their own stream (same order
+            # on every rank: the bucket order), the update stream only waits for its bucket's collective
+            comm = _ops.aux_stream(self.device, "comm")
+            for ev in events:
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                all_reduce(self.grad_all[bk.glo:bk.ghi])
+                ev_c = torch.cuda.Event()
+                ev_c.record(comm)
+            events, all_reduce = [ev_c], None
         for ev in events:
             upd.wait_event(ev)
         opt_ = self.optimizer_G if bk.net == "G" else self.optimizer_D

@@ -549,7 +549,7 @@ _branch_streams = {}
 STREAM_PRIORITY = os.environ.get("MDCTGAN_STREAM_PRIORITY", "1") == "1"
 _HI = -1 if STREAM_PRIORITY else 0
 # r02 (cfg4 step): no priorities 4.91 ms; chain high / update low 4.71; discriminator sweep low as well 4.69 (it hides behind the generator's)
-_LOW_PRIORITY = set(os.environ.get("MDCTGAN_LOW_PRIORITY_STREAMS", "update,sweep_D").split(","))
+_LOW_PRIORITY = set(os.environ.get("MDCTGAN_LOW_PRIORITY_STREAMS", "update,sweep_D,comm").split(","))
 PARALLEL_BRANCHES = os.environ.get("MDCTGAN_PARALLEL_BRANCHES", "1") != "0"
 
 
