@@ -212,6 +212,16 @@ int mdctgan_mse_const_fwd(const float* x, int64_t n, float target, double coef, 
 int mdctgan_mse_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream);
 /* The same pair for nn.BCELoss on sigmoid outputs (GANLoss with --no_lsgan, networks.py:107-108; torch's -100 log clamp and 1e-12
  * denominator clamp). */
+/* Every loss term of a step in ONE launch (and every gradient seed in another): up to 24 items, copied by value into the kernel
+ * parameters.  kind 0: MSE of `a` against the constant `target`; 1: L1 between `a` and `b`; 2: BCE of probabilities `a` against `target`.
+ * fwd: acc[slot] += coef * sum (acc: fp64 device array of n_slots, zeroed by the caller).  bwd: g = coef * (*gscale) * d(sum)/da. */
+typedef struct mdctgan_loss_item {
+  const float* a; const float* b; float* g;
+  int64_t n; double coef; const float* gscale;
+  float target; int32_t kind; int32_t slot; int32_t pad_;
+} mdctgan_loss_item;
+int mdctgan_multi_loss_fwd(const mdctgan_loss_item* items, int n_items, double* acc, int n_slots, void* stream);
+int mdctgan_multi_loss_bwd(const mdctgan_loss_item* items, int n_items, void* stream);
 int mdctgan_bce_const_fwd(const float* x, int64_t n, float target, double coef, double* slot, void* stream);
 int mdctgan_bce_const_bwd(const float* x, int64_t n, float target, float coef, const float* gscale, float* g, int accumulate, void* stream);
 /* feature matching (pix2pixHD_model.py:447-451): *slot += coef * sum|a - b|; g (+)= coef*(*gscale)*sign(a - b) */

@@ -330,6 +330,46 @@ int mdctgan_l1_pair_bwd(const float* a, const float* b, int64_t n, float coef, c
   return 0;
 }
 
+/* items: n_items records of mdctgan_loss_item (host memory; copied into the kernel parameters) */
+static int loss_table_of(const mdctgan_loss_item* items, int n_items, LossTable* tab, long long* max_n, const char* who) {
+  if (!items || n_items <= 0) return mdctgan_set_error(-1, "%s: empty item table", who);
+  if (n_items > kLossItems) return mdctgan_set_error(-2, "%s: %d items > %d", who, n_items, kLossItems);
+  tab->n = n_items;
+  *max_n = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const mdctgan_loss_item& s = items[i];
+    if (!s.a || (s.kind == 1 && !s.b) || s.kind < 0 || s.kind > 2 || s.n < 0) return mdctgan_set_error(-1, "%s: bad item %d", who, i);
+    tab->it[i] = LossItem{s.a, s.b, s.g, (long long)s.n, s.coef, s.gscale, s.target, s.kind, s.slot};
+    if (s.n > *max_n) *max_n = s.n;
+  }
+  return 0;
+}
+
+int mdctgan_multi_loss_fwd(const mdctgan_loss_item* items, int n_items, double* acc, int n_slots, void* stream) {
+  if (!acc) return mdctgan_set_error(-1, "multi_loss_fwd: NULL accumulator");
+  LossTable tab; long long max_n;
+  if (int rc = loss_table_of(items, n_items, &tab, &max_n, "multi_loss_fwd")) return rc;
+  for (int i = 0; i < n_items; ++i) if (items[i].slot < 0 || items[i].slot >= n_slots) return mdctgan_set_error(-1, "multi_loss_fwd: slot %d", items[i].slot);
+  if (max_n == 0) return 0;
+  int gx = (int)((max_n + 256 * 8 - 1) / (256 * 8)); if (gx > 64) gx = 64;
+  multi_loss_fwd_kernel<<<dim3(gx, n_items), 256, 0, (cudaStream_t)stream>>>(tab, acc);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_multi_loss_bwd(const mdctgan_loss_item* items, int n_items, void* stream) {
+  LossTable tab; long long max_n;
+  if (int rc = loss_table_of(items, n_items, &tab, &max_n, "multi_loss_bwd")) return rc;
+  for (int i = 0; i < n_items; ++i) if (!items[i].g) return mdctgan_set_error(-1, "multi_loss_bwd: item %d has no gradient buffer", i);
+  if (max_n == 0) return 0;
+  int gx = (int)((max_n + 256 * 4 - 1) / (256 * 4)); if (gx > 128) gx = 128;
+  multi_loss_bwd_kernel<<<dim3(gx, n_items), 256, 0, (cudaStream_t)stream>>>(tab);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
 int mdctgan_f64_to_f32(const double* a, float* y, int n, void* stream) {
   if (!a || !y) return mdctgan_set_error(-1, "f64_to_f32: NULL buffer");
   if (n <= 0) return 0;

@@ -761,6 +761,44 @@ __global__ void l1_pair_bwd_kernel(const float* __restrict__ a, const float* __r
     g[i] = accumulate ? g[i] + v : v;
   }
 }
+// All loss reductions of a step in ONE launch, and all their gradient seeds in another (cfg4: 9 GAN terms + 12 feature-matching terms
+// were 21 + 21 launches of a few microseconds each on the dependent chain between the discriminator forward and the sweeps).
+// The table travels by value in the kernel parameters (captured by value in a CUDA graph: no host table to keep alive).
+constexpr int kLossItems = 24;
+struct LossItem {
+  const float* a; const float* b;   // kind 0 / 2: a = predictions (b unused); kind 1: L1 pair (a, b)
+  float* g;                         // backward: gradient w.r.t. a (written, not accumulated)
+  long long n;
+  double coef;                      // forward: loss += coef * sum; backward: d/da scaled by coef * (*gscale)
+  const float* gscale;              // backward: upstream gradient of the 0-dim loss tensor (device scalar, nullable = 1)
+  float target;                     // kind 0 / 2
+  int kind;                         // 0 MSE against a constant, 1 L1 between two tensors, 2 BCE against a constant (on probabilities)
+  int slot;                         // forward: index into the fp64 accumulator
+};
+struct LossTable { LossItem it[kLossItems]; int n; };
+
+__global__ void __launch_bounds__(256) multi_loss_fwd_kernel(const LossTable tab, double* __restrict__ acc) {
+  const LossItem& L = tab.it[blockIdx.y];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)L.n; i += (size_t)gridDim.x * 256) {
+    if (L.kind == 0) { const float e = L.a[i] - L.target; s = fmaf(e, e, s); }
+    else if (L.kind == 1) s += fabsf(L.a[i] - L.b[i]);
+    else { const float p = L.a[i]; s -= L.target * fmaxf(logf(p), -100.f) + (1.f - L.target) * fmaxf(log1pf(-p), -100.f); }
+  }
+  const double t = block_sum_256((double)s);
+  if (threadIdx.x == 0 && (size_t)blockIdx.x * 256 < (size_t)L.n) atomicAdd(acc + L.slot, L.coef * t);
+}
+__global__ void __launch_bounds__(256) multi_loss_bwd_kernel(const LossTable tab) {
+  const LossItem& L = tab.it[blockIdx.y];
+  const float k = (float)L.coef * (L.gscale ? __ldg(L.gscale) : 1.f);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)L.n; i += (size_t)gridDim.x * 256) {
+    float v;
+    if (L.kind == 0) v = 2.f * k * (L.a[i] - L.target);
+    else if (L.kind == 1) { const float e = L.a[i] - L.b[i]; v = e > 0.f ? k : (e < 0.f ? -k : 0.f); }
+    else { const float p = L.a[i]; v = k * (p - L.target) / fmaxf((1.f - p) * p, 1e-12f); }
+    L.g[i] = v;
+  }
+}
 __global__ void f64_to_f32_kernel(const double* __restrict__ a, float* __restrict__ y, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = (float)a[i];

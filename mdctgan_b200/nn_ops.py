@@ -74,6 +74,8 @@ def _L():
         L.mdctgan_mse_const_fwd.argtypes = [c_void_p, c_int64, c_float, c_double, c_void_p, c_void_p]
         L.mdctgan_mse_const_bwd.argtypes = [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]
         L.mdctgan_bce_const_fwd.argtypes = [c_void_p, c_int64, c_float, c_double, c_void_p, c_void_p]
+        L.mdctgan_multi_loss_fwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p]
+        L.mdctgan_multi_loss_bwd.argtypes = [c_void_p, c_int, c_void_p]
         L.mdctgan_bce_const_bwd.argtypes = [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]
         L.mdctgan_l1_pair_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]
         L.mdctgan_l1_pair_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -31,6 +33,28 @@ LOSS_NAMES = ["G_GAN", "G_GAN_Feat", "D_real", "D_fake"]
 
 def _st(t):
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _LossItem(ctypes.Structure):
+    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("g", ctypes.c_void_p), ("n", ctypes.c_int64), ("coef", ctypes.c_double),
+                ("gscale", ctypes.c_void_p), ("target", ctypes.c_float), ("kind", ctypes.c_int32), ("slot", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
+MAX_LOSS_ITEMS = 24
+
+
+def _multi_loss(L, items, acc_ptr, stream, backward=False):
+    """items: list of dicts (a, b, g, n, coef, gscale, target, kind, slot).  One launch for up to MAX_LOSS_ITEMS of them."""
+    for i in range(0, len(items), MAX_LOSS_ITEMS):
+        chunk = items[i:i + MAX_LOSS_ITEMS]
+        arr = (_LossItem * len(chunk))()
+        for r, it in zip(arr, chunk):
+            r.a, r.b, r.g, r.n, r.coef = it["a"], it.get("b"), it.get("g"), it["n"], it["coef"]
+            r.gscale, r.target, r.kind, r.slot = it.get("gscale"), it.get("target", 0.0), it["kind"], it.get("slot", 0)
+        if backward:
+            _lib.check(L.mdctgan_multi_loss_bwd(arr, len(chunk), stream))
+        else:
+            _lib.check(L.mdctgan_multi_loss_fwd(arr, len(chunk), acc_ptr, 4, stream))
 
 
 class GanGraph:
@@ -81,18 +105,20 @@ class GanGraph:
             st = _st(acc)
             a = acc.data_ptr()
             self.feat_coef = (1.0 / m.num_D) * (4.0 / (m.n_layers_D + 1)) * float(m.lambda_feat)
+            gan_kind = 2 if m.no_lsgan else 0                                 # GANLoss: nn.BCELoss / nn.MSELoss (networks.py:105-108)
+            items = []
             for scale in self.feats:
                 pred = scale[-1].x                                        # [2B,h,w,1]
                 n = pred[:B].numel()
                 fake_p, real_p = pred.data_ptr(), pred[B:].data_ptr()
-                gan_fwd = L.mdctgan_bce_const_fwd if m.no_lsgan else L.mdctgan_mse_const_fwd     # GANLoss: nn.BCELoss / nn.MSELoss (networks.py:105-108)
-                _lib.check(gan_fwd(fake_p, n, 1.0, 1.0 / n, a + 0 * 8, st))      # G_GAN
-                _lib.check(gan_fwd(real_p, n, 1.0, 1.0 / n, a + 2 * 8, st))      # D_real
-                _lib.check(gan_fwd(fake_p, n, 0.0, 1.0 / n, a + 3 * 8, st))      # D_fake
+                items.append(dict(a=fake_p, n=n, target=1.0, coef=1.0 / n, kind=gan_kind, slot=0))      # G_GAN
+                items.append(dict(a=real_p, n=n, target=1.0, coef=1.0 / n, kind=gan_kind, slot=2))      # D_real
+                items.append(dict(a=fake_p, n=n, target=0.0, coef=1.0 / n, kind=gan_kind, slot=3))      # D_fake
                 if not m.no_ganFeat_loss:
                     for f in scale[:-1]:
                         nf = f.x[:B].numel()
-                        _lib.check(L.mdctgan_l1_pair_fwd(f.x.data_ptr(), f.x[B:].data_ptr(), nf, self.feat_coef / nf, a + 1 * 8, st))
+                        items.append(dict(a=f.x.data_ptr(), b=f.x[B:].data_ptr(), n=nf, coef=self.feat_coef / nf, kind=1, slot=1))
+            _multi_loss(L, items, a, st)                                      # every loss term of the step: one launch
             self.losses = torch.empty(4, dtype=torch.float32, device=dev)
             _lib.check(L.mdctgan_f64_to_f32(a, self.losses.data_ptr(), 4, st))
         return self.losses
@@ -107,21 +133,24 @@ class GanGraph:
         L = ops._L()
         G = ops.GradMap()
         with torch.cuda.device(m.device):
+            items = []
             for scale in self.feats:
                 pred = scale[-1]
                 if use_gan:
                     g = torch.empty_like(pred.x[:B])
                     n = g.numel()
-                    gan_bwd = L.mdctgan_bce_const_bwd if m.no_lsgan else L.mdctgan_mse_const_bwd
-                    _lib.check(gan_bwd(pred.x.data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_gan), g.data_ptr(), 0, _st(g)))
+                    items.append(dict(a=pred.x.data_ptr(), g=g.data_ptr(), n=n, target=1.0, coef=1.0 / n, gscale=ops._ptr(g_gan),
+                                      kind=2 if m.no_lsgan else 0))
                     G.add(pred, g)
                 if use_feat and not m.no_ganFeat_loss:
                     for f in scale[:-1]:
                         g = torch.empty_like(f.x[:B])
                         n = g.numel()
-                        _lib.check(L.mdctgan_l1_pair_bwd(f.x.data_ptr(), f.x[B:].data_ptr(), n, self.feat_coef / n, ops._ptr(g_feat),
-                                                         g.data_ptr(), 0, _st(g)))
+                        items.append(dict(a=f.x.data_ptr(), b=f.x[B:].data_ptr(), g=g.data_ptr(), n=n, coef=self.feat_coef / n,
+                                          gscale=ops._ptr(g_feat), kind=1))
                         G.add(f, g)
+            if items:
+                _multi_loss(L, items, None, _st(self.din.x), backward=True)     # every gradient seed of the sweep: one launch
             self.tapeD.backward(G, wgrad=False, nb=B, join=False)
             if after_D is not None:                                       # from here on nothing reads the discriminator's weights
                 after_D()
@@ -143,14 +172,16 @@ class GanGraph:
         self.din.needs_grad = False                                       # the inputs are data / detached here
         try:
             with torch.cuda.device(m.device):
+                items = []
+                kind = 2 if m.no_lsgan else 0
                 for scale in self.feats:
                     pred = scale[-1]
                     g = torch.empty_like(pred.x)
                     n = pred.x[:B].numel()
-                    gan_bwd = L.mdctgan_bce_const_bwd if m.no_lsgan else L.mdctgan_mse_const_bwd
-                    _lib.check(gan_bwd(pred.x.data_ptr(), n, 0.0, 1.0 / n, ops._ptr(g_fake), g.data_ptr(), 0, _st(g)))
-                    _lib.check(gan_bwd(pred.x[B:].data_ptr(), n, 1.0, 1.0 / n, ops._ptr(g_real), g[B:].data_ptr(), 0, _st(g)))
+                    items.append(dict(a=pred.x.data_ptr(), g=g.data_ptr(), n=n, target=0.0, coef=1.0 / n, gscale=ops._ptr(g_fake), kind=kind))
+                    items.append(dict(a=pred.x[B:].data_ptr(), g=g[B:].data_ptr(), n=n, target=1.0, coef=1.0 / n, gscale=ops._ptr(g_real), kind=kind))
                     G.add(pred, g)
+                _multi_loss(L, items, None, _st(self.din.x), backward=True)
                 self.tapeD.backward(G, wgrad=True, nb=None, join=False)
                 if join:
                     ops.join_side_work(m.device)
