@@ -522,7 +522,7 @@ NCU_TRAFFIC = {
 KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_wgrad", "mdctgan_norm_finalize", "mdctgan_norm_apply",
                   "mdctgan_norm_act_bwd", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_avgpool3s2_nhwc",
                   "mdctgan_avgpool3s2_bwd", "mdctgan_attention_abs_pos", "mdctgan_attention_abs_pos_bwd", "mdctgan_mse_const_fwd",
-                  "mdctgan_mse_const_bwd", "mdctgan_l1_pair_fwd", "mdctgan_l1_pair_bwd", "mdctgan_f64_to_f32", "mdctgan_disc_input_fwd",
+                  "mdctgan_mse_const_bwd", "mdctgan_l1_pair_fwd", "mdctgan_l1_pair_bwd", "mdctgan_multi_loss_fwd", "mdctgan_multi_loss_bwd", "mdctgan_f64_to_f32", "mdctgan_disc_input_fwd",
                   "mdctgan_disc_input_bwd", "mdctgan_adam_flat", "mdctgan_counter_inc", "mdctgan_conv2d_umma_pack_weight",
                   "mdctgan_pack_weights_multi", "mdctgan_pack_weights_tiled",
                   "mdctgan_nchw_to_nhwc", "mdctgan_nhwc_to_nchw", "mdctgan_residual_scale_add", "mdctgan_audio2mdct_forward",

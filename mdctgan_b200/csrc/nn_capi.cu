@@ -52,7 +52,12 @@ int mdctgan_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const floa
   const int HWo = Ho * Wo;
   if (Cout == 1 && !stats && Cin % 4 == 0 && Cin <= 512 && (in_act == kActNone || in_act == kActRelu || in_act == kActLeaky)) {
     // one output channel: LANES lanes per pixel with the thread's normalisation in registers (conv2d_cout1_kernel)
-    if (Cin <= 32) conv2d_cout1_kernel<8, 1><<<B * ((HWo + 31) / 32), 256, 0, st>>>(p);
+    if (kw == 7 && stride == 1 && !transposed && Cin <= 64 && Wo % 4 == 0) {        // the generator head: four pixels per 8-lane group
+      const int blocks = B * ((Ho * (Wo / 4) + 31) / 32);
+      if (Cin <= 32) conv2d_cout1_row4_kernel<7, 1><<<blocks, 256, 0, st>>>(p);
+      else conv2d_cout1_row4_kernel<7, 2><<<blocks, 256, 0, st>>>(p);
+    }
+    else if (Cin <= 32) conv2d_cout1_kernel<8, 1><<<B * ((HWo + 31) / 32), 256, 0, st>>>(p);
     else if (Cin <= 64) conv2d_cout1_kernel<8, 2><<<B * ((HWo + 31) / 32), 256, 0, st>>>(p);
     else if (Cin <= 128) conv2d_cout1_kernel<32, 1><<<B * ((HWo + 7) / 8), 256, 0, st>>>(p);
     else if (Cin <= 256) conv2d_cout1_kernel<32, 2><<<B * ((HWo + 7) / 8), 256, 0, st>>>(p);
