@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_umma_kernel(const ConvUmma
               const double mean = v[u].x * inv_n;
               double var = v[u].y * inv_n - mean * mean;
               var = var < 0.0 ? 0.0 : var;
-              const double rstd = 1.0 / sqrt(var + (double)p.in.eps);
+              const double rstd = rsqrt(var + (double)p.in.eps);
               s_scale[cc] = (float)rstd; s_shift[cc] = (float)(-mean * rstd);
             }
           }

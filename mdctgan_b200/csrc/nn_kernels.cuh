@@ -46,7 +46,9 @@ struct ConvParams {
   int tiles_per_sample;
 };
 
-// scale / shift of sample `b` into shared memory: ready-made, or derived from the raw InstanceNorm statistics
+// scale / shift of sample `b` into shared memory: ready-made, or derived from the raw InstanceNorm statistics.  rstd = rsqrt(var + eps) in
+// fp64 (1 ulp, a dozen instructions) everywhere it is derived -- `1.0 / sqrt()` is ~100 fp64-pipe instructions per value, which was
+// 1 - 2 us of every consumer's prologue (four values per thread of a 4 x 512-channel table)
 __device__ __forceinline__ void norm_to_smem(const InputNorm& in, int b, int C, float* s_scale, float* s_shift, int tid, int nthreads) {
   const size_t off = in.per_sample ? (size_t)b * C : 0;
   if (in.stats) {
@@ -55,7 +57,7 @@ __device__ __forceinline__ void norm_to_smem(const InputNorm& in, int b, int C, 
       const double mean = in.stats[2 * (off + c)] * inv_n;
       double var = in.stats[2 * (off + c) + 1] * inv_n - mean * mean;
       var = var < 0.0 ? 0.0 : var;
-      const double rstd = 1.0 / sqrt(var + (double)in.eps);
+      const double rstd = rsqrt(var + (double)in.eps);
       s_scale[c] = (float)rstd;
       s_shift[c] = (float)(-mean * rstd);
     }
@@ -477,7 +479,7 @@ static __global__ void norm_finalize_kernel(const NormFinalizeParams p) {
     const double mean = p.stats[2 * (size_t)i] / p.count;
     double var = p.stats[2 * (size_t)i + 1] / p.count - mean * mean;
     if (var < 0) var = 0;
-    const double rstd = 1.0 / sqrt(var + (double)p.eps);
+    const double rstd = rsqrt(var + (double)p.eps);
     p.scale[i] = (float)rstd;
     p.shift[i] = (float)(-mean * rstd);
     return;
@@ -499,7 +501,7 @@ static __global__ void norm_finalize_kernel(const NormFinalizeParams p) {
     mean = p.running_mean[i];
     var = p.running_var[i];
   }
-  const double rstd = 1.0 / sqrt(var + (double)p.eps);
+  const double rstd = rsqrt(var + (double)p.eps);
   const double g = p.gamma ? (double)p.gamma[i] : 1.0, be = p.beta ? (double)p.beta[i] : 0.0;
   p.scale[i] = (float)(rstd * g);
   p.shift[i] = (float)(be - mean * rstd * g);

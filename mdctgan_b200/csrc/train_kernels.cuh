@@ -316,7 +316,7 @@ __device__ __forceinline__ void norm_bwd_coeffs(const NormBwdParams& p, int b, f
     double var = q / n - mean * mean;
     if (var < 0) var = 0;
     s_mean[c] = (float)mean;
-    s_rstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+    s_rstd[c] = (float)(rsqrt(var + (double)p.eps));
     s_gam[c] = (p.mode == 1 && p.gamma) ? __ldg(p.gamma + c) : 1.f;
     s_bet[c] = (p.mode == 1 && p.beta) ? __ldg(p.beta + c) : 0.f;
   }
@@ -406,16 +406,19 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const NormBwdPa
   const int b = blockIdx.y, c0 = blockIdx.x * 8;
   const int cl = threadIdx.x & 1, pl = threadIdx.x >> 1;          // float4 half of the group, pixel lane
   const int cb = c0 + cl * 4;
-  float mean[4], rstd[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const double s = p.stats[2 * ((size_t)b * p.C + cb + u)], q = p.stats[2 * ((size_t)b * p.C + cb + u) + 1];
+  __shared__ float s_stat[2][8];      // mean / rstd of the CTA's 8 channels: derived once (8 threads), not by all 256 in fp64
+  if (threadIdx.x < 8) {
+    const double s = p.stats[2 * ((size_t)b * p.C + c0 + threadIdx.x)], q = p.stats[2 * ((size_t)b * p.C + c0 + threadIdx.x) + 1];
     const double m = s / p.count;
     double var = q / p.count - m * m;
     if (var < 0) var = 0;
-    mean[u] = (float)m;
-    rstd[u] = (float)(1.0 / sqrt(var + (double)p.eps));
+    s_stat[0][threadIdx.x] = (float)m;
+    s_stat[1][threadIdx.x] = (float)(rsqrt(var + (double)p.eps));
   }
+  __syncthreads();
+  float mean[4], rstd[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { mean[u] = s_stat[0][cl * 4 + u]; rstd[u] = s_stat[1][cl * 4 + u]; }
   const size_t base = (size_t)b * p.HW * p.C + cb;
   double sg[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
   for (int pix = pl; pix < p.HW; pix += 128) {

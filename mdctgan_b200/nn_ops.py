@@ -487,7 +487,7 @@ class _SideWork:
 
     def __init__(self, device):
         self.device = device
-        self.streams = [torch.cuda.Stream(device) for _ in range(N_SIDE_STREAMS)]
+        self.streams = [torch.cuda.Stream(device, priority=int(os.environ.get("MDCTGAN_SIDE_PRIORITY", "0"))) for _ in range(N_SIDE_STREAMS)]
         self.next = 0
         self.keep = []          # tensors read on the side streams: kept alive until join() so the allocator cannot recycle them
         self.active = False
@@ -549,7 +549,8 @@ _branch_streams = {}
 # MDCTGAN_STREAM_PRIORITY=1: the streams of the dependent chain (sweeps, branches) get a higher CUDA priority than the weight-gradient
 # side stream and the update stream, whose kernels only have to finish by the end of the step
 STREAM_PRIORITY = os.environ.get("MDCTGAN_STREAM_PRIORITY", "1") == "1"
-_HI = -1 if STREAM_PRIORITY else 0
+_HI = int(os.environ.get("MDCTGAN_CHAIN_PRIORITY", "-2")) if STREAM_PRIORITY else 0
+_MID = set(os.environ.get("MDCTGAN_MID_PRIORITY_STREAMS", "").split(","))      # streams between the chain and the rest (priority -1)
 # r02 (cfg4 step): no priorities 4.91 ms; chain high / update low 4.71; discriminator sweep low as well 4.69 (it hides behind the generator's)
 _LOW_PRIORITY = set(os.environ.get("MDCTGAN_LOW_PRIORITY_STREAMS", "update,sweep_D,comm").split(","))
 PARALLEL_BRANCHES = os.environ.get("MDCTGAN_PARALLEL_BRANCHES", "1") != "0"
@@ -569,7 +570,10 @@ def aux_stream(device, name: str):
     """A named long-lived stream (e.g. the discriminator sweep of the train step)."""
     key = (torch.device(device).index, name)
     if key not in _branch_streams:
-        _branch_streams[key] = torch.cuda.Stream(device, priority=0 if name in _LOW_PRIORITY else _HI)
+        prio = 0 if name in _LOW_PRIORITY else _HI
+        if STREAM_PRIORITY and name in _MID:
+            prio = -1
+        _branch_streams[key] = torch.cuda.Stream(device, priority=prio)
     return _branch_streams[key]
 
 
