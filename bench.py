@@ -520,7 +520,7 @@ NCU_TRAFFIC = {
 }
 
 KERNEL_ENTRIES = ["mdctgan_conv2d_nhwc", "mdctgan_conv2d_umma", "mdctgan_conv2d_wgrad", "mdctgan_norm_finalize", "mdctgan_norm_apply",
-                  "mdctgan_norm_act_bwd", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_avgpool3s2_nhwc",
+                  "mdctgan_norm_act_bwd", "mdctgan_norm_act_bwd_folded", "mdctgan_act_bwd", "mdctgan_add", "mdctgan_reflect_pad_bwd", "mdctgan_reflect_pad_bwd_add", "mdctgan_avgpool3s2_nhwc",
                   "mdctgan_avgpool3s2_bwd", "mdctgan_attention_abs_pos", "mdctgan_attention_abs_pos_bwd", "mdctgan_mse_const_fwd",
                   "mdctgan_mse_const_bwd", "mdctgan_l1_pair_fwd", "mdctgan_l1_pair_bwd", "mdctgan_multi_loss_fwd", "mdctgan_multi_loss_bwd", "mdctgan_f64_to_f32", "mdctgan_disc_input_fwd",
                   "mdctgan_disc_input_bwd", "mdctgan_adam_flat", "mdctgan_counter_inc", "mdctgan_conv2d_umma_pack_weight",
@@ -573,6 +573,8 @@ class LaunchProfiler:
                     nbytes = 28.0 * a[4]          # p, g, m, v read (16 B) + p, m, v written (12 B) per parameter
                 elif _n == "mdctgan_norm_act_bwd":
                     nbytes = 4.0 * a[13] * a[14] * a[15] * 5   # x, dv read twice + dx written
+                elif _n == "mdctgan_norm_act_bwd_folded":
+                    nbytes = 4.0 * a[13] * a[14] * a[15] * a[16] * 5
                 elif _n == "mdctgan_norm_apply":
                     nbytes = 4.0 * a[15] * a[16] * a[17] * (3 if a[6] else 2)
                 self.records.append((tag, _n, e0, e1, flops, nbytes))

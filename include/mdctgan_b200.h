@@ -192,6 +192,13 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
  * stats = the forward (sum, sumsq) [B][C][2]; red = zeroed [B][C][2] scratch; dgamma / dbeta accumulated (mode 1, nullable). */
 int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
                          const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int HW, int C, void* stream);
+/* The same with the gradient arriving in the reflection-padded geometry of the consumer ([B][H + 2 fold_pad][W + 2 fold_pad][C], the raw
+ * output of the input-gradient convolution): nn.ReflectionPad2d's backward is applied while loading.  fold_pad = 0: plain. */
+int mdctgan_norm_act_bwd_folded(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode,
+                                const float* gamma, const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int H, int W,
+                                int C, int fold_pad, void* stream);
+/* nn.ReflectionPad2d backward fused with the accumulation into an existing gradient: dx = fold(dpad) + other (C % 4 == 0) */
+int mdctgan_reflect_pad_bwd_add(const float* dpad, const float* other, float* dx, int B, int H, int W, int C, int pad, void* stream);
 /* g = dy * act'(y) from the activated value y (epilogue LeakyReLU / tanh, plain ReLU views) */
 int mdctgan_act_bwd(const float* dy, const float* y, float* g, int64_t n, int act, void* stream);
 int mdctgan_add(const float* a, const float* b, float* y, int64_t n, void* stream);

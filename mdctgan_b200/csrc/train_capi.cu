@@ -167,13 +167,22 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
 
 int mdctgan_norm_act_bwd(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode, const float* gamma,
                          const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int HW, int C, void* stream) {
+  return mdctgan_norm_act_bwd_folded(x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, 1, C, 0, stream);
+}
+
+/* fold_pad > 0: dv is [B][H + 2 fold_pad][W + 2 fold_pad][C], the gradient of the reflection-padded view (folded while loading) */
+int mdctgan_norm_act_bwd_folded(const float* x, const float* dv, float* dx, const double* stats, double count, float eps, int mode,
+                                const float* gamma, const float* beta, int act, double* red, float* dgamma, float* dbeta, int B, int H, int W,
+                                int C, int fold_pad, void* stream) {
+  const int HW = H * W;
+  if (fold_pad < 0 || (fold_pad > 0 && (fold_pad >= H || fold_pad >= W))) return mdctgan_set_error(-1, "norm_act_bwd: fold_pad %d vs %dx%d", fold_pad, H, W);
   if (!x || !dv || !dx || !stats) return mdctgan_set_error(-1, "norm_act_bwd: NULL buffer");
   if (mode != 0 && mode != 1) return mdctgan_set_error(-1, "norm_act_bwd: mode %d (0 InstanceNorm2d, 1 train-mode BatchNorm2d)", mode);
   if (C % 4 || C > 1024) return mdctgan_set_error(-2, "norm_act_bwd: C %d must be a multiple of 4, <= 1024", C);
   if (act == kActTanh) return mdctgan_set_error(-2, "norm_act_bwd: tanh after a normalisation is not a reference configuration");
   if (B == 0 || HW == 0) return 0;
   if (B > 65535) return mdctgan_set_error(-2, "norm_act_bwd: batch %d > 65535", B);
-  NormBwdParams p{x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, C, B};
+  NormBwdParams p{x, dv, dx, stats, count, eps, mode, gamma, beta, act, red, dgamma, dbeta, B, HW, C, B, fold_pad, H, W};
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0 && C % 8 == 0 && C / 8 <= 65535 && (long long)B * (C / 8) * 256 >= (long long)HW * 2) {
     // InstanceNorm2d, one launch, no scratch: when the (sample, 8-channel) groups alone give enough CTAs for the plane size
@@ -223,6 +232,18 @@ int mdctgan_reflect_pad_bwd(const float* dpad, float* dx, int B, int H, int W, i
   const size_t total = (size_t)B * H * W * C;
   if (!total) return 0;
   reflect_fold_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpad, dx, B, H, W, C, pad);
+  mdctgan_count_launch();
+  CKT(cudaGetLastError());
+  return 0;
+}
+
+int mdctgan_reflect_pad_bwd_add(const float* dpad, const float* other, float* dx, int B, int H, int W, int C, int pad, void* stream) {
+  if (!dpad || !other || !dx) return mdctgan_set_error(-1, "reflect_pad_bwd_add: NULL buffer");
+  if (C % 4) return mdctgan_set_error(-2, "reflect_pad_bwd_add: C %d must be a multiple of 4", C);
+  if (pad < 0 || pad >= H || pad >= W) return mdctgan_set_error(-1, "reflect_pad_bwd_add: pad %d vs %dx%d", pad, H, W);
+  const size_t total = (size_t)B * H * W * (C / 4);
+  if (!total) return 0;
+  reflect_fold_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpad, other, dx, B, H, W, C / 4, pad);
   mdctgan_count_launch();
   CKT(cudaGetLastError());
   return 0;

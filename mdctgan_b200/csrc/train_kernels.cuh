@@ -301,7 +301,31 @@ struct NormBwdParams {
   double* red;                 // [B][C][2]
   float* dgamma; float* dbeta; // BatchNorm parameter gradients (accumulated), nullable
   int B, HW, C, stats_B;       // stats_B: batch size the forward statistics were taken over (BatchNorm; >= B)
+  // fold_pad > 0: `dv` is the gradient of the ReflectionPad2d(fold_pad)-ed view, [B][H + 2p][W + 2p][C] (the raw output of the dgrad
+  // convolution); the fold back onto [H][W] (reflect_fold_kernel) happens while loading -- one launch less on the dgrad chain
+  int fold_pad, H, W;
 };
+
+// float4 of dv for (sample b, pixel pix, channels c .. c+3), folded when the gradient arrives in the padded geometry
+__device__ __forceinline__ float4 load_dv4(const NormBwdParams& p, int b, int pix, int c) {
+  if (p.fold_pad == 0) return __ldg(reinterpret_cast<const float4*>(p.dv + ((size_t)b * p.HW + pix) * p.C + c));
+  const int P = p.fold_pad, Hp = p.H + 2 * P, Wp = p.W + 2 * P;
+  const int iy = pix / p.W, ix = pix - iy * p.W;
+  int ys[3], xs[3], ny = 0, nx = 0;
+  ys[ny++] = iy;
+  if (iy >= 1 && iy <= P) ys[ny++] = -iy;
+  if (p.H - 1 - iy >= 1 && p.H - 1 - iy <= P) ys[ny++] = 2 * (p.H - 1) - iy;
+  xs[nx++] = ix;
+  if (ix >= 1 && ix <= P) xs[nx++] = -ix;
+  if (p.W - 1 - ix >= 1 && p.W - 1 - ix <= P) xs[nx++] = 2 * (p.W - 1) - ix;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < ny; ++a)
+    for (int q = 0; q < nx; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.dv + (((size_t)b * Hp + ys[a] + P) * Wp + xs[q] + P) * p.C + c));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+  return s;
+}
 
 // mean / rstd (and the forward affine) of sample b into shared memory
 __device__ __forceinline__ void norm_bwd_coeffs(const NormBwdParams& p, int b, float* s_mean, float* s_rstd, float* s_gam, float* s_bet) {
@@ -337,7 +361,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
     for (int pix = blockIdx.x * pstep + prow; pix < p.HW; pix += gridDim.x * pstep) {
       const size_t e = base + (size_t)pix * p.C + cg * 4;
       const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + e));
-      const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + e));
+      const float4 dv = load_dv4(p, b, pix, cg * 4);
       const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -384,7 +408,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams
     const size_t e = i * 4;
     const int c0 = (int)(e % p.C);
     const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + e));
-    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + e));
+    const float4 dv = load_dv4(p, b, (int)(e / p.C), c0);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
     float o[4];
 #pragma unroll
@@ -423,7 +447,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const NormBwdPa
   double sg[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
   for (int pix = pl; pix < p.HW; pix += 128) {
     const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + (size_t)pix * p.C));
-    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + (size_t)pix * p.C));
+    const float4 dv = load_dv4(p, b, pix, cb);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -456,7 +480,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const NormBwdPa
   for (int u = 0; u < 4; ++u) { mg[u] = s_m[0][cl * 4 + u]; mgx[u] = s_m[1][cl * 4 + u]; }
   for (int pix = pl; pix < p.HW; pix += 128) {
     const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + base + (size_t)pix * p.C));
-    const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dv + base + (size_t)pix * p.C));
+    const float4 dv = load_dv4(p, b, pix, cb);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
     float o[4];
 #pragma unroll
@@ -557,6 +581,35 @@ __global__ void reflect_fold_kernel(const float* __restrict__ dpad, float* __res
     for (int a = 0; a < ny; ++a)
       for (int q = 0; q < nx; ++q) s += __ldg(dpad + (((size_t)b * Hp + ys[a] + pad) * Wp + xs[q] + pad) * C + c);
     dx[i] = s;
+  }
+}
+
+// the same fold fused with the accumulation into an existing gradient of the unpadded tensor: dx = fold(dpad) + other
+__global__ void reflect_fold_add_kernel(const float* __restrict__ dpad, const float* __restrict__ other, float* __restrict__ dx, int B, int H, int W,
+                                        int C4, int pad) {
+  const size_t total = (size_t)B * H * W * C4;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const float4* d4 = reinterpret_cast<const float4*>(dpad);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = iy;
+    if (iy >= 1 && iy <= pad) ys[ny++] = -iy;
+    if (H - 1 - iy >= 1 && H - 1 - iy <= pad) ys[ny++] = 2 * (H - 1) - iy;
+    xs[nx++] = ix;
+    if (ix >= 1 && ix <= pad) xs[nx++] = -ix;
+    if (W - 1 - ix >= 1 && W - 1 - ix <= pad) xs[nx++] = 2 * (W - 1) - ix;
+    float4 s = __ldg(reinterpret_cast<const float4*>(other) + i);
+    for (int a = 0; a < ny; ++a)
+      for (int q = 0; q < nx; ++q) {
+        const float4 t = __ldg(d4 + (((size_t)b * Hp + ys[a] + pad) * Wp + xs[q] + pad) * C4 + c);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+    reinterpret_cast<float4*>(dx)[i] = s;
   }
 }
 

@@ -65,6 +65,9 @@ def _L():
         L.mdctgan_conv2d_wgrad_umma_supported.argtypes = [c_int, c_int]
         L.mdctgan_norm_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_int, c_void_p, c_void_p, c_int,
                                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_norm_act_bwd_folded.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_int, c_void_p, c_void_p, c_int,
+                                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        L.mdctgan_reflect_pad_bwd_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.mdctgan_act_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
         L.mdctgan_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
         L.mdctgan_reflect_pad_bwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
@@ -673,21 +676,58 @@ class recording:
         _tape = self.prev
 
 
+class _Folded:
+    """A gradient that still sits in the reflection-padded geometry of its consumer: `dpad` [B, H + 2p, W + 2p, C] = the raw output of an
+    input-gradient convolution whose forward had nn.ReflectionPad2d(p) in front.  The fold back onto [B, H, W, C] is deferred so that the
+    next kernel of the chain does it while loading (InstanceNorm / BatchNorm backward), or fuses it with the accumulation into a gradient
+    that already exists (residual skip): one launch less per convolution on the dependent chain of the sweep."""
+
+    def __init__(self, dpad: torch.Tensor, pad: int):
+        self.dpad, self.pad = dpad, pad
+        B, Hp, Wp, C = dpad.shape
+        self.shape = (B, Hp - 2 * pad, Wp - 2 * pad, C)
+
+    def materialize(self, other: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, H, W, C = self.shape
+        dx = torch.empty(self.shape, dtype=torch.float32, device=self.dpad.device)
+        with torch.cuda.device(dx.device):
+            if other is not None and C % 4 == 0:
+                _lib.check(_L().mdctgan_reflect_pad_bwd_add(self.dpad.data_ptr(), other.data_ptr(), dx.data_ptr(), B, H, W, C, self.pad, _stream(dx)))
+                return dx
+            _lib.check(_L().mdctgan_reflect_pad_bwd(self.dpad.data_ptr(), dx.data_ptr(), B, H, W, C, self.pad, _stream(dx)))
+        return dx if other is None else add(dx, other)
+
+
+FOLD_FUSION = os.environ.get("MDCTGAN_FOLD_FUSION", "1") != "0"
+
+
 class GradMap:
     def __init__(self):
         self.g = {}
 
-    def add(self, f: Feat, t: torch.Tensor):
+    def add(self, f: Feat, t):
+        """t: a gradient tensor, or a _Folded one (kept lazy until something needs the plain tensor)."""
         if not f.needs_grad:
             return
         cur = self.g.get(id(f))
-        self.g[id(f)] = t if cur is None else add(cur, t)
+        if cur is None:
+            self.g[id(f)] = t
+        elif isinstance(t, _Folded):
+            self.g[id(f)] = t.materialize(cur.materialize() if isinstance(cur, _Folded) else cur)
+        elif isinstance(cur, _Folded):
+            self.g[id(f)] = cur.materialize(t)
+        else:
+            self.g[id(f)] = add(cur, t)
 
-    def pop(self, f: Feat):
-        return self.g.pop(id(f), None)
+    def pop(self, f: Feat, lazy_ok: bool = False):
+        t = self.g.pop(id(f), None)
+        return t.materialize() if (isinstance(t, _Folded) and not lazy_ok) else t
 
     def get(self, f: Feat):
-        return self.g.get(id(f))
+        t = self.g.get(id(f))
+        if isinstance(t, _Folded):
+            t = self.g[id(f)] = t.materialize()
+        return t
 
 
 def _sl(t: Optional[torch.Tensor], nb: Optional[int]):
@@ -810,11 +850,10 @@ class _ConvOp:
                               out_hw=hw, role="dgrad").x
         if self.pad_mode == PAD_REFLECT:
             assert dv.shape[1:3] == (H + 2 * self.pad, W + 2 * self.pad), (dv.shape, H, W, self.pad)
-            dx = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dv.device)
-            with torch.cuda.device(dv.device):
-                _lib.check(L.mdctgan_reflect_pad_bwd(dv.data_ptr(), dx.data_ptr(), B, H, W, Cin, self.pad, _stream(dv)))
-            dv = dx
-        assert dv.shape == fv.x.shape, (dv.shape, fv.x.shape)
+            dv = _Folded(dv, self.pad)                # nn.ReflectionPad2d backward: deferred into the next kernel of the chain
+            if not FOLD_FUSION:
+                dv = dv.materialize()
+        assert tuple(dv.shape) == tuple(fv.x.shape), (dv.shape, fv.x.shape)
         G.add(self.f, dv)
 
 
@@ -826,13 +865,19 @@ class _ViewOp:
         self.stats, self.count, self.eps, self.gamma, self.beta = stats, count, eps, gamma, beta
 
     def backward(self, G: GradMap, wgrad: bool, nb):
-        dv = G.pop(self.out)
+        dv = G.pop(self.out, lazy_ok=self.kind != "act")
         if dv is None:
             return
         x = _sl(self.src.x, nb)
         if self.kind == "act":
             G.add(self.src, act_bwd(dv, x, self.act))
             return
+        fold = 0
+        if isinstance(dv, _Folded):
+            if x.shape[-1] % 4 == 0:
+                fold, dv = dv.pad, dv.dpad            # folded while the normalisation backward loads it
+            else:
+                dv = dv.materialize()
         if self.kind == "bn" and nb is not None:
             raise NotImplementedError("BatchNorm2d backward on a batch slice")
         B, H, W, C = x.shape
@@ -843,9 +888,9 @@ class _ViewOp:
         dgam = grad_of(gam) if (gam is not None and wgrad and gam.requires_grad) else None
         dbet = grad_of(bet) if (bet is not None and wgrad and bet.requires_grad) else None
         with torch.cuda.device(x.device):
-            _lib.check(_L().mdctgan_norm_act_bwd(x.data_ptr(), dv.data_ptr(), dx.data_ptr(), _sl(self.stats, nb).data_ptr(), self.count, self.eps,
-                                                 0 if self.kind == "in" else 1, _ptr(gam), _ptr(bet), self.act, red.data_ptr(), _ptr(dgam),
-                                                 _ptr(dbet), B, H * W, C, _stream(x)))
+            _lib.check(_L().mdctgan_norm_act_bwd_folded(x.data_ptr(), dv.data_ptr(), dx.data_ptr(), _sl(self.stats, nb).data_ptr(), self.count,
+                                                        self.eps, 0 if self.kind == "in" else 1, _ptr(gam), _ptr(bet), self.act, red.data_ptr(),
+                                                        _ptr(dgam), _ptr(dbet), B, H, W, C, fold, _stream(x)))
         G.add(self.src, dx)
 
 
