@@ -4,7 +4,7 @@ Restates the forward passes of the reference's generator / discriminator stacks 
 reference-layout state_dict (citations into /root/reference/models/networks.py):
 
   global_generator   GlobalGenerator.forward        :301-357   (conv / transconv configuration)
-  local_enhancer     LocalEnhancer.forward          :173-267   (n_local_enhancers = 1, n_attn_l = 0)
+  local_enhancer     LocalEnhancer.forward          :173-267   (n_local_enhancers = 1; n_attn_l >= 0: the attention sandwich of :218-237)
   resnet_block       ResnetBlock.forward            :421-463
   bottle_stack       bottleneck_transformer_pytorch==0.1.4 BottleStack (third party, PARITY UNPINNED:
                      see oracle/bottlestack_ref.py), eval or train-mode BatchNorm
@@ -83,6 +83,9 @@ def bottle_stack(sd, prefix, x, num_layers, heads, dim_head, training=False):
         h = attention(sd, p + ".3", h, heads, dim_head)
         h = F.relu(_bn(sd, p + ".5", h, training))
         h = _bn(sd, p + ".8", F.conv2d(h, sd[p + ".7.weight"]), training)
+        sc = f"{prefix}.net.{i}.shortcut"
+        if sc + ".0.weight" in sd:       # projection shortcut (dim != dim_out): conv1x1 -> BN -> activation
+            x = F.relu(_bn(sd, sc + ".1", F.conv2d(x, sd[sc + ".0.weight"]), training))
         x = F.relu(h + x)
     return x
 
@@ -118,27 +121,47 @@ def avgpool(x):
 
 
 def local_enhancer(sd, x, n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128, training=False, down="conv",
-                   up="transconv"):
+                   up="transconv", n_attn_l=0, heads_l=4, dim_head_l=128):
     coarse = _global_trunk(sd, "model", avgpool(x), n_down, n_blocks_global, n_attn, heads, dim_head, training, with_head=False, down=down,
                            up=up)
     h = F.relu(_in(_conv(sd, "model1_1.1", x, reflect=3)))
     h = F.relu(_in(_down(sd, "model1_1.4", h, down)))
     h = h + coarse
-    for b in range(n_blocks_local):
-        h = resnet_block(sd, f"model1_2.{b}", h)
-    i = n_blocks_local
+    if n_attn_l == 0:
+        for b in range(n_blocks_local):
+            h = resnet_block(sd, f"model1_2.{b}", h)
+        i = n_blocks_local
+    else:
+        # networks.py:218-237: [res x middle, down (8x: three stride-2 layers, the 2nd and 3rd share weights), BottleStack, res ...,
+        # three applications of ONE up layer, up].  The state_dict lists the shared layers once per position.
+        middle = n_blocks_local // 2
+        for b in range(middle):
+            h = resnet_block(sd, f"model1_2.{b}", h)
+        for j in (0, 3, 3):        # positions 3 and 6 are ONE layer object: its first state_dict entry carries the (summed) gradient
+            h = F.relu(_in(_down(sd, f"model1_2.{middle}.{j}", h, down)))
+        h = bottle_stack(sd, f"model1_2.{middle + 1}", h, n_attn_l, heads_l, dim_head_l, training)
+        for b in range(middle, n_blocks_local):
+            h = resnet_block(sd, f"model1_2.{b + 2}", h)
+        i = n_blocks_local + 2
+        for _ in range(3):         # one layer object at positions i, i + 3, i + 6
+            h = F.relu(_in(_up(sd, f"model1_2.{i}", h, up)))
+        i += 9
     h = F.relu(_in(_up(sd, f"model1_2.{i}", h, up)))
     return torch.tanh(_conv(sd, f"model1_2.{i + 4}", h, reflect=3))
 
 
-def multiscale_d(sd, x, num_D=3, n_layers=3):
-    """getIntermFeat=True layout: list[num_D] of list[n_layers+2] feature maps."""
+def multiscale_d(sd, x, num_D=3, n_layers=3, interm=True, sigmoid=False):
+    """getIntermFeat=True layout (default): list[num_D] of list[n_layers+2] feature maps, the sigmoid stage of --no_lsgan never applied
+    (networks.py:686).  interm=False (--no_ganFeat_loss): list[num_D] of [output], keys `layer{s}.{index in the flat Sequential}`, the
+    sigmoid applied when the discriminator was built with it (networks.py:671-672)."""
     result = []
     for i in range(num_D):
         s = num_D - 1 - i
         feats, h = [], x
+        flat = 0
         for j in range(n_layers + 2):
-            key = f"scale{s}_layer{j}.0"
+            key = f"scale{s}_layer{j}.0" if interm else f"layer{s}.{flat}"
+            flat += 2 if (j == 0 or j == n_layers + 1) else 3          # [conv, lrelu] | [conv, norm, lrelu] | [conv]
             stride = 2 if j < n_layers else 1
             h = _conv(sd, key, h, stride=stride, padding=2)
             if 0 < j < n_layers + 1:
@@ -146,6 +169,8 @@ def multiscale_d(sd, x, num_D=3, n_layers=3):
             if j < n_layers + 1:
                 h = F.leaky_relu(h, 0.2)
             feats.append(h)
+        if not interm:
+            feats = [torch.sigmoid(feats[-1]) if sigmoid else feats[-1]]
         result.append(feats)
         if i != num_D - 1:
             x = avgpool(x)

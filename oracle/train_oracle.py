@@ -23,23 +23,27 @@ def spectro(audio, gain=1000.0, src_range=(-5.0, 5.0), norm_range=(-1.0, 1.0)):
 
 
 def losses(pG, pD, lr_spectro, hr_spectro, *, netG="local", n_down=3, n_blocks_global=9, n_blocks_local=3, n_attn=0, heads=4, dim_head=128,
-           num_D=3, n_layers_D=3, lambda_feat=10.0, fit_residual=True, lo=-1.0, use_feat=True, down="conv", up="transconv"):
+           num_D=3, n_layers_D=3, lambda_feat=10.0, fit_residual=True, lo=-1.0, use_feat=True, down="conv", up="transconv", lsgan=True,
+           n_attn_l=0, heads_l=4, dim_head_l=128):
     """The four loss tensors [G_GAN, G_GAN_Feat, D_real, D_fake] as autograd functions of the parameter dicts."""
     x = torch.cat((lr_spectro, lr_spectro.abs() * 2 + lo), dim=1)
     if netG == "global":
         sr = NO.global_generator(pG, x, n_down, n_blocks_global, n_attn, heads, dim_head, training=True, down=down, up=up)
     else:
-        sr = NO.local_enhancer(pG, x, n_down, n_blocks_global, n_blocks_local, n_attn, heads, dim_head, training=True, down=down, up=up)
+        sr = NO.local_enhancer(pG, x, n_down, n_blocks_global, n_blocks_local, n_attn, heads, dim_head, training=True, down=down, up=up,
+                               n_attn_l=n_attn_l, heads_l=heads_l, dim_head_l=dim_head_l)
     if fit_residual:
         sr = sr + lr_spectro
     sr_in = torch.cat((sr, sr.abs() * 2 + lo), dim=1)
     hr_in = torch.cat((hr_spectro, hr_spectro.abs() * 2 + lo), dim=1)
-    pred_fake_pool = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in.detach()), dim=1), num_D, n_layers_D)
-    pred_real = NO.multiscale_d(pD, torch.cat((lr_spectro, hr_in), dim=1), num_D, n_layers_D)
-    pred_fake = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in), dim=1), num_D, n_layers_D)
-    d_fake = sum(F.mse_loss(p[-1], torch.zeros_like(p[-1])) for p in pred_fake_pool)
-    d_real = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_real)
-    g_gan = sum(F.mse_loss(p[-1], torch.ones_like(p[-1])) for p in pred_fake)
+    dkw = dict(interm=use_feat, sigmoid=not lsgan)          # define_D(..., use_sigmoid = no_lsgan, getIntermFeat = not no_ganFeat_loss)
+    pred_fake_pool = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in.detach()), dim=1), num_D, n_layers_D, **dkw)
+    pred_real = NO.multiscale_d(pD, torch.cat((lr_spectro, hr_in), dim=1), num_D, n_layers_D, **dkw)
+    pred_fake = NO.multiscale_d(pD, torch.cat((lr_spectro, sr_in), dim=1), num_D, n_layers_D, **dkw)
+    gan = F.mse_loss if lsgan else F.binary_cross_entropy       # GANLoss: nn.MSELoss / nn.BCELoss (networks.py:105-108)
+    d_fake = sum(gan(p[-1], torch.zeros_like(p[-1])) for p in pred_fake_pool)
+    d_real = sum(gan(p[-1], torch.ones_like(p[-1])) for p in pred_real)
+    g_gan = sum(gan(p[-1], torch.ones_like(p[-1])) for p in pred_fake)
     g_feat = torch.zeros((), device=lr_spectro.device)
     if use_feat:
         fw, dw = 4.0 / (n_layers_D + 1), 1.0 / num_D

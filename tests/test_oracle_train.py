@@ -85,3 +85,44 @@ def test_train_oracle_matches_reference(train_golden, name):
 
     check_after(out["paramsG"], train_golden[f"{name}_G_cksum_after"])
     check_after(out["paramsD"], train_golden[f"{name}_D_cksum_after"])
+
+
+@pytest.mark.parametrize("name", ["tr_small_bce", "tr_small_attnl"])
+def test_train_oracle_option_branches_match_reference(name):
+    """The oracle's --no_lsgan (sigmoid head + BCE, no intermediate features) and --n_blocks_attn_l (local attention sandwich) branches
+    against the reference's own train iteration (tests/golden/train_{bce,attnl}_golden.npz): losses and every gradient tensor of the first
+    iteration.  The attention-sandwich configuration is badly conditioned (see tests/test_train_gpu.py): on the same CPU, in fp32, this
+    functional restatement and the reference's module graph already differ by percent-level amounts on the far end of the generator."""
+    from make_golden_nets import TRAIN_ATTNL_FLAGS, TRAIN_BCE_FLAGS
+    from mdctgan_b200.models import networks
+
+    bce = name == "tr_small_bce"
+    gold = dict(np.load(os.path.join(GOLDEN, "train_bce_golden.npz" if bce else "train_attnl_golden.npz")))
+    flags, batch, T, seed = (TRAIN_BCE_FLAGS if bce else TRAIN_ATTNL_FLAGS)[name]
+    cfg = flags_to_cfg(flags)
+    g = lambda k, d: int(flags[flags.index(k) + 1]) if k in flags else d   # noqa: E731
+    n_attn_l, heads_l, dim_head_l = g("--n_blocks_attn_l", 0), g("--heads_l", 4), g("--dim_head_l", 128)
+    torch.manual_seed(seed)
+    G = networks.define_G(2, 1, cfg["ngf"], cfg["netG"], cfg["n_down"], cfg["n_blocks_global"], 1, cfg["n_blocks_local"], "instance",
+                          input_size=(cfg["bins"], 256), n_attn_g=cfg["n_attn"], heads_g=cfg["heads"], dim_head_g=cfg["dim_head"],
+                          n_attn_l=n_attn_l, heads_l=heads_l, dim_head_l=dim_head_l)
+    D = networks.define_D(3, cfg["ndf"], cfg["n_layers_D"], "instance", bce, cfg["num_D"], not bce)
+    np.testing.assert_allclose(state_checksum(G.state_dict()), gold[f"{name}_G_cksum0"], rtol=1e-12)
+    np.testing.assert_allclose(state_checksum(D.state_dict()), gold[f"{name}_D_cksum0"], rtol=1e-12)
+    kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D",
+                              "fit_residual", "down", "up")}
+    kw.update(lsgan=not bce, use_feat=not bce, n_attn_l=n_attn_l, heads_l=heads_l, dim_head_l=dim_head_l)
+    out = TO.train_step(G.state_dict(), D.state_dict(), gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"], steps=1, **kw)
+    names = list(gold[f"{name}_loss_names"])
+    got = dict(zip(["G_GAN", "G_GAN_Feat", "D_real", "D_fake"], out["losses"][0]))
+    np.testing.assert_allclose([got[k] for k in names], gold[f"{name}_losses"][0], rtol=2e-4)
+    for tag in ("gradG", "gradD"):
+        ref = {k[len(name) + len(tag) + 3:]: v for k, v in gold.items() if k.startswith(f"{name}_{tag}::")}
+        gmax = max(float(np.abs(v).max()) for v in ref.values())
+        worst = 0.0
+        for k, v in ref.items():
+            if float(np.abs(v).max()) < 1e-4 * gmax:
+                continue
+            assert k in out[tag], (tag, k)
+            worst = max(worst, rel_l2(out[tag][k].numpy(), v))
+        assert worst < (1e-3 if bce else 0.25), (tag, worst)

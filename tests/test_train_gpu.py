@@ -562,11 +562,30 @@ def test_option_branches_train_step_matches_reference(dev, api, name):
             allerr.append((round(e, 5), tag, k, float(np.abs(v).max())))
     print(f"{name}/{api}: worst gradient rel-L2 {worst}")
     print(sorted(allerr, reverse=True)[:12])
-    # tr_small_attnl is badly conditioned: measured on the REFERENCE itself (CPU, fp32), a 1e-6 relative perturbation of the input audio
-    # moves its own generator gradients by 0.9 - 1.6 rel-L2 on a dozen tensors (losses by 3e-5); our gradients sit within 0.13 of its
-    # unperturbed ones (worst: the BatchNorm biases of the local BottleBlock), the losses within 5e-4.  The bar documents that, it
-    # cannot be tighter than the reference's own reproducibility.
-    bar = 2e-2 if bce else 0.25
+    bar = 2e-2
+    if not bce:
+        # tr_small_attnl is badly conditioned.  Three-way gate like the cfg4 one above: ground truth = the oracle (bit-identical to the
+        # reference's module graph on CPU: tests/test_oracle_train.py) run in fp64 on the same fp32 weights and audio; yardstick = the
+        # distance of the reference's OWN fp32 gradients (the golden) from it -- 6 - 7 % on the BatchNorm / qkv tensors of the local
+        # BottleBlock.  Every gradient tensor of the CUDA path must lie within 3 x that distance of the truth (floor 2e-3).
+        from oracle import train_oracle as TO
+
+        kw = {k: cfg[k] for k in ("netG", "n_down", "n_blocks_global", "n_blocks_local", "n_attn", "heads", "dim_head", "num_D", "n_layers_D",
+                                  "fit_residual", "down", "up")}
+        kw.update(n_attn_l=g("--n_blocks_attn_l", 0), heads_l=g("--heads_l", 4), dim_head_l=g("--dim_head_l", 128))
+        truth = TO.train_step(G0.state_dict(), D0.state_dict(), gold[f"{name}_lr_audio"], gold[f"{name}_hr_audio"], steps=1, dtype=torch.float64, **kw)
+        ratios = []
+        for k, v in gold.items():
+            if not k.startswith(f"{name}_gradG::") or float(np.abs(v).max()) < 1e-4 * max(float(np.abs(u).max()) for kk, u in gold.items() if kk.startswith(f"{name}_gradG::")):
+                continue
+            kk = k[len(name) + 8:]
+            t = truth["gradG"][kk].numpy()
+            ref_d, our_d = rel_l2(v, t), rel_l2(gG[kk].numpy(), t)
+            ratios.append((our_d / max(ref_d, 2e-3), our_d, ref_d, kk))
+        ratios.sort(reverse=True)
+        print("ours vs fp64 truth / reference fp32 vs fp64 truth, worst tensors:", ratios[:4])
+        assert ratios[0][0] < 3.0, ratios[:4]
+        bar = 0.25        # (and nothing is further than 25 % from the reference's own fp32 gradients)
     assert worst["gradG"][0] < bar and worst["gradD"][0] < 2e-2, worst
 
 
