@@ -510,6 +510,99 @@ def bench_gpu_baseline(dev, sd0, lr, hr, steps):
     return out
 
 
+def bench_reference_transform_and_longform(dev):
+    """Baselines for BASELINE configs[0] / [4] by the reference's OWN code (baseline/_ref, unmodified):
+      mdct      models.mdct.MDCT4 / IMDCT4 (complex128 512-point FFT formulation) on `cuda` -- torch / cuFFT, the kernel to beat for
+                the transform half -- at the README shape [64, 32512] and at [1024, 8192], and on the host cores at the README shape
+                (README.md:102-109 publishes 9.61 ms for it on an RTX 3070 laptop GPU)
+      longform  generate_audio.py's loop (seg_pad_audio -> model.inference per batch of 16 segments -> .cpu() -> fold overlap-add,
+                generate_audio.py:24-53) on a 60 s clip, on `cuda`, and on the host cores on a bounded sample (one batch of 16 segments,
+                scaled to the 89 segments of the clip)"""
+    import torch
+
+    from baseline import ref_runner as R
+    from oracle import longform_oracle as LO
+
+    if not R.available():
+        return {"unavailable": "baseline/_ref is missing"}
+    R.import_reference()
+    from models.mdct import IMDCT4 as RefIMDCT4, MDCT4 as RefMDCT4
+    from util.util import kbdwin as ref_kbdwin
+
+    out = {"mdct": {}, "longform": {}}
+
+    def wall(fn, reps, sync):
+        fn()
+        if sync:
+            torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        if sync:
+            torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    for where, shapes in (("cuda", ((64, 32512), (1024, 8192))), ("cpu", ((64, 32512),))):
+        d = dev if where == "cuda" else torch.device("cpu")
+        w = ref_kbdwin(N_FFT).to(d)
+        fwd = RefMDCT4(n_fft=N_FFT, hop_length=HOP, win_length=N_FFT, window=w, device=d)
+        inv = RefIMDCT4(n_fft=N_FFT, hop_length=HOP, win_length=N_FFT, window=w, device=d)
+        for (B, T) in shapes:
+            torch.manual_seed(7)
+            x = (0.1 * torch.randn(B, T)).to(d)
+            with torch.no_grad():
+                spec = fwd(x)[0]
+                t_f = wall(lambda: fwd(x), 5 if where == "cuda" else 3, where == "cuda")
+                t_i = wall(lambda: inv(spec), 5 if where == "cuda" else 3, where == "cuda")
+            n = B * T
+            out["mdct"][f"reference_{where}_{B}x{T}"] = {"forward_ms": t_f, "inverse_ms": t_i, "forward_gsamp_per_s": n / t_f / 1e6,
+                                                         "inverse_gsamp_per_s": n / t_i / 1e6,
+                                                         "what": f"models.mdct.MDCT4 / IMDCT4 of the unmodified reference on {where}"
+                                                                 + (f" ({os.cpu_count()} threads)" if where == "cpu" else " (torch eager, cuFFT)")}
+            del x, spec
+    # ---- long-form
+    seg, ov, secs = 32512, 256, 60
+    args = [a for a in OPT_ARGS]
+    for k, v in (("--segment_length", str(seg)), ("--bins", "128"), ("--lr_sampling_rate", "16000")):
+        args[args.index(k) + 1] = v
+    clip = make_lr_audio(1, secs * SR, 5)
+    segs = LO.seg_pad_audio(clip.clone(), seg, ov)                       # AudioTestDataset.seg_pad_audio (pinned to the reference by tests)
+    n_seg = segs.shape[0]
+    for where in ("cuda", "cpu"):
+        d = dev if where == "cuda" else torch.device("cpu")
+        _, model = R.make_stepper(args, segs[:4], segs[:4], device=d, seed=99)
+        model.eval()
+
+        def generate(n_batches):
+            outs = []
+            with torch.no_grad():
+                for i in range(0, min(n_seg, 16 * n_batches), 16):
+                    sr_audio = model.inference(segs[i:i + 16].to(d))[1]
+                    outs.append(sr_audio.cpu())                        # generate_audio.py:36 copies every batch to the host
+            return torch.cat(outs, dim=0)
+
+        if where == "cuda":
+            generate(1)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            au = generate(10 ** 6)
+            LO.overlap_add(au.double().reshape(-1, 1, 1, au.shape[-1]), seg, ov)
+            dt = time.perf_counter() - t0
+            out["longform"]["reference_cuda"] = {"seconds_per_clip": dt, "real_time_factor": secs / dt, "segments": n_seg,
+                                                 "what": "generate_audio.py:24-53 with the unmodified reference model on cuda (torch eager), 60 s clip"}
+        else:
+            t0 = time.perf_counter()
+            generate(1)
+            dt16 = time.perf_counter() - t0
+            dt = dt16 * n_seg / 16.0
+            out["longform"]["reference_cpu"] = {"seconds_per_clip": dt, "real_time_factor": secs / dt, "cores": os.cpu_count(),
+                                                "sample": f"one batch of 16 of the {n_seg} segments ({dt16:.2f} s), scaled to the clip",
+                                                "what": "the same loop on the host cores"}
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- per-launch profile
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same workload (profiles/, gpurun s5f / s5m)
 NCU_TRAFFIC = {
@@ -790,7 +883,7 @@ def run_ours(args):
         mdct["aggregate"] = {"n_gpus": world, "scaling": "weak (8192 x 8192 samples per GPU, no collective)",
                              "raw_forward_gsamp_per_s": world * nsamp / (mf_ms * 1e-3) / 1e9, "raw_inverse_gsamp_per_s": world * nsamp / (mi_ms * 1e-3) / 1e9,
                              "raw_round_trip_gsamp_per_s": world * nsamp / ((mf_ms + mi_ms) * 1e-3) / 1e9}
-        configs = gpu_base = None
+        configs = gpu_base = ref_tl = None
         if world == 1 and not args.no_extras:
             try:
                 configs = bench_configs(dev, max(5, min(args.steps, 30)), bf16_peak)
@@ -800,6 +893,10 @@ def run_ours(args):
                 gpu_base = bench_gpu_baseline(dev, sd0, lr, hr, max(5, min(args.steps, 20)))
             except Exception as e:  # noqa: BLE001
                 gpu_base = {"error": repr(e)[:300]}
+            try:
+                ref_tl = bench_reference_transform_and_longform(dev)
+            except Exception as e:  # noqa: BLE001
+                ref_tl = {"error": repr(e)[:300]}
         cpu = cpu_baseline_run(seconds_budget=args.cpu_seconds, warmup=1, init=sd0)
         # world 1: the GPU's first step and the CPU baseline's first step saw the same weights and the same batch
         err = max(abs(a - b) / abs(b) for a, b in zip(first, cpu["first_losses"])) if world == 1 else None
@@ -859,6 +956,7 @@ def run_ours(args):
             "longform": longform,
             "configs": configs,
             "gpu_baseline": gpu_base,
+            "reference_transform_longform": ref_tl,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * SEG * 4, "d2h_bytes_per_step": 16,
                     "ms_per_step": e2e_ms, "api": "runtime.GraphedTrainStep(model)(pinned lr_audio, pinned hr_audio) -> 4 losses copied to "
