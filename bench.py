@@ -340,10 +340,22 @@ def bench_longform(dev, rank=0, world=1, reps=3):
         torch.cuda.synchronize(dev)
     dt = (time.perf_counter() - t0) / reps
     n_seg = gen.last_segments
+    dt0 = None
+    try:        # the reference script's own value, --gen_overlap 0 (generate_audio.sh:4-15)
+        gen.generate_shard(clip.to(dev, non_blocking=True), seg, 0, rank, world)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o0, _ = gen.generate_shard(clip.to(dev, non_blocking=True), seg, 0, rank, world)
+            o0.cpu()
+        dt0 = (time.perf_counter() - t0) / reps
+    except Exception as e:  # noqa: BLE001
+        dt0 = repr(e)[:200]
     del gen, model
     return {"workload": f"{secs} s clip @48 kHz -> {n_seg[1]} x {seg}-sample segments, gen_overlap {ov}, LocalEnhancer+2 attn at 128 frames, "
                         f"batches of 16, fp32; {world} rank(s), contiguous segment runs, no collective", "seconds_per_clip": dt,
-            "segments_this_rank": n_seg[0], "clip_seconds": secs, "h2d_bytes": clip.numel() * 4, "d2h_bytes": out.numel() * out.element_size()}
+            "segments_this_rank": n_seg[0], "clip_seconds": secs, "h2d_bytes": clip.numel() * 4, "d2h_bytes": out.numel() * out.element_size(),
+            "seconds_per_clip_gen_overlap_0": dt0}
 
 
 # ---------------------------------------------------------------------------------------------- other BASELINE configs
