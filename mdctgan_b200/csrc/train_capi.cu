@@ -130,7 +130,24 @@ int mdctgan_conv2d_wgrad(const float* x, int B, int H, int W, int Cin, const flo
   p.dw = dw; p.s_co = s_co; p.s_ci = s_ci; p.s_tap = s_tap; p.dbias = dbias;
   const int K = kh * kw * Cin, HWo = Ho * Wo;
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cout <= 4) {
+  if (Cout == 1 && stride == 1 && !transposed && Cin % 4 == 0 && (kw == 7 || kw == 4) && (size_t)K * sizeof(float) <= 64 * 1024 &&
+      (in_act == kActNone || in_act == kActRelu || in_act == kActLeaky) && !getenv("MDCTGAN_WGRAD_COUT1_OLD")) {
+    // the heads: register reuse along the row (conv_wgrad_cout1_kernel)
+    const long long units = (long long)B * Ho * ((Wo + kWgSegW - 1) / kWgSegW);
+    const long long threads = units * (Cin / 4) * kh;
+    const long long blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffLL) return mdctgan_set_error(-2, "conv2d_wgrad: grid too large");
+    const size_t smem = (size_t)K * sizeof(float);
+    if (kw == 7) {
+      static bool a7 = false;
+      if (!a7) { CKT(cudaFuncSetAttribute(conv_wgrad_cout1_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); a7 = true; }
+      conv_wgrad_cout1_kernel<7><<<(unsigned)blocks, 256, smem, st>>>(p);
+    } else {
+      static bool a4 = false;
+      if (!a4) { CKT(cudaFuncSetAttribute(conv_wgrad_cout1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); a4 = true; }
+      conv_wgrad_cout1_kernel<4><<<(unsigned)blocks, 256, smem, st>>>(p);
+    }
+  } else if (Cout <= 4) {
     const int kblocks = (K + 255) / 256;
     int chunks = (1184 + kblocks * B - 1) / (kblocks * B);
     const int max_chunks = (HWo + 255) / 256;

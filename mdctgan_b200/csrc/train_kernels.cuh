@@ -287,6 +287,99 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_cout_kernel(const WgradP
   if (p.dbias && blockIdx.x == 0 && tid < p.Cout) atomicAdd(p.dbias + tid, bsum[0]);
 }
 
+// Cout == 1, stride 1, Cin % 4 == 0 (generator head 7x7, PatchGAN heads 4x4) with register reuse along the row.  The kernel above walks
+// its pixels with one scalar load and ~15 instructions per multiply-add (187 us on the cfg4 generator head, 6 ms on the train.sh one).
+// Here a thread owns (tap row ky, channel quad) for a segment of kSegW output columns of one output row: it walks the padded input
+// columns t of that segment once, loading x[iy(ky)][ix(t)] (float4, normalised + activated on the fly) and keeping the last KW values
+// of dy in registers, so that one load feeds KW * 4 multiply-adds:  dW[ky][kx][c] += x[t][c] * dy[t - kx].
+// Partial sums meet in shared memory per CTA, then one global atomic per element and CTA.  grid.x = ceil(units * G * kh / 256),
+// unit = (sample, output row, column segment), G = Cin / 4; dynamic shared memory kh * KW * Cin floats.
+constexpr int kWgSegW = 64;
+template <int KW>
+__global__ void __launch_bounds__(256) conv_wgrad_cout1_kernel(const WgradParams p) {
+  extern __shared__ float s_part[];              // [kh][KW][Cin]
+  const int G = p.Cin / 4, per_unit = G * p.kh;
+  const int nelem = p.kh * KW * p.Cin;
+  for (int i = threadIdx.x; i < nelem; i += 256) s_part[i] = 0.f;
+  __syncthreads();
+  const int segs = (p.Wo + kWgSegW - 1) / kWgSegW;
+  const long long units = (long long)p.B * p.Ho * segs;
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long unit = gid / per_unit;
+  if (unit < units) {
+    const int idx = (int)(gid - unit * per_unit);
+    const int cq = idx % G, ky = idx / G, c = cq * 4;
+    const int seg = (int)(unit % segs);
+    const long long row = unit / segs;
+    const int oy = (int)(row % p.Ho), b = (int)(row / p.Ho);
+    const int x0 = seg * kWgSegW, x1 = min(p.Wo, x0 + kWgSegW);
+    const float* dyr = p.dy + ((size_t)b * p.Ho + oy) * p.Wo;
+    if (p.dbias && idx == 0) {
+      float sb = 0.f;
+      for (int ox = x0; ox < x1; ++ox) sb += __ldg(dyr + ox);
+      atomicAdd(p.dbias, sb);
+    }
+    const int iy = in_coord(oy, ky, p.H, 1, p.pad, p.pad_mode, 0);
+    if (iy >= 0) {
+      // deferred normalisation of the thread's four channels (sample b)
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool has_norm = p.in.scale != nullptr || p.in.stats != nullptr;
+      if (p.in.scale) {
+        const size_t o = (p.in.per_sample ? (size_t)b * p.Cin : 0) + c;
+        sc = __ldg(reinterpret_cast<const float4*>(p.in.scale + o));
+        sh = __ldg(reinterpret_cast<const float4*>(p.in.shift + o));
+      } else if (p.in.stats) {
+        float scv[4], shv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t o = 2 * ((size_t)b * p.Cin + c + u);
+          const double mean = p.in.stats[o] / (double)p.in.count;
+          double var = p.in.stats[o + 1] / (double)p.in.count - mean * mean;
+          var = var < 0.0 ? 0.0 : var;
+          const double rstd = rsqrt(var + (double)p.in.eps);
+          scv[u] = (float)rstd; shv[u] = (float)(-mean * rstd);
+        }
+        sc = make_float4(scv[0], scv[1], scv[2], scv[3]); sh = make_float4(shv[0], shv[1], shv[2], shv[3]);
+      }
+      const float slope = !has_norm ? 1.f : (p.in.act == kActRelu ? 0.f : (p.in.act == kActLeaky ? 0.2f : 1.f));
+      const float* xrow = p.x + (((size_t)b * p.H + iy) * p.W) * p.Cin + c;
+      float acc[KW][4];
+      float dyw[KW];
+#pragma unroll
+      for (int k = 0; k < KW; ++k) { dyw[k] = 0.f; acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+#pragma unroll 2
+      for (int t = x0; t < x1 + KW - 1; ++t) {           // padded column t feeds the outputs ox = t - kx inside [x0, x1)
+#pragma unroll
+        for (int k = KW - 1; k > 0; --k) dyw[k] = dyw[k - 1];
+        dyw[0] = t < x1 ? __ldg(dyr + t) : 0.f;
+        const int ix = in_coord(t, 0, p.W, 1, p.pad, p.pad_mode, 0);
+        if (ix >= 0) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(xrow + (size_t)ix * p.Cin));
+          float e0 = fmaf(q.x, sc.x, sh.x), e1 = fmaf(q.y, sc.y, sh.y), e2 = fmaf(q.z, sc.z, sh.z), e3 = fmaf(q.w, sc.w, sh.w);
+          e0 = fmaxf(e0, slope * e0); e1 = fmaxf(e1, slope * e1); e2 = fmaxf(e2, slope * e2); e3 = fmaxf(e3, slope * e3);
+#pragma unroll
+          for (int k = 0; k < KW; ++k) {
+            acc[k][0] = fmaf(e0, dyw[k], acc[k][0]); acc[k][1] = fmaf(e1, dyw[k], acc[k][1]);
+            acc[k][2] = fmaf(e2, dyw[k], acc[k][2]); acc[k][3] = fmaf(e3, dyw[k], acc[k][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KW; ++k)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) atomicAdd(&s_part[(ky * KW + k) * p.Cin + c + u], acc[k][u]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nelem; i += 256) {
+    const float v = s_part[i];
+    if (v != 0.f) {
+      const int tap = i / p.Cin, ci = i - tap * p.Cin;
+      atomicAdd(p.dw + (long long)ci * p.s_ci + (long long)tap * p.s_tap, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward of v = act(norm(x)), norm = InstanceNorm2d(affine=False) (mode 0) or train-mode BatchNorm2d (mode 1):
 //   pre = (x - mean) * rstd * gamma + beta,  g = dv * act'(pre),  xhat = (x - mean) * rstd
