@@ -44,7 +44,9 @@ int launch_wgrad_umma(umma::WgradUmmaParams& p, cudaStream_t st) {
   const int tiles = m_tiles * p.n_tiles;
   // split the reduction over pixels while the CTAs still fit ONE wave (1 CTA per SM: the ring takes most of the shared memory);
   // every split costs one more set of output reductions
-  int psplit = tiles >= 148 ? 1 : 148 / tiles;
+  static int cta_cap = 0;       // MDCTGAN_WGRAD_CTA_CAP: CTAs a weight-gradient launch may spread over (default: the whole device)
+  if (!cta_cap) { const char* e = getenv("MDCTGAN_WGRAD_CTA_CAP"); cta_cap = e ? atoi(e) : 148; if (cta_cap < 1) cta_cap = 1; }
+  int psplit = tiles >= cta_cap ? 1 : cta_cap / tiles;
   if (psplit > p.chunks) psplit = p.chunks;
   if (psplit > 65535) psplit = 65535;
   umma::conv_wgrad_umma_kernel<NBLK, SPLIT3><<<dim3(tiles, psplit), umma::kWgThreads, C::kSmemBytes, st>>>(p);
@@ -57,9 +59,11 @@ int pick_wgrad_nblk(int K, int Cout, int chunks) {
   const int m_tiles = (K + umma::kBM - 1) / umma::kBM;
   const int blocks = (Cout + 31) / 32;
   const int max_split = chunks / 4 > 0 ? chunks / 4 : 1;
+  static int min_ctas = 0;
+  if (!min_ctas) { const char* e = getenv("MDCTGAN_WGRAD_MIN_CTAS"); min_ctas = e ? atoi(e) : 120; if (min_ctas < 1) min_ctas = 1; }
   for (int nblk = blocks < 8 ? blocks : 8; nblk >= 1; --nblk) {
     const long long ctas = (long long)m_tiles * ((blocks + nblk - 1) / nblk) * max_split;
-    if (ctas >= 120) return nblk;
+    if (ctas >= min_ctas) return nblk;
   }
   return 1;
 }
